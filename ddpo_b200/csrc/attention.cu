@@ -1,0 +1,270 @@
+// Fused softmax attention (forward) on tcgen05, head dim 64 -- self- and cross-attention of the
+// Flax U-Net's BasicTransformerBlock (3P diffusers==0.12.1 attention_flax.py FlaxAttention:
+// S = (Q K^T) * d^-0.5, P = softmax(S), O = P V; reached from the reference at
+// pipeline_flax_stable_diffusion.py:219-224 / training/policy_gradient.py:87-102).
+//
+// The [B*h, N, N] score tensor XLA materialises never exists here.  One CTA owns a 128-query
+// tile of one (sample, head); K/V stream through a 2-stage TMA ring in 128-key blocks:
+//   S_j   = Q K_j^T          tcgen05.mma (SS, both K-major)        -> TMEM  X[j&1] (128 cols fp32)
+//   P_j   = exp2((S_j - m) c)   softmax warps (1 thread = 1 query row, tcgen05.ld), bf16 -> smem
+//   O_j   = P_j V_j          tcgen05.mma (A = P K-major, B = V MN-major) -> TMEM X[j&1][0:64]
+//   O_acc = O_acc * alpha + O_j    in registers (fp32), normalised by the row sum at the end.
+// S_{j+1} is issued before P_j is ready, so QK^T overlaps the softmax; two CTAs are resident
+// per SM (256 TMEM columns, 113 KB shared each) so one CTA's softmax hides the other's MMAs.
+// Fixed reduction order; no atomics.
+#include "common.cuh"
+
+namespace ddpo {
+
+constexpr int AT_THREADS = 192;  // warp0: TMA + TMEM alloc, warp1: MMA, warps 2..5: softmax
+constexpr int AT_BQ = 128, AT_BKV = 128, AT_D = 64;
+constexpr int AT_TILE = AT_BQ * AT_D * 2;  // 16 KB: a [128 x 64] bf16 SW128 tile
+constexpr int AT_KV_STAGES = 2;
+constexpr int AT_SMEM_Q = 0;
+constexpr int AT_SMEM_KV = AT_TILE;                                   // stages x (K | V)
+constexpr int AT_SMEM_P = AT_SMEM_KV + AT_KV_STAGES * 2 * AT_TILE;     // 2 tiles (keys 0-63 | 64-127)
+constexpr int AT_SMEM_BAR = AT_SMEM_P + 2 * AT_TILE;
+constexpr int AT_SMEM_TOTAL = AT_SMEM_BAR + 256;
+
+struct AttnArgs {
+  CUtensorMap tmQ, tmK, tmV;
+  __nv_bfloat16* out;
+  float* lse;  // [B, heads, Nq] or null
+  int nq, nk, heads, ldo;
+  float scale_log2e;  // d^-0.5 * log2(e)
+  float scale;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __grid_constant__ AttnArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_SMEM_BAR);
+  uint64_t* q_full = bars;               // 1
+  uint64_t* kv_full = bars + 1;          // [2]
+  uint64_t* kv_empty = bars + 3;         // [2]
+  uint64_t* s_full = bars + 5;           // [2]
+  uint64_t* o_full = bars + 7;           // [2]
+  uint64_t* x_free = bars + 9;           // [2]
+  uint64_t* p_full = bars + 11;          // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, b = blockIdx.z;
+  const int nkb = (p.nk + AT_BKV - 1) / AT_BKV;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();  // SW128 tiles need 1024-byte alignment
+    prefetch_tmap(&p.tmQ);
+    prefetch_tmap(&p.tmK);
+    prefetch_tmap(&p.tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&x_free[i], 4);
+    }
+    mbar_init(p_full, 4);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, AT_TILE);
+      tma_load_4d(smem + AT_SMEM_Q, &p.tmQ, q_full, 0, head, q0, b);
+      for (int j = 0; j < nkb; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        uint8_t* sK = smem + AT_SMEM_KV + st * 2 * AT_TILE;
+        mbar_expect_tx(&kv_full[st], 2 * AT_TILE);
+        tma_load_4d(sK, &p.tmK, &kv_full[st], 0, head, j * AT_BKV, b);
+        tma_load_4d(sK + AT_TILE, &p.tmV, &kv_full[st], 0, head, j * AT_BKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(AT_BQ, AT_BKV, 0, 0);  // S = Q K^T: N = 128 keys
+      const uint32_t idesc_o = umma_idesc_bf16(AT_BQ, AT_D, 0, 1);    // O = P V : N = 64, B (V) MN-major
+      const uint32_t q_addr = smem_u32(smem + AT_SMEM_Q);
+      const uint32_t p_addr = smem_u32(smem + AT_SMEM_P);
+      auto issue_s = [&](int j) {
+        const int st = j & 1, xb = j & 1;
+        mbar_wait(&x_free[xb], ((j >> 1) & 1) ^ 1);
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem + AT_SMEM_KV + st * 2 * AT_TILE);
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_bf16(tmem_base + xb * 128, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024),
+                    idesc_s, k != 0);
+        umma_commit(&s_full[xb]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nkb; ++j) {
+        if (j + 1 < nkb) issue_s(j + 1);
+        const int st = j & 1, xb = j & 1;
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem + AT_SMEM_KV + st * 2 * AT_TILE + AT_TILE);
+#pragma unroll
+        for (int k = 0; k < AT_BKV / 16; ++k) {
+          // A = P: K-major, 64-key sub-tiles; B = V: MN-major, 16 keys = 16 rows of 128 B
+          const uint32_t a = p_addr + (k >> 2) * AT_TILE + (k & 3) * 32;
+          const uint32_t bb = v_addr + k * 16 * 128;
+          umma_bf16(tmem_base + xb * 128, umma_desc(a, 16, 1024), umma_desc(bb, 8192, 1024), idesc_o, k != 0);
+        }
+        umma_commit(&o_full[xb]);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warps
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float o_acc[AT_D];
+#pragma unroll
+    for (int i = 0; i < AT_D; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float c = p.scale_log2e;
+    uint8_t* sP = smem + AT_SMEM_P;
+    for (int j = 0; j < nkb; ++j) {
+      const int xb = j & 1;
+      mbar_wait(&s_full[xb], (j >> 1) & 1);
+      tc_fence_after();
+      const int kbase = j * AT_BKV;
+      const int valid = min(AT_BKV, p.nk - kbase);
+      // pass 1: row max
+      float m_blk = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + xb * 128 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m_run, m_blk);
+      const float alpha = exp2f((m_run - m_new) * c);
+      const float mc = m_new * c;
+      float l_blk = 0.f;
+      // pass 2: P = exp2(S*c - m*c) -> bf16 -> swizzled smem (K-major SW128, 2 sub-tiles of 64 keys)
+#pragma unroll 1
+      for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + xb * 128 + c0, v);
+        tmem_ld_wait();
+        float pr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = exp2f(__uint_as_float(v[i]) * c - mc);
+          pr[i] = (c0 + i < valid) ? e : 0.f;
+          l_blk += pr[i];
+        }
+        uint8_t* tile = sP + (c0 >> 6) * AT_TILE + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = ((c0 & 63) >> 3) + g;  // 16-byte chunk index within the 128-byte row
+          uint4 u;
+          u.x = pack_bf16(pr[g * 8 + 0], pr[g * 8 + 1]);
+          u.y = pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]);
+          u.z = pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]);
+          u.w = pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(tile + ((chunk ^ (r & 7)) << 4)) = u;
+        }
+      }
+      l_run = l_run * alpha + l_blk;
+      m_run = m_new;
+      // S consumed + P visible to the tensor core (generic -> async proxy)
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // O_j
+      mbar_wait(&o_full[xb], (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < AT_D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + xb * 128 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c0 + i] = o_acc[c0 + i] * alpha + __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_free[xb]);
+    }
+    const int row = q0 + r;
+    if (row < p.nq) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* o = p.out + (static_cast<size_t>(b) * p.nq + row) * p.ldo + head * AT_D;
+#pragma unroll
+      for (int i = 0; i < AT_D; i += 8) {
+        uint4 u;
+        u.x = pack_bf16(o_acc[i] * inv, o_acc[i + 1] * inv);
+        u.y = pack_bf16(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+        u.z = pack_bf16(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
+        u.w = pack_bf16(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+        *reinterpret_cast<uint4*>(o + i) = u;
+      }
+      if (p.lse != nullptr)
+        p.lse[(static_cast<size_t>(b) * p.heads + head) * p.nq + row] = m_run * p.scale + logf(l_run);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static int make_qkv_map(CUtensorMap* m, const void* base, int heads, int n, int batch, int ld) {
+  uint64_t dims[4] = {(uint64_t)AT_D, (uint64_t)heads, (uint64_t)n, (uint64_t)batch};
+  uint64_t strides[3] = {(uint64_t)AT_D * 2, (uint64_t)ld * 2, (uint64_t)ld * 2 * n};
+  uint32_t box[4] = {(uint32_t)AT_D, 1, (uint32_t)AT_BQ, 1};
+  uint32_t es[4] = {1, 1, 1, 1};
+  return make_tensor_map(m, base, 2, 4, dims, strides, box, es, 1);
+}
+
+}  // namespace ddpo
+
+using namespace ddpo;
+
+extern "C" int ddpo_attention_fwd(const ddpo_attention_args* a, void* stream) {
+  DDPO_REQUIRE(a && a->q && a->k && a->v && a->out, "attention_fwd: null pointer");
+  DDPO_REQUIRE(a->head_dim == AT_D, "attention_fwd: head_dim must be 64 (got %d)", a->head_dim);
+  DDPO_REQUIRE(a->nq > 0 && a->nk > 0 && a->heads > 0 && a->batch > 0, "attention_fwd: bad sizes");
+  AttnArgs p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = make_qkv_map(&p.tmQ, a->q, a->heads, a->nq, a->batch, a->ldq))) return rc;
+  if ((rc = make_qkv_map(&p.tmK, a->k, a->heads, a->nk, a->batch, a->ldk))) return rc;
+  if ((rc = make_qkv_map(&p.tmV, a->v, a->heads, a->nk, a->batch, a->ldv))) return rc;
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.lse = a->lse;
+  p.nq = a->nq, p.nk = a->nk, p.heads = a->heads, p.ldo = a->ldo;
+  p.scale = 1.0f / sqrtf(static_cast<float>(AT_D));
+  p.scale_log2e = p.scale * 1.4426950408889634f;
+  static bool attr = false;
+  if (!attr) {
+    DDPO_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_TOTAL));
+    attr = true;
+  }
+  dim3 grid((a->nq + AT_BQ - 1) / AT_BQ, a->heads, a->batch);
+  attention_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(p);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}

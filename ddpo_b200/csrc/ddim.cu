@@ -1,0 +1,340 @@
+// JAX-compatible threefry2x32 noise, the fused CFG + DDIM step + Gaussian log-prob kernels
+// (sample / score / backward) and the PPO clipped-surrogate kernel.
+//
+// Reference semantics:
+//   ddpo/diffusers_patch/scheduling_ddim_flax.py:213-227 (_get_variance), :279-359 (step)
+//   ddpo/diffusers_patch/pipeline_flax_stable_diffusion.py:226-235 (CFG, split, step)
+//   ddpo/training/policy_gradient.py:103-134 (CFG, score-mode step, PPO loss/info)
+//   3P jax==0.4.8 jax/_src/prng.py (threefry_2x32, random_bits) and random.py (normal)
+//
+// All of these are HBM/latency-bound: one pass over eps_u, eps_c, x (and x_prev), 128-bit
+// loads, noise generated in registers, warp-shuffle + fixed-order partial reductions
+// (no float atomics -> bit-reproducible log-probs).
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ddpo {
+
+// ------------------------------------------------------------------ threefry ----
+struct u32x2 {
+  uint32_t a, b;
+};
+__host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+__host__ __device__ __forceinline__ u32x2 threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  const int rot[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  x0 += ks[0];
+  x1 += ks[1];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      x0 += x1;
+      x1 = rotl32(x1, rot[i & 1][j]);
+      x1 ^= x0;
+    }
+    x0 += ks[(i + 1) % 3];
+    x1 += ks[(i + 2) % 3] + static_cast<uint32_t>(i + 1);
+  }
+  return {x0, x1};
+}
+
+// bits of element i of random_bits(key, n): counters are iota(n) padded to even and split in halves
+__device__ __forceinline__ uint32_t random_bits_at(uint32_t k0, uint32_t k1, uint32_t i, uint32_t half,
+                                                   uint32_t n) {
+  if (i < half) {
+    uint32_t hi = i + half;
+    u32x2 r = threefry2x32(k0, k1, i, hi < n ? hi : 0u);  // odd n: padded counter is 0
+    return r.a;
+  }
+  u32x2 r = threefry2x32(k0, k1, i - half, i);
+  return r.b;
+}
+
+__device__ __forceinline__ float erfinv_xla(float x) {
+  // XLA ErfInv (float32): Giles' polynomial, evaluated without FMA contraction to match the
+  // CPU oracle / XLA:CPU op order
+  float w = -log1pf(-__fmul_rn(x, x));
+  const bool lt = w < 5.0f;
+  w = lt ? __fadd_rn(w, -2.5f) : __fadd_rn(sqrtf(w), -3.0f);
+  float p = lt ? 2.81022636e-08f : -0.000200214257f;
+  p = __fadd_rn(lt ? 3.43273939e-07f : 0.000100950558f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? -3.5233877e-06f : 0.00134934322f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? -4.39150654e-06f : -0.00367342844f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? 0.00021858087f : 0.00573950773f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? -0.00125372503f : -0.0076224613f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? -0.00417768164f : 0.00943887047f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? 0.246640727f : 1.00167406f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? 1.50140941f : 2.83297682f, __fmul_rn(p, w));
+  return fabsf(x) == 1.0f ? copysignf(INFINITY, x) : __fmul_rn(p, x);
+}
+
+__device__ __forceinline__ float bits_to_normal(uint32_t bits) {
+  const float lo = -0.99999994f;  // nextafter(-1, 0)
+  const float scale = 1.0f - lo;  // rounds to 2.0f exactly as in float32 numpy / XLA
+  float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  float u = fmaxf(lo, __fadd_rn(__fmul_rn(f, scale), lo));
+  return __fmul_rn(1.41421356237309504880f, erfinv_xla(u));
+}
+
+__global__ void threefry_normal_kernel(const uint32_t* __restrict__ key, float* __restrict__ out, uint32_t n) {
+  const uint32_t k0 = key[0], k1 = key[1];
+  const uint32_t half = (n + 1) / 2;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < half; i += gridDim.x * blockDim.x) {
+    uint32_t hi = i + half;
+    u32x2 r = threefry2x32(k0, k1, i, hi < n ? hi : 0u);
+    out[i] = bits_to_normal(r.a);
+    if (hi < n) out[hi] = bits_to_normal(r.b);
+  }
+}
+
+// ---------------------------------------------------------------- DDIM step ----
+struct DdimCoef {
+  float sqrt_at, sqrt_bt, sqrt_aprev, dir, sigma, sd;
+};
+
+__device__ __forceinline__ DdimCoef ddim_coef(const ddpo_ddim_common& c, int b) {
+  const int t = c.timesteps[b * c.timestep_stride];
+  const int pt = t - c.step_ratio;
+  const float a_t = c.alphas_cumprod[t];
+  const float a_prev = pt >= 0 ? c.alphas_cumprod[pt] : c.final_alpha_cumprod;
+  const float b_t = 1.0f - a_t;
+  const float b_prev = 1.0f - a_prev;
+  const float var = __fmul_rn(__fdiv_rn(b_prev, b_t), 1.0f - __fdiv_rn(a_t, a_prev));
+  DdimCoef k;
+  k.sigma = __fmul_rn(c.eta, sqrtf(var));
+  k.sqrt_at = sqrtf(a_t);
+  k.sqrt_bt = sqrtf(b_t);
+  k.sqrt_aprev = sqrtf(a_prev);
+  k.dir = sqrtf(1.0f - a_prev - __fmul_rn(k.sigma, k.sigma));
+  k.sd = fmaxf(k.sigma, 1e-6f);
+  return k;
+}
+
+constexpr int DDIM_THREADS = 256;
+
+// MODE 0: sample (draw noise, write prev_sample, log_prob); MODE 1: score (read prev_sample, log_prob)
+template <int MODE>
+__global__ void __launch_bounds__(DDIM_THREADS) ddim_step_kernel(const ddpo_ddim_common c, const uint32_t* __restrict__ key,
+                                                                 float* __restrict__ prev_sample,
+                                                                 float* __restrict__ log_prob) {
+  const int b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const DdimCoef k = ddim_coef(c, b);
+  const int n = c.n;
+  const int per_chunk = ((n / 4 + DDPO_DDIM_CHUNKS - 1) / DDPO_DDIM_CHUNKS) * 4;
+  const int begin = chunk * per_chunk;
+  const int end = min(n, begin + per_chunk);
+  const size_t base = static_cast<size_t>(b) * n;
+  uint32_t k0 = 0, k1 = 0, ntot = 0, half = 0;
+  if (MODE == 0) {
+    k0 = key[0], k1 = key[1];
+    ntot = static_cast<uint32_t>(c.batch) * n;
+    half = (ntot + 1) / 2;
+  }
+  const float g = c.guidance_scale;
+  const float inv_sqrt_at = 1.0f / k.sqrt_at;
+  float acc = 0.0f;
+  for (int i = begin + threadIdx.x * 4; i < end; i += DDIM_THREADS * 4) {
+    const float4 eu = *reinterpret_cast<const float4*>(c.eps_uncond + base + i);
+    const float4 ec = *reinterpret_cast<const float4*>(c.eps_cond + base + i);
+    const float4 x = *reinterpret_cast<const float4*>(c.sample + base + i);
+    const float e_u[4] = {eu.x, eu.y, eu.z, eu.w}, e_c[4] = {ec.x, ec.y, ec.z, ec.w}, xs[4] = {x.x, x.y, x.z, x.w};
+    float pv[4];
+    if (MODE == 1) {
+      const float4 p4 = *reinterpret_cast<const float4*>(prev_sample + base + i);
+      pv[0] = p4.x, pv[1] = p4.y, pv[2] = p4.z, pv[3] = p4.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float eps = e_u[j] + g * (e_c[j] - e_u[j]);
+      const float x0 = (xs[j] - k.sqrt_bt * eps) * inv_sqrt_at;
+      const float mean = k.sqrt_aprev * x0 + k.dir * eps;
+      if (MODE == 0) {
+        const uint32_t gi = static_cast<uint32_t>(base) + i + j;
+        const float z = bits_to_normal(random_bits_at(k0, k1, gi, half, ntot));
+        pv[j] = mean + k.sigma * z;
+      }
+      const float d = pv[j] - mean;
+      acc += d * d;
+    }
+    if (MODE == 0) *reinterpret_cast<float4*>(prev_sample + base + i) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+  }
+  __shared__ float warp_part[DDIM_THREADS / 32];
+  __shared__ bool is_last;
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  float* partials = c.workspace;
+  unsigned int* counters = reinterpret_cast<unsigned int*>(c.workspace + c.batch * DDPO_DDIM_CHUNKS);
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < DDIM_THREADS / 32; ++w) s += warp_part[w];
+    partials[b * DDPO_DDIM_CHUNKS + chunk] = s;
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&counters[b], 1u);
+    is_last = (ticket == DDPO_DDIM_CHUNKS - 1);
+    if (is_last) {
+      __threadfence();
+      float tot = 0.0f;
+      for (int q = 0; q < DDPO_DDIM_CHUNKS; ++q) tot += *(volatile float*)&partials[b * DDPO_DDIM_CHUNKS + q];
+      // mean over C*H*W of  -(d^2)/(2 sd^2) - log(sd) - log(sqrt(2 pi))
+      log_prob[b] = -tot / (2.0f * k.sd * k.sd * static_cast<float>(n)) - logf(k.sd) - 0.91893853320467274178f;
+      counters[b] = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DDIM_THREADS) ddim_logprob_bwd_kernel(const ddpo_ddim_common c,
+                                                                        const float* __restrict__ prev_sample,
+                                                                        const float* __restrict__ dlogp,
+                                                                        float* __restrict__ d_eu, float* __restrict__ d_ec) {
+  const int b = blockIdx.y;
+  const DdimCoef k = ddim_coef(c, b);
+  const int n = c.n;
+  const size_t base = static_cast<size_t>(b) * n;
+  const float g = c.guidance_scale;
+  const float inv_sqrt_at = 1.0f / k.sqrt_at;
+  // d mean / d eps
+  const float c_eps = k.dir - k.sqrt_aprev * k.sqrt_bt * inv_sqrt_at;
+  const float scale = dlogp[b] * c_eps / (k.sd * k.sd * static_cast<float>(n));
+  for (int i = (blockIdx.x * DDIM_THREADS + threadIdx.x) * 4; i < n; i += gridDim.x * DDIM_THREADS * 4) {
+    const float4 eu = *reinterpret_cast<const float4*>(c.eps_uncond + base + i);
+    const float4 ec = *reinterpret_cast<const float4*>(c.eps_cond + base + i);
+    const float4 x = *reinterpret_cast<const float4*>(c.sample + base + i);
+    const float4 p4 = *reinterpret_cast<const float4*>(prev_sample + base + i);
+    const float e_u[4] = {eu.x, eu.y, eu.z, eu.w}, e_c[4] = {ec.x, ec.y, ec.z, ec.w}, xs[4] = {x.x, x.y, x.z, x.w},
+                pv[4] = {p4.x, p4.y, p4.z, p4.w};
+    float du[4], dc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float eps = e_u[j] + g * (e_c[j] - e_u[j]);
+      const float x0 = (xs[j] - k.sqrt_bt * eps) * inv_sqrt_at;
+      const float mean = k.sqrt_aprev * x0 + k.dir * eps;
+      const float de = (pv[j] - mean) * scale;
+      dc[j] = g * de;
+      du[j] = (1.0f - g) * de;
+    }
+    *reinterpret_cast<float4*>(d_ec + base + i) = make_float4(dc[0], dc[1], dc[2], dc[3]);
+    if (d_eu != nullptr) *reinterpret_cast<float4*>(d_eu + base + i) = make_float4(du[0], du[1], du[2], du[3]);
+  }
+}
+
+// ---------------------------------------------------------------------- PPO ----
+__global__ void ppo_loss_kernel(const float* __restrict__ lp, const float* __restrict__ old_lp,
+                                const float* __restrict__ adv, int n, float clip, float* __restrict__ info,
+                                float* __restrict__ dlogp) {
+  __shared__ float s_loss[32], s_kl[32], s_cf[32];
+  float loss = 0.f, kl = 0.f, cf = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = fminf(fmaxf(adv[i], -10.0f), 10.0f);
+    const float d = lp[i] - old_lp[i];
+    const float ratio = expf(d);
+    const float unclipped = -a * ratio;
+    const float clipped = -a * fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip);
+    loss += fmaxf(unclipped, clipped);
+    kl += d * d;
+    cf += (fabsf(ratio - 1.0f) > clip) ? 1.0f : 0.0f;
+    if (dlogp != nullptr) dlogp[i] = (unclipped >= clipped) ? unclipped / static_cast<float>(n) : 0.0f;
+  }
+  loss = warp_sum(loss), kl = warp_sum(kl), cf = warp_sum(cf);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) s_loss[w] = loss, s_kl[w] = kl, s_cf[w] = cf;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float L = 0.f, K = 0.f, C = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) L += s_loss[i], K += s_kl[i], C += s_cf[i];
+    info[0] = 0.5f * K / n;  // approx_kl
+    info[1] = C / n;         // clipfrac
+    info[2] = L / n;         // loss
+  }
+}
+
+}  // namespace ddpo
+
+using namespace ddpo;
+
+extern "C" int ddpo_prng_key_host(uint64_t seed, uint32_t out[2]) {
+  out[0] = static_cast<uint32_t>(seed >> 32);
+  out[1] = static_cast<uint32_t>(seed & 0xFFFFFFFFu);
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_threefry_split_host(const uint32_t key[2], int num, uint32_t* out) {
+  DDPO_REQUIRE(num > 0, "ddpo_threefry_split_host: num must be positive");
+  // counts = iota(2*num) split in halves: word0 gets [0,num), word1 gets [num,2num); output = cat(y0, y1)
+  for (int i = 0; i < num; ++i) {
+    u32x2 r = threefry2x32(key[0], key[1], static_cast<uint32_t>(i), static_cast<uint32_t>(i + num));
+    out[i] = r.a;
+    out[num + i] = r.b;
+  }
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_threefry_normal(const uint32_t* key_dev, float* out, int64_t n, void* stream) {
+  DDPO_REQUIRE(n > 0 && n < (int64_t(1) << 32), "ddpo_threefry_normal: n out of range");
+  const int threads = 256;
+  int64_t blocks = ((n + 1) / 2 + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  threefry_normal_kernel<<<(int)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(key_dev, out, (uint32_t)n);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+static int check_ddim(const ddpo_ddim_common* c) {
+  DDPO_REQUIRE(c != nullptr && c->eps_uncond && c->eps_cond && c->sample && c->alphas_cumprod && c->timesteps &&
+                   c->workspace,
+               "ddim: null pointer in arguments");
+  DDPO_REQUIRE(c->batch > 0 && c->n > 0 && c->n % 4 == 0, "ddim: batch=%d n=%d (n must be a multiple of 4)", c->batch,
+               c->n);
+  DDPO_REQUIRE(c->timestep_stride == 0 || c->timestep_stride == 1, "ddim: timestep_stride must be 0 or 1");
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_ddim_step_sample(const ddpo_ddim_common* c, const uint32_t* key_dev, float* prev_sample,
+                                     float* log_prob, void* stream) {
+  int rc = check_ddim(c);
+  if (rc) return rc;
+  DDPO_REQUIRE(key_dev && prev_sample && log_prob, "ddim_step_sample: null output/key");
+  dim3 grid(DDPO_DDIM_CHUNKS, c->batch);
+  ddim_step_kernel<0><<<grid, DDIM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*c, key_dev, prev_sample, log_prob);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_ddim_logprob_fwd(const ddpo_ddim_common* c, const float* prev_sample, float* log_prob,
+                                     void* stream) {
+  int rc = check_ddim(c);
+  if (rc) return rc;
+  DDPO_REQUIRE(prev_sample && log_prob, "ddim_logprob_fwd: null pointer");
+  dim3 grid(DDPO_DDIM_CHUNKS, c->batch);
+  ddim_step_kernel<1><<<grid, DDIM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      *c, nullptr, const_cast<float*>(prev_sample), log_prob);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_ddim_logprob_bwd(const ddpo_ddim_common* c, const float* prev_sample, const float* dlogp,
+                                     float* d_eps_uncond, float* d_eps_cond, void* stream) {
+  int rc = check_ddim(c);
+  if (rc) return rc;
+  DDPO_REQUIRE(prev_sample && dlogp && d_eps_cond, "ddim_logprob_bwd: null pointer");
+  dim3 grid(DDPO_DDIM_CHUNKS, c->batch);
+  ddim_logprob_bwd_kernel<<<grid, DDIM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*c, prev_sample, dlogp,
+                                                                                      d_eps_uncond, d_eps_cond);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_ppo_loss(const float* log_prob, const float* old_log_prob, const float* advantages, int batch,
+                             float clip_range, float* info3, float* dlogp, void* stream) {
+  DDPO_REQUIRE(log_prob && old_log_prob && advantages && info3, "ppo_loss: null pointer");
+  DDPO_REQUIRE(batch > 0 && batch <= 65536, "ppo_loss: batch=%d out of range", batch);
+  ppo_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(log_prob, old_log_prob, advantages, batch,
+                                                                   clip_range, info3, dlogp);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}

@@ -1,0 +1,387 @@
+// Implicit-GEMM convolution / linear layer on tcgen05 (sm_100a).
+//
+//   out[m, n] = epilogue( sum_{tap, c} A[(b, y*s+dy-p, x*s+dx-p), c] * Wt[n, (tap, c)] )
+//
+// replaces every dense contraction of the Flax U-Net the reference runs through
+// `unet.apply` (reference call sites: pipeline_flax_stable_diffusion.py:219-224,
+// training/policy_gradient.py:87-102): nn.Conv 3x3 / 3x3 stride-2 / 1x1 and nn.Dense.
+//
+// Design (B200-first, not a translation of anything):
+//  * persistent kernel, one CTA per SM, static round-robin tile scheduler (n fastest so
+//    the 128-row activation tile is re-used out of L2 by consecutive CTAs);
+//  * warp 0 = TMA producer.  The activation operand is fetched straight from the NHWC
+//    bf16 tensor with a 4-D tiled tensor map whose box is (64 ch, bw, bh, bb) pixels;
+//    the 3x3 taps are the same box shifted by (dx-1, dy-1) and TMA's out-of-bounds
+//    zero fill IS the conv padding -> no im2col buffer ever exists.  Channel-concatenated
+//    inputs (U-Net skip connections) are two tensor maps walked back to back;
+//  * warp 1 = single-thread tcgen05.mma issuer, 128 x BN x 16 bf16 UMMAs, fp32
+//    accumulators in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i
+//    overlaps the main loop of tile i+1;
+//  * warps 4..7 = epilogue: tcgen05.ld 32x32b, fused bias / per-sample time-embedding
+//    row vector / fp32 residual / GEGLU, 128-bit stores;
+//  * K order is fixed and independent of the batch size and of the position of a row in
+//    its tile -> results are batch-invariant and bit-reproducible (the PPO ratio of an
+//    unchanged policy must be exactly 1; reference config/base.py:88 clip 1e-4).
+#include "common.cuh"
+
+namespace ddpo {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int IGEMM_THREADS = 256;
+constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+
+struct IGemmArgs {
+  CUtensorMap tmA0, tmA1, tmB;
+  int M_total, N_total, BN, stages;
+  int taps, kc0, kc1;
+  int is_conv, W, H, conv_stride, pad;
+  const float* bias;      // [N] or null
+  const float* rowvec;    // [B, rowvec_ld] or null: added per sample (time-embedding projection)
+  int rows_per_sample, rowvec_ld;
+  const float* residual;  // [M, ld_res] fp32 or null
+  int ld_res;
+  float* out_f32;         // [M, ld_out] or null
+  __nv_bfloat16* out_bf16;  // [M, ld_out] or null  (GEGLU: [M, ld_out] with N/2 useful columns)
+  int ld_out;
+  int geglu;
+  int accumulate_out;     // out_f32 += result (used by backward passes that sum two branches)
+};
+
+__global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_constant__ IGemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int BN = p.BN;
+  const int stages = p.stages;
+  const int b_tile_bytes = BN * BK * 2;
+  const int stage_bytes = A_TILE_BYTES + b_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full = empty_bar + stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (p.M_total + BM - 1) / BM;
+  const int tiles_n = p.N_total / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int kcs = p.kc0 + p.kc1;
+  const int kiters = p.taps * kcs;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA0);
+    prefetch_tmap(&p.tmA1);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int HW = p.W * p.H;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / tiles_n, tn = tile % tiles_n;
+        const int m0 = tm * BM, n0 = tn * BN;
+        int b0 = 0, h0 = 0;
+        if (p.is_conv) {
+          b0 = m0 / HW;
+          h0 = (m0 % HW) / p.W;
+        }
+        for (int kit = 0; kit < kiters; ++kit) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * stage_bytes;
+          uint8_t* sB = sA + A_TILE_BYTES;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          if (p.is_conv) {
+            const int tap = kit / kcs, ch = kit - tap * kcs;
+            int dy = 0, dx = 0;
+            if (p.taps == 9) {
+              dy = tap / 3;
+              dx = tap - dy * 3;
+            }
+            const int cx = dx - p.pad;
+            const int cy = h0 * p.conv_stride + dy - p.pad;
+            if (ch < p.kc0)
+              tma_load_4d(sA, &p.tmA0, &full_bar[stage], ch * BK, cx, cy, b0);
+            else
+              tma_load_4d(sA, &p.tmA1, &full_bar[stage], (ch - p.kc0) * BK, cx, cy, b0);
+          } else {
+            tma_load_2d(sA, &p.tmA0, &full_bar[stage], kit * BK, m0);
+          }
+          tma_load_2d(sB, &p.tmB, &full_bar[stage], kit * BK, n0);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256;
+        for (int kit = 0; kit < kiters; ++kit) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_base = a_base + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16(d_tmem, umma_desc(a_base + k * 32, 16, 1024), umma_desc(b_base + k * 32, 16, 1024), idesc,
+                      (kit | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile / tiles_n, tn = tile % tiles_n;
+      const int m0 = tm * BM, n0 = tn * BN;
+      const int buf = it & 1;
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M_total;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
+      const float* rv = nullptr;
+      if (p.rowvec != nullptr && row_ok) rv = p.rowvec + static_cast<size_t>(row / p.rows_per_sample) * p.rowvec_ld;
+      if (!p.geglu) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c0, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int n = n0 + c0;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+              }
+            }
+            if (rv != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + n + j));
+                f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+              }
+            }
+            if (p.residual != nullptr) {
+              const float* r = p.residual + static_cast<size_t>(row) * p.ld_res + n;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 b4 = *reinterpret_cast<const float4*>(r + j);
+                f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+              }
+            }
+            if (p.out_f32 != nullptr) {
+              float* o = p.out_f32 + static_cast<size_t>(row) * p.ld_out + n;
+              if (p.accumulate_out) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 b4 = *reinterpret_cast<const float4*>(o + j);
+                  f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            }
+            if (p.out_bf16 != nullptr) {
+              __nv_bfloat16* o = p.out_bf16 + static_cast<size_t>(row) * p.ld_out + n;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u;
+                u.x = pack_bf16(f[j], f[j + 1]);
+                u.y = pack_bf16(f[j + 2], f[j + 3]);
+                u.z = pack_bf16(f[j + 4], f[j + 5]);
+                u.w = pack_bf16(f[j + 6], f[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = u;
+              }
+            }
+          }
+        }
+      } else {
+        // GEGLU: the weight rows of this N tile are [BN/2 linear | BN/2 gate] for the same
+        // output channels (host-side row permutation), out = lin * gelu_tanh(gate)
+        const int half = BN >> 1;
+        for (int c0 = 0; c0 < half; c0 += 32) {
+          uint32_t a[32], g[32];
+          tmem_ld_32x32(t_row + c0, a);
+          tmem_ld_32x32(t_row + half + c0, g);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int n = n0 + c0;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float lin = __uint_as_float(a[j]) + __ldg(p.bias + n + j);
+              float gate = __uint_as_float(g[j]) + __ldg(p.bias + n + half + j);
+              f[j] = lin * gelu_tanh_f(gate);
+            }
+            __nv_bfloat16* o = p.out_bf16 + static_cast<size_t>(row) * p.ld_out + tn * half + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16(f[j], f[j + 1]);
+              u.y = pack_bf16(f[j + 2], f[j + 3]);
+              u.z = pack_bf16(f[j + 4], f[j + 5]);
+              u.w = pack_bf16(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int pick_bn(int N, int geglu) {
+  // widest UMMA N (multiple of 32, <=256) that divides N exactly; GEGLU needs BN/2 % 32 == 0
+  const int step = geglu ? 64 : 32;
+  for (int bn = 256; bn >= step; bn -= step)
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
+}  // namespace ddpo
+
+using namespace ddpo;
+
+extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPO_REQUIRE(a != nullptr, "ddpo_igemm: null args");
+  const int cin0 = a->c0, cin1 = a->c1;
+  DDPO_REQUIRE(cin0 > 0 && cin0 % BK == 0 && cin1 % BK == 0, "ddpo_igemm: channel counts must be multiples of 64 (c0=%d c1=%d)", cin0, cin1);
+  DDPO_REQUIRE(a->taps == 1 || a->taps == 9, "ddpo_igemm: taps must be 1 or 9");
+  DDPO_REQUIRE(a->n % 32 == 0, "ddpo_igemm: N=%d must be a multiple of 32", a->n);
+  DDPO_REQUIRE(a->out_f32 != nullptr || a->out_bf16 != nullptr, "ddpo_igemm: no output");
+  int BN = a->bn_override > 0 ? a->bn_override : pick_bn(a->n, a->geglu);
+  DDPO_REQUIRE(BN > 0 && a->n % BN == 0 && BN % 32 == 0 && BN <= 256, "ddpo_igemm: no valid BN for N=%d", a->n);
+  if (a->geglu) DDPO_REQUIRE(BN % 64 == 0 && a->out_bf16 != nullptr && a->bias != nullptr, "ddpo_igemm: bad GEGLU config");
+
+  IGemmArgs p;
+  memset(&p, 0, sizeof(p));
+  const int ktot = a->taps * (cin0 + cin1);
+  int M_total;
+  if (a->is_conv) {
+    // output grid W x H per sample (input grid is stride x larger)
+    const int W = a->w, H = a->h, B = a->batch, s = a->conv_stride;
+    DDPO_REQUIRE(s == 1 || s == 2, "ddpo_igemm: stride must be 1 or 2");
+    DDPO_REQUIRE(W > 0 && H > 0 && (W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128, "ddpo_igemm: W,H must be powers of two, W<=128 (W=%d H=%d)", W, H);
+    int bw = W, bh = (BM / W < H) ? BM / W : H;
+    int bb = BM / (bw * bh);
+    M_total = B * W * H;
+    const int Wi = W * s, Hi = H * s;
+    for (int src = 0; src < (cin1 > 0 ? 2 : 1); ++src) {
+      const int C = src == 0 ? cin0 : cin1;
+      const void* base = src == 0 ? a->a0 : a->a1;
+      const int ld = src == 0 ? a->lda0 : a->lda1;  // channel pitch (elements) of a pixel row
+      DDPO_REQUIRE(base != nullptr && ld >= C, "ddpo_igemm: bad A source %d", src);
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
+      uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * Wi, (uint64_t)ld * 2 * Wi * Hi};
+      uint32_t box[4] = {(uint32_t)BK, (uint32_t)(bw * s), (uint32_t)(bh * s), (uint32_t)bb};
+      uint32_t es[4] = {1, (uint32_t)s, (uint32_t)s, 1};
+      int rc = make_tensor_map(src == 0 ? &p.tmA0 : &p.tmA1, base, 2, 4, dims, strides, box, es, 1);
+      if (rc) return rc;
+    }
+    if (cin1 == 0) p.tmA1 = p.tmA0;
+    p.W = W, p.H = H, p.conv_stride = s, p.pad = a->taps == 9 ? 1 : 0;
+  } else {
+    DDPO_REQUIRE(a->taps == 1 && cin1 == 0, "ddpo_igemm: linear mode takes one source, one tap");
+    M_total = a->m;
+    uint64_t dims[2] = {(uint64_t)cin0, (uint64_t)M_total};
+    uint64_t strides[1] = {(uint64_t)a->lda0 * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+    uint32_t es[2] = {1, 1};
+    int rc = make_tensor_map(&p.tmA0, a->a0, 2, 2, dims, strides, box, es, 1);
+    if (rc) return rc;
+    p.tmA1 = p.tmA0;
+    p.W = 1, p.H = 1, p.conv_stride = 1, p.pad = 0;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)a->n};
+    uint64_t strides[1] = {(uint64_t)ktot * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    uint32_t es[2] = {1, 1};
+    int rc = make_tensor_map(&p.tmB, a->wt, 2, 2, dims, strides, box, es, 1);
+    if (rc) return rc;
+  }
+  p.M_total = M_total, p.N_total = a->n, p.BN = BN;
+  p.taps = a->taps, p.kc0 = cin0 / BK, p.kc1 = cin1 / BK, p.is_conv = a->is_conv;
+  p.bias = a->bias, p.rowvec = a->rowvec, p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : 1;
+  p.rowvec_ld = a->rowvec_ld;
+  p.residual = a->residual, p.ld_res = a->ld_res > 0 ? a->ld_res : a->n;
+  p.out_f32 = a->out_f32, p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
+  p.ld_out = a->ld_out > 0 ? a->ld_out : (a->geglu ? a->n / 2 : a->n);
+  p.geglu = a->geglu, p.accumulate_out = a->accumulate_out;
+  const int stage_bytes = A_TILE_BYTES + BN * BK * 2;
+  int stages = SMEM_BUDGET / stage_bytes;
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DDPO_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int tiles = ((M_total + BM - 1) / BM) * (a->n / BN);
+  int grid = num_sms();
+  if (grid > tiles) grid = tiles;
+  igemm_kernel<<<grid, IGEMM_THREADS, smem, stream>>>(p);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}

@@ -1,0 +1,513 @@
+// GroupNorm(32)+SiLU and LayerNorm, forward and backward (HBM-bound; fp32 statistics).
+//
+// Replaces flax.linen.GroupNorm / LayerNorm (+ nn.swish) inside the 3P diffusers Flax
+// U-Net (FlaxResnetBlock2D norm1/norm2, FlaxTransformer2DModel.norm, conv_norm_out,
+// FlaxBasicTransformerBlock norm1..3), reached from the reference at
+// pipeline_flax_stable_diffusion.py:219-224 / training/policy_gradient.py:87-102.
+// Flax statistics: mean, var = max(0, E[x^2] - E[x]^2), eps = 1e-5 everywhere.
+//
+// Layout: x fp32 NHWC [B, HW, C] (optionally the channel concat of two tensors: the
+// U-Net skip connection is never materialised), y bf16 (the next GEMM's A operand).
+// Statistics use a two-level fixed-order reduction: per (sample, pixel-chunk) partial
+// sums written by the stats kernel, summed in chunk order by the apply kernel.  The
+// chunking depends only on HW, never on the batch size -> batch-invariant results.
+#include "common.cuh"
+
+namespace ddpo {
+
+constexpr int GN_THREADS = 512;
+constexpr int GN_GROUPS = 32;
+
+struct GnArgs {
+  const float* x0;
+  const float* x1;
+  int c0, c1, ld0, ld1;
+  int hw, chunks, pix_per_chunk;
+  const float* scale;
+  const float* bias;
+  float* partial;  // [B, chunks, 32, 2]
+  float eps;
+  int silu;
+  __nv_bfloat16* y_bf16;   // [B, HW, C] or null
+  float* y_f32;            // [B, HW, C] or null
+  __nv_bfloat16* raw_bf16;  // [B, HW, C] un-normalised copy or null
+};
+
+__device__ __forceinline__ float2 gn_load2(const GnArgs& a, size_t pix, int c) {
+  if (c < a.c0) return *reinterpret_cast<const float2*>(a.x0 + pix * a.ld0 + c);
+  return *reinterpret_cast<const float2*>(a.x1 + pix * a.ld1 + (c - a.c0));
+}
+
+// grid (chunks, B).  thread -> (row r, channel pair); loops pixels r, r+R, ...
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const GnArgs a) {
+  const int C = a.c0 + a.c1, C2 = C >> 1, cpg = C / GN_GROUPS;
+  const int cols = C2 < GN_THREADS ? C2 : GN_THREADS;
+  const int R = GN_THREADS / cols;
+  const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int p_begin = chunk * a.pix_per_chunk;
+  const int p_end = min(a.hw, p_begin + a.pix_per_chunk);
+  // per-group accumulation in shared memory in a fixed order:
+  // each thread owns a private slot per column pass; slots are then summed by one warp per group.
+  extern __shared__ float sm[];  // [passes][GN_THREADS][2]
+  const int passes = (C2 + cols - 1) / cols;
+  for (int ps = 0; ps < passes; ++ps) {
+    const int c2 = tc + ps * cols;
+    float s = 0.f, ss = 0.f;
+    if (tr < R && c2 < C2) {
+      for (int p = p_begin + tr; p < p_end; p += R) {
+        const float2 v = gn_load2(a, static_cast<size_t>(b) * a.hw + p, c2 * 2);
+        s += v.x + v.y;
+        ss += v.x * v.x + v.y * v.y;
+      }
+    }
+    sm[(ps * GN_THREADS + threadIdx.x) * 2 + 0] = s;
+    sm[(ps * GN_THREADS + threadIdx.x) * 2 + 1] = ss;
+  }
+  __syncthreads();
+  // group g owns channel pairs [g*cpg/2, (g+1)*cpg/2); each warp reduces groups warp, warp+16
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cp2 = cpg >> 1;
+  for (int g = warp; g < GN_GROUPS; g += GN_THREADS / 32) {
+    float s = 0.f, ss = 0.f;
+    const int n_items = cp2 * R;
+    for (int i = lane; i < n_items; i += 32) {
+      const int c2 = g * cp2 + i % cp2, r = i / cp2;
+      const int ps = c2 / cols, t = r * cols + (c2 - ps * cols);
+      s += sm[(ps * GN_THREADS + t) * 2 + 0];
+      ss += sm[(ps * GN_THREADS + t) * 2 + 1];
+    }
+    s = warp_sum(s), ss = warp_sum(ss);
+    if (lane == 0) {
+      float* o = a.partial + ((static_cast<size_t>(b) * a.chunks + chunk) * GN_GROUPS + g) * 2;
+      o[0] = s, o[1] = ss;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
+  const int C = a.c0 + a.c1, C2 = C >> 1, cpg = C / GN_GROUPS;
+  const int cols = C2 < GN_THREADS ? C2 : GN_THREADS;
+  const int R = GN_THREADS / cols;
+  const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int p_begin = chunk * a.pix_per_chunk;
+  const int p_end = min(a.hw, p_begin + a.pix_per_chunk);
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  if (threadIdx.x < GN_GROUPS) {
+    float s = 0.f, ss = 0.f;
+    for (int ch = 0; ch < a.chunks; ++ch) {
+      const float* o = a.partial + ((static_cast<size_t>(b) * a.chunks + ch) * GN_GROUPS + threadIdx.x) * 2;
+      s += o[0], ss += o[1];
+    }
+    const float inv_n = 1.0f / (static_cast<float>(a.hw) * cpg);
+    const float mean = s * inv_n;
+    const float var = fmaxf(0.f, ss * inv_n - mean * mean);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
+  }
+  __syncthreads();
+  if (tr >= R) return;
+  for (int c2 = tc; c2 < C2; c2 += cols) {
+    const int c = c2 * 2;
+    const int g = c / cpg;
+    const float mean = s_mean[g], rstd = s_rstd[g];
+    const float2 sc = *reinterpret_cast<const float2*>(a.scale + c);
+    const float2 bi = *reinterpret_cast<const float2*>(a.bias + c);
+    for (int p = p_begin + tr; p < p_end; p += R) {
+      const size_t pix = static_cast<size_t>(b) * a.hw + p;
+      const float2 v = gn_load2(a, pix, c);
+      float y0 = (v.x - mean) * rstd * sc.x + bi.x;
+      float y1 = (v.y - mean) * rstd * sc.y + bi.y;
+      if (a.silu) y0 = silu_f(y0), y1 = silu_f(y1);
+      if (a.y_bf16) *reinterpret_cast<uint32_t*>(a.y_bf16 + pix * C + c) = pack_bf16(y0, y1);
+      if (a.y_f32) *reinterpret_cast<float2*>(a.y_f32 + pix * C + c) = make_float2(y0, y1);
+      if (a.raw_bf16) *reinterpret_cast<uint32_t*>(a.raw_bf16 + pix * C + c) = pack_bf16(v.x, v.y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- GN backward ----
+// y = xhat * scale + bias (then optional SiLU).  Given dy (fp32, w.r.t. the post-activation
+// output) computes dx = rstd * (dy' * scale - mean_g(dy' * scale) - xhat * mean_g(dy' * scale * xhat))
+// and per-(sample, chunk) partial dscale / dbias (summed in fixed order by gn_param_grad_kernel).
+struct GnBwdArgs {
+  GnArgs f;
+  const float* dy;     // [B, HW, C] gradient w.r.t. GN(+SiLU) output
+  float* partial2;     // [B, chunks, 32, 2]: sum(dyh), sum(dyh * xhat)
+  float* dx0;          // [B, HW, ld] gradient into x0 (+= if accumulate)
+  float* dx1;
+  int ldd0, ldd1;
+  int accumulate;
+  float* dparam_part;  // [B, chunks, 2, C]  partial (dscale, dbias)
+};
+
+__device__ __forceinline__ float silu_grad_f(float z) {
+  const float s = sigmoid_f(z);
+  return s * (1.0f + z * (1.0f - s));
+}
+
+// pass 1: per-group sums of dyh = dy*act'(z)*scale and dyh*xhat ; also dscale/dbias partials
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const GnBwdArgs a) {
+  const GnArgs& f = a.f;
+  const int C = f.c0 + f.c1, C2 = C >> 1, cpg = C / GN_GROUPS;
+  const int cols = C2 < GN_THREADS ? C2 : GN_THREADS;
+  const int R = GN_THREADS / cols;
+  const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int p_begin = chunk * f.pix_per_chunk;
+  const int p_end = min(f.hw, p_begin + f.pix_per_chunk);
+  extern __shared__ float sm[];  // [passes][GN_THREADS][6]
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  if (threadIdx.x < GN_GROUPS) {
+    float s = 0.f, ss = 0.f;
+    for (int ch = 0; ch < f.chunks; ++ch) {
+      const float* o = f.partial + ((static_cast<size_t>(b) * f.chunks + ch) * GN_GROUPS + threadIdx.x) * 2;
+      s += o[0], ss += o[1];
+    }
+    const float inv_n = 1.0f / (static_cast<float>(f.hw) * cpg);
+    const float mean = s * inv_n;
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(fmaxf(0.f, ss * inv_n - mean * mean) + f.eps);
+  }
+  __syncthreads();
+  const int passes = (C2 + cols - 1) / cols;
+  for (int ps = 0; ps < passes; ++ps) {
+    const int c2 = tc + ps * cols;
+    float a0 = 0.f, a1 = 0.f, ds0 = 0.f, ds1 = 0.f, db0 = 0.f, db1 = 0.f;
+    if (tr < R && c2 < C2) {
+      const int c = c2 * 2, g = c / cpg;
+      const float mean = s_mean[g], rstd = s_rstd[g];
+      const float2 sc = *reinterpret_cast<const float2*>(f.scale + c);
+      const float2 bi = *reinterpret_cast<const float2*>(f.bias + c);
+      for (int p = p_begin + tr; p < p_end; p += R) {
+        const size_t pix = static_cast<size_t>(b) * f.hw + p;
+        const float2 v = gn_load2(f, pix, c);
+        float2 d = *reinterpret_cast<const float2*>(a.dy + pix * C + c);
+        const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
+        if (f.silu) {
+          d.x *= silu_grad_f(xh0 * sc.x + bi.x);
+          d.y *= silu_grad_f(xh1 * sc.y + bi.y);
+        }
+        ds0 += d.x * xh0, ds1 += d.y * xh1;
+        db0 += d.x, db1 += d.y;
+        a0 += d.x * sc.x + d.y * sc.y;
+        a1 += d.x * sc.x * xh0 + d.y * sc.y * xh1;
+      }
+    }
+    float* s = sm + (ps * GN_THREADS + threadIdx.x) * 6;
+    s[0] = a0, s[1] = a1, s[2] = ds0, s[3] = ds1, s[4] = db0, s[5] = db1;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cp2 = cpg >> 1;
+  for (int g = warp; g < GN_GROUPS; g += GN_THREADS / 32) {
+    float s = 0.f, ss = 0.f;
+    const int n_items = cp2 * R;
+    for (int i = lane; i < n_items; i += 32) {
+      const int c2 = g * cp2 + i % cp2, r = i / cp2;
+      const int ps = c2 / cols, t = r * cols + (c2 - ps * cols);
+      s += sm[(ps * GN_THREADS + t) * 6 + 0];
+      ss += sm[(ps * GN_THREADS + t) * 6 + 1];
+    }
+    s = warp_sum(s), ss = warp_sum(ss);
+    if (lane == 0) {
+      float* o = a.partial2 + ((static_cast<size_t>(b) * f.chunks + chunk) * GN_GROUPS + g) * 2;
+      o[0] = s, o[1] = ss;
+    }
+  }
+  // dscale/dbias partials: sum over the R rows of this CTA for each channel pair
+  float* dp = a.dparam_part + (static_cast<size_t>(b) * f.chunks + chunk) * 2 * C;
+  for (int c2 = threadIdx.x; c2 < C2; c2 += GN_THREADS) {
+    const int ps = c2 / cols, t0 = c2 - ps * cols;
+    float ds0 = 0.f, ds1 = 0.f, db0 = 0.f, db1 = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const float* s = sm + (ps * GN_THREADS + r * cols + t0) * 6;
+      ds0 += s[2], ds1 += s[3], db0 += s[4], db1 += s[5];
+    }
+    dp[c2 * 2] = ds0, dp[c2 * 2 + 1] = ds1;
+    dp[C + c2 * 2] = db0, dp[C + c2 * 2 + 1] = db1;
+  }
+}
+
+// pass 2: dx
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const GnBwdArgs a) {
+  const GnArgs& f = a.f;
+  const int C = f.c0 + f.c1, C2 = C >> 1, cpg = C / GN_GROUPS;
+  const int cols = C2 < GN_THREADS ? C2 : GN_THREADS;
+  const int R = GN_THREADS / cols;
+  const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int p_begin = chunk * f.pix_per_chunk;
+  const int p_end = min(f.hw, p_begin + f.pix_per_chunk);
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS], s_m1[GN_GROUPS], s_m2[GN_GROUPS];
+  if (threadIdx.x < GN_GROUPS) {
+    float s = 0.f, ss = 0.f, p1 = 0.f, p2 = 0.f;
+    for (int ch = 0; ch < f.chunks; ++ch) {
+      const size_t o = ((static_cast<size_t>(b) * f.chunks + ch) * GN_GROUPS + threadIdx.x) * 2;
+      s += f.partial[o], ss += f.partial[o + 1];
+      p1 += a.partial2[o], p2 += a.partial2[o + 1];
+    }
+    const float inv_n = 1.0f / (static_cast<float>(f.hw) * cpg);
+    const float mean = s * inv_n;
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(fmaxf(0.f, ss * inv_n - mean * mean) + f.eps);
+    s_m1[threadIdx.x] = p1 * inv_n;
+    s_m2[threadIdx.x] = p2 * inv_n;
+  }
+  __syncthreads();
+  if (tr >= R) return;
+  for (int c2 = tc; c2 < C2; c2 += cols) {
+    const int c = c2 * 2, g = c / cpg;
+    const float mean = s_mean[g], rstd = s_rstd[g], m1 = s_m1[g], m2 = s_m2[g];
+    const float2 sc = *reinterpret_cast<const float2*>(f.scale + c);
+    const float2 bi = *reinterpret_cast<const float2*>(f.bias + c);
+    for (int p = p_begin + tr; p < p_end; p += R) {
+      const size_t pix = static_cast<size_t>(b) * f.hw + p;
+      const float2 v = gn_load2(f, pix, c);
+      float2 d = *reinterpret_cast<const float2*>(a.dy + pix * C + c);
+      const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
+      if (f.silu) {
+        d.x *= silu_grad_f(xh0 * sc.x + bi.x);
+        d.y *= silu_grad_f(xh1 * sc.y + bi.y);
+      }
+      const float g0 = rstd * (d.x * sc.x - m1 - xh0 * m2);
+      const float g1 = rstd * (d.y * sc.y - m1 - xh1 * m2);
+      float* dst = c < f.c0 ? a.dx0 + pix * a.ldd0 + c : a.dx1 + pix * a.ldd1 + (c - f.c0);
+      float2 o = make_float2(g0, g1);
+      if (a.accumulate) {
+        const float2 old = *reinterpret_cast<const float2*>(dst);
+        o.x += old.x, o.y += old.y;
+      }
+      *reinterpret_cast<float2*>(dst) = o;
+    }
+  }
+}
+
+// dscale/dbias: sum partial [rows, 2, C] over rows in fixed order, accumulate into grads
+__global__ void param_grad_reduce_kernel(const float* __restrict__ part, int rows, int C, float* __restrict__ dscale,
+                                         float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float ds = 0.f, db = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    ds += part[(static_cast<size_t>(r) * 2) * C + c];
+    db += part[(static_cast<size_t>(r) * 2 + 1) * C + c];
+  }
+  dscale[c] += ds;
+  dbias[c] += db;
+}
+
+// ------------------------------------------------------------------ LayerNorm ----
+// one warp per row; x fp32 [M, C] -> y bf16 [M, C]
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                            float* __restrict__ stats, int M, int C, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + static_cast<size_t>(row) * C;
+  float s = 0.f, ss = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    s += (v.x + v.y) + (v.z + v.w);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  s = warp_sum(s), ss = warp_sum(ss);
+  const float mean = s / C;
+  const float rstd = rsqrtf(fmaxf(0.f, ss / C - mean * mean) + eps);
+  if (stats != nullptr && lane == 0) stats[row * 2] = mean, stats[row * 2 + 1] = rstd;
+  __nv_bfloat16* yr = y + static_cast<size_t>(row) * C;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+    const float4 bi = __ldg(reinterpret_cast<const float4*>(bias + c));
+    uint2 o;
+    o.x = pack_bf16((v.x - mean) * rstd * sc.x + bi.x, (v.y - mean) * rstd * sc.y + bi.y);
+    o.y = pack_bf16((v.z - mean) * rstd * sc.z + bi.z, (v.w - mean) * rstd * sc.w + bi.w);
+    *reinterpret_cast<uint2*>(yr + c) = o;
+  }
+}
+
+// backward: dx (+)= rstd * (dy*scale - mean(dy*scale) - xhat * mean(dy*scale*xhat)); per-CTA dscale/dbias partials
+constexpr int LN_BWD_ROWS = 64;  // rows per CTA (8 warps x 8 rows)
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                            const float* __restrict__ stats, const float* __restrict__ dy,
+                                                            float* __restrict__ dx, float* __restrict__ dparam_part,
+                                                            int M, int C, int accumulate) {
+  extern __shared__ float sm[];  // [8 warps][2][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* my_ds = sm + static_cast<size_t>(warp) * 2 * C;
+  float* my_db = my_ds + C;
+  for (int c = lane; c < C; c += 32) my_ds[c] = 0.f, my_db[c] = 0.f;
+  __syncwarp();
+  for (int i = 0; i < LN_BWD_ROWS / 8; ++i) {
+    const int row = blockIdx.x * LN_BWD_ROWS + i * 8 + warp;
+    if (row >= M) break;
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    const float* xr = x + static_cast<size_t>(row) * C;
+    const float* dr = dy + static_cast<size_t>(row) * C;
+    float m1 = 0.f, m2 = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      const float4 d = *reinterpret_cast<const float4*>(dr + c);
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+      const float xh[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
+      const float dd[4] = {d.x, d.y, d.z, d.w}, s4[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        m1 += dd[j] * s4[j];
+        m2 += dd[j] * s4[j] * xh[j];
+        my_ds[c + j] += dd[j] * xh[j];
+        my_db[c + j] += dd[j];
+      }
+    }
+    m1 = warp_sum(m1) / C, m2 = warp_sum(m2) / C;
+    float* gr = dx + static_cast<size_t>(row) * C;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      const float4 d = *reinterpret_cast<const float4*>(dr + c);
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+      float4 o;
+      o.x = rstd * (d.x * sc.x - m1 - (v.x - mean) * rstd * m2);
+      o.y = rstd * (d.y * sc.y - m1 - (v.y - mean) * rstd * m2);
+      o.z = rstd * (d.z * sc.z - m1 - (v.z - mean) * rstd * m2);
+      o.w = rstd * (d.w * sc.w - m1 - (v.w - mean) * rstd * m2);
+      if (accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(gr + c);
+        o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+      }
+      *reinterpret_cast<float4*>(gr + c) = o;
+    }
+  }
+  __syncthreads();
+  float* dp = dparam_part + static_cast<size_t>(blockIdx.x) * 2 * C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float ds = 0.f, db = 0.f;
+    for (int w = 0; w < 8; ++w) ds += sm[(w * 2) * C + c], db += sm[(w * 2 + 1) * C + c];
+    dp[c] = ds;
+    dp[C + c] = db;
+  }
+}
+
+static int gn_chunking(int hw, int* chunks, int* ppc) {
+  int p = hw / 32;
+  if (p < 8) p = 8;
+  if (p > hw) p = hw;
+  *ppc = p;
+  *chunks = (hw + p - 1) / p;
+  return 0;
+}
+
+static int fill_gn(GnArgs& g, const ddpo_groupnorm_args* a) {
+  const int C = a->c0 + a->c1;
+  DDPO_REQUIRE(a->x0 != nullptr && a->c0 > 0 && C % (2 * GN_GROUPS) == 0 && a->c0 % 2 == 0,
+               "groupnorm: channels must be a multiple of 64 and c0 even (c0=%d c1=%d)", a->c0, a->c1);
+  DDPO_REQUIRE(a->scale && a->bias && a->workspace, "groupnorm: null scale/bias/workspace");
+  g.x0 = a->x0, g.x1 = a->x1, g.c0 = a->c0, g.c1 = a->c1;
+  g.ld0 = a->ld0 > 0 ? a->ld0 : a->c0, g.ld1 = a->ld1 > 0 ? a->ld1 : a->c1;
+  g.hw = a->hw;
+  gn_chunking(a->hw, &g.chunks, &g.pix_per_chunk);
+  g.scale = a->scale, g.bias = a->bias, g.partial = a->workspace, g.eps = a->eps, g.silu = a->silu;
+  g.y_bf16 = static_cast<__nv_bfloat16*>(a->y_bf16), g.y_f32 = a->y_f32;
+  g.raw_bf16 = static_cast<__nv_bfloat16*>(a->raw_bf16);
+  return DDPO_OK;
+}
+
+static size_t gn_smem(int C, int per) {
+  const int C2 = C / 2, cols = C2 < GN_THREADS ? C2 : GN_THREADS;
+  const int passes = (C2 + cols - 1) / cols;
+  return static_cast<size_t>(passes) * GN_THREADS * per * sizeof(float);
+}
+
+}  // namespace ddpo
+
+using namespace ddpo;
+
+extern "C" int64_t ddpo_groupnorm_workspace_floats(int batch, int hw, int channels) {
+  int chunks, ppc;
+  gn_chunking(hw, &chunks, &ppc);
+  // fwd partials + bwd partials + dparam partials
+  return static_cast<int64_t>(batch) * chunks * GN_GROUPS * 2 * 2 + static_cast<int64_t>(batch) * chunks * 2 * channels;
+}
+
+extern "C" int ddpo_groupnorm_fwd(const ddpo_groupnorm_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GnArgs g;
+  int rc = fill_gn(g, a);
+  if (rc) return rc;
+  dim3 grid(g.chunks, a->batch);
+  const size_t smem = gn_smem(a->c0 + a->c1, 2);
+  if (!a->stats_only_skip) {
+    gn_stats_kernel<<<grid, GN_THREADS, smem, stream>>>(g);
+    DDPO_LAUNCH_OK();
+  }
+  if (g.y_bf16 || g.y_f32 || g.raw_bf16) {
+    gn_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(g);
+    DDPO_LAUNCH_OK();
+  }
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const float* dy, float* dx0, float* dx1, int ldd0,
+                                  int ldd1, int accumulate, float* dscale, float* dbias, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GnBwdArgs b;
+  int rc = fill_gn(b.f, a);
+  if (rc) return rc;
+  const int C = a->c0 + a->c1;
+  DDPO_REQUIRE(dy && dx0 && dscale && dbias, "groupnorm_bwd: null pointer");
+  b.dy = dy, b.dx0 = dx0, b.dx1 = dx1, b.ldd0 = ldd0 > 0 ? ldd0 : a->c0, b.ldd1 = ldd1 > 0 ? ldd1 : a->c1;
+  b.accumulate = accumulate;
+  b.partial2 = a->workspace + static_cast<size_t>(a->batch) * b.f.chunks * GN_GROUPS * 2;
+  b.dparam_part = b.partial2 + static_cast<size_t>(a->batch) * b.f.chunks * GN_GROUPS * 2;
+  dim3 grid(b.f.chunks, a->batch);
+  const size_t smem = gn_smem(C, 6);
+  static bool attr = false;
+  if (!attr) {
+    DDPO_CUDA_OK(cudaFuncSetAttribute(gn_bwd_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  DDPO_REQUIRE(smem <= 96 * 1024, "groupnorm_bwd: too many channels (%d)", C);
+  gn_bwd_stats_kernel<<<grid, GN_THREADS, smem, stream>>>(b);
+  DDPO_LAUNCH_OK();
+  gn_bwd_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(b);
+  DDPO_LAUNCH_OK();
+  param_grad_reduce_kernel<<<(C + 127) / 128, 128, 0, stream>>>(b.dparam_part, a->batch * b.f.chunks, C, dscale, dbias);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_layernorm_fwd(const float* x, const float* scale, const float* bias, void* y_bf16, float* stats,
+                                  int m, int c, float eps, void* stream) {
+  DDPO_REQUIRE(x && scale && bias && y_bf16 && m > 0 && c % 4 == 0, "layernorm_fwd: bad arguments (m=%d c=%d)", m, c);
+  layernorm_fwd_kernel<<<(m + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, scale, bias, static_cast<__nv_bfloat16*>(y_bf16), stats, m, c, eps);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int64_t ddpo_layernorm_bwd_workspace_floats(int m, int c) {
+  return static_cast<int64_t>((m + LN_BWD_ROWS - 1) / LN_BWD_ROWS) * 2 * c;
+}
+
+extern "C" int ddpo_layernorm_bwd(const float* x, const float* scale, const float* stats, const float* dy, float* dx,
+                                  int accumulate, float* dscale, float* dbias, float* workspace, int m, int c,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPO_REQUIRE(x && scale && stats && dy && dx && dscale && dbias && workspace && c % 4 == 0,
+               "layernorm_bwd: bad arguments");
+  const int ctas = (m + LN_BWD_ROWS - 1) / LN_BWD_ROWS;
+  const size_t smem = static_cast<size_t>(8) * 2 * c * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    DDPO_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    attr = true;
+  }
+  DDPO_REQUIRE(smem <= 128 * 1024, "layernorm_bwd: C=%d too large", c);
+  layernorm_bwd_kernel<<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate);
+  DDPO_LAUNCH_OK();
+  param_grad_reduce_kernel<<<(c + 127) / 128, 128, 0, stream>>>(workspace, ctas, c, dscale, dbias);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}

@@ -1,0 +1,387 @@
+"""Host-side assembly of the Stable-Diffusion U-Net on the libddpo_b200 kernels.
+
+Mirrors what the reference reaches through ``pipeline.unet.apply({"params": p}, latents,
+timesteps, encoder_hidden_states).sample`` (3P diffusers==0.12.1 FlaxUNet2DConditionModel;
+reference call sites ``ddpo/diffusers_patch/pipeline_flax_stable_diffusion.py:219-224`` and
+``ddpo/training/policy_gradient.py:87-102``), with the Flax semantics listed in
+``ddpo_b200/unet_spec.py``.  This file only sequences kernel launches and owns buffers;
+all arithmetic happens in the CUDA library.
+
+Data flow design (B200-first):
+  * the residual stream is fp32 NHWC; every GEMM/conv A operand is the bf16 output of the
+    preceding norm kernel; accumulation is fp32 in TMEM; bias / time-embedding / residual /
+    GEGLU are fused in GEMM epilogues;
+  * U-Net skip concatenations are never materialised (two-source norm + two-source conv);
+  * cross-attention K/V projections depend only on the text context and are computed once per
+    prompt batch (``prepare_context``), not once per denoising step;
+  * buffers come from a deterministic free-list arena so a whole step can be captured in a
+    CUDA graph.
+"""
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .unet_spec import UNetConfig, param_offsets
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+class Arena:
+    """Deterministic free-list allocator (persistent torch tensors, reused by byte size)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free: Dict[int, List[torch.Tensor]] = {}
+        self.total_bytes = 0
+
+    def alloc(self, shape, dtype):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        n = (n + 255) // 256 * 256
+        lst = self.free.get(n)
+        if lst:
+            raw = lst.pop()
+        else:
+            raw = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self.total_bytes += n
+        t = raw[: int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+        t._ddpo_raw = raw
+        return t
+
+    def release(self, t):
+        if t is None:
+            return
+        raw = getattr(t, "_ddpo_raw", None)
+        if raw is not None:
+            self.free.setdefault(raw.numel(), []).append(raw)
+            t._ddpo_raw = None
+
+
+class UNet:
+    def __init__(self, cfg: UNetConfig, flat_params: torch.Tensor, device="cuda"):
+        assert all(c % 64 == 0 for c in cfg.block_out_channels), "channel counts must be multiples of 64"
+        for c, h in zip(cfg.block_out_channels, cfg.attention_head_dim):
+            assert c // h == 64, "only head_dim 64 (SD2 family) is implemented"
+        assert cfg.cross_attention_dim % 64 == 0
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.table, self.total = param_offsets(cfg)
+        assert flat_params.numel() == self.total
+        self.params = flat_params.to(self.device, F32).contiguous()
+        self.arena = Arena(self.device)
+        self.w: Dict[str, torch.Tensor] = {}       # bf16 forward GEMM operands
+        self.aux: Dict[str, torch.Tensor] = {}     # permuted biases etc.
+        self.ctx_kv: Optional[Dict[str, torch.Tensor]] = None
+        self.ctx_batch = 0
+        self._layers = self._enumerate_layers()
+        self.refresh_weights()
+
+    # ------------------------------------------------------------------ params ----
+    def p(self, name):
+        off, shape = self.table[name]
+        return self.params[off:off + int(np.prod(shape))].view(*shape)
+
+    def _enumerate_layers(self):
+        """(kind, name, ...) for every tensor-core GEMM weight."""
+        cfg = self.cfg
+        out = []
+        for name, shape in ((k, v[1]) for k, v in self.table.items()):
+            if not name.endswith("/kernel"):
+                continue
+            base = name[: -len("/kernel")]
+            if base in ("conv_in", "conv_out") or base.startswith("time_embedding") or base.endswith("time_emb_proj"):
+                continue
+            out.append((base, shape))
+        return out
+
+    def refresh_weights(self):
+        """fp32 Flax params -> bf16 [N, K] GEMM operands (run after every optimizer step)."""
+        for base, shape in self._layers:
+            leaf = base.rsplit("/", 1)[1]
+            src = self.p(base + "/kernel")
+            k = int(np.prod(shape[:-1]))
+            n = int(shape[-1])
+            if leaf in ("to_q", "to_k", "to_v"):
+                attn = base.rsplit("/", 1)[0]
+                is_self = attn.endswith("attn1")
+                if is_self:
+                    key = attn + "/qkv"
+                    if key not in self.w:
+                        self.w[key] = torch.empty(3 * n, k, dtype=BF16, device=self.device)
+                    ops.prep_weight(src, self.w[key], k, n, row_offset={"to_q": 0, "to_k": n, "to_v": 2 * n}[leaf])
+                elif leaf == "to_q":
+                    key = attn + "/q"
+                    if key not in self.w:
+                        self.w[key] = torch.empty(n, k, dtype=BF16, device=self.device)
+                    ops.prep_weight(src, self.w[key], k, n)
+                else:
+                    key = attn + "/kv"
+                    if key not in self.w:
+                        self.w[key] = torch.empty(2 * n, k, dtype=BF16, device=self.device)
+                    ops.prep_weight(src, self.w[key], k, n, row_offset=0 if leaf == "to_k" else n)
+                continue
+            if base not in self.w:
+                self.w[base] = torch.empty(n, k, dtype=BF16, device=self.device)
+            if base.endswith("ff/net_0/proj"):
+                ops.prep_weight(src, self.w[base], k, n, geglu_bn=256)
+                if base not in self.aux:
+                    self.aux[base] = torch.empty(n, dtype=F32, device=self.device)
+                ops.permute_geglu_bias(self.p(base + "/bias"), self.aux[base], n, 256)
+            else:
+                ops.prep_weight(src, self.w[base], k, n)
+
+    # ----------------------------------------------------------------- context ----
+    def prepare_context(self, ctx: torch.Tensor):
+        """ctx fp32 [B, L, D]: computes every cross-attention K/V projection once."""
+        b, l, d = ctx.shape
+        ctx = ctx.to(self.device, F32).contiguous()
+        ctx_bf = torch.empty(b * l, d, dtype=BF16, device=self.device)
+        ops.cast_bf16(ctx, ctx_bf)
+        kv = {}
+        for key, w in self.w.items():
+            if key.endswith("attn2/kv"):
+                c2 = w.shape[0]
+                out = torch.empty(b * l, c2, dtype=BF16, device=self.device)
+                ops.igemm(a0=ctx_bf, wt=w, n=c2, c0=d, m=b * l, out_bf16=out)
+                kv[key] = out
+        self.ctx_kv = kv
+        self.ctx_batch = b
+        self.ctx_len = l
+        self._ctx_bf = ctx_bf
+        return kv
+
+    # ------------------------------------------------------------------ blocks ----
+    def _resnet(self, name, x0, x1, c0, c1, cout, b, h, w, temb_act, tape):
+        A = self.arena
+        hw, m, cin = h * w, b * h * w, c0 + c1
+        has_sc = (name + "/conv_shortcut/kernel") in self.table
+        assert has_sc or x1 is None
+        gws = A.alloc((ops.groupnorm_workspace_floats(b, hw, cin),), F32)
+        a = A.alloc((m, cin), BF16)
+        raw = A.alloc((m, cin), BF16) if has_sc else None
+        ops.groupnorm_fwd(x0, self.p(name + "/norm1/scale"), self.p(name + "/norm1/bias"), gws, b, hw, c0, x1=x1,
+                          c1=c1, silu=True, y_bf16=a, raw_bf16=raw)
+        tproj = A.alloc((b, cout), F32)
+        ops.dense_small(temb_act, self.p(name + "/time_emb_proj/kernel"), self.p(name + "/time_emb_proj/bias"),
+                        tproj, b, temb_act.shape[1], cout)
+        hbuf = A.alloc((m, cout), F32)
+        ops.igemm(a0=a, wt=self.w[name + "/conv1"], n=cout, c0=cin, conv=(b, h, w), taps=9,
+                  bias=self.p(name + "/conv1/bias"), rowvec=tproj, rows_per_sample=hw, rowvec_ld=cout, out_f32=hbuf)
+        gws2 = A.alloc((ops.groupnorm_workspace_floats(b, hw, cout),), F32)
+        a2 = A.alloc((m, cout), BF16)
+        ops.groupnorm_fwd(hbuf, self.p(name + "/norm2/scale"), self.p(name + "/norm2/bias"), gws2, b, hw, cout,
+                          silu=True, y_bf16=a2)
+        if has_sc:
+            sc = A.alloc((m, cout), F32)
+            ops.igemm(a0=raw, wt=self.w[name + "/conv_shortcut"], n=cout, c0=cin, conv=(b, h, w), taps=1,
+                      bias=self.p(name + "/conv_shortcut/bias"), out_f32=sc)
+        else:
+            sc = x0
+        out = A.alloc((m, cout), F32)
+        ops.igemm(a0=a2, wt=self.w[name + "/conv2"], n=cout, c0=cout, conv=(b, h, w), taps=9,
+                  bias=self.p(name + "/conv2/bias"), residual=sc, out_f32=out)
+        if tape is None:
+            for t in (gws, a, raw, tproj, hbuf, gws2, a2, sc if has_sc else None):
+                A.release(t)
+        else:
+            tape.append(("resnet", dict(name=name, x0=x0, x1=x1, c0=c0, c1=c1, cout=cout, b=b, h=h, w=w, gws=gws,
+                                        a=a, raw=raw, hbuf=hbuf, gws2=gws2, a2=a2, has_sc=has_sc, tproj=tproj,
+                                        sc=sc if has_sc else None, out=out)))
+        return out
+
+    def _transformer(self, name, x, c, heads, b, h, w, tape):
+        A = self.arena
+        hw, m = h * w, b * h * w
+        bl = name + "/transformer_blocks_0"
+        L = self.ctx_len
+        gws = A.alloc((ops.groupnorm_workspace_floats(b, hw, c),), F32)
+        g = A.alloc((m, c), BF16)
+        ops.groupnorm_fwd(x, self.p(name + "/norm/scale"), self.p(name + "/norm/bias"), gws, b, hw, c, silu=False,
+                          y_bf16=g)
+        h0 = A.alloc((m, c), F32)
+        ops.igemm(a0=g, wt=self.w[name + "/proj_in"], n=c, c0=c, m=m, bias=self.p(name + "/proj_in/bias"), out_f32=h0)
+        # --- self attention
+        ln1 = A.alloc((m, c), BF16)
+        st1 = A.alloc((m, 2), F32)
+        ops.layernorm_fwd(h0, self.p(bl + "/norm1/scale"), self.p(bl + "/norm1/bias"), ln1, m, c, stats=st1)
+        qkv = A.alloc((m, 3 * c), BF16)
+        ops.igemm(a0=ln1, wt=self.w[bl + "/attn1/qkv"], n=3 * c, c0=c, m=m, out_bf16=qkv)
+        ao1 = A.alloc((m, c), BF16)
+        lse1 = A.alloc((b, heads, hw), F32) if tape is not None else None
+        ops.attention_fwd(qkv, qkv[:, c:], qkv[:, 2 * c:], ao1, b, heads, hw, hw, 3 * c, 3 * c, 3 * c, c, lse=lse1)
+        h1 = A.alloc((m, c), F32)
+        ops.igemm(a0=ao1, wt=self.w[bl + "/attn1/to_out_0"], n=c, c0=c, m=m, bias=self.p(bl + "/attn1/to_out_0/bias"),
+                  residual=h0, out_f32=h1)
+        # --- cross attention
+        ln2 = A.alloc((m, c), BF16)
+        st2 = A.alloc((m, 2), F32)
+        ops.layernorm_fwd(h1, self.p(bl + "/norm2/scale"), self.p(bl + "/norm2/bias"), ln2, m, c, stats=st2)
+        q2 = A.alloc((m, c), BF16)
+        ops.igemm(a0=ln2, wt=self.w[bl + "/attn2/q"], n=c, c0=c, m=m, out_bf16=q2)
+        kv = self.ctx_kv[bl + "/attn2/kv"]
+        ao2 = A.alloc((m, c), BF16)
+        lse2 = A.alloc((b, heads, hw), F32) if tape is not None else None
+        ops.attention_fwd(q2, kv, kv[:, c:], ao2, b, heads, hw, L, c, 2 * c, 2 * c, c, lse=lse2)
+        h2 = A.alloc((m, c), F32)
+        ops.igemm(a0=ao2, wt=self.w[bl + "/attn2/to_out_0"], n=c, c0=c, m=m, bias=self.p(bl + "/attn2/to_out_0/bias"),
+                  residual=h1, out_f32=h2)
+        # --- GEGLU feed-forward
+        ln3 = A.alloc((m, c), BF16)
+        st3 = A.alloc((m, 2), F32)
+        ops.layernorm_fwd(h2, self.p(bl + "/norm3/scale"), self.p(bl + "/norm3/bias"), ln3, m, c, stats=st3)
+        ff = A.alloc((m, 4 * c), BF16)
+        ffpre = None
+        if tape is None:
+            ops.igemm(a0=ln3, wt=self.w[bl + "/ff/net_0/proj"], n=8 * c, c0=c, m=m, bias=self.aux[bl + "/ff/net_0/proj"],
+                      out_bf16=ff, geglu=True, bn=256)
+        else:
+            # training keeps the pre-activation (bf16, tile-interleaved [lin|gate]) for the GEGLU backward
+            ffpre = A.alloc((m, 8 * c), BF16)
+            ops.igemm(a0=ln3, wt=self.w[bl + "/ff/net_0/proj"], n=8 * c, c0=c, m=m, bias=self.aux[bl + "/ff/net_0/proj"],
+                      out_bf16=ffpre, bn=256)
+            ops.geglu_fwd(ffpre, ff, m, 8 * c, 256)
+        h3 = A.alloc((m, c), F32)
+        h3b = A.alloc((m, c), BF16)
+        ops.igemm(a0=ff, wt=self.w[bl + "/ff/net_2"], n=c, c0=4 * c, m=m, bias=self.p(bl + "/ff/net_2/bias"),
+                  residual=h2, out_f32=h3, out_bf16=h3b)
+        out = A.alloc((m, c), F32)
+        ops.igemm(a0=h3b, wt=self.w[name + "/proj_out"], n=c, c0=c, m=m, bias=self.p(name + "/proj_out/bias"),
+                  residual=x, out_f32=out)
+        if tape is None:
+            for t in (gws, g, h0, ln1, st1, qkv, ao1, h1, ln2, st2, q2, ao2, h2, ln3, st3, ff, h3, h3b):
+                A.release(t)
+        else:
+            tape.append(("transformer", dict(name=name, x=x, c=c, heads=heads, b=b, h=h, w=w, gws=gws, g=g, h0=h0,
+                                             ln1=ln1, st1=st1, qkv=qkv, ao1=ao1, lse1=lse1, h1=h1, ln2=ln2, st2=st2,
+                                             q2=q2, ao2=ao2, lse2=lse2, h2=h2, ln3=ln3, st3=st3, ffpre=ffpre, ff=ff,
+                                             h3=h3, h3b=h3b, out=out)))
+        return out
+
+    # ----------------------------------------------------------------- forward ----
+    def forward(self, latents: torch.Tensor, timesteps: torch.Tensor, out: Optional[torch.Tensor] = None,
+                tape: Optional[list] = None, taps: Optional[dict] = None):
+        """latents fp32 NCHW [B,4,H,W]; timesteps int32 [B] or [1]; returns eps fp32 NCHW [B,4,H,W].
+        ``prepare_context`` must have been called with a context of the same batch size.
+        ``tape``: list that receives what backward needs (training); ``taps``: debug dict name->tensor."""
+        cfg, A = self.cfg, self.arena
+        b, cin_lat, H, W = latents.shape
+        assert self.ctx_kv is not None and self.ctx_batch == b, "prepare_context(ctx) with matching batch first"
+        boc = cfg.block_out_channels
+        te = cfg.time_embed_dim
+
+        def tap(name, t, shape=None):
+            if taps is not None:
+                taps[name] = t.clone() if shape is None else t.view(*shape).clone()
+
+        # time embedding: silu(temb) is what every consumer needs
+        sincos = A.alloc((b, boc[0]), F32)
+        ops.timestep_sincos(timesteps, sincos, b, boc[0])
+        t1 = A.alloc((b, te), F32)
+        ops.dense_small(sincos, self.p("time_embedding/linear_1/kernel"), self.p("time_embedding/linear_1/bias"), t1, b,
+                        boc[0], te, silu_out=True)
+        temb_act = A.alloc((b, te), F32)
+        ops.dense_small(t1, self.p("time_embedding/linear_2/kernel"), self.p("time_embedding/linear_2/bias"), temb_act,
+                        b, te, te, silu_out=True)
+        x = A.alloc((b * H * W, boc[0]), F32)
+        ops.conv_in(latents, self.p("conv_in/kernel"), self.p("conv_in/bias"), x, b, cin_lat, H, W, boc[0])
+        tap("conv_in", x, (b, H, W, boc[0]))
+        if tape is not None:
+            tape.append(("head", dict(latents=latents, sincos=sincos, t1=t1, temb_act=temb_act, b=b, H=H, W=W)))
+        skips = [(x, boc[0], H, W)]
+        h, w, c_prev = H, W, boc[0]
+        for i, c in enumerate(boc):
+            for l in range(cfg.layers_per_block):
+                name = f"down_blocks_{i}/resnets_{l}"
+                y = self._resnet(name, x, None, c_prev, 0, c, b, h, w, temb_act, tape)
+                tap(name, y, (b, h, w, c))
+                x, c_prev = y, c
+                if cfg.down_has_attn[i]:
+                    name = f"down_blocks_{i}/attentions_{l}"
+                    y = self._transformer(name, x, c, cfg.attention_head_dim[i], b, h, w, tape)
+                    tap(name, y, (b, h, w, c))
+                    if tape is None:
+                        A.release(x)  # resnet output is dead once the transformer consumed it (not a skip)
+                    x = y
+                skips.append((x, c, h, w))
+            if i < len(boc) - 1:
+                name = f"down_blocks_{i}/downsamplers_0"
+                xb = A.alloc((b * h * w, c), BF16)
+                ops.cast_bf16(x, xb)
+                y = A.alloc((b * (h // 2) * (w // 2), c), F32)
+                ops.igemm(a0=xb, wt=self.w[name + "/conv"], n=c, c0=c, conv=(b, h // 2, w // 2), taps=9, stride=2,
+                          bias=self.p(name + "/conv/bias"), out_f32=y)
+                if tape is None:
+                    A.release(xb)
+                else:
+                    tape.append(("down", dict(name=name, x=x, xb=xb, c=c, b=b, h=h, w=w, out=y)))
+                h, w = h // 2, w // 2
+                x = y
+                tap(name, x, (b, h, w, c))
+                skips.append((x, c, h, w))
+        cm = boc[-1]
+        y = self._resnet("mid_block/resnets_0", x, None, cm, 0, cm, b, h, w, temb_act, tape)
+        tap("mid_block/resnets_0", y, (b, h, w, cm))
+        x = y
+        y = self._transformer("mid_block/attentions_0", x, cm, cfg.attention_head_dim[-1], b, h, w, tape)
+        tap("mid_block/attentions_0", y, (b, h, w, cm))
+        if tape is None:
+            A.release(x)
+        x = y
+        y = self._resnet("mid_block/resnets_1", x, None, cm, 0, cm, b, h, w, temb_act, tape)
+        tap("mid_block/resnets_1", y, (b, h, w, cm))
+        if tape is None:
+            A.release(x)
+        x = y
+        rev = tuple(reversed(boc))
+        rev_heads = tuple(reversed(cfg.attention_head_dim))
+        has_attn = tuple(reversed(cfg.down_has_attn))
+        c_prev = rev[0]
+        for i, c in enumerate(rev):
+            for l in range(cfg.layers_per_block + 1):
+                sk, sc_, sh, sw = skips.pop()
+                assert (sh, sw) == (h, w)
+                name = f"up_blocks_{i}/resnets_{l}"
+                y = self._resnet(name, x, sk, c_prev, sc_, c, b, h, w, temb_act, tape)
+                tap(name, y, (b, h, w, c))
+                if tape is None:
+                    A.release(x)
+                    A.release(sk)
+                x, c_prev = y, c
+                if has_attn[i]:
+                    name = f"up_blocks_{i}/attentions_{l}"
+                    y = self._transformer(name, x, c, rev_heads[i], b, h, w, tape)
+                    tap(name, y, (b, h, w, c))
+                    if tape is None:
+                        A.release(x)
+                    x = y
+            if i < len(rev) - 1:
+                name = f"up_blocks_{i}/upsamplers_0"
+                up = A.alloc((b * 4 * h * w, c), BF16)
+                ops.upsample2x_bf16(x, up, b, h, w, c)
+                y = A.alloc((b * 4 * h * w, c), F32)
+                ops.igemm(a0=up, wt=self.w[name + "/conv"], n=c, c0=c, conv=(b, 2 * h, 2 * w), taps=9,
+                          bias=self.p(name + "/conv/bias"), out_f32=y)
+                if tape is None:
+                    A.release(up)
+                    A.release(x)
+                else:
+                    tape.append(("up", dict(name=name, x=x, up=up, c=c, b=b, h=h, w=w, out=y)))
+                h, w = 2 * h, 2 * w
+                x = y
+                tap(name, x, (b, h, w, c))
+        c0 = boc[0]
+        gws = A.alloc((ops.groupnorm_workspace_floats(b, h * w, c0),), F32)
+        yf = A.alloc((b * h * w, c0), F32)
+        ops.groupnorm_fwd(x, self.p("conv_norm_out/scale"), self.p("conv_norm_out/bias"), gws, b, h * w, c0, silu=True,
+                          y_f32=yf)
+        if out is None:
+            out = torch.empty(b, cfg.out_channels, h, w, dtype=F32, device=self.device)
+        ops.conv_out(yf, self.p("conv_out/kernel"), self.p("conv_out/bias"), out, b, h, w, c0, cfg.out_channels)
+        if tape is None:
+            for t in (gws, yf, x, sincos, t1, temb_act):
+                A.release(t)
+        else:
+            tape.append(("tail", dict(x=x, gws=gws, yf=yf, b=b, h=h, w=w, c=c0)))
+        return out

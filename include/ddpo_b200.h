@@ -1,0 +1,183 @@
+/* libddpo_b200 -- C ABI of the B200-native DDPO hot path.
+ *
+ * The reference (jannerm/ddpo) has no FFI layer: its seam is a set of Python call
+ * signatures between pipeline/*.py and ddpo.* whose arithmetic runs inside XLA.  This
+ * header is what a binding for that path binds to; each entry point names the
+ * reference code it replaces (file:line relative to the reference repo; "3P" marks
+ * un-vendored diffusers 0.12.1 / optax 0.1.5 / jax 0.4.8 code reached from that line).
+ *
+ * Conventions
+ *   - every pointer is CALLER-OWNED DEVICE memory (16-byte aligned, contiguous unless a
+ *     leading dimension is given); the library never allocates tensors;
+ *   - activations are NHWC ([B, H, W, C] == [M, C] row major); GEMM weights are bf16
+ *     [N, K] with K contiguous (for a conv K = (tap, c_in), tap = ky*3+kx);
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), issue no
+ *     host synchronisation and are re-entrant across streams;
+ *   - return value: DDPO_OK (0) or a negative ddpo_status; ddpo_last_error() returns a
+ *     thread-local message.  No exception crosses the ABI.
+ *   - reductions use fixed orders (no float atomics): results are bit-reproducible and
+ *     independent of the batch size.
+ */
+#ifndef DDPO_B200_H_
+#define DDPO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  DDPO_OK = 0,
+  DDPO_ERR_INVALID = -1, /* bad argument */
+  DDPO_ERR_CUDA = -2,    /* CUDA runtime / driver error */
+  DDPO_ERR_UNSUPPORTED = -3
+} ddpo_status;
+
+const char* ddpo_last_error(void);
+/* library / device sanity: returns the SM count of the current device (>0) or <0 */
+int ddpo_device_sm_count(void);
+int ddpo_abi_version(void);
+
+/* ---------------------------------------------------------------- PRNG -------------
+ * jax.random (threefry2x32), 3P jax==0.4.8; reference call sites
+ * pipeline/policy_gradient.py:51,201,244-245; pipeline_flax_stable_diffusion.py:196-197,232,252 */
+/* host: split(key) -> num keys (out: [num][2]) */
+int ddpo_threefry_split_host(const uint32_t key[2], int num, uint32_t* out);
+/* host: PRNGKey(seed) */
+int ddpo_prng_key_host(uint64_t seed, uint32_t out[2]);
+/* device: jax.random.normal(key, shape with n elements) -> out[n] fp32; key is a DEVICE pointer to 2 words */
+int ddpo_threefry_normal(const uint32_t* key_dev, float* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------ DDIM scheduler -------
+ * FlaxDDIMScheduler.step  (ddpo/diffusers_patch/scheduling_ddim_flax.py:229-361) fused with the
+ * classifier-free-guidance combine (pipeline_flax_stable_diffusion.py:226-229,
+ * training/policy_gradient.py:103-105). */
+typedef struct {
+  const float* eps_uncond;     /* [B, n] model output, unconditional branch */
+  const float* eps_cond;       /* [B, n] model output, text branch (== eps_uncond & guidance 1 for no CFG) */
+  const float* sample;         /* [B, n] x_t */
+  const float* alphas_cumprod; /* [num_train_timesteps] */
+  const int32_t* timesteps;    /* [B] (timestep_stride 1) or [1] (timestep_stride 0) */
+  int timestep_stride;
+  float final_alpha_cumprod;
+  int step_ratio;              /* num_train_timesteps // num_inference_steps */
+  float guidance_scale;
+  float eta;
+  int batch;
+  int n;                       /* C*H*W elements per sample */
+  float* workspace;            /* >= batch*DDPO_DDIM_CHUNKS floats + batch uint32 counters, zero-initialised once */
+} ddpo_ddim_common;
+#define DDPO_DDIM_CHUNKS 8
+
+/* sample mode (scheduling_ddim_flax.py:346-348): prev = mean + sigma * normal(key) ; log_prob */
+int ddpo_ddim_step_sample(const ddpo_ddim_common* c, const uint32_t* key_dev, float* prev_sample /*[B,n]*/,
+                          float* log_prob /*[B]*/, void* stream);
+/* score mode (:351-359 with prev_sample given): log_prob of prev_sample */
+int ddpo_ddim_logprob_fwd(const ddpo_ddim_common* c, const float* prev_sample, float* log_prob, void* stream);
+/* backward of score mode + CFG: d_eps_uncond, d_eps_cond given dL/dlog_prob [B] */
+int ddpo_ddim_logprob_bwd(const ddpo_ddim_common* c, const float* prev_sample, const float* dlogp,
+                          float* d_eps_uncond, float* d_eps_cond, void* stream);
+
+/* ------------------------------------------------------------------ PPO ------------
+ * ddpo/training/policy_gradient.py:121-134 (clipped surrogate, info) and its gradient.
+ * info = {approx_kl, clipfrac, loss}.  batch <= 1024. */
+int ddpo_ppo_loss(const float* log_prob, const float* old_log_prob, const float* advantages, int batch,
+                  float clip_range, float* info3, float* dlogp, void* stream);
+
+/* --------------------------------------------------------- dense contractions ------
+ * nn.Conv / nn.Dense of 3P diffusers FlaxUNet2DConditionModel (reached from
+ * pipeline_flax_stable_diffusion.py:219-224 and training/policy_gradient.py:87-102). */
+typedef struct {
+  /* A operand: bf16 NHWC activations.  conv: [batch, h*stride, w*stride, c] per source (two sources =
+   * channel concat [a0 | a1]); linear: a0 is [m, c0].  lda = elements between consecutive pixels/rows. */
+  const void* a0;
+  const void* a1;
+  int c0, c1, lda0, lda1;
+  int is_conv, batch, h, w; /* h, w: OUTPUT grid */
+  int conv_stride;          /* 1, or 2 (3x3, symmetric pad 1: Flax padding ((1,1),(1,1))) */
+  int taps;                 /* 9 (3x3, pad 1) or 1 (1x1 / linear) */
+  int m;                    /* linear: rows */
+  int n;                    /* output channels */
+  const void* wt;           /* bf16 [n, taps*(c0+c1)] */
+  const float* bias;        /* [n] or NULL */
+  const float* rowvec;      /* [batch, rowvec_ld] or NULL: per-sample vector added to every row of the sample */
+  int rows_per_sample, rowvec_ld;
+  const float* residual;    /* fp32 [M, ld_res] or NULL */
+  int ld_res;
+  float* out_f32;           /* [M, ld_out] or NULL */
+  void* out_bf16;           /* [M, ld_out] or NULL */
+  int ld_out;
+  int geglu;                /* out_bf16[M, n/2] = lin * gelu_tanh(gate); weight rows tile-interleaved */
+  int accumulate_out;       /* out_f32 += */
+  int bn_override;          /* 0 = auto */
+} ddpo_igemm_args;
+int ddpo_igemm(const ddpo_igemm_args* a, void* stream);
+
+/* ------------------------------------------------------------ normalisation --------
+ * flax.linen.GroupNorm(32, eps 1e-5)(+nn.swish) / LayerNorm(eps 1e-5) of the 3P Flax U-Net
+ * (FlaxResnetBlock2D norm1/2, FlaxTransformer2DModel.norm, conv_norm_out, BasicTransformerBlock norm1-3). */
+typedef struct {
+  const float* x0;      /* fp32 [batch, hw, c0] (pixel pitch ld0) */
+  const float* x1;      /* optional second tensor: channel concat [x0 | x1] */
+  int c0, c1, ld0, ld1;
+  int batch, hw;
+  const float* scale;   /* [c0+c1] */
+  const float* bias;
+  float eps;
+  int silu;
+  void* y_bf16;         /* bf16 [batch, hw, c] or NULL */
+  float* y_f32;         /* fp32 [batch, hw, c] or NULL */
+  void* raw_bf16;       /* bf16 copy of the un-normalised input or NULL */
+  float* workspace;     /* ddpo_groupnorm_workspace_floats(); the first batch*chunks*64 floats (forward
+                           statistics) must be kept until the backward call */
+  int stats_only_skip;  /* 1: statistics already in workspace, only apply */
+} ddpo_groupnorm_args;
+int64_t ddpo_groupnorm_workspace_floats(int batch, int hw, int channels);
+int ddpo_groupnorm_fwd(const ddpo_groupnorm_args* a, void* stream);
+/* dx0/dx1 (+)= d/dx ; dscale/dbias += (parameter gradients always accumulate) */
+int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const float* dy, float* dx0, float* dx1, int ldd0, int ldd1,
+                       int accumulate, float* dscale, float* dbias, void* stream);
+int ddpo_layernorm_fwd(const float* x, const float* scale, const float* bias, void* y_bf16, float* stats /*[m,2] or NULL*/,
+                       int m, int c, float eps, void* stream);
+int64_t ddpo_layernorm_bwd_workspace_floats(int m, int c);
+int ddpo_layernorm_bwd(const float* x, const float* scale, const float* stats, const float* dy, float* dx,
+                       int accumulate, float* dscale, float* dbias, float* workspace, int m, int c, void* stream);
+
+/* --------------------------------------------------- layout / small layers ---------
+ * weight re-layout: fp32 Flax params ([in,out] Dense, HWIO Conv == [(tap,cin), cout]) -> bf16 GEMM operands */
+int ddpo_prep_weight(const float* src, void* dst_bf16, int k, int n, int ldk, int row_offset, int col_offset,
+                     int geglu_bn, void* stream);
+int ddpo_prep_weight_dgrad(const float* src, void* dst_bf16, int taps, int k, int n, void* stream);
+int ddpo_permute_geglu_bias(const float* src, float* dst, int n, int bn, void* stream);
+int ddpo_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* FlaxUpsample2D's jax.image.resize(nearest): out[i] = in[i/2] */
+int ddpo_upsample2x_bf16(const float* x, void* y_bf16, int batch, int h, int w, int c, void* stream);
+int ddpo_upsample2x_bwd(const float* dy, float* dx, int batch, int h, int w, int c, int accumulate, void* stream);
+/* conv_in: NCHW fp32 latents -> NHWC fp32; conv_out: NHWC fp32 -> NCHW fp32 (N = 4) */
+int ddpo_conv_in(const float* x_nchw, const float* w_hwio, const float* bias, float* y_nhwc, int batch, int cin,
+                 int h, int w, int cout, void* stream);
+int ddpo_conv_out(const float* x_nhwc, const float* w_hwio, const float* bias, float* y_nchw, int batch, int h,
+                  int w, int cin, int cout, void* stream);
+/* FlaxTimesteps(flip_sin_to_cos=True, freq_shift=0) and the M=batch Dense layers of the time embedding */
+int ddpo_timestep_sincos(const int32_t* t, int t_stride, float* out, int batch, int dim, void* stream);
+int ddpo_dense_small(const float* x, const float* w_in_out, const float* bias, float* y, int batch, int k, int n,
+                     int silu_in, int silu_out, void* stream);
+
+/* ---------------------------------------------------------------- attention --------
+ * FlaxAttention core (3P diffusers attention_flax.py): softmax(Q K^T d^-0.5) V, head_dim 64. */
+typedef struct {
+  const void* q;  /* bf16 [batch, nq, ldq], head h at columns [h*64, h*64+64) */
+  const void* k;  /* bf16 [batch, nk, ldk] */
+  const void* v;  /* bf16 [batch, nk, ldv] */
+  void* out;      /* bf16 [batch, nq, ldo] */
+  float* lse;     /* fp32 [batch, heads, nq] log-sum-exp of the scaled scores, or NULL */
+  int batch, heads, nq, nk, head_dim;
+  int ldq, ldk, ldv, ldo;
+} ddpo_attention_args;
+int ddpo_attention_fwd(const ddpo_attention_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDPO_B200_H_ */

@@ -1,0 +1,325 @@
+"""GPU parity tests of the individual CUDA kernels (through the C ABI) against plain
+PyTorch fp32 references and the CPU oracle.  Run on the B200 box: ``pytest -m gpu``."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from ddpo_b200 import _lib
+    assert _lib.lib().ddpo_device_sm_count() > 0
+    yield
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def rel_err(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+# ----------------------------------------------------------------------- PRNG ----
+@pytest.mark.parametrize("n", [2, 7, 4096, 2 * 4 * 64 * 64 + 3])
+def test_threefry_normal_matches_oracle(n):
+    from ddpo_b200 import ops
+    from oracle import threefry
+    key = (0x9E3779B9, 12345)
+    kd = ops.key_tensor([key], DEV)
+    out = torch.empty(n, device=DEV)
+    ops.threefry_normal(kd, out)
+    ref = threefry.normal(np.array(key, np.uint32), (n,))
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=2e-6)
+
+
+def test_threefry_host_split_matches_oracle():
+    from ddpo_b200 import ops
+    from oracle import threefry
+    k = ops.prng_key(0)
+    assert k == (0, 0)
+    s = ops.threefry_split(k, 2)
+    assert s == [(4146024105, 967050713), (2718843009, 1272950319)]  # published JAX values
+    s5 = ops.threefry_split((123, 456), 5)
+    ref = threefry.split(np.array([123, 456], np.uint32), 5)
+    assert [tuple(int(v) for v in r) for r in ref] == s5
+
+
+# ----------------------------------------------------------------------- DDIM ----
+def _sched():
+    from oracle import scheduler as S
+    st = S.set_timesteps(S.SD_CONFIG, S.create_state(S.SD_CONFIG), 50)
+    return S, st
+
+
+@pytest.mark.parametrize("batch,t_scalar", [(2, True), (3, True), (4, False)])
+def test_ddim_step_sample_and_score(batch, t_scalar):
+    from ddpo_b200 import ops
+    from oracle import threefry
+    from oracle.ppo import cfg_combine
+    S, st = _sched()
+    n = 4 * 16 * 16
+    rng = np.random.default_rng(0)
+    eu = rng.standard_normal((batch, n)).astype(np.float32)
+    ec = rng.standard_normal((batch, n)).astype(np.float32)
+    x = rng.standard_normal((batch, n)).astype(np.float32)
+    ts = np.array([981] if t_scalar else [981, 21, 1, 501][:batch], np.int32)
+    key = (7, 9)
+    g, eta = 5.0, 1.0
+    ac = torch.tensor(st.alphas_cumprod, device=DEV)
+    ws = ops.ddim_workspace(batch, DEV)
+    prev = torch.empty(batch, n, device=DEV)
+    lp = torch.empty(batch, device=DEV)
+    teu, tec, tx = (torch.tensor(a, device=DEV) for a in (eu, ec, x))
+    tts = torch.tensor(ts, device=DEV)
+    ops.ddim_step_sample(teu, tec, tx, ac, tts, float(st.final_alpha_cumprod), 20, g, eta, ops.key_tensor([key], DEV),
+                         prev, lp, ws)
+    eps = cfg_combine(eu, ec, g)
+    tt = int(ts[0]) if t_scalar else ts
+    rprev, _, rlp = S.step(S.SD_CONFIG, st, eps, tt, x, key=np.array(key, np.uint32), eta=eta)
+    np.testing.assert_allclose(prev.cpu().numpy(), rprev, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(lp.cpu().numpy(), rlp, rtol=1e-5, atol=1e-5)
+    # score mode on the produced sample returns the same log-prob (bit-reproducible reduction)
+    lp2 = torch.empty(batch, device=DEV)
+    ops.ddim_logprob_fwd(teu, tec, tx, prev, ac, tts, float(st.final_alpha_cumprod), 20, g, eta, lp2, ws)
+    _, _, rlp2 = S.step(S.SD_CONFIG, st, eps, tt if not t_scalar else np.full(batch, tt), x,
+                        prev_sample=prev.cpu().numpy(), eta=eta)
+    np.testing.assert_allclose(lp2.cpu().numpy(), rlp2, rtol=1e-5, atol=1e-5)
+    assert torch.equal(lp, lp2), "sample-mode and score-mode log-probs must be bit identical"
+    # backward
+    dl = torch.tensor(rng.standard_normal(batch).astype(np.float32), device=DEV)
+    du = torch.empty(batch, n, device=DEV)
+    dc = torch.empty(batch, n, device=DEV)
+    ops.ddim_logprob_bwd(teu, tec, tx, prev, ac, tts, float(st.final_alpha_cumprod), 20, g, eta, dl, du, dc, ws)
+    gref = S.logprob_grad_eps(S.SD_CONFIG, st, eps, tt if not t_scalar else np.full(batch, tt), x,
+                              prev.cpu().numpy(), eta, dl.cpu().numpy())
+    np.testing.assert_allclose(dc.cpu().numpy(), g * gref, rtol=2e-4, atol=1e-7)
+    np.testing.assert_allclose(du.cpu().numpy(), (1 - g) * gref, rtol=2e-4, atol=1e-7)
+
+
+def test_ppo_loss_matches_oracle():
+    from ddpo_b200 import ops
+    from oracle import ppo
+    rng = np.random.default_rng(1)
+    n = 16
+    old = rng.standard_normal(n).astype(np.float32)
+    lp = (old + 3e-4 * rng.standard_normal(n)).astype(np.float32)
+    lp[:4] = old[:4]
+    adv = (20 * rng.standard_normal(n)).astype(np.float32)
+    info = torch.empty(3, device=DEV)
+    dl = torch.empty(n, device=DEV)
+    ops.ppo_loss(torch.tensor(lp, device=DEV), torch.tensor(old, device=DEV), torch.tensor(adv, device=DEV), 1e-4, info,
+                 dl)
+    loss, rinfo, rdl = ppo.ppo_loss(lp, old, adv, 1e-4)
+    np.testing.assert_allclose(info.cpu().numpy(), [rinfo["approx_kl"], rinfo["clipfrac"], rinfo["loss"]], rtol=1e-5,
+                               atol=1e-9)
+    np.testing.assert_allclose(dl.cpu().numpy(), rdl, rtol=1e-5, atol=1e-9)
+
+
+# ----------------------------------------------------------------------- GEMM ----
+def _prep_w(w_kn):
+    """fp32 [K, N] -> bf16 [N, K] through the library's own prep kernel."""
+    from ddpo_b200 import ops
+    k, n = w_kn.shape
+    dst = torch.empty(n, k, dtype=torch.bfloat16, device=DEV)
+    ops.prep_weight(w_kn.contiguous(), dst, k, n)
+    return dst
+
+
+@pytest.mark.parametrize("m,k,n,bn", [(128, 64, 64, 0), (256, 128, 128, 0), (300, 320, 320, 0), (1000, 640, 1920, 0),
+                                      (4096, 1280, 1280, 256), (77 * 2, 1024, 640, 0), (128, 64, 256, 64)])
+def test_igemm_linear(m, k, n, bn):
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(0)
+    a = torch.randn(m, k, generator=g).to(DEV)
+    w = (torch.randn(k, n, generator=g) / math.sqrt(k)).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV)
+    res = torch.randn(m, n, generator=g).to(DEV)
+    ab = bf(a).contiguous()
+    wt = _prep_w(w)
+    assert torch.equal(wt, bf(w).t().contiguous())
+    out = torch.zeros(m, n, device=DEV)
+    outb = torch.zeros(m, n, dtype=torch.bfloat16, device=DEV)
+    ops.igemm(a0=ab, wt=wt, n=n, c0=k, m=m, bias=bias, residual=res, out_f32=out, out_bf16=outb, bn=bn)
+    torch.cuda.synchronize()
+    ref = ab.float() @ bf(w).float() + bias + res
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max err {err}"
+    assert rel_err(outb, ref) < 5e-3
+
+
+def test_igemm_geglu():
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(1)
+    m, c = 384, 128
+    a = bf(torch.randn(m, c, generator=g)).to(DEV)
+    w = (torch.randn(c, 8 * c, generator=g) / math.sqrt(c)).to(DEV)
+    bias = torch.randn(8 * c, generator=g).to(DEV)
+    wt = torch.empty(8 * c, c, dtype=torch.bfloat16, device=DEV)
+    ops.prep_weight(w, wt, c, 8 * c, geglu_bn=256)
+    bp = torch.empty_like(bias)
+    ops.permute_geglu_bias(bias, bp, 8 * c, 256)
+    out = torch.zeros(m, 4 * c, dtype=torch.bfloat16, device=DEV)
+    ops.igemm(a0=a, wt=wt, n=8 * c, c0=c, m=m, bias=bp, out_bf16=out, geglu=True, bn=256)
+    torch.cuda.synchronize()
+    f = a.float() @ bf(w).float() + bias
+    lin, gate = f.chunk(2, dim=-1)
+    ref = lin * torch.nn.functional.gelu(gate, approximate="tanh")
+    assert rel_err(out, ref) < 6e-3
+
+
+def _conv_ref(x_nhwc, w_hwio, bias, stride):
+    y = torch.nn.functional.conv2d(x_nhwc.permute(0, 3, 1, 2), w_hwio.permute(3, 2, 0, 1), bias, stride=stride,
+                                   padding=w_hwio.shape[0] // 2)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("b,h,c0,c1,n,ks,stride", [
+    (2, 8, 64, 0, 64, 3, 1), (1, 16, 128, 0, 128, 3, 1), (3, 8, 64, 0, 128, 3, 1), (2, 64, 64, 0, 64, 3, 1),
+    (2, 32, 128, 64, 160, 3, 1), (2, 16, 64, 64, 64, 1, 1), (2, 16, 64, 0, 64, 3, 2), (2, 8, 128, 0, 64, 3, 2),
+    (1, 4, 64, 0, 64, 3, 1), (5, 2, 64, 0, 64, 3, 1), (2, 64, 320, 0, 320, 3, 1)])
+def test_igemm_conv(b, h, c0, c1, n, ks, stride):
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(2)
+    hi = h * stride
+    x0 = bf(torch.randn(b, hi, hi, c0, generator=g)).to(DEV)
+    x1 = bf(torch.randn(b, hi, hi, c1, generator=g)).to(DEV) if c1 else None
+    cin = c0 + c1
+    w = (torch.randn(ks, ks, cin, n, generator=g) / math.sqrt(ks * ks * cin)).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV)
+    tvec = torch.randn(b, n, generator=g).to(DEV)
+    wt = _prep_w(w.reshape(ks * ks * cin, n))
+    out = torch.zeros(b * h * h, n, device=DEV)
+    ops.igemm(a0=x0, a1=x1, wt=wt, n=n, c0=c0, c1=c1, conv=(b, h, h), taps=ks * ks, stride=stride, bias=bias,
+              rowvec=tvec, rows_per_sample=h * h, rowvec_ld=n, out_f32=out)
+    torch.cuda.synchronize()
+    xin = x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], dim=-1)
+    ref = _conv_ref(xin, bf(w).float(), bias, stride) + tvec[:, None, None, :]
+    ref = ref.reshape(b * h * h, n)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max err {err}"
+
+
+def test_igemm_batch_invariance():
+    """The same sample must produce bit-identical rows whatever the batch size / tile position."""
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    c, n, h = 128, 128, 8
+    x = bf(torch.randn(6, h, h, c, generator=g)).to(DEV)
+    w = (torch.randn(9 * c, n, generator=g) / math.sqrt(9 * c)).to(DEV)
+    wt = _prep_w(w)
+    big = torch.zeros(6 * h * h, n, device=DEV)
+    ops.igemm(a0=x, wt=wt, n=n, c0=c, conv=(6, h, h), taps=9, out_f32=big)
+    for i in (1, 4, 5):
+        small = torch.zeros(h * h, n, device=DEV)
+        ops.igemm(a0=x[i:i + 1].contiguous(), wt=wt, n=n, c0=c, conv=(1, h, h), taps=9, out_f32=small)
+        assert torch.equal(small, big[i * h * h:(i + 1) * h * h])
+
+
+# ------------------------------------------------------------------ attention ----
+@pytest.mark.parametrize("b,heads,nq,nk", [(1, 1, 128, 128), (2, 2, 256, 256), (1, 1, 1024, 1024), (2, 5, 4096, 4096),
+                                           (2, 2, 256, 77), (3, 4, 64, 64), (2, 2, 64, 77)])
+def test_attention_fwd(b, heads, nq, nk):
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(4)
+    c = heads * 64
+    q = bf(torch.randn(b, nq, c, generator=g)).to(DEV)
+    kv = bf(torch.randn(b, nk, 2 * c, generator=g)).to(DEV)
+    out = torch.zeros(b, nq, c, dtype=torch.bfloat16, device=DEV)
+    lse = torch.zeros(b, heads, nq, device=DEV)
+    ops.attention_fwd(q, kv, kv[:, :, c:], out, b, heads, nq, nk, c, 2 * c, 2 * c, c, lse=lse)
+    torch.cuda.synchronize()
+    qh = q.float().view(b, nq, heads, 64).permute(0, 2, 1, 3)
+    kh = kv[:, :, :c].float().reshape(b, nk, heads, 64).permute(0, 2, 1, 3)
+    vh = kv[:, :, c:].float().reshape(b, nk, heads, 64).permute(0, 2, 1, 3)
+    s = (qh @ kh.transpose(-1, -2)) * 0.125
+    ref = (torch.softmax(s, dim=-1) @ vh).permute(0, 2, 1, 3).reshape(b, nq, c)
+    assert rel_err(out, ref) < 1e-2
+    assert (lse - torch.logsumexp(s, dim=-1)).abs().max().item() < 1e-3
+
+
+# ---------------------------------------------------------------------- norms ----
+@pytest.mark.parametrize("b,hw,c0,c1,silu", [(2, 64, 64, 0, True), (2, 4096, 320, 0, True), (3, 1024, 1280, 640, True),
+                                             (2, 256, 1280, 1280, False), (1, 16, 128, 64, True)])
+def test_groupnorm_fwd(b, hw, c0, c1, silu):
+    from ddpo_b200 import ops
+    from oracle.unet import group_norm, silu as silu_ref
+    g = torch.Generator(device="cpu").manual_seed(5)
+    c = c0 + c1
+    x0 = (torch.randn(b, hw, c0, generator=g) * 2 + 0.5).to(DEV)
+    x1 = torch.randn(b, hw, c1, generator=g).to(DEV) if c1 else None
+    sc = (1 + 0.1 * torch.randn(c, generator=g)).to(DEV)
+    bi = (0.1 * torch.randn(c, generator=g)).to(DEV)
+    ws = torch.zeros(ops.groupnorm_workspace_floats(b, hw, c), device=DEV)
+    y = torch.zeros(b, hw, c, dtype=torch.bfloat16, device=DEV)
+    yf = torch.zeros(b, hw, c, device=DEV)
+    raw = torch.zeros(b, hw, c, dtype=torch.bfloat16, device=DEV)
+    ops.groupnorm_fwd(x0, sc, bi, ws, b, hw, c0, x1=x1, c1=c1, silu=silu, y_bf16=y, y_f32=yf, raw_bf16=raw)
+    torch.cuda.synchronize()
+    x = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
+    ref = group_norm(x.view(b, hw, 1, c), sc, bi).view(b, hw, c)
+    if silu:
+        ref = silu_ref(ref)
+    assert (yf - ref).abs().max().item() < 2e-4
+    assert rel_err(y, ref) < 4e-3
+    assert torch.equal(raw, bf(x))
+
+
+@pytest.mark.parametrize("m,c", [(64, 64), (1000, 320), (4096, 1280)])
+def test_layernorm_fwd(m, c):
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(6)
+    x = (torch.randn(m, c, generator=g) * 3 + 1).to(DEV)
+    sc = (1 + 0.1 * torch.randn(c, generator=g)).to(DEV)
+    bi = (0.1 * torch.randn(c, generator=g)).to(DEV)
+    y = torch.zeros(m, c, dtype=torch.bfloat16, device=DEV)
+    ops.layernorm_fwd(x, sc, bi, y, m, c)
+    ref = torch.nn.functional.layer_norm(x, (c,), sc, bi, 1e-5)
+    assert rel_err(y, ref) < 4e-3
+
+
+# --------------------------------------------------------------- small layers ----
+def test_conv_in_out_dense_upsample():
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(7)
+    b, h, c = 3, 16, 64
+    lat = torch.randn(b, 4, h, h, generator=g).to(DEV)
+    w = torch.randn(3, 3, 4, c, generator=g).to(DEV) / 6
+    bias = torch.randn(c, generator=g).to(DEV)
+    y = torch.zeros(b * h * h, c, device=DEV)
+    ops.conv_in(lat, w, bias, y, b, 4, h, h, c)
+    ref = torch.nn.functional.conv2d(lat, w.permute(3, 2, 0, 1), bias, padding=1).permute(0, 2, 3, 1).reshape(b * h * h, c)
+    assert (y - ref).abs().max().item() < 1e-4
+    x = torch.randn(b, h, h, c, generator=g).to(DEV)
+    w2 = torch.randn(3, 3, c, 4, generator=g).to(DEV) / 24
+    b2 = torch.randn(4, generator=g).to(DEV)
+    o = torch.zeros(b, 4, h, h, device=DEV)
+    ops.conv_out(x, w2, b2, o, b, h, h, c, 4)
+    ref2 = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w2.permute(3, 2, 0, 1), b2, padding=1)
+    assert (o - ref2).abs().max().item() < 1e-4
+    xin = torch.randn(b, 320, generator=g).to(DEV)
+    wd = torch.randn(320, 1280, generator=g).to(DEV) / 18
+    bd = torch.randn(1280, generator=g).to(DEV)
+    yd = torch.zeros(b, 1280, device=DEV)
+    ops.dense_small(xin, wd, bd, yd, b, 320, 1280, silu_in=True, silu_out=True)
+    refd = torch.nn.functional.silu(torch.nn.functional.silu(xin) @ wd + bd)
+    assert (yd - refd).abs().max().item() < 1e-4
+    up = torch.zeros(b, 2 * h, 2 * h, c, dtype=torch.bfloat16, device=DEV)
+    ops.upsample2x_bf16(x, up, b, h, h, c)
+    assert torch.equal(up, bf(x).repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
+    ts = torch.tensor([981, 1, 500], dtype=torch.int32, device=DEV)
+    emb = torch.zeros(b, 320, device=DEV)
+    ops.timestep_sincos(ts, emb, b, 320)
+    from oracle.unet import timestep_embedding
+    refe = timestep_embedding(ts.cpu(), 320, torch.float32)
+    assert (emb.cpu() - refe).abs().max().item() < 2e-4
