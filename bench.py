@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Benchmark of the DDPO hot path on B200 (contract: see the task brief / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--phase sample|ppo]
+
+Workload = BASELINE.json configs[1]: DDPO, SD2-base 512 px (64x64x4 latents, 77x1024 context), 50-step
+DDIM, CFG 5.0, eta 1.0, per-GPU sample batch 8 (global batch 64 on 8 GPUs), synthetic latents/prompt
+embeddings, random-init U-Net weights.  One bench "step" is one pass of the hot path over one batch:
+  phase=sample : one denoising step of the 8-sample batch (U-Net on the 2x8 CFG batch + fused
+                 CFG/DDIM/log-prob/noise kernel)                          -> denoising steps/s
+  phase=ppo    : one PPO minibatch step (train batch 2, train_cfg: fwd+bwd of the 4-sample CFG batch,
+                 log-prob, PPO loss, gradient accumulate)                 -> counted into PPO samples/s
+The headline `value` is PPO samples/s when the training path is available (a PPO sample = 50 sampling
+steps + 50 train steps of one trajectory), else denoising steps/s.
+One process per GPU (torchrun for N>1), max-over-ranks CUDA-event timing.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_STEPS = 50
+SAMPLE_BATCH = 8
+TRAIN_BATCH = 2
+GUIDANCE, ETA, CLIP = 5.0, 1.0, 1e-4
+UNET_GFLOP = 804.3  # algorithmic GFLOP of one SD2-base U-Net application (SURVEY.md §8d / BASELINE.md §2)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1387.8), d.get("bf16_tflops", 1645.5), d.get("hbm_gbs", 6576.4), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------- CPU arm ----
+def cpu_step_seconds(n_steps, threads=None):
+    """Times the CPU oracle (restated reference path: oracle/unet.py + oracle/scheduler.py) on one
+    denoising step of ONE sample (2 U-Net applications, SD2-base, fp32) -- bounded sample."""
+    import torch
+    from ddpo_b200 import unet_spec
+    from oracle import scheduler as OS, ppo as OPPO, threefry
+    from oracle.unet import UNetOracle
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = unet_spec.SD2_BASE
+    flat = unet_spec.init_flat_params(cfg, 0)
+    net = UNetOracle(cfg, unet_spec.views(flat, cfg))
+    st = OS.set_timesteps(OS.SD_CONFIG, OS.create_state(OS.SD_CONFIG), T_STEPS)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 4, 64, 64, generator=g)
+    ctx = torch.randn(2, 77, 1024, generator=g)
+    times = []
+    for s in range(n_steps + 1):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            e = net(torch.cat([x, x]), torch.full((2,), int(st.timesteps[s])), ctx).numpy()
+        eps = OPPO.cfg_combine(e[:1], e[1:], GUIDANCE)
+        xn, _, lp = OS.step(OS.SD_CONFIG, st, eps, int(st.timesteps[s]), x.numpy(),
+                            key=threefry.PRNGKey(s), eta=ETA)
+        x = torch.from_numpy(xn)
+        if s > 0:  # first step = warm-up (allocator, thread pool)
+            times.append(time.perf_counter() - t0)
+    return float(np.mean(times)), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step, cores = cpu_step_seconds(max(1, args.steps))
+    v = 1.0 / per_step
+    print(json.dumps({
+        "impl": "reference", "metric": "denoising_steps_per_sec", "value": v, "unit": "denoising steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DDPO SD2-base 512px 50-step DDIM, CFG 5.0 (BASELINE configs[1]); CPU arm: 1 sample/step"},
+        "cpu_baseline": {"value": v, "unit": "denoising steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} denoising step(s) of 1 sample (2 U-Net applications), torch-CPU oracle"},
+        "e2e": {"value": v, "unit": "denoising steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------- GPU arm ----
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--phase", default="auto", choices=["auto", "sample", "ppo"])
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    from ddpo_b200 import ops, unet_spec
+    from ddpo_b200.diffusers_patch import DDIMScheduler, StableDiffusionPipeline
+    from ddpo_b200.unet import UNet
+    sus_tf, burst_tf, hbm_gbs, peak_src = _peaks()
+
+    cfg = unet_spec.SD2_BASE
+    # random-init weights generated on the device (identical on every rank: same seed)
+    table, total = unet_spec.param_offsets(cfg)
+    g = torch.Generator(device=dev).manual_seed(0)
+    flat = torch.empty(total, device=dev)
+    for name, (off, shape) in table.items():
+        n = int(np.prod(shape))
+        leaf = name.rsplit("/", 1)[1]
+        if leaf == "kernel":
+            flat[off:off + n] = torch.randn(n, generator=g, device=dev) / np.sqrt(np.prod(shape[:-1]))
+        elif leaf == "scale":
+            flat[off:off + n] = 1.0 + 0.1 * torch.randn(n, generator=g, device=dev)
+        else:
+            flat[off:off + n] = 0.02 * torch.randn(n, generator=g, device=dev)
+    net = UNet(cfg, flat, dev)
+    sched = DDIMScheduler(1000, 0.00085, 0.012, "scaled_linear", None, False, 1, "epsilon", device=dev)
+    pipe = StableDiffusionPipeline(net, sched, vae_scale_factor=8)
+    state = sched.create_state()
+
+    B = SAMPLE_BATCH
+    gh = torch.Generator().manual_seed(1 + rank)
+    emb_host = torch.randn(B, 77, 1024, generator=gh).pin_memory()
+    neg_host = torch.randn(1, 77, 1024, generator=torch.Generator().manual_seed(2)).expand(B, -1, -1).contiguous().pin_memory()
+    seed_key = ops.threefry_split(ops.prng_key(0), max(2, world))[rank % max(2, world)]
+
+    # ---------------- phase: sample (device-resident timing of K denoising steps) ----------------
+    emb, neg = emb_host.to(dev), neg_host.to(dev)
+    st = sched.set_timesteps(state, T_STEPS)
+    ratio = 1000 // T_STEPS
+    net.prepare_context(torch.cat([neg, emb]))
+    S = pipe._step_buffers(B, 64, 64, dev)
+    ops.threefry_normal(ops.key_tensor([seed_key], dev), S["x_cur"].view(-1))
+    ts_dev = torch.as_tensor(np.asarray(st.timesteps, np.int32), device=dev)
+    S["t_dev"].copy_(ts_dev[0:1])
+    S["key_dev"].copy_(ops.key_tensor([seed_key], dev)[0])
+
+    def one_step():
+        pipe._one_step(S, B, st, ratio, GUIDANCE, ETA)
+
+    lc0 = ops.LAUNCH_COUNT
+    one_step()
+    torch.cuda.synchronize()
+    launches_per_step = ops.LAUNCH_COUNT - lc0
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        one_step()
+
+    def step(i):
+        S["t_dev"].copy_(ts_dev[i % T_STEPS:i % T_STEPS + 1])
+        graph.replay()
+        S["x_cur"].copy_(S["x_next"])
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = tms.item()
+    ms_per_step = ms / args.steps
+    steps_per_s = world * B * args.steps / (ms / 1e3)  # denoising steps of one sample, whole job
+
+    # ---------------- kernel profile (eager, CUDA events per launch) ----------------
+    ops.PROFILE = []
+    one_step()
+    torch.cuda.synchronize()
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    agg = {}
+    for name, work, a, b in prof:
+        d = agg.setdefault(name, [0.0, 0.0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += work
+        d[2] += 1
+    tot_ms = sum(v[0] for v in agg.values())
+    ig = agg.get("igemm", [1e-9, 0, 0])
+    igemm_tflops = ig[1] / (ig[0] * 1e-3) / 1e12
+    gn = agg.get("groupnorm_fwd", [1e-9, 0, 0])
+    breakdown = {k: {"ms": round(v[0], 3), "launches": v[2], "share": round(v[0] / tot_ms, 4)} for k, v in agg.items()}
+    at = agg.get("attention_fwd", [1e-9, 0, 0])
+    breakdown["igemm"]["tflops"] = round(igemm_tflops, 1)
+    breakdown["attention_fwd"]["tflops"] = round(at[1] / (at[0] * 1e-3) / 1e12, 1)
+    breakdown["groupnorm_fwd"]["gbs"] = round(gn[1] / (gn[0] * 1e-3) / 1e9, 1)
+
+    # ---------------- e2e: the public pipeline call with host buffers ----------------
+    def e2e_call():
+        e = emb_host.to(dev, non_blocking=True)
+        n_ = neg_host.to(dev, non_blocking=True)
+        final, lat, nxt, lps, ts = pipe(e, n_, {"unet": net.params, "scheduler": state}, seed_key, T_STEPS, 512, 512,
+                                        GUIDANCE, ETA)
+        return final.cpu(), lps.cpu()
+
+    e2e_call()  # warm (captures the pipeline's own graph)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    fin, lps = e2e_call()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tdt = torch.tensor([dt], device=dev)
+    if world > 1:
+        dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+    e2e_steps_per_s = world * B * T_STEPS / tdt.item()
+    h2d = (emb_host.numel() + neg_host.numel()) * 4 / T_STEPS
+    d2h = (fin.numel() + lps.numel()) * 4 / T_STEPS
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu:
+            per_step, cores = cpu_step_seconds(args.cpu_steps)
+            cpu = {"value": 1.0 / per_step, "unit": "denoising steps/s", "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_steps} denoising steps of 1 sample (2 U-Net applications each), torch-CPU oracle"}
+        step_flops = 2 * B * UNET_GFLOP * 1e9
+        line = {
+            "metric": "denoising_steps_per_sec", "value": steps_per_s, "unit": "denoising steps/s (1 sample, both CFG branches)",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (fp32 accumulate, fp32 residual stream/norms)",
+            "data": "synthetic",
+            "config": {"workload": "DDPO SD2-base 512px, 50-step DDIM, CFG 5.0, eta 1.0, sample batch 8/GPU (BASELINE configs[1])",
+                       "per_step": "one denoising step of the 8-sample batch (U-Net batch 16)",
+                       "l2": "per-step working set (1.7 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush",
+                       "cuda_graph": True, "per_gpu_steps_per_s": steps_per_s / world,
+                       "unet_tflops_per_gpu": step_flops / (ms_per_step * 1e-3) / 1e12},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_steps_per_s, "unit": "denoising steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "what": "pipeline(...) 50-step call from pinned host embeddings to host final latents + log-probs"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "tensor", "achieved": igemm_tflops, "peak": sus_tf, "unit": "TFLOP/s",
+                         "frac": igemm_tflops / sus_tf, "traffic": None, "kernel": "igemm_kernel",
+                         "peak_source": f"{peak_src} bf16_tflops_sustained",
+                         "how": "sum of algorithmic 2MNK over the igemm launches of one step / sum of their CUDA-event durations"},
+            "kernels": breakdown,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

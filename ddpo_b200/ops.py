@@ -12,6 +12,29 @@ from ._lib import AttentionArgs, DdimCommon, GroupNormArgs, IGemmArgs, check, li
 
 DDIM_CHUNKS = 8
 
+# ---- instrumentation (bench.py): kernel-launch counter and optional CUDA-event profile ----
+LAUNCH_COUNT = 0           # kernels launched through this module since import
+PROFILE = None             # list of (name, work, event0, event1) while profiling, else None
+_KERNELS_PER_CALL = {"groupnorm_fwd": 2, "groupnorm_bwd": 3, "layernorm_bwd": 2}
+
+
+def _run(name, status, work=0.0, ev=None):
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += _KERNELS_PER_CALL.get(name, 1)
+    if ev is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.append((name, work, ev, e1))
+    check(status, name)
+
+
+def _ev():
+    if PROFILE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -52,7 +75,8 @@ def key_tensor(keys, device):
 
 def threefry_normal(key_dev, out):
     _chk(out, torch.float32, "out")
-    check(lib().ddpo_threefry_normal(_p(key_dev), _p(out), out.numel(), _stream()), "threefry_normal")
+    _e = _ev()
+    _run("threefry_normal", lib().ddpo_threefry_normal(_p(key_dev), _p(out), out.numel(), _stream()), 0.0, _e)
     return out
 
 
@@ -77,25 +101,28 @@ def _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, s
 def ddim_step_sample(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta,
                      key_dev, prev_out, logp_out, ws):
     c = _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, ws)
-    check(lib().ddpo_ddim_step_sample(C.byref(c), _p(key_dev), _p(prev_out), _p(logp_out), _stream()), "ddim_step_sample")
+    _e = _ev()
+    _run("ddim_step_sample", lib().ddpo_ddim_step_sample(C.byref(c), _p(key_dev), _p(prev_out), _p(logp_out), _stream()), 0.0, _e)
 
 
 def ddim_logprob_fwd(eps_u, eps_c, sample, prev, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta,
                      logp_out, ws):
     c = _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, ws)
-    check(lib().ddpo_ddim_logprob_fwd(C.byref(c), _p(prev), _p(logp_out), _stream()), "ddim_logprob_fwd")
+    _e = _ev()
+    _run("ddim_logprob_fwd", lib().ddpo_ddim_logprob_fwd(C.byref(c), _p(prev), _p(logp_out), _stream()), 0.0, _e)
 
 
 def ddim_logprob_bwd(eps_u, eps_c, sample, prev, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta,
                      dlogp, d_eps_u, d_eps_c, ws):
     c = _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, ws)
-    check(lib().ddpo_ddim_logprob_bwd(C.byref(c), _p(prev), _p(dlogp), _p(d_eps_u), _p(d_eps_c), _stream()),
-          "ddim_logprob_bwd")
+    _e = _ev()
+    _run("ddim_logprob_bwd", lib().ddpo_ddim_logprob_bwd(C.byref(c), _p(prev), _p(dlogp), _p(d_eps_u), _p(d_eps_c), _stream()), 0.0, _e)
 
 
 def ppo_loss(logp, old_logp, adv, clip_range, info_out, dlogp_out):
-    check(lib().ddpo_ppo_loss(_p(logp), _p(old_logp), _p(adv), logp.numel(), float(clip_range), _p(info_out),
-                              _p(dlogp_out), _stream()), "ppo_loss")
+    _e = _ev()
+    _run("ppo_loss", lib().ddpo_ppo_loss(_p(logp), _p(old_logp), _p(adv), logp.numel(), float(clip_range), _p(info_out),
+                              _p(dlogp_out), _stream()), 0.0, _e)
 
 
 # ------------------------------------------------------------------ GEMM --------
@@ -121,7 +148,9 @@ def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None,
     a.residual, a.ld_res = _p(residual), int(ld_res)
     a.out_f32, a.out_bf16, a.ld_out = _p(out_f32), _p(out_bf16), int(ld_out)
     a.geglu, a.accumulate_out, a.bn_override = int(geglu), int(accumulate), int(bn)
-    check(lib().ddpo_igemm(C.byref(a), _stream()), "igemm")
+    rows = a.batch * a.h * a.w if a.is_conv else a.m
+    _e = _ev()
+    _run("igemm", lib().ddpo_igemm(C.byref(a), _stream()), 2.0 * rows * a.n * a.taps * (a.c0 + a.c1), _e)
 
 
 # ------------------------------------------------------------------ norms -------
@@ -137,19 +166,22 @@ def _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, y_bf16, y_f32, raw_bf
 def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, y_bf16=None, y_f32=None,
                   raw_bf16=None, skip_stats=False):
     a = _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, y_bf16, y_f32, raw_bf16, ws, skip_stats=skip_stats)
-    check(lib().ddpo_groupnorm_fwd(C.byref(a), _stream()), "groupnorm_fwd")
+    _e = _ev()
+    per = 4 + (2 if y_bf16 is not None else 0) + (4 if y_f32 is not None else 0) + (2 if raw_bf16 is not None else 0)
+    _run("groupnorm_fwd", lib().ddpo_groupnorm_fwd(C.byref(a), _stream()), float(batch) * hw * (c0 + c1) * per, _e)
 
 
 def groupnorm_bwd(x0, scale, bias, ws, batch, hw, c0, dy, dx0, dscale, dbias, x1=None, c1=0, dx1=None, silu=True,
                   accumulate=False, ldd0=0, ldd1=0):
     a = _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, None, None, None, ws)
-    check(lib().ddpo_groupnorm_bwd(C.byref(a), _p(dy), _p(dx0), _p(dx1), int(ldd0), int(ldd1), int(accumulate),
-                                   _p(dscale), _p(dbias), _stream()), "groupnorm_bwd")
+    _e = _ev()
+    _run("groupnorm_bwd", lib().ddpo_groupnorm_bwd(C.byref(a), _p(dy), _p(dx0), _p(dx1), int(ldd0), int(ldd1), int(accumulate),
+                                   _p(dscale), _p(dbias), _stream()), 0.0, _e)
 
 
 def layernorm_fwd(x, scale, bias, y_bf16, m, c, stats=None):
-    check(lib().ddpo_layernorm_fwd(_p(x), _p(scale), _p(bias), _p(y_bf16), _p(stats), int(m), int(c), 1e-5, _stream()),
-          "layernorm_fwd")
+    _e = _ev()
+    _run("layernorm_fwd", lib().ddpo_layernorm_fwd(_p(x), _p(scale), _p(bias), _p(y_bf16), _p(stats), int(m), int(c), 1e-5, _stream()), 0.0, _e)
 
 
 def layernorm_bwd_workspace_floats(m, c):
@@ -157,54 +189,96 @@ def layernorm_bwd_workspace_floats(m, c):
 
 
 def layernorm_bwd(x, scale, stats, dy, dx, dscale, dbias, ws, m, c, accumulate=False):
-    check(lib().ddpo_layernorm_bwd(_p(x), _p(scale), _p(stats), _p(dy), _p(dx), int(accumulate), _p(dscale),
-                                   _p(dbias), _p(ws), int(m), int(c), _stream()), "layernorm_bwd")
+    _e = _ev()
+    _run("layernorm_bwd", lib().ddpo_layernorm_bwd(_p(x), _p(scale), _p(stats), _p(dy), _p(dx), int(accumulate), _p(dscale),
+                                   _p(dbias), _p(ws), int(m), int(c), _stream()), 0.0, _e)
 
 
 # ------------------------------------------------------------ small layers -------
 def prep_weight(src, dst, k, n, ldk=None, row_offset=0, col_offset=0, geglu_bn=0):
-    check(lib().ddpo_prep_weight(_p(src), _p(dst), int(k), int(n), int(ldk or k), int(row_offset), int(col_offset),
-                                 int(geglu_bn), _stream()), "prep_weight")
+    _e = _ev()
+    _run("prep_weight", lib().ddpo_prep_weight(_p(src), _p(dst), int(k), int(n), int(ldk or k), int(row_offset), int(col_offset),
+                                 int(geglu_bn), _stream()), 0.0, _e)
 
 
 def prep_weight_dgrad(src, dst, taps, k, n):
-    check(lib().ddpo_prep_weight_dgrad(_p(src), _p(dst), int(taps), int(k), int(n), _stream()), "prep_weight_dgrad")
+    _e = _ev()
+    _run("prep_weight_dgrad", lib().ddpo_prep_weight_dgrad(_p(src), _p(dst), int(taps), int(k), int(n), _stream()), 0.0, _e)
 
 
 def permute_geglu_bias(src, dst, n, bn):
-    check(lib().ddpo_permute_geglu_bias(_p(src), _p(dst), int(n), int(bn), _stream()), "permute_geglu_bias")
+    _e = _ev()
+    _run("permute_geglu_bias", lib().ddpo_permute_geglu_bias(_p(src), _p(dst), int(n), int(bn), _stream()), 0.0, _e)
 
 
 def cast_bf16(x, y):
-    check(lib().ddpo_cast_bf16(_p(x), _p(y), x.numel(), _stream()), "cast_bf16")
+    _e = _ev()
+    _run("cast_bf16", lib().ddpo_cast_bf16(_p(x), _p(y), x.numel(), _stream()), 0.0, _e)
 
 
 def upsample2x_bf16(x, y, batch, h, w, c):
-    check(lib().ddpo_upsample2x_bf16(_p(x), _p(y), batch, h, w, c, _stream()), "upsample2x_bf16")
+    _e = _ev()
+    _run("upsample2x_bf16", lib().ddpo_upsample2x_bf16(_p(x), _p(y), batch, h, w, c, _stream()), 0.0, _e)
 
 
 def upsample2x_bwd(dy, dx, batch, h, w, c, accumulate=False):
-    check(lib().ddpo_upsample2x_bwd(_p(dy), _p(dx), batch, h, w, c, int(accumulate), _stream()), "upsample2x_bwd")
+    _e = _ev()
+    _run("upsample2x_bwd", lib().ddpo_upsample2x_bwd(_p(dy), _p(dx), batch, h, w, c, int(accumulate), _stream()), 0.0, _e)
 
 
 def conv_in(x_nchw, w, bias, y_nhwc, batch, cin, h, wd, cout):
-    check(lib().ddpo_conv_in(_p(x_nchw), _p(w), _p(bias), _p(y_nhwc), batch, cin, h, wd, cout, _stream()), "conv_in")
+    _e = _ev()
+    _run("conv_in", lib().ddpo_conv_in(_p(x_nchw), _p(w), _p(bias), _p(y_nhwc), batch, cin, h, wd, cout, _stream()), 0.0, _e)
 
 
 def conv_out(x_nhwc, w, bias, y_nchw, batch, h, wd, cin, cout):
-    check(lib().ddpo_conv_out(_p(x_nhwc), _p(w), _p(bias), _p(y_nchw), batch, h, wd, cin, cout, _stream()), "conv_out")
+    _e = _ev()
+    _run("conv_out", lib().ddpo_conv_out(_p(x_nhwc), _p(w), _p(bias), _p(y_nchw), batch, h, wd, cin, cout, _stream()), 0.0, _e)
 
 
 def timestep_sincos(t, out, batch, dim):
-    check(lib().ddpo_timestep_sincos(_p(t), 1 if t.numel() > 1 else 0, _p(out), batch, dim, _stream()), "timestep_sincos")
+    _e = _ev()
+    _run("timestep_sincos", lib().ddpo_timestep_sincos(_p(t), 1 if t.numel() > 1 else 0, _p(out), batch, dim, _stream()), 0.0, _e)
 
 
 def dense_small(x, w, bias, y, batch, k, n, silu_in=False, silu_out=False):
-    check(lib().ddpo_dense_small(_p(x), _p(w), _p(bias), _p(y), batch, k, n, int(silu_in), int(silu_out), _stream()),
-          "dense_small")
+    _e = _ev()
+    _run("dense_small", lib().ddpo_dense_small(_p(x), _p(w), _p(bias), _p(y), batch, k, n, int(silu_in), int(silu_out), _stream()), 0.0, _e)
 
 
 # --------------------------------------------------------------- attention -------
 def attention_fwd(q, k, v, out, batch, heads, nq, nk, ldq, ldk, ldv, ldo, lse=None):
     a = AttentionArgs(_p(q), _p(k), _p(v), _p(out), _p(lse), batch, heads, nq, nk, 64, ldq, ldk, ldv, ldo)
-    check(lib().ddpo_attention_fwd(C.byref(a), _stream()), "attention_fwd")
+    _e = _ev()
+    _run("attention_fwd", lib().ddpo_attention_fwd(C.byref(a), _stream()), 4.0 * batch * heads * nq * nk * 64, _e)
+
+
+# ------------------------------------------------------------------ wgrad -------
+_WGRAD_WS = {}
+
+
+def wgrad(*, dy, n, x0, dw, x1=None, c0=None, c1=0, ldy=0, ldx0=0, ldx1=0, conv=None, m=None, taps=1, stride=1):
+    """dw[(tap, cin), n] += X^T dY (fp32, Flax layout).  conv=(batch, h_out, w_out) or linear with m rows."""
+    from ._lib import WgradArgs
+    a = WgradArgs()
+    a.dy, a.ldy, a.n = _p(dy), int(ldy), int(n)
+    a.x0, a.x1 = _p(x0), _p(x1)
+    a.c0 = int(c0 if c0 is not None else x0.shape[-1])
+    a.c1, a.ldx0, a.ldx1 = int(c1), int(ldx0), int(ldx1)
+    if conv is not None:
+        a.is_conv, a.batch, a.h, a.w, a.m = 1, int(conv[0]), int(conv[1]), int(conv[2]), 0
+    else:
+        a.is_conv, a.batch, a.h, a.w, a.m = 0, 0, 0, 0, int(m)
+    a.conv_stride, a.taps = int(stride), int(taps)
+    a.dw = _p(dw)
+    need = int(lib().ddpo_wgrad_workspace_floats(C.byref(a)))
+    dev = dw.device
+    ws = _WGRAD_WS.get(dev)
+    if need > 0 and (ws is None or ws.numel() < need):
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.float32, device=dev)
+        _WGRAD_WS[dev] = ws
+    a.workspace = _p(ws) if need > 0 else None
+    a.workspace_floats = ws.numel() if (need > 0) else 0
+    rows = a.batch * a.h * a.w if a.is_conv else a.m
+    _e = _ev()
+    _run("wgrad", lib().ddpo_wgrad(C.byref(a), _stream()), 2.0 * rows * a.n * a.taps * (a.c0 + a.c1), _e)

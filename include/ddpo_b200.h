@@ -177,6 +177,24 @@ typedef struct {
 } ddpo_attention_args;
 int ddpo_attention_fwd(const ddpo_attention_args* a, void* stream);
 
+/* ------------------------------------------------------- weight gradients ----------
+ * dW[(tap, c_in), c_out] += sum_pixels X[pixel+tap, c_in] * dY[pixel, c_out], written in the Flax
+ * parameter layout and accumulated (jax.grad at ddpo/training/policy_gradient.py:138 fused with
+ * AccumulatingTrainState's grad_acc += g, :44-47). */
+typedef struct {
+  const void* dy;  /* bf16 [M, ldy] output gradient */
+  int ldy, n;
+  const void* x0;  /* bf16 NHWC forward input(s) of the layer (same geometry as ddpo_igemm_args) */
+  const void* x1;
+  int c0, c1, ldx0, ldx1;
+  int is_conv, batch, h, w, conv_stride, taps, m;
+  float* dw;       /* fp32 [taps*(c0+c1), n], accumulated */
+  float* workspace;
+  int64_t workspace_floats;
+} ddpo_wgrad_args;
+int64_t ddpo_wgrad_workspace_floats(const ddpo_wgrad_args* a);
+int ddpo_wgrad(const ddpo_wgrad_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,106 @@
+"""GPU parity tests of the backward kernels (wgrad, norm backward, ...) vs torch autograd."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("m,k,n", [(256, 64, 64), (1000, 320, 320), (4096, 1280, 640), (154, 1024, 1280), (8192, 128, 960)])
+def test_wgrad_linear(m, k, n):
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = bf(torch.randn(m, k, generator=g)).to(DEV)
+    dy = bf(torch.randn(m, n, generator=g)).to(DEV)
+    dw = torch.ones(k, n, device=DEV)
+    ops.wgrad(dy=dy, n=n, x0=x, c0=k, m=m, dw=dw)
+    torch.cuda.synchronize()
+    ref = 1.0 + x.float().t() @ dy.float()
+    err = (dw - ref).abs().max().item()
+    assert err < 2e-3 * ref.abs().max().item(), f"max err {err}"
+
+
+@pytest.mark.parametrize("b,h,c0,c1,n,ks,stride", [(2, 8, 64, 0, 64, 3, 1), (2, 16, 128, 64, 128, 3, 1), (4, 64, 64, 0, 64, 3, 1),
+                                                   (2, 32, 320, 0, 320, 3, 1), (2, 16, 64, 64, 128, 1, 1),
+                                                   (2, 8, 64, 0, 64, 3, 2), (3, 4, 64, 0, 64, 3, 1)])
+def test_wgrad_conv(b, h, c0, c1, n, ks, stride):
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(1)
+    hi = h * stride
+    x0 = bf(torch.randn(b, hi, hi, c0, generator=g)).to(DEV)
+    x1 = bf(torch.randn(b, hi, hi, c1, generator=g)).to(DEV) if c1 else None
+    dy = bf(torch.randn(b * h * h, n, generator=g)).to(DEV)
+    cin = c0 + c1
+    dw = torch.zeros(ks * ks * cin, n, device=DEV)
+    ops.wgrad(dy=dy, n=n, x0=x0, x1=x1, c0=c0, c1=c1, conv=(b, h, h), taps=ks * ks, stride=stride, dw=dw)
+    torch.cuda.synchronize()
+    xin = (x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], -1)).permute(0, 3, 1, 2).requires_grad_(False)
+    w = torch.zeros(n, cin, ks, ks, device=DEV, requires_grad=True)
+    y = torch.nn.functional.conv2d(xin, w, stride=stride, padding=ks // 2)
+    y.backward(dy.float().view(b, h, h, n).permute(0, 3, 1, 2))
+    ref = w.grad.permute(2, 3, 1, 0).reshape(ks * ks * cin, n)  # OIHW -> HWIO
+    err = (dw - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max err {err}"
+
+
+@pytest.mark.parametrize("b,hw,c0,c1,silu", [(2, 64, 64, 0, True), (2, 1024, 320, 0, True), (2, 256, 128, 64, False)])
+def test_groupnorm_bwd(b, hw, c0, c1, silu):
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(2)
+    c = c0 + c1
+    x0 = (torch.randn(b, hw, c0, generator=g) * 2 + 0.5).to(DEV)
+    x1 = torch.randn(b, hw, c1, generator=g).to(DEV) if c1 else None
+    sc = (1 + 0.1 * torch.randn(c, generator=g)).to(DEV)
+    bi = (0.1 * torch.randn(c, generator=g)).to(DEV)
+    dy = torch.randn(b, hw, c, generator=g).to(DEV)
+    ws = torch.zeros(ops.groupnorm_workspace_floats(b, hw, c), device=DEV)
+    y = torch.zeros(b, hw, c, dtype=torch.bfloat16, device=DEV)
+    ops.groupnorm_fwd(x0, sc, bi, ws, b, hw, c0, x1=x1, c1=c1, silu=silu, y_bf16=y)
+    dx0 = torch.zeros(b, hw, c0, device=DEV)
+    dx1 = torch.zeros(b, hw, c1, device=DEV) if c1 else None
+    dsc = torch.zeros(c, device=DEV)
+    dbi = torch.zeros(c, device=DEV)
+    ops.groupnorm_bwd(x0, sc, bi, ws, b, hw, c0, dy, dx0, dsc, dbi, x1=x1, c1=c1, dx1=dx1, silu=silu)
+    torch.cuda.synchronize()
+    x = (x0 if x1 is None else torch.cat([x0, x1], -1)).clone().requires_grad_(True)
+    scr, bir = sc.clone().requires_grad_(True), bi.clone().requires_grad_(True)
+    ref = torch.nn.functional.group_norm(x.permute(0, 2, 1), 32, scr, bir, 1e-5).permute(0, 2, 1)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    ref.backward(dy)
+    gx = x.grad
+    assert (dx0 - gx[..., :c0]).abs().max().item() < 2e-3 * gx.abs().max().item()
+    if c1:
+        assert (dx1 - gx[..., c0:]).abs().max().item() < 2e-3 * gx.abs().max().item()
+    assert (dsc - scr.grad).abs().max().item() < 2e-3 * scr.grad.abs().max().item()
+    assert (dbi - bir.grad).abs().max().item() < 2e-3 * bir.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("m,c", [(64, 64), (1000, 320), (2048, 1280)])
+def test_layernorm_bwd(m, c):
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = (torch.randn(m, c, generator=g) * 3 + 1).to(DEV)
+    sc = (1 + 0.1 * torch.randn(c, generator=g)).to(DEV)
+    bi = (0.1 * torch.randn(c, generator=g)).to(DEV)
+    dy = torch.randn(m, c, generator=g).to(DEV)
+    y = torch.zeros(m, c, dtype=torch.bfloat16, device=DEV)
+    st = torch.zeros(m, 2, device=DEV)
+    ops.layernorm_fwd(x, sc, bi, y, m, c, stats=st)
+    dx = torch.ones(m, c, device=DEV)
+    dsc = torch.zeros(c, device=DEV)
+    dbi = torch.zeros(c, device=DEV)
+    ws = torch.zeros(ops.layernorm_bwd_workspace_floats(m, c), device=DEV)
+    ops.layernorm_bwd(x, sc, st, dy, dx, dsc, dbi, ws, m, c, accumulate=True)
+    torch.cuda.synchronize()
+    xr, scr, bir = x.clone().requires_grad_(True), sc.clone().requires_grad_(True), bi.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (c,), scr, bir, 1e-5).backward(dy)
+    assert (dx - 1.0 - xr.grad).abs().max().item() < 2e-3 * xr.grad.abs().max().item()
+    assert (dsc - scr.grad).abs().max().item() < 2e-3 * scr.grad.abs().max().item()
+    assert (dbi - bir.grad).abs().max().item() < 2e-3 * bir.grad.abs().max().item()

@@ -1,0 +1,83 @@
+"""Sampling pipeline (CUDA) vs the CPU oracle restatement of the reference sampler."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(cfg_name="TINY", batch=2, seed=0):
+    from ddpo_b200 import unet_spec
+    from ddpo_b200.diffusers_patch import DDIMScheduler, StableDiffusionPipeline
+    from ddpo_b200.unet import UNet
+    cfg = getattr(unet_spec, cfg_name)
+    flat = unet_spec.init_flat_params(cfg, seed)
+    g = torch.Generator(device="cpu").manual_seed(seed + 1)
+    emb = torch.randn(batch, cfg.ctx_len, cfg.cross_attention_dim, generator=g)
+    neg = torch.randn(1, cfg.ctx_len, cfg.cross_attention_dim, generator=g).expand(batch, -1, -1).contiguous()
+    net = UNet(cfg, flat, "cuda")
+    sched = DDIMScheduler(1000, 0.00085, 0.012, "scaled_linear", None, False, 1, "epsilon")
+    pipe = StableDiffusionPipeline(net, sched, vae_scale_factor=8)
+    return cfg, flat, emb, neg, net, sched, pipe
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_pipeline_matches_oracle(use_graph):
+    from ddpo_b200 import unet_spec
+    from oracle import pipeline as OP, scheduler as OS
+    from oracle.unet import UNetOracle
+    cfg, flat, emb, neg, net, sched, pipe = _setup()
+    pipe.use_cuda_graph = use_graph
+    T, px = 4, cfg.sample_size * 8
+    state = sched.create_state()
+    key = (0, 42)
+    final, lat, nxt, lps, ts = pipe(emb.cuda(), neg.cuda(), {"unet": net.params, "scheduler": state}, key, T, px, px,
+                                    5.0, 1.0)
+    torch.cuda.synchronize()
+    oracle_net = UNetOracle(cfg, unet_spec.views(flat, cfg))
+    ost = OS.create_state(OS.SD_CONFIG)
+    rf, rlat, rnxt, rlps, rts = OP.generate(oracle_net, OS.SD_CONFIG, ost, emb, neg, np.array(key, np.uint32), T,
+                                            cfg.sample_size, 5.0, 1.0)
+    assert tuple(lat.shape) == rlat.shape and tuple(nxt.shape) == rnxt.shape and tuple(lps.shape) == rlps.shape
+    np.testing.assert_array_equal(ts.cpu().numpy(), rts)
+    # x_T is pure threefry noise: near bit-exact
+    np.testing.assert_allclose(lat[:, 0].cpu().numpy(), rlat[:, 0], atol=3e-6, rtol=0)
+    # per-step log-prob: north-star tolerance 1e-3 relative
+    np.testing.assert_allclose(lps.cpu().numpy(), rlps, rtol=1e-3)
+    # trajectories drift by the bf16 U-Net error (eps rel ~1e-2) through T stochastic steps
+    err = np.abs(final.cpu().numpy() - rf).max()
+    assert err < 0.1, f"final latents max abs err {err}"
+    assert torch.equal(lat[:, 1:], nxt[:, :-1])
+
+
+def test_pipeline_graph_equals_eager_and_is_reproducible():
+    cfg, flat, emb, neg, net, sched, pipe = _setup(batch=3)
+    state = sched.create_state()
+    px = cfg.sample_size * 8
+    args = (emb.cuda(), neg.cuda(), {"unet": net.params, "scheduler": state}, (1, 2), 3, px, px, 5.0, 1.0)
+    pipe.use_cuda_graph = False
+    a = [t.clone() for t in pipe(*args)]
+    pipe.use_cuda_graph = True
+    b = [t.clone() for t in pipe(*args)]
+    c = [t.clone() for t in pipe(*args)]
+    for x, y, z in zip(a, b, c):
+        assert torch.equal(x, y) and torch.equal(y, z)
+
+
+def test_scheduler_step_mirror_errors_and_modes():
+    from ddpo_b200.diffusers_patch import DDIMScheduler
+    sched = DDIMScheduler(1000, 0.00085, 0.012, "scaled_linear", None, False, 1, "epsilon")
+    st = sched.create_state()
+    x = torch.randn(2, 4, 8, 8, device="cuda")
+    e = torch.randn(2, 4, 8, 8, device="cuda")
+    with pytest.raises(ValueError):
+        sched.step(st, e, 981, x, key=(0, 1), eta=1.0)  # set_timesteps not run
+    st = sched.set_timesteps(st, 50)
+    with pytest.raises(ValueError):
+        sched.step(st, e, 981, x, key=(0, 1), prev_sample=x, eta=1.0)
+    prev, _, lp = sched.step(st, e, 981, x, key=(0, 1), eta=1.0)
+    _, _, lp2 = sched.step(st, e, torch.tensor([981, 981]), x, prev_sample=prev, eta=1.0)
+    assert torch.equal(lp, lp2)
+    # eta = 0: sigma clamps to 1e-6, prev == mean, log_prob = -log(1e-6) - log(sqrt(2 pi))
+    prev0, _, lp0 = sched.step(st, e, 981, x, key=(0, 1), eta=0.0)
+    assert abs(lp0[0].item() - (-np.log(1e-6) - 0.5 * np.log(2 * np.pi))) < 1e-3
