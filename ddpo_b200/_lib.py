@@ -23,7 +23,7 @@ class IGemmArgs(C.Structure):
                 ("is_conv", i32), ("batch", i32), ("h", i32), ("w", i32), ("conv_stride", i32), ("taps", i32),
                 ("m", i32), ("n", i32), ("wt", vp), ("bias", vp), ("rowvec", vp), ("rows_per_sample", i32),
                 ("rowvec_ld", i32), ("residual", vp), ("ld_res", i32), ("out_f32", vp), ("out_bf16", vp),
-                ("ld_out", i32), ("geglu", i32), ("accumulate_out", i32), ("bn_override", i32)]
+                ("ld_out", i32), ("geglu", i32), ("accumulate_out", i32), ("bn_override", i32), ("aux_bf16", vp)]
 
 
 class GroupNormArgs(C.Structure):
@@ -84,6 +84,20 @@ SIGNATURES = {
     "ddpo_attention_fwd": (i32, [C.POINTER(AttentionArgs), vp]),
     "ddpo_wgrad_workspace_floats": (i64, [C.POINTER(WgradArgs)]),
     "ddpo_wgrad": (i32, [C.POINTER(WgradArgs), vp]),
+    "ddpo_attention_bwd": (i32, [C.POINTER(AttentionBwdArgs), vp]),
+    "ddpo_colsum_workspace_floats": (i64, [i32, i32, i32]),
+    "ddpo_colsum_cast": (i32, [vp, i32, vp, vp, i32, i32, vp, i32, i32, vp]),
+    "ddpo_colsum_bf16": (i32, [vp, i32, vp, i32, vp, i32, i32, vp]),
+    "ddpo_geglu_bwd": (i32, [vp, vp, vp, i64, i32, i32, vp]),
+    "ddpo_conv_out_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "ddpo_conv_in_wgrad_workspace_floats": (i64, [i32, i32]),
+    "ddpo_conv_in_wgrad": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "ddpo_dense_small_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "ddpo_dilate2x_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "ddpo_copy2d": (i32, [vp, i32, vp, i32, i64, i32, i32, vp]),
+    "ddpo_optim_workspace_bytes": (i64, []),
+    "ddpo_grad_sumsq": (i32, [vp, i64, vp, vp, vp]),
+    "ddpo_clip_adamw": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, f32, i32, vp, vp]),
 }
 
 _lib = None

@@ -1,0 +1,406 @@
+// Memory-bound pieces of the U-Net backward pass (the hand-written counterpart of what
+// `jax.grad(compute_loss)` -- reference ddpo/training/policy_gradient.py:138 -- derives for the
+// non-GEMM layers of the 3P Flax U-Net): bias / per-sample column sums fused with the bf16 cast of
+// the incoming gradient, GEGLU backward, conv_in / conv_out backward, the M=batch dense layers of
+// the time embedding, zero-dilation for the stride-2 conv's data gradient, strided accumulate.
+// All reductions are two-stage with fixed order (deterministic).
+#include "common.cuh"
+
+namespace ddpo {
+
+// ------------------------------------------------------------ colsum + cast ----
+// dy fp32 [M, N] -> optional bf16 copy; partial column sums per 256-row chunk -> part[chunk][N]
+constexpr int CS_ROWS = 256;
+__global__ void __launch_bounds__(256) colsum_cast_kernel(const float* __restrict__ dy, int ld, __nv_bfloat16* __restrict__ yb,
+                                                          float* __restrict__ part, int M, int N, int chunk_rows) {
+  const int chunk = blockIdx.x;
+  const int r0 = chunk * chunk_rows, r1 = min(M, r0 + chunk_rows);
+  for (int c = (blockIdx.y * 256 + threadIdx.x) * 2; c < N; c += gridDim.y * 512) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float2 v = *reinterpret_cast<const float2*>(dy + static_cast<size_t>(r) * ld + c);
+      s0 += v.x, s1 += v.y;
+      if (yb != nullptr) *reinterpret_cast<uint32_t*>(yb + static_cast<size_t>(r) * N + c) = pack_bf16(v.x, v.y);
+    }
+    if (part != nullptr) {
+      part[static_cast<size_t>(chunk) * N + c] = s0;
+      part[static_cast<size_t>(chunk) * N + c + 1] = s1;
+    }
+  }
+}
+// same for a bf16 input (no copy): partial column sums of x_bf16 [M, N]
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ld, float* __restrict__ part,
+                                                          int M, int N, int chunk_rows) {
+  const int chunk = blockIdx.x;
+  const int r0 = chunk * chunk_rows, r1 = min(M, r0 + chunk_rows);
+  for (int c = (blockIdx.y * 256 + threadIdx.x) * 2; c < N; c += gridDim.y * 512) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(x + static_cast<size_t>(r) * ld + c);
+      s0 += bf16_lo(v), s1 += bf16_hi(v);
+    }
+    part[static_cast<size_t>(chunk) * N + c] = s0;
+    part[static_cast<size_t>(chunk) * N + c + 1] = s1;
+  }
+}
+// out[g][n] (+)= sum over the chunks of group g (chunks_per_group consecutive chunks), fixed order
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int N, int groups,
+                                     int chunks_per_group, int accumulate, float* __restrict__ out2) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks_per_group; ++c) s += part[(static_cast<size_t>(g) * chunks_per_group + c) * N + n];
+  float* o = out + static_cast<size_t>(g) * N + n;
+  *o = accumulate ? *o + s : s;
+  (void)out2;
+}
+
+// ------------------------------------------------------------------- GEGLU ----
+// pre: bf16 [M, N] tile-interleaved ([bn/2 lin | bn/2 gate] per bn columns, bias included)
+// dff: fp32 [M, N/2] gradient w.r.t. lin*gelu(gate);  dpre: bf16 [M, N] in PLAIN order [lin(N/2) | gate(N/2)]
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const float* __restrict__ dff,
+                                 __nv_bfloat16* __restrict__ dpre, int64_t M, int N, int bn) {
+  const int half = bn >> 1, hn = N >> 1;
+  const int64_t total = M * (hn >> 1);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / (hn >> 1);
+    const int j = static_cast<int>(i % (hn >> 1)) * 2;  // output channel pair j, j+1
+    const int tile = j / half, pos = j % half;
+    const __nv_bfloat16* pr = pre + r * N + tile * bn + pos;
+    const uint32_t lin2 = *reinterpret_cast<const uint32_t*>(pr);
+    const uint32_t gate2 = *reinterpret_cast<const uint32_t*>(pr + half);
+    const float2 d = *reinterpret_cast<const float2*>(dff + r * hn + j);
+    const float l0 = bf16_lo(lin2), l1 = bf16_hi(lin2), g0 = bf16_lo(gate2), g1 = bf16_hi(gate2);
+    *reinterpret_cast<uint32_t*>(dpre + r * N + j) = pack_bf16(d.x * gelu_tanh_f(g0), d.y * gelu_tanh_f(g1));
+    *reinterpret_cast<uint32_t*>(dpre + r * N + hn + j) =
+        pack_bf16(d.x * l0 * gelu_tanh_grad_f(g0), d.y * l1 * gelu_tanh_grad_f(g1));
+  }
+}
+
+// ---------------------------------------------------------------- conv_out ----
+// forward: y[b,n,q] = bias[n] + sum_{tap,c} x[b, q+off(tap), c] w[tap,c,n]   (x NHWC fp32, y NCHW)
+// dx[b,p,c] = sum_{tap,n} dy[b,n,p-off(tap)] w[tap,c,n]
+__global__ void conv_out_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                                      int B, int H, int W, int C) {
+  const int64_t total = static_cast<int64_t>(B) * H * W * C;
+  const int HW = H * W;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = i % C;
+    const int64_t pix = i / C;
+    const int b = pix / HW, hw = pix % HW, h = hw / W, x = hw % W;
+    float acc = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = h - (tap / 3 - 1), xx = x - (tap % 3 - 1);
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (static_cast<size_t>(tap) * C + c) * 4));
+      const float* d = dy + static_cast<size_t>(b) * 4 * HW + yy * W + xx;
+      acc += d[0] * wv.x + d[HW] * wv.y + d[2 * HW] * wv.z + d[3 * HW] * wv.w;
+    }
+    dx[i] = acc;
+  }
+}
+// dw[tap,c,n] += sum_p x[p+off, c] dy[n, p] ; grid (9, C/32), block 256 = 32 channels x 8 pixel lanes
+__global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                             float* __restrict__ dw, float* __restrict__ dbias, int B,
+                                                             int H, int W, int C) {
+  const int tap = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), pl = threadIdx.x >> 5;
+  const int HW = H * W;
+  const int oy = tap / 3 - 1, ox = tap % 3 - 1;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int64_t p = pl; p < static_cast<int64_t>(B) * HW; p += 8) {
+    const int b = p / HW, hw = p % HW, h = hw / W, xx0 = hw % W;
+    const int yy = h + oy, xx = xx0 + ox;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const float v = x[((static_cast<size_t>(b) * H + yy) * W + xx) * C + c];
+    const float* d = dy + static_cast<size_t>(b) * 4 * HW + hw;
+    a0 += v * d[0], a1 += v * d[HW], a2 += v * d[2 * HW], a3 += v * d[3 * HW];
+  }
+  __shared__ float sm[8][32][4];
+  sm[pl][threadIdx.x & 31][0] = a0, sm[pl][threadIdx.x & 31][1] = a1, sm[pl][threadIdx.x & 31][2] = a2,
+  sm[pl][threadIdx.x & 31][3] = a3;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int cl = threadIdx.x >> 2, n = threadIdx.x & 3;
+    float s = 0.f;
+    for (int q = 0; q < 8; ++q) s += sm[q][cl][n];
+    dw[(static_cast<size_t>(tap) * C + blockIdx.y * 32 + cl) * 4 + n] += s;
+  }
+  if (dbias != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) {
+    float s = 0.f;
+    for (int64_t p = 0; p < static_cast<int64_t>(B) * HW; ++p) {
+      const int b = p / HW, hw = p % HW;
+      s += dy[(static_cast<size_t>(b) * 4 + threadIdx.x) * HW + hw];
+    }
+    dbias[threadIdx.x] += s;
+  }
+}
+
+// ----------------------------------------------------------------- conv_in ----
+// dw[tap,ci,co] += sum_p lat[b,ci,p+off] dx[p,co]; two stage: part[split][36][Cout]
+constexpr int CIW_SPLITS = 32;
+__global__ void conv_in_wgrad_kernel(const float* __restrict__ lat, const float* __restrict__ dx, float* __restrict__ part,
+                                     int B, int Cin, int H, int W, int Cout) {
+  const int k = blockIdx.x;  // tap*Cin + ci
+  const int split = blockIdx.y;
+  const int tap = k / Cin, ci = k % Cin;
+  const int oy = tap / 3 - 1, ox = tap % 3 - 1;
+  const int HW = H * W;
+  const int64_t P = static_cast<int64_t>(B) * HW;
+  const int64_t per = (P + CIW_SPLITS - 1) / CIW_SPLITS;
+  const int64_t p0 = split * per, p1 = min(P, p0 + per);
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float acc = 0.f;
+    for (int64_t p = p0; p < p1; ++p) {
+      const int b = p / HW, hw = p % HW, h = hw / W, x = hw % W;
+      const int yy = h + oy, xx = x + ox;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      acc += lat[((static_cast<size_t>(b) * Cin + ci) * H + yy) * W + xx] * dx[p * Cout + co];
+    }
+    part[(static_cast<size_t>(split) * gridDim.x + k) * Cout + co] = acc;
+  }
+}
+__global__ void conv_in_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float s = 0.f;
+  for (int q = 0; q < CIW_SPLITS; ++q) s += part[static_cast<size_t>(q) * total + i];
+  dw[i] += s;
+}
+
+// ------------------------------------------------------------- dense (M = B) ----
+// forward was y = act_out(x' @ w + b), x' = silu_in ? silu(x) : x.
+// dpre[b,n] = dy[b,n] * (silu_out ? silu'(pre) : 1) with pre recomputed.
+__global__ void dense_small_dpre_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                        const float* __restrict__ bias, const float* __restrict__ dy,
+                                        float* __restrict__ dpre, int B, int K, int N, int silu_in, int silu_out) {
+  extern __shared__ float xs[];
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float v = x[static_cast<size_t>(b) * K + k];
+    xs[k] = silu_in ? silu_f(v) : v;
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float d = dy[static_cast<size_t>(b) * N + n];
+  if (silu_out) {
+    float acc = bias ? bias[n] : 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(xs[k], w[static_cast<size_t>(k) * N + n], acc);
+    const float s = sigmoid_f(acc);
+    d *= s * (1.0f + acc * (1.0f - s));
+  }
+  dpre[static_cast<size_t>(b) * N + n] = d;
+}
+// dw[k,n] += sum_b x'[b,k] dpre[b,n] ; db[n] += sum_b dpre[b,n]
+__global__ void dense_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dpre,
+                                         float* __restrict__ dw, float* __restrict__ db, int B, int K, int N,
+                                         int silu_in) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (n >= N) return;
+  float acc = 0.f, accb = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float xv = x[static_cast<size_t>(b) * K + k];
+    if (silu_in) xv = silu_f(xv);
+    const float d = dpre[static_cast<size_t>(b) * N + n];
+    acc = fmaf(xv, d, acc);
+    accb += d;
+  }
+  dw[static_cast<size_t>(k) * N + n] += acc;
+  if (k == 0 && db != nullptr) db[n] += accb;
+}
+// dx[b,k] (+)= (silu_in ? silu'(x) : 1) * sum_n dpre[b,n] w[k,n] ; one warp per (b,k)
+__global__ void dense_small_dgrad_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                         const float* __restrict__ dpre, float* __restrict__ dx, int B, int K, int N,
+                                         int silu_in, int accumulate) {
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int n = lane; n < N; n += 32) acc = fmaf(dpre[static_cast<size_t>(b) * N + n], w[static_cast<size_t>(k) * N + n], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (silu_in) {
+      const float v = x[static_cast<size_t>(b) * K + k];
+      const float s = sigmoid_f(v);
+      acc *= s * (1.0f + v * (1.0f - s));
+    }
+    float* o = dx + static_cast<size_t>(b) * K + k;
+    *o = accumulate ? *o + acc : acc;
+  }
+}
+
+// ----------------------------------------------------------------- misc ------
+// zero-dilated bf16 copy: y[b,2h,2w,:] = x[b,h,w,:], zeros elsewhere
+__global__ void dilate2x_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C4) {
+  const int64_t total = static_cast<int64_t>(B) * 4 * H * W * C4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = i % C4;
+    int64_t p = i / C4;
+    const int w2 = p % (2 * W);
+    p /= 2 * W;
+    const int h2 = p % (2 * H);
+    const int b = p / (2 * H);
+    uint2 o = make_uint2(0u, 0u);
+    if (((h2 | w2) & 1) == 0) {
+      const float4 v = reinterpret_cast<const float4*>(x)[((static_cast<size_t>(b) * H + (h2 >> 1)) * W + (w2 >> 1)) * C4 + c4];
+      o.x = pack_bf16(v.x, v.y), o.y = pack_bf16(v.z, v.w);
+    }
+    reinterpret_cast<uint2*>(y)[i] = o;
+  }
+}
+// dst[r, 0:cols] (+)= src[r, 0:cols]
+__global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int64_t rows,
+                              int cols4, int accumulate) {
+  const int64_t total = rows * cols4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols4;
+    const int c = static_cast<int>(i % cols4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(src + r * lds + c);
+    float4* d = reinterpret_cast<float4*>(dst + r * ldd + c);
+    if (accumulate) {
+      const float4 o = *d;
+      v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+    }
+    *d = v;
+  }
+}
+
+static inline int grid_for(int64_t n, int threads) {
+  int64_t g = (n + threads - 1) / threads;
+  const int64_t cap = 148 * 32;
+  return static_cast<int>(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+}  // namespace ddpo
+
+using namespace ddpo;
+
+extern "C" int64_t ddpo_colsum_workspace_floats(int m, int n, int rows_per_group) {
+  const int cr = rows_per_group < CS_ROWS ? rows_per_group : CS_ROWS;
+  return static_cast<int64_t>((m + cr - 1) / cr) * n;
+}
+
+// out[g][n] (+)= sum of rows of group g (groups of rows_per_group consecutive rows; rows_per_group == m: one
+// group = bias gradient); optional bf16 copy of dy.
+extern "C" int ddpo_colsum_cast(const float* dy, int ld, void* y_bf16, float* out, int rows_per_group, int accumulate,
+                                float* workspace, int m, int n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPO_REQUIRE(dy && n % 2 == 0 && m > 0 && rows_per_group > 0, "colsum_cast: bad arguments");
+  const int cr = rows_per_group < CS_ROWS ? rows_per_group : CS_ROWS;
+  const int chunks = (m + cr - 1) / cr;
+  int groups = 1, cpg = chunks;
+  if (rows_per_group < m) {
+    DDPO_REQUIRE(m % rows_per_group == 0 && rows_per_group % cr == 0, "colsum_cast: rows_per_group=%d does not tile m=%d",
+                 rows_per_group, m);
+    groups = m / rows_per_group;
+    cpg = rows_per_group / cr;
+  }
+  DDPO_REQUIRE(out == nullptr || workspace != nullptr, "colsum_cast: workspace required");
+  dim3 grid(chunks, (n + 511) / 512);
+  colsum_cast_kernel<<<grid, 256, 0, stream>>>(dy, ld > 0 ? ld : n, static_cast<__nv_bfloat16*>(y_bf16),
+                                              out ? workspace : nullptr, m, n, cr);
+  DDPO_LAUNCH_OK();
+  if (out != nullptr) {
+    dim3 g2((n + 127) / 128, groups);
+    colsum_reduce_kernel<<<g2, 128, 0, stream>>>(workspace, out, n, groups, cpg, accumulate, nullptr);
+    DDPO_LAUNCH_OK();
+  }
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_colsum_bf16(const void* x_bf16, int ld, float* out, int accumulate, float* workspace, int m, int n,
+                                void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPO_REQUIRE(x_bf16 && out && workspace && n % 2 == 0 && m > 0, "colsum_bf16: bad arguments");
+  const int chunks = (m + CS_ROWS - 1) / CS_ROWS;
+  dim3 grid(chunks, (n + 511) / 512);
+  colsum_bf16_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x_bf16), ld > 0 ? ld : n, workspace, m, n,
+                                              CS_ROWS);
+  DDPO_LAUNCH_OK();
+  dim3 g2((n + 127) / 128, 1);
+  colsum_reduce_kernel<<<g2, 128, 0, stream>>>(workspace, out, n, 1, chunks, accumulate, nullptr);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_geglu_bwd(const void* pre_bf16, const float* dff, void* dpre_bf16, int64_t m, int n, int bn,
+                              void* stream) {
+  DDPO_REQUIRE(pre_bf16 && dff && dpre_bf16 && n % bn == 0 && bn % 4 == 0, "geglu_bwd: bad arguments");
+  geglu_bwd_kernel<<<grid_for(m * (n / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(pre_bf16), dff, static_cast<__nv_bfloat16*>(dpre_bf16), m, n, bn);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_conv_out_bwd(const float* x_nhwc, const float* w_hwio, const float* dy_nchw, float* dx_nhwc,
+                                 float* dw, float* dbias, int batch, int h, int w, int cin, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPO_REQUIRE(x_nhwc && w_hwio && dy_nchw && dx_nhwc && dw && cin % 32 == 0, "conv_out_bwd: bad arguments");
+  conv_out_dgrad_kernel<<<grid_for(static_cast<int64_t>(batch) * h * w * cin, 256), 256, 0, stream>>>(
+      dy_nchw, w_hwio, dx_nhwc, batch, h, w, cin);
+  DDPO_LAUNCH_OK();
+  dim3 grid(9, cin / 32);
+  conv_out_wgrad_kernel<<<grid, 256, 0, stream>>>(x_nhwc, dy_nchw, dw, dbias, batch, h, w, cin);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int64_t ddpo_conv_in_wgrad_workspace_floats(int cin, int cout) {
+  return static_cast<int64_t>(CIW_SPLITS) * 9 * cin * cout;
+}
+
+extern "C" int ddpo_conv_in_wgrad(const float* lat_nchw, const float* dx_nhwc, float* dw, float* workspace, int batch,
+                                  int cin, int h, int w, int cout, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPO_REQUIRE(lat_nchw && dx_nhwc && dw && workspace, "conv_in_wgrad: null pointer");
+  dim3 grid(9 * cin, CIW_SPLITS);
+  conv_in_wgrad_kernel<<<grid, 320, 0, stream>>>(lat_nchw, dx_nhwc, workspace, batch, cin, h, w, cout);
+  DDPO_LAUNCH_OK();
+  const int total = 9 * cin * cout;
+  conv_in_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(workspace, dw, total);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_dense_small_bwd(const float* x, const float* w, const float* bias, const float* dy, float* dpre_ws,
+                                    float* dw, float* db, float* dx, int dx_accumulate, int batch, int k, int n,
+                                    int silu_in, int silu_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPO_REQUIRE(x && w && dy && dpre_ws && dw && k * 4 <= 48 * 1024, "dense_small_bwd: bad arguments");
+  dim3 g1((n + 127) / 128, batch);
+  dense_small_dpre_kernel<<<g1, 128, k * sizeof(float), stream>>>(x, w, bias, dy, dpre_ws, batch, k, n, silu_in, silu_out);
+  DDPO_LAUNCH_OK();
+  dim3 g2((n + 127) / 128, k);
+  dense_small_wgrad_kernel<<<g2, 128, 0, stream>>>(x, dpre_ws, dw, db, batch, k, n, silu_in);
+  DDPO_LAUNCH_OK();
+  if (dx != nullptr) {
+    dim3 g3((k + 7) / 8, batch);
+    dense_small_dgrad_kernel<<<g3, 256, 0, stream>>>(x, w, dpre_ws, dx, batch, k, n, silu_in, dx_accumulate);
+    DDPO_LAUNCH_OK();
+  }
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_dilate2x_bf16(const float* x, void* y_bf16, int batch, int h, int w, int c, void* stream) {
+  DDPO_REQUIRE(x && y_bf16 && c % 4 == 0, "dilate2x: bad arguments");
+  dilate2x_bf16_kernel<<<grid_for(static_cast<int64_t>(batch) * 4 * h * w * (c / 4), 256), 256, 0,
+                         static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y_bf16), batch, h, w, c / 4);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_copy2d(const float* src, int lds, float* dst, int ldd, int64_t rows, int cols, int accumulate,
+                           void* stream) {
+  DDPO_REQUIRE(src && dst && cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "copy2d: bad arguments");
+  copy2d_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, dst, ldd, rows,
+                                                                                                cols / 4, accumulate);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}

@@ -206,31 +206,48 @@ __global__ void timestep_sincos_kernel(const int32_t* __restrict__ t, int t_stri
 }
 
 // y[b, n] = act_out( sum_k act_in(x[b,k]) * w[k, n] + bias[n] ), fp32, w in Flax [in,out] layout.
-// M = batch is tiny: one thread per (b, n), coalesced over n, K split across `KSPLIT` lanes? -> keep
-// it simple and deterministic: sequential K per thread.
-__global__ void dense_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                   const float* __restrict__ bias, float* __restrict__ y, int B, int K, int N,
-                                   int silu_in, int silu_out) {
-  extern __shared__ float xs[];  // [K]
-  const int b = blockIdx.y;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float v = x[static_cast<size_t>(b) * K + k];
-    xs[k] = silu_in ? silu_f(v) : v;
+// M = batch is tiny (<= 32): a CTA owns 32 output columns for ALL samples; lane -> column (coalesced
+// 128-byte rows of w, each weight read exactly once), warp -> K slice, batch accumulators in registers,
+// cross-warp reduction through shared memory in fixed order (deterministic).
+constexpr int DS_MAXB = 32;
+__global__ void __launch_bounds__(256) dense_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ y, int B,
+                                                          int K, int N, int silu_in, int silu_out) {
+  extern __shared__ float sm[];  // xs[B][K] then red[8][B][32]
+  float* xs = sm;
+  float* red = sm + static_cast<size_t>(B) * K;
+  for (int i = threadIdx.x; i < B * K; i += 256) {
+    const float v = x[i];
+    xs[i] = silu_in ? silu_f(v) : v;
   }
   __syncthreads();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-  int k = 0;
-  for (; k + 3 < K; k += 4) {
-    acc0 = fmaf(xs[k], w[static_cast<size_t>(k) * N + n], acc0);
-    acc1 = fmaf(xs[k + 1], w[static_cast<size_t>(k + 1) * N + n], acc1);
-    acc2 = fmaf(xs[k + 2], w[static_cast<size_t>(k + 2) * N + n], acc2);
-    acc3 = fmaf(xs[k + 3], w[static_cast<size_t>(k + 3) * N + n], acc3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 32 + lane;
+  float acc[DS_MAXB];
+#pragma unroll
+  for (int b = 0; b < DS_MAXB; ++b) acc[b] = 0.f;
+  const int kper = (K + 7) / 8;
+  const int k0 = warp * kper, k1 = min(K, k0 + kper);
+  if (n < N) {
+    for (int k = k0; k < k1; ++k) {
+      const float wv = w[static_cast<size_t>(k) * N + n];
+#pragma unroll
+      for (int b = 0; b < DS_MAXB; ++b)
+        if (b < B) acc[b] = fmaf(xs[b * K + k], wv, acc[b]);
+    }
   }
-  for (; k < K; ++k) acc0 = fmaf(xs[k], w[static_cast<size_t>(k) * N + n], acc0);
-  float r = (acc0 + acc1) + (acc2 + acc3) + (bias ? bias[n] : 0.f);
-  y[static_cast<size_t>(b) * N + n] = silu_out ? silu_f(r) : r;
+#pragma unroll
+  for (int b = 0; b < DS_MAXB; ++b)
+    if (b < B) red[(warp * B + b) * 32 + lane] = acc[b];
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * 32; i += 256) {
+    const int b = i >> 5, l = i & 31;
+    const int nn = blockIdx.x * 32 + l;
+    if (nn >= N) continue;
+    float r = bias ? bias[nn] : 0.f;
+    for (int wq = 0; wq < 8; ++wq) r += red[(wq * B + b) * 32 + l];
+    y[static_cast<size_t>(b) * N + nn] = silu_out ? silu_f(r) : r;
+  }
 }
 
 static inline int grid_for(int64_t n, int threads) {
@@ -325,10 +342,16 @@ extern "C" int ddpo_timestep_sincos(const int32_t* t, int t_stride, float* out, 
 
 extern "C" int ddpo_dense_small(const float* x, const float* w, const float* bias, float* y, int batch, int k, int n,
                                 int silu_in, int silu_out, void* stream) {
-  DDPO_REQUIRE(x && w && y && k > 0 && n > 0 && k * 4 <= 48 * 1024, "dense_small: bad arguments");
-  dim3 grid((n + 127) / 128, batch);
-  dense_small_kernel<<<grid, 128, k * sizeof(float), static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, batch, k, n,
-                                                                                         silu_in, silu_out);
+  DDPO_REQUIRE(x && w && y && k > 0 && n > 0 && batch > 0 && batch <= DS_MAXB, "dense_small: bad arguments (batch <= 32)");
+  const size_t smem = (static_cast<size_t>(batch) * k + 8 * batch * 32) * sizeof(float);
+  DDPO_REQUIRE(smem <= 200 * 1024, "dense_small: batch*k too large");
+  static bool attr = false;
+  if (!attr) {
+    DDPO_CUDA_OK(cudaFuncSetAttribute(dense_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dense_small_kernel<<<(n + 31) / 32, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, batch, k, n, silu_in,
+                                                                                     silu_out);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }

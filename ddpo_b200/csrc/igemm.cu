@@ -47,6 +47,7 @@ struct IGemmArgs {
   int ld_out;
   int geglu;
   int accumulate_out;     // out_f32 += result (used by backward passes that sum two branches)
+  __nv_bfloat16* aux_bf16;  // GEGLU only: pre-activation [M, N] (tile-interleaved, bias included) kept for backward
 };
 
 __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_constant__ IGemmArgs p) {
@@ -261,6 +262,24 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
               float lin = __uint_as_float(a[j]) + __ldg(p.bias + n + j);
               float gate = __uint_as_float(g[j]) + __ldg(p.bias + n + half + j);
               f[j] = lin * gelu_tanh_f(gate);
+              a[j] = __float_as_uint(lin), g[j] = __float_as_uint(gate);
+            }
+            if (p.aux_bf16 != nullptr) {
+              __nv_bfloat16* ax = p.aux_bf16 + static_cast<size_t>(row) * p.N_total + n;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u, w;
+                u.x = pack_bf16(__uint_as_float(a[j]), __uint_as_float(a[j + 1]));
+                u.y = pack_bf16(__uint_as_float(a[j + 2]), __uint_as_float(a[j + 3]));
+                u.z = pack_bf16(__uint_as_float(a[j + 4]), __uint_as_float(a[j + 5]));
+                u.w = pack_bf16(__uint_as_float(a[j + 6]), __uint_as_float(a[j + 7]));
+                w.x = pack_bf16(__uint_as_float(g[j]), __uint_as_float(g[j + 1]));
+                w.y = pack_bf16(__uint_as_float(g[j + 2]), __uint_as_float(g[j + 3]));
+                w.z = pack_bf16(__uint_as_float(g[j + 4]), __uint_as_float(g[j + 5]));
+                w.w = pack_bf16(__uint_as_float(g[j + 6]), __uint_as_float(g[j + 7]));
+                *reinterpret_cast<uint4*>(ax + j) = u;
+                *reinterpret_cast<uint4*>(ax + half + j) = w;
+              }
             }
             __nv_bfloat16* o = p.out_bf16 + static_cast<size_t>(row) * p.ld_out + tn * half + c0;
 #pragma unroll
@@ -368,6 +387,7 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
   p.out_f32 = a->out_f32, p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
   p.ld_out = a->ld_out > 0 ? a->ld_out : (a->geglu ? a->n / 2 : a->n);
   p.geglu = a->geglu, p.accumulate_out = a->accumulate_out;
+  p.aux_bf16 = static_cast<__nv_bfloat16*>(a->aux_bf16);
   const int stage_bytes = A_TILE_BYTES + BN * BK * 2;
   int stages = SMEM_BUDGET / stage_bytes;
   if (stages > 8) stages = 8;

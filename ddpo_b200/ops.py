@@ -128,7 +128,7 @@ def ppo_loss(logp, old_logp, adv, clip_range, info_out, dlogp_out):
 # ------------------------------------------------------------------ GEMM --------
 def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None, m=None, taps=1, stride=1,
           bias=None, rowvec=None, rows_per_sample=0, rowvec_ld=0, residual=None, ld_res=0, out_f32=None,
-          out_bf16=None, ld_out=0, geglu=False, accumulate=False, bn=0):
+          out_bf16=None, ld_out=0, geglu=False, accumulate=False, bn=0, aux_bf16=None):
     """conv=(batch, h_out, w_out) for convolutions, else linear with m rows."""
     a = IGemmArgs()
     a.a0, a.a1 = _p(a0), _p(a1)
@@ -148,6 +148,7 @@ def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None,
     a.residual, a.ld_res = _p(residual), int(ld_res)
     a.out_f32, a.out_bf16, a.ld_out = _p(out_f32), _p(out_bf16), int(ld_out)
     a.geglu, a.accumulate_out, a.bn_override = int(geglu), int(accumulate), int(bn)
+    a.aux_bf16 = _p(aux_bf16)
     rows = a.batch * a.h * a.w if a.is_conv else a.m
     _e = _ev()
     _run("igemm", lib().ddpo_igemm(C.byref(a), _stream()), 2.0 * rows * a.n * a.taps * (a.c0 + a.c1), _e)
@@ -282,3 +283,104 @@ def wgrad(*, dy, n, x0, dw, x1=None, c0=None, c1=0, ldy=0, ldx0=0, ldx1=0, conv=
     rows = a.batch * a.h * a.w if a.is_conv else a.m
     _e = _ev()
     _run("wgrad", lib().ddpo_wgrad(C.byref(a), _stream()), 2.0 * rows * a.n * a.taps * (a.c0 + a.c1), _e)
+
+
+# ------------------------------------------------------- backward wrappers -------
+def attention_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, batch, heads, nq, nk, ldq, ldk, ldv, ldo, lddo, lddq,
+                  lddk, lddv):
+    from ._lib import AttentionBwdArgs
+    a = AttentionBwdArgs(_p(q), _p(k), _p(v), _p(out), _p(dout), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), batch,
+                         heads, nq, nk, 64, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, None)
+    _e = _ev()
+    _run("attention_bwd", lib().ddpo_attention_bwd(C.byref(a), _stream()), 14.0 * batch * heads * nq * nk * 64, _e)
+
+
+_KERNELS_PER_CALL.update({"attention_bwd": 3, "colsum_cast": 2, "conv_out_bwd": 2, "conv_in_wgrad": 2,
+                          "dense_small_bwd": 3, "grad_sumsq": 2, "wgrad": 2, "colsum_bf16": 2})
+_COLSUM_WS = {}
+
+
+def colsum_cast(dy, m, n, y_bf16=None, out=None, rows_per_group=None, accumulate=True, ld=0):
+    """Optional bf16 copy of dy [m, n] and out[g, n] (+)= per-group column sums (bias / per-sample grads)."""
+    rpg = int(rows_per_group or m)
+    ws = None
+    if out is not None:
+        need = int(lib().ddpo_colsum_workspace_floats(m, n, rpg))
+        ws = _COLSUM_WS.get(dy.device)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 1 << 20), dtype=torch.float32, device=dy.device)
+            _COLSUM_WS[dy.device] = ws
+    _e = _ev()
+    _run("colsum_cast", lib().ddpo_colsum_cast(_p(dy), int(ld), _p(y_bf16), _p(out), rpg, int(accumulate), _p(ws), int(m),
+                                               int(n), _stream()), float(m) * n * 6, _e)
+
+
+def colsum_bf16(x, m, n, out, accumulate=True, ld=0):
+    need = int(lib().ddpo_colsum_workspace_floats(m, n, m))
+    ws = _COLSUM_WS.get(x.device)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.float32, device=x.device)
+        _COLSUM_WS[x.device] = ws
+    _e = _ev()
+    _run("colsum_bf16", lib().ddpo_colsum_bf16(_p(x), int(ld), _p(out), int(accumulate), _p(ws), int(m), int(n), _stream()),
+         float(m) * n * 2, _e)
+
+
+def geglu_bwd(pre, dff, dpre, m, n, bn=256):
+    _e = _ev()
+    _run("geglu_bwd", lib().ddpo_geglu_bwd(_p(pre), _p(dff), _p(dpre), int(m), int(n), int(bn), _stream()), 0.0, _e)
+
+
+def conv_out_bwd(x_nhwc, w, dy_nchw, dx_nhwc, dw, dbias, batch, h, wd, cin):
+    _e = _ev()
+    _run("conv_out_bwd", lib().ddpo_conv_out_bwd(_p(x_nhwc), _p(w), _p(dy_nchw), _p(dx_nhwc), _p(dw), _p(dbias), batch, h,
+                                                 wd, cin, _stream()), 0.0, _e)
+
+
+_CIW_WS = {}
+
+
+def conv_in_wgrad(lat, dx_nhwc, dw, batch, cin, h, wd, cout):
+    need = int(lib().ddpo_conv_in_wgrad_workspace_floats(cin, cout))
+    ws = _CIW_WS.get(dw.device)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.float32, device=dw.device)
+        _CIW_WS[dw.device] = ws
+    _e = _ev()
+    _run("conv_in_wgrad", lib().ddpo_conv_in_wgrad(_p(lat), _p(dx_nhwc), _p(dw), _p(ws), batch, cin, h, wd, cout,
+                                                   _stream()), 0.0, _e)
+
+
+def dense_small_bwd(x, w, bias, dy, dpre_ws, dw, db, dx, batch, k, n, silu_in=False, silu_out=False, dx_accumulate=False):
+    _e = _ev()
+    _run("dense_small_bwd", lib().ddpo_dense_small_bwd(_p(x), _p(w), _p(bias), _p(dy), _p(dpre_ws), _p(dw), _p(db), _p(dx),
+                                                       int(dx_accumulate), batch, k, n, int(silu_in), int(silu_out),
+                                                       _stream()), 0.0, _e)
+
+
+def dilate2x_bf16(x, y, batch, h, w, c):
+    _e = _ev()
+    _run("dilate2x_bf16", lib().ddpo_dilate2x_bf16(_p(x), _p(y), batch, h, w, c, _stream()), 0.0, _e)
+
+
+def copy2d(src, lds, dst, ldd, rows, cols, accumulate=False):
+    _e = _ev()
+    _run("copy2d", lib().ddpo_copy2d(_p(src), int(lds), _p(dst), int(ldd), int(rows), int(cols), int(accumulate),
+                                     _stream()), 0.0, _e)
+
+
+def optim_workspace(device):
+    return torch.empty(int(lib().ddpo_optim_workspace_bytes()), dtype=torch.uint8, device=device)
+
+
+def grad_sumsq(g, ws, out):
+    _e = _ev()
+    _run("grad_sumsq", lib().ddpo_grad_sumsq(_p(g), g.numel(), _p(ws), _p(out), _stream()), float(g.numel()) * 4, _e)
+
+
+def clip_adamw(params, grad_acc, mu, nu, sumsq, grad_scale, max_norm, lr, b1, b2, eps, wd, step, norm_out=None):
+    _e = _ev()
+    _run("clip_adamw", lib().ddpo_clip_adamw(_p(params), _p(grad_acc), _p(mu), _p(nu), params.numel(), _p(sumsq),
+                                             float(grad_scale), float(max_norm), float(lr), float(b1), float(b2),
+                                             float(eps), float(wd), int(step), _p(norm_out), _stream()),
+         float(params.numel()) * 24, _e)

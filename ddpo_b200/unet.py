@@ -76,6 +76,9 @@ class UNet:
         self.ctx_kv: Optional[Dict[str, torch.Tensor]] = None
         self.ctx_batch = 0
         self._layers = self._enumerate_layers()
+        self.wd: Dict[str, torch.Tensor] = {}      # bf16 backward (dgrad) GEMM operands, built on demand
+        self.grads: Optional[torch.Tensor] = None  # flat fp32 gradient accumulator (same layout as params)
+        self.train_mode = False
         self.refresh_weights()
 
     # ------------------------------------------------------------------ params ----
@@ -131,6 +134,30 @@ class UNet:
                 ops.permute_geglu_bias(self.p(base + "/bias"), self.aux[base], n, 256)
             else:
                 ops.prep_weight(src, self.w[base], k, n)
+        if self.train_mode:
+            self._refresh_dgrad_weights()
+
+    def enable_training(self):
+        """Allocates the gradient accumulator and the dgrad-layout bf16 weights."""
+        if self.grads is None:
+            self.grads = torch.zeros_like(self.params)
+        self.train_mode = True
+        self._refresh_dgrad_weights()
+
+    def _refresh_dgrad_weights(self):
+        for base, shape in self._layers:
+            leaf = base.rsplit("/", 1)[1]
+            if leaf in ("to_k", "to_v") and "/attn2/" in base:
+                continue  # the text context receives no gradient
+            cin, n = int(shape[-2]), int(shape[-1])
+            taps = int(np.prod(shape[:-2])) if len(shape) == 4 else 1
+            if base not in self.wd:
+                self.wd[base] = torch.empty(cin, taps * n, dtype=BF16, device=self.device)
+            ops.prep_weight_dgrad(self.p(base + "/kernel"), self.wd[base], taps, cin, n)
+
+    def g(self, name):
+        off, shape = self.table[name]
+        return self.grads[off:off + int(np.prod(shape))].view(*shape)
 
     # ----------------------------------------------------------------- context ----
     def prepare_context(self, ctx: torch.Tensor):
@@ -232,16 +259,11 @@ class UNet:
         st3 = A.alloc((m, 2), F32)
         ops.layernorm_fwd(h2, self.p(bl + "/norm3/scale"), self.p(bl + "/norm3/bias"), ln3, m, c, stats=st3)
         ff = A.alloc((m, 4 * c), BF16)
-        ffpre = None
-        if tape is None:
-            ops.igemm(a0=ln3, wt=self.w[bl + "/ff/net_0/proj"], n=8 * c, c0=c, m=m, bias=self.aux[bl + "/ff/net_0/proj"],
-                      out_bf16=ff, geglu=True, bn=256)
-        else:
-            # training keeps the pre-activation (bf16, tile-interleaved [lin|gate]) for the GEGLU backward
-            ffpre = A.alloc((m, 8 * c), BF16)
-            ops.igemm(a0=ln3, wt=self.w[bl + "/ff/net_0/proj"], n=8 * c, c0=c, m=m, bias=self.aux[bl + "/ff/net_0/proj"],
-                      out_bf16=ffpre, bn=256)
-            ops.geglu_fwd(ffpre, ff, m, 8 * c, 256)
+        # training keeps the bf16 pre-activation (tile-interleaved [lin|gate]) for the GEGLU backward; the
+        # activation itself always comes from the fp32 accumulators -> identical to the sampling forward
+        ffpre = A.alloc((m, 8 * c), BF16) if tape is not None else None
+        ops.igemm(a0=ln3, wt=self.w[bl + "/ff/net_0/proj"], n=8 * c, c0=c, m=m, bias=self.aux[bl + "/ff/net_0/proj"],
+                  out_bf16=ff, geglu=True, bn=256, aux_bf16=ffpre)
         h3 = A.alloc((m, c), F32)
         h3b = A.alloc((m, c), BF16)
         ops.igemm(a0=ff, wt=self.w[bl + "/ff/net_2"], n=c, c0=4 * c, m=m, bias=self.p(bl + "/ff/net_2/bias"),
@@ -288,7 +310,8 @@ class UNet:
         ops.conv_in(latents, self.p("conv_in/kernel"), self.p("conv_in/bias"), x, b, cin_lat, H, W, boc[0])
         tap("conv_in", x, (b, H, W, boc[0]))
         if tape is not None:
-            tape.append(("head", dict(latents=latents, sincos=sincos, t1=t1, temb_act=temb_act, b=b, H=H, W=W)))
+            tape.append(("head", dict(latents=latents, sincos=sincos, t1=t1, temb_act=temb_act, b=b, H=H, W=W, x=x)))
+            self._temb_act = temb_act
         skips = [(x, boc[0], H, W)]
         h, w, c_prev = H, W, boc[0]
         for i, c in enumerate(boc):
@@ -385,3 +408,269 @@ class UNet:
         else:
             tape.append(("tail", dict(x=x, gws=gws, yf=yf, b=b, h=h, w=w, c=c0)))
         return out
+
+    # ---------------------------------------------------------------- backward ----
+    def backward(self, tape: list, d_eps: torch.Tensor):
+        """Back-propagates d(loss)/d(eps) [B,4,H,W] through the taped forward; parameter gradients are
+        ACCUMULATED into ``self.grads`` (AccumulatingTrainState semantics).  Releases the tape's buffers."""
+        assert self.train_mode and self.grads is not None
+        A = self.arena
+        grads: Dict[int, torch.Tensor] = {}
+
+        def put(x, d, m, c, lds=None):
+            """register contribution d [m, c] (row pitch lds) to the gradient of stream tensor x"""
+            if id(x) in grads:
+                ops.copy2d(d, lds or c, grads[id(x)], c, m, c, accumulate=True)
+                return False  # caller still owns d
+            if lds is None or lds == c:
+                grads[id(x)] = d
+                return True   # ownership moved
+            t = A.alloc((m, c), F32)
+            ops.copy2d(d, lds, t, c, m, c, accumulate=False)
+            grads[id(x)] = t
+            return False
+
+        temb_state = {"d": None}
+
+        def bias_grad_and_cast(dy, m, n, bias_names):
+            dyb = A.alloc((m, n), BF16)
+            if len(bias_names) == 1:
+                ops.colsum_cast(dy, m, n, y_bf16=dyb, out=self.g(bias_names[0]).view(1, n), accumulate=True)
+            else:
+                tmp = A.alloc((1, n), F32)
+                ops.colsum_cast(dy, m, n, y_bf16=dyb, out=tmp, accumulate=False)
+                for nm in bias_names:
+                    ops.copy2d(tmp, n, self.g(nm).view(1, n), n, 1, n, accumulate=True)
+                A.release(tmp)
+            return dyb
+
+        for kind, r in reversed(tape):
+            if kind == "tail":
+                b, h, w, c = r["b"], r["h"], r["w"], r["c"]
+                m = b * h * w
+                d_yf = A.alloc((m, c), F32)
+                ops.conv_out_bwd(r["yf"], self.p("conv_out/kernel"), d_eps, d_yf, self.g("conv_out/kernel"),
+                                 self.g("conv_out/bias"), b, h, w, c)
+                dx = A.alloc((m, c), F32)
+                ops.groupnorm_bwd(r["x"], self.p("conv_norm_out/scale"), self.p("conv_norm_out/bias"), r["gws"], b, h * w,
+                                  c, d_yf, dx, self.g("conv_norm_out/scale"), self.g("conv_norm_out/bias"), silu=True)
+                grads[id(r["x"])] = dx
+                for t in (d_yf, r["yf"], r["gws"]):
+                    A.release(t)
+            elif kind == "up":
+                name, b, h, w, c = r["name"], r["b"], r["h"], r["w"], r["c"]
+                m2 = b * 4 * h * w
+                dy = grads.pop(id(r["out"]))
+                dyb = bias_grad_and_cast(dy, m2, c, [name + "/conv/bias"])
+                ops.wgrad(dy=dyb, n=c, x0=r["up"], c0=c, conv=(b, 2 * h, 2 * w), taps=9, dw=self.g(name + "/conv/kernel"))
+                d_up = A.alloc((m2, c), F32)
+                ops.igemm(a0=dyb, wt=self.wd[name + "/conv"], n=c, c0=c, conv=(b, 2 * h, 2 * w), taps=9, out_f32=d_up)
+                if id(r["x"]) in grads:
+                    ops.upsample2x_bwd(d_up, grads[id(r["x"])], b, h, w, c, accumulate=True)
+                else:
+                    dx = A.alloc((b * h * w, c), F32)
+                    ops.upsample2x_bwd(d_up, dx, b, h, w, c, accumulate=False)
+                    grads[id(r["x"])] = dx
+                for t in (dy, dyb, d_up, r["up"], r["out"]):
+                    A.release(t)
+            elif kind == "down":
+                name, b, h, w, c = r["name"], r["b"], r["h"], r["w"], r["c"]
+                mo = b * (h // 2) * (w // 2)
+                dy = grads.pop(id(r["out"]))
+                dyb = bias_grad_and_cast(dy, mo, c, [name + "/conv/bias"])
+                ops.wgrad(dy=dyb, n=c, x0=r["xb"], c0=c, conv=(b, h // 2, w // 2), taps=9, stride=2,
+                          dw=self.g(name + "/conv/kernel"))
+                dil = A.alloc((b * h * w, c), BF16)
+                ops.dilate2x_bf16(dy, dil, b, h // 2, w // 2, c)
+                if id(r["x"]) in grads:
+                    ops.igemm(a0=dil, wt=self.wd[name + "/conv"], n=c, c0=c, conv=(b, h, w), taps=9,
+                              out_f32=grads[id(r["x"])], accumulate=True)
+                else:
+                    dx = A.alloc((b * h * w, c), F32)
+                    ops.igemm(a0=dil, wt=self.wd[name + "/conv"], n=c, c0=c, conv=(b, h, w), taps=9, out_f32=dx)
+                    grads[id(r["x"])] = dx
+                for t in (dy, dyb, dil, r["xb"], r["out"]):
+                    A.release(t)
+            elif kind == "resnet":
+                self._resnet_bwd(r, grads, put, bias_grad_and_cast, temb_state)
+            elif kind == "transformer":
+                self._transformer_bwd(r, grads, put, bias_grad_and_cast)
+            elif kind == "head":
+                b, H, W = r["b"], r["H"], r["W"]
+                c0 = self.cfg.block_out_channels[0]
+                te = self.cfg.time_embed_dim
+                x = r.get("x")
+                dx = grads.pop(id(x))
+                ops.colsum_cast(dx, b * H * W, c0, out=self.g("conv_in/bias").view(1, c0), accumulate=True)
+                ops.conv_in_wgrad(r["latents"], dx, self.g("conv_in/kernel"), b, self.cfg.in_channels, H, W, c0)
+                A.release(dx)
+                A.release(x)
+                d_temb = temb_state["d"]
+                if d_temb is not None:
+                    dpre = A.alloc((b, te), F32)
+                    d_t1 = A.alloc((b, te), F32)
+                    ops.dense_small_bwd(r["t1"], self.p("time_embedding/linear_2/kernel"),
+                                        self.p("time_embedding/linear_2/bias"), d_temb, dpre,
+                                        self.g("time_embedding/linear_2/kernel"), self.g("time_embedding/linear_2/bias"),
+                                        d_t1, b, te, te, silu_out=True)
+                    ops.dense_small_bwd(r["sincos"], self.p("time_embedding/linear_1/kernel"),
+                                        self.p("time_embedding/linear_1/bias"), d_t1, dpre,
+                                        self.g("time_embedding/linear_1/kernel"), self.g("time_embedding/linear_1/bias"),
+                                        None, b, c0, te, silu_out=True)
+                    for t in (dpre, d_t1, d_temb):
+                        A.release(t)
+                for t in (r["sincos"], r["t1"], r["temb_act"]):
+                    A.release(t)
+        assert not grads, f"{len(grads)} stream gradients were never consumed"
+
+    def _resnet_bwd(self, r, grads, put, bias_grad_and_cast, temb_state):
+        A = self.arena
+        name, b, h, w = r["name"], r["b"], r["h"], r["w"]
+        c0, c1, cout = r["c0"], r["c1"], r["cout"]
+        cin, hw, m = c0 + c1, h * w, b * h * w
+        te = self.cfg.time_embed_dim
+        dy = grads.pop(id(r["out"]))
+        names = [name + "/conv2/bias"] + ([name + "/conv_shortcut/bias"] if r["has_sc"] else [])
+        dyb = bias_grad_and_cast(dy, m, cout, names)
+        ops.wgrad(dy=dyb, n=cout, x0=r["a2"], c0=cout, conv=(b, h, w), taps=9, dw=self.g(name + "/conv2/kernel"))
+        d_a2 = A.alloc((m, cout), F32)
+        ops.igemm(a0=dyb, wt=self.wd[name + "/conv2"], n=cout, c0=cout, conv=(b, h, w), taps=9, out_f32=d_a2)
+        d_h = A.alloc((m, cout), F32)
+        ops.groupnorm_bwd(r["hbuf"], self.p(name + "/norm2/scale"), self.p(name + "/norm2/bias"), r["gws2"], b, hw, cout,
+                          d_a2, d_h, self.g(name + "/norm2/scale"), self.g(name + "/norm2/bias"), silu=True)
+        A.release(d_a2)
+        # h = conv1(a) + bias1 + time_emb_proj(silu(temb))[b]
+        d_hb = A.alloc((m, cout), BF16)
+        d_tproj = A.alloc((b, cout), F32)
+        ops.colsum_cast(d_h, m, cout, y_bf16=d_hb, out=d_tproj, rows_per_group=hw, accumulate=False)
+        A.release(d_h)
+        ops.colsum_cast(d_tproj, b, cout, out=self.g(name + "/conv1/bias").view(1, cout), accumulate=True)
+        first = temb_state["d"] is None
+        if first:
+            temb_state["d"] = A.alloc((b, te), F32)
+        dpre = A.alloc((b, cout), F32)
+        ops.dense_small_bwd(self._temb_act, self.p(name + "/time_emb_proj/kernel"), None, d_tproj, dpre,
+                            self.g(name + "/time_emb_proj/kernel"), self.g(name + "/time_emb_proj/bias"),
+                            temb_state["d"], b, te, cout, dx_accumulate=not first)
+        A.release(dpre)
+        A.release(d_tproj)
+        ops.wgrad(dy=d_hb, n=cout, x0=r["a"], c0=cin, conv=(b, h, w), taps=9, dw=self.g(name + "/conv1/kernel"))
+        d_a = A.alloc((m, cin), F32)
+        ops.igemm(a0=d_hb, wt=self.wd[name + "/conv1"], n=cin, c0=cout, conv=(b, h, w), taps=9, out_f32=d_a)
+        A.release(d_hb)
+        if r["has_sc"]:
+            ops.wgrad(dy=dyb, n=cout, x0=r["raw"], c0=cin, conv=(b, h, w), taps=1,
+                      dw=self.g(name + "/conv_shortcut/kernel"))
+            dcat = A.alloc((m, cin), F32)
+            ops.igemm(a0=dyb, wt=self.wd[name + "/conv_shortcut"], n=cin, c0=cout, conv=(b, h, w), taps=1, out_f32=dcat)
+            ops.groupnorm_bwd(r["x0"], self.p(name + "/norm1/scale"), self.p(name + "/norm1/bias"), r["gws"], b, hw, c0,
+                              d_a, dcat, self.g(name + "/norm1/scale"), self.g(name + "/norm1/bias"), x1=r["x1"], c1=c1,
+                              dx1=dcat[:, c0:] if c1 else None, silu=True, accumulate=True, ldd0=cin, ldd1=cin)
+            if c1 == 0:
+                if not put(r["x0"], dcat, m, cin):
+                    A.release(dcat)
+            else:
+                put(r["x0"], dcat, m, c0, lds=cin)
+                put(r["x1"], dcat[:, c0:], m, c1, lds=cin)
+                A.release(dcat)
+            A.release(dy)
+        else:
+            if id(r["x0"]) in grads:
+                tgt = grads[id(r["x0"])]
+                ops.copy2d(dy, cout, tgt, cout, m, cout, accumulate=True)
+                A.release(dy)
+            else:
+                tgt = dy
+                grads[id(r["x0"])] = dy
+            ops.groupnorm_bwd(r["x0"], self.p(name + "/norm1/scale"), self.p(name + "/norm1/bias"), r["gws"], b, hw, c0,
+                              d_a, tgt, self.g(name + "/norm1/scale"), self.g(name + "/norm1/bias"), silu=True,
+                              accumulate=True)
+        A.release(d_a)
+        A.release(dyb)
+        for t in (r["gws"], r["a"], r["raw"], r["hbuf"], r["gws2"], r["a2"], r["tproj"], r["sc"], r["out"]):
+            A.release(t)
+
+    def _transformer_bwd(self, t, grads, put, bias_grad_and_cast):
+        A = self.arena
+        name, b, h, w, c, heads = t["name"], t["b"], t["h"], t["w"], t["c"], t["heads"]
+        hw, m = h * w, b * h * w
+        bl = name + "/transformer_blocks_0"
+        L = self.ctx_len
+        dctx = self.cfg.cross_attention_dim
+        dy = grads.pop(id(t["out"]))
+        # out = proj_out(h3b) + x
+        dyb = bias_grad_and_cast(dy, m, c, [name + "/proj_out/bias"])
+        ops.wgrad(dy=dyb, n=c, x0=t["h3b"], c0=c, m=m, dw=self.g(name + "/proj_out/kernel").view(c, c))
+        d_h = A.alloc((m, c), F32)   # running gradient of the transformer-internal residual stream
+        ops.igemm(a0=dyb, wt=self.wd[name + "/proj_out"], n=c, c0=c, m=m, out_f32=d_h)
+        A.release(dyb)
+        x_owned = put(t["x"], dy, m, c)
+        if not x_owned:
+            A.release(dy)
+        # h3 = ff2(ff) + h2
+        d3b = bias_grad_and_cast(d_h, m, c, [bl + "/ff/net_2/bias"])
+        ops.wgrad(dy=d3b, n=c, x0=t["ff"], c0=4 * c, m=m, dw=self.g(bl + "/ff/net_2/kernel"))
+        d_ff = A.alloc((m, 4 * c), F32)
+        ops.igemm(a0=d3b, wt=self.wd[bl + "/ff/net_2"], n=4 * c, c0=c, m=m, out_f32=d_ff)
+        A.release(d3b)
+        d_pre = A.alloc((m, 8 * c), BF16)
+        ops.geglu_bwd(t["ffpre"], d_ff, d_pre, m, 8 * c, 256)
+        A.release(d_ff)
+        ops.colsum_bf16(d_pre, m, 8 * c, self.g(bl + "/ff/net_0/proj/bias").view(1, 8 * c), accumulate=True)
+        ops.wgrad(dy=d_pre, n=8 * c, x0=t["ln3"], c0=c, m=m, dw=self.g(bl + "/ff/net_0/proj/kernel"))
+        d_ln = A.alloc((m, c), F32)
+        ops.igemm(a0=d_pre, wt=self.wd[bl + "/ff/net_0/proj"], n=c, c0=8 * c, m=m, out_f32=d_ln)
+        A.release(d_pre)
+        lws = A.alloc((ops.layernorm_bwd_workspace_floats(m, c),), F32)
+        ops.layernorm_bwd(t["h2"], self.p(bl + "/norm3/scale"), t["st3"], d_ln, d_h, self.g(bl + "/norm3/scale"),
+                          self.g(bl + "/norm3/bias"), lws, m, c, accumulate=True)
+        # h2 = out2(ao2) + h1   (cross attention)
+        d2b = bias_grad_and_cast(d_h, m, c, [bl + "/attn2/to_out_0/bias"])
+        ops.wgrad(dy=d2b, n=c, x0=t["ao2"], c0=c, m=m, dw=self.g(bl + "/attn2/to_out_0/kernel"))
+        d_ao = A.alloc((m, c), BF16)
+        ops.igemm(a0=d2b, wt=self.wd[bl + "/attn2/to_out_0"], n=c, c0=c, m=m, out_bf16=d_ao)
+        A.release(d2b)
+        kv = self.ctx_kv[bl + "/attn2/kv"]
+        dq2 = A.alloc((m, c), BF16)
+        dkv = A.alloc((b * L, 2 * c), BF16)
+        delta = A.alloc((b, heads, hw), F32)
+        ops.attention_bwd(t["q2"], kv, kv[:, c:], t["ao2"], d_ao, t["lse2"], delta, dq2, dkv, dkv[:, c:], b, heads, hw, L,
+                          c, 2 * c, 2 * c, c, c, c, 2 * c, 2 * c)
+        ops.wgrad(dy=dq2, n=c, x0=t["ln2"], c0=c, m=m, dw=self.g(bl + "/attn2/to_q/kernel"))
+        ops.wgrad(dy=dkv, ldy=2 * c, n=c, x0=self._ctx_bf, c0=dctx, m=b * L, dw=self.g(bl + "/attn2/to_k/kernel"))
+        ops.wgrad(dy=dkv[:, c:], ldy=2 * c, n=c, x0=self._ctx_bf, c0=dctx, m=b * L, dw=self.g(bl + "/attn2/to_v/kernel"))
+        ops.igemm(a0=dq2, wt=self.wd[bl + "/attn2/to_q"], n=c, c0=c, m=m, out_f32=d_ln)
+        ops.layernorm_bwd(t["h1"], self.p(bl + "/norm2/scale"), t["st2"], d_ln, d_h, self.g(bl + "/norm2/scale"),
+                          self.g(bl + "/norm2/bias"), lws, m, c, accumulate=True)
+        A.release(dq2)
+        A.release(dkv)
+        # h1 = out1(ao1) + h0   (self attention)
+        d1b = bias_grad_and_cast(d_h, m, c, [bl + "/attn1/to_out_0/bias"])
+        ops.wgrad(dy=d1b, n=c, x0=t["ao1"], c0=c, m=m, dw=self.g(bl + "/attn1/to_out_0/kernel"))
+        ops.igemm(a0=d1b, wt=self.wd[bl + "/attn1/to_out_0"], n=c, c0=c, m=m, out_bf16=d_ao)
+        A.release(d1b)
+        qkv = t["qkv"]
+        dqkv = A.alloc((m, 3 * c), BF16)
+        ops.attention_bwd(qkv, qkv[:, c:], qkv[:, 2 * c:], t["ao1"], d_ao, t["lse1"], delta, dqkv, dqkv[:, c:],
+                          dqkv[:, 2 * c:], b, heads, hw, hw, 3 * c, 3 * c, 3 * c, c, c, 3 * c, 3 * c, 3 * c)
+        for i, nm in enumerate(("to_q", "to_k", "to_v")):
+            ops.wgrad(dy=dqkv[:, i * c:], ldy=3 * c, n=c, x0=t["ln1"], c0=c, m=m, dw=self.g(f"{bl}/attn1/{nm}/kernel"))
+            ops.igemm(a0=dqkv[:, i * c:], lda0=3 * c, c0=c, wt=self.wd[f"{bl}/attn1/{nm}"], n=c, m=m, out_f32=d_ln,
+                      accumulate=i > 0)
+        ops.layernorm_bwd(t["h0"], self.p(bl + "/norm1/scale"), t["st1"], d_ln, d_h, self.g(bl + "/norm1/scale"),
+                          self.g(bl + "/norm1/bias"), lws, m, c, accumulate=True)
+        for z in (dqkv, d_ao, delta, lws):
+            A.release(z)
+        # h0 = proj_in(g)
+        d0b = bias_grad_and_cast(d_h, m, c, [name + "/proj_in/bias"])
+        ops.wgrad(dy=d0b, n=c, x0=t["g"], c0=c, m=m, dw=self.g(name + "/proj_in/kernel").view(c, c))
+        ops.igemm(a0=d0b, wt=self.wd[name + "/proj_in"], n=c, c0=c, m=m, out_f32=d_ln)
+        A.release(d0b)
+        A.release(d_h)
+        ops.groupnorm_bwd(t["x"], self.p(name + "/norm/scale"), self.p(name + "/norm/bias"), t["gws"], b, hw, c, d_ln,
+                          grads[id(t["x"])], self.g(name + "/norm/scale"), self.g(name + "/norm/bias"), silu=False,
+                          accumulate=True)
+        A.release(d_ln)
+        for key in ("gws", "g", "h0", "ln1", "st1", "qkv", "ao1", "lse1", "h1", "ln2", "st2", "q2", "ao2", "lse2", "h2",
+                    "ln3", "st3", "ffpre", "ff", "h3", "h3b", "out"):
+            A.release(t[key])

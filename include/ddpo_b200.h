@@ -111,6 +111,7 @@ typedef struct {
   int geglu;                /* out_bf16[M, n/2] = lin * gelu_tanh(gate); weight rows tile-interleaved */
   int accumulate_out;       /* out_f32 += */
   int bn_override;          /* 0 = auto */
+  void* aux_bf16;           /* GEGLU only, optional: bf16 [M, n] pre-activation (tile-interleaved, bias included) */
 } ddpo_igemm_args;
 int ddpo_igemm(const ddpo_igemm_args* a, void* stream);
 
@@ -194,6 +195,46 @@ typedef struct {
 } ddpo_wgrad_args;
 int64_t ddpo_wgrad_workspace_floats(const ddpo_wgrad_args* a);
 int ddpo_wgrad(const ddpo_wgrad_args* a, void* stream);
+
+/* attention backward (dQ, dK, dV; deterministic two-kernel scheme), see csrc/attention_bwd.cu */
+typedef struct {
+  const void* q; const void* k; const void* v; const void* out; const void* dout; /* bf16 */
+  const float* lse;  /* [batch, heads, nq] from the forward */
+  float* delta;      /* [batch, heads, nq] scratch */
+  void* dq; void* dk; void* dv; /* bf16 outputs */
+  int batch, heads, nq, nk, head_dim;
+  int ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+  void* workspace;   /* unused, reserved */
+} ddpo_attention_bwd_args;
+int ddpo_attention_bwd(const ddpo_attention_bwd_args* a, void* stream);
+
+/* ------------------------------------------------ memory-bound backward pieces ----- */
+int64_t ddpo_colsum_workspace_floats(int m, int n, int rows_per_group);
+/* out[g][n] (+)= sum of the rows of group g of dy (fp32 [m, ld]); optional bf16 copy of dy (GEMM operand).
+ * rows_per_group == m: bias gradient; rows_per_group == H*W: per-sample sums (time-embedding projection). */
+int ddpo_colsum_cast(const float* dy, int ld, void* y_bf16, float* out, int rows_per_group, int accumulate,
+                     float* workspace, int m, int n, void* stream);
+int ddpo_colsum_bf16(const void* x_bf16, int ld, float* out, int accumulate, float* workspace, int m, int n, void* stream);
+int ddpo_geglu_bwd(const void* pre_bf16, const float* dff, void* dpre_bf16, int64_t m, int n, int bn, void* stream);
+int ddpo_conv_out_bwd(const float* x_nhwc, const float* w_hwio, const float* dy_nchw, float* dx_nhwc, float* dw,
+                      float* dbias, int batch, int h, int w, int cin, void* stream);
+int64_t ddpo_conv_in_wgrad_workspace_floats(int cin, int cout);
+int ddpo_conv_in_wgrad(const float* lat_nchw, const float* dx_nhwc, float* dw, float* workspace, int batch, int cin,
+                       int h, int w, int cout, void* stream);
+int ddpo_dense_small_bwd(const float* x, const float* w, const float* bias, const float* dy, float* dpre_ws, float* dw,
+                         float* db, float* dx, int dx_accumulate, int batch, int k, int n, int silu_in, int silu_out,
+                         void* stream);
+int ddpo_dilate2x_bf16(const float* x, void* y_bf16, int batch, int h, int w, int c, void* stream);
+int ddpo_copy2d(const float* src, int lds, float* dst, int ldd, int64_t rows, int cols, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- optimizer --------
+ * optax.chain(clip_by_global_norm, adamw(mu_dtype=bf16)) + AccumulatingTrainState.apply_gradients(do_update=True)
+ * (pipeline/policy_gradient.py:130-150, ddpo/training/policy_gradient.py:32-43). */
+int64_t ddpo_optim_workspace_bytes(void);
+int ddpo_grad_sumsq(const float* g, int64_t n, void* workspace, float* sumsq_out, void* stream);
+int ddpo_clip_adamw(float* params, float* grad_acc, void* mu_bf16, float* nu, int64_t n, const float* sumsq_dev,
+                    float grad_scale, float max_norm, float lr, float b1, float b2, float eps, float weight_decay,
+                    int step, float* norm_out, void* stream);
 
 #ifdef __cplusplus
 }

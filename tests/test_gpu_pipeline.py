@@ -44,9 +44,18 @@ def test_pipeline_matches_oracle(use_graph):
     np.testing.assert_allclose(lat[:, 0].cpu().numpy(), rlat[:, 0], atol=3e-6, rtol=0)
     # per-step log-prob: north-star tolerance 1e-3 relative
     np.testing.assert_allclose(lps.cpu().numpy(), rlps, rtol=1e-3)
-    # trajectories drift by the bf16 U-Net error (eps rel ~1e-2) through T stochastic steps
-    err = np.abs(final.cpu().numpy() - rf).max()
-    assert err < 0.1, f"final latents max abs err {err}"
+    # trajectories drift by the bf16 U-Net error (eps rel ~1e-2), amplified by 1/sqrt(alpha_t) at the
+    # noisy end of a 4-step schedule and by the random-init network: first step tight, final loose
+    f, r0 = nxt[:, 0].cpu().numpy(), rnxt[:, 0]
+    rel1 = np.linalg.norm(f - r0) / np.linalg.norm(r0)
+    relT = np.linalg.norm(final.cpu().numpy() - rf) / np.linalg.norm(rf)
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/pipeline_parity.txt", "a") as fh:
+        fh.write(f"graph={use_graph} first-step rel {rel1:.3e} final rel {relT:.3e} "
+                 f"logp max rel {np.abs(lps.cpu().numpy() / rlps - 1).max():.3e}\n")
+    assert rel1 < 2e-2, f"first-step latents rel err {rel1}"
+    assert relT < 0.25, f"final latents rel err {relT}"
     assert torch.equal(lat[:, 1:], nxt[:, :-1])
 
 
