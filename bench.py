@@ -275,6 +275,95 @@ def main():
     h2d = (emb_host.numel() + neg_host.numel()) * 4 / T_STEPS
     d2h = (fin.numel() + lps.numel()) * 4 / T_STEPS
 
+    # ---------------- phase: ppo train steps (fwd+bwd of the 2x2 CFG batch) + one optimizer update ----------------
+    ppo = None
+    if args.phase in ("auto", "ppo"):
+        from ddpo_b200.training import policy_gradient as pg
+        Bt = TRAIN_BATCH
+        tstate = pg.AccumulatingTrainState(apply_fn=net)
+        # a short real trajectory to train on (device resident)
+        final, lat, nxt, lps, tss = pipe(emb[:Bt], neg[:Bt], {"unet": net.params, "scheduler": state}, seed_key, T_STEPS,
+                                         512, 512, GUIDANCE, ETA)
+        adv = torch.tensor([1.0, -1.0], device=dev)
+
+        def make_batch(j, host=False):
+            bt = {"latents": lat[:, j].contiguous(), "next_latents": nxt[:, j].contiguous(), "ts": tss[:, j].contiguous(),
+                  "log_probs": lps[:, j].contiguous(), "advantages": adv, "prompt_embeds": emb[:Bt],
+                  "uncond_embeds": neg[:Bt]}
+            if host:
+                bt = {k: v.cpu().pin_memory() for k, v in bt.items()}
+            return bt
+
+        batches = [make_batch(j % T_STEPS) for j in range(max(args.steps, 4))]
+        lc0 = ops.LAUNCH_COUNT
+        pg.USE_CUDA_GRAPH = False
+        pg.train_step(tstate, batches[0], st, sched, True, GUIDANCE, ETA, CLIP, False)
+        torch.cuda.synchronize()
+        train_launches = ops.LAUNCH_COUNT - lc0
+        pg.USE_CUDA_GRAPH = True
+        for i in range(max(3, args.warmup)):
+            _, info = pg.train_step(tstate, batches[i % len(batches)], st, sched, True, GUIDANCE, ETA, CLIP, False)
+        first_pass_kl = float(info["approx_kl"].item())
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for i in range(args.steps):
+            pg.train_step(tstate, batches[i % len(batches)], st, sched, True, GUIDANCE, ETA, CLIP, False)
+        t1e.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        tt = torch.tensor([t0e.elapsed_time(t1e)], device=dev)
+        # one optimizer update: NCCL all-reduce of the flat gradient + global norm + clip/AdamW + bf16 weight refresh
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        pg.train_step(tstate, batches[0], st, sched, True, GUIDANCE, ETA, CLIP, True)
+        u1.record()
+        torch.cuda.synchronize()
+        tu = torch.tensor([u0.elapsed_time(u1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tu, op=dist.ReduceOp.MAX)
+        ms_train = tt.item() / args.steps
+        ms_update = max(0.0, tu.item() - ms_train)
+        # e2e train step: host-resident batch in, loss out
+        hb = make_batch(1, host=True)
+        pg.train_step(tstate, hb, st, sched, True, GUIDANCE, ETA, CLIP, False)
+        torch.cuda.synchronize()
+        te0 = time.perf_counter()
+        for _ in range(3):
+            _, info = pg.train_step(tstate, hb, st, sched, True, GUIDANCE, ETA, CLIP, False)
+            _loss = float(info["loss"].item())
+        ms_train_e2e = (time.perf_counter() - te0) / 3 * 1e3
+        # profile one eager train step
+        pg.USE_CUDA_GRAPH = False
+        ops.PROFILE = []
+        pg.train_step(tstate, batches[1], st, sched, True, GUIDANCE, ETA, CLIP, False)
+        torch.cuda.synchronize()
+        tprof = ops.PROFILE
+        ops.PROFILE = None
+        pg.USE_CUDA_GRAPH = True
+        tagg = {}
+        for name, work, a, b in tprof:
+            d = tagg.setdefault(name, [0.0, 0.0, 0])
+            d[0] += a.elapsed_time(b)
+            d[1] += work
+            d[2] += 1
+        ttot = sum(v[0] for v in tagg.values())
+        tbreak = {k: {"ms": round(v[0], 3), "launches": v[2], "share": round(v[0] / ttot, 4)} for k, v in tagg.items()}
+        for k in ("igemm", "wgrad", "attention_fwd", "attention_bwd"):
+            if k in tagg and tagg[k][0] > 0:
+                tbreak[k]["tflops"] = round(tagg[k][1] / (tagg[k][0] * 1e-3) / 1e12, 1)
+        # one PPO sample = T sampling steps (batch 8) + T train steps (batch 2) + its share of the update
+        s_per_sample = T_STEPS * (ms_per_step / B) + T_STEPS * (ms_train / Bt) + ms_update / Bt
+        s_per_sample_e2e = T_STEPS * (1e3 / (e2e_steps_per_s / world)) + T_STEPS * (ms_train_e2e / Bt) + ms_update / Bt
+        ppo = {"ms_per_train_step": ms_train, "ms_per_update": ms_update, "train_launches": train_launches,
+               "samples_per_s": world * 1e3 / s_per_sample, "samples_per_s_e2e": world * 1e3 / s_per_sample_e2e,
+               "ms_train_step_e2e": ms_train_e2e, "first_pass_approx_kl": first_pass_kl,
+               "train_tflops_per_gpu": 3 * 2 * Bt * UNET_GFLOP * 1e9 / (ms_train * 1e-3) / 1e12, "kernels": tbreak}
+
     if rank == 0:
         cpu = None
         if not args.no_cpu:
@@ -282,8 +371,14 @@ def main():
             cpu = {"value": 1.0 / per_step, "unit": "denoising steps/s", "cores": cores, "kind": "port",
                    "sample": f"{args.cpu_steps} denoising steps of 1 sample (2 U-Net applications each), torch-CPU oracle"}
         step_flops = 2 * B * UNET_GFLOP * 1e9
+        if ppo is not None:
+            head = {"metric": "ppo_samples_per_sec", "value": ppo["samples_per_s"],
+                    "unit": "PPO samples/s (50 sampling steps + 50 train steps + optimizer share per sample)"}
+        else:
+            head = {"metric": "denoising_steps_per_sec", "value": steps_per_s,
+                    "unit": "denoising steps/s (1 sample, both CFG branches)"}
         line = {
-            "metric": "denoising_steps_per_sec", "value": steps_per_s, "unit": "denoising steps/s (1 sample, both CFG branches)",
+            **head, "denoising_steps_per_sec": steps_per_s, "denoising_steps_per_sec_per_gpu": steps_per_s / world,
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (fp32 accumulate, fp32 residual stream/norms)",
             "data": "synthetic",
@@ -293,9 +388,14 @@ def main():
                        "cuda_graph": True, "per_gpu_steps_per_s": steps_per_s / world,
                        "unet_tflops_per_gpu": step_flops / (ms_per_step * 1e-3) / 1e12},
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_steps_per_s, "unit": "denoising steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "what": "pipeline(...) 50-step call from pinned host embeddings to host final latents + log-probs"},
-            "gpu_launches": launches_per_step * args.steps,
+            "e2e": ({"value": ppo["samples_per_s_e2e"], "unit": "PPO samples/s", "h2d_bytes_per_step": h2d + 2 * 2 * 65536 + 2 * 2 * 77 * 1024 * 4,
+                     "d2h_bytes_per_step": d2h + 12, "denoising_steps_per_sec": e2e_steps_per_s,
+                     "what": "pipeline(...) from pinned host embeddings to host latents/log-probs + train_step(...) from a pinned host batch to host loss"}
+                    if ppo is not None else
+                    {"value": e2e_steps_per_s, "unit": "denoising steps/s", "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h, "what": "pipeline(...) 50-step call from pinned host embeddings to host final latents + log-probs"}),
+            "gpu_launches": launches_per_step * args.steps + (ppo["train_launches"] * args.steps if ppo else 0),
+            "ppo": ppo,
             "roofline": {"bound": "tensor", "achieved": igemm_tflops, "peak": sus_tf, "unit": "TFLOP/s",
                          "frac": igemm_tflops / sus_tf, "traffic": None, "kernel": "igemm_kernel",
                          "peak_source": f"{peak_src} bf16_tflops_sustained",

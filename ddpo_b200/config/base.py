@@ -1,0 +1,51 @@
+"""Experiment configuration -- same keys and defaults as the reference's ``config/base.py:3-103``
+(``base["sample"|"train"|"pg"]``) plus the dataset overrides this build exercises.  ``pretrained_model`` is
+a label only: weights are random-init (no checkpoints offline); the U-Net shape comes from ``unet_config``."""
+
+base = {
+    "sample": {
+        "loadpath": "f:models/{iteration}", "savepath": "f:samples/{iteration}", "load_epoch": "latest",
+        "n_samples_per_device": 4, "pretrained_model": "stabilityai/stable-diffusion-2-base", "prompt_kwargs": {},
+        "n_inference_steps": 50, "eta": 1.0, "resolution": 512, "max_samples": 50e3, "max_steps": None,
+        "local_size": 1600, "guidance_scale": 5.0, "filter_field": "labels", "mask_mode": "streaming_percentile",
+        "mask_param": 95, "identical_batch": False, "iteration": 0, "evaluate": False, "cache": "cache", "seed": None,
+    },
+    "train": {
+        "modelpath": "f:models/{iteration}", "loadpath": "f:samples/{iteration}", "savepath": "f:models/{iteration+1}",
+        "pretrained_model": "stabilityai/stable-diffusion-2-base", "finetuned_model": None, "load_epoch": "latest",
+        "max_train_samples": None, "resolution": 512, "train_cfg": False, "guidance_scale": 5.0,
+        "train_batch_size": 2, "num_train_epochs": 40, "max_train_steps": None, "learning_rate": 1e-5, "beta1": 0.9,
+        "beta2": 0.999, "weight_decay": 1e-4, "epsilon": 1e-8, "max_grad_norm": 1.0, "iteration": 0,
+        "weighted_batch": False, "weighted_dataset": False, "dtype": "float32", "cache": "cache", "verbose": False,
+        "save_freq": 100, "per_prompt_weights": False, "seed": 0,
+    },
+    "pg": {
+        "loadpath": "", "load_epoch": "latest", "modelpath": "models/pg", "savepath": "f:models/pg",
+        "pretrained_model": "stabilityai/stable-diffusion-2-base", "resolution": 512, "filter_field": None,
+        "guidance_scale": 5.0, "dtype": "float32", "cache": "cache", "verbose": False, "seed": 0, "iteration": 0,
+        "sample_batch_size": 8, "num_sample_batches_per_epoch": 1, "n_inference_steps": 50, "identical_batch": False,
+        "evaluate": False, "eta": 1.0,
+        "train_batch_size": 2, "train_accumulation_steps": 1, "num_train_epochs": 200, "num_inner_epochs": 1,
+        "ppo_clip_range": 1e-4, "train_cfg": True, "learning_rate": 1e-5, "beta1": 0.9, "beta2": 0.999,
+        "weight_decay": 1e-4, "epsilon": 1e-8, "max_grad_norm": 1.0, "save_freq": 10, "optimizer": "adamw",
+        "train_timestep_ratio": 1.0, "prompt_kwargs": {}, "per_prompt_stats_bufsize": 32,
+        "per_prompt_stats_min_count": 16,
+    },
+}
+
+compressed_animals = {
+    "common": {"logbase": "logs/compressed-animals", "prompt_fn": "imagenet_animals", "filter_field": "jpeg"},
+    "pg": {},
+}
+aesthetic_animals = {
+    "common": {"logbase": "logs/aesthetic-animals", "prompt_fn": "common_animals", "filter_field": "aesthetic"},
+    "pg": {},
+}
+neg_compressed_animals = {
+    "common": {"logbase": "logs/neg-compressed-animals", "prompt_fn": "imagenet_animals", "filter_field": "neg_jpeg"},
+    "pg": {},
+}
+llava_alignment = {
+    "common": {"logbase": "logs/llava-alignment", "prompt_fn": "nouns_activities", "filter_field": "llava_bertscore"},
+    "pg": {"per_prompt_stats_bufsize": 32},
+}

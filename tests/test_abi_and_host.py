@@ -1,0 +1,102 @@
+"""CPU tests: the C-ABI library loads and exports every symbol the header declares (no compute calls without
+a GPU), header <-> ctypes agreement, host-side logic (PRNG key lineage, stat tracker, parser, prompts, rewards)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "ddpo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ddpo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ddpo_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    fns = _header_functions()
+    assert len(fns) >= 40
+    for f in fns:
+        assert hasattr(L, f), f"{f} declared in include/ddpo_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == fns, set(fns) ^ set(_lib.SIGNATURES)
+    lib = _lib.lib()
+    assert lib.ddpo_abi_version() == 1
+
+
+def test_no_gpu_calls_fail_loudly():
+    import torch
+    if torch.cuda.is_available():
+        return
+    from ddpo_b200 import _lib
+    n = _lib.lib().ddpo_device_sm_count()
+    assert n < 0 and b"CUDA" in _lib.lib().ddpo_last_error()
+    import pytest
+    from ddpo_b200 import ops
+    with pytest.raises(AssertionError):
+        ops.cast_bf16(torch.zeros(8), torch.zeros(8, dtype=torch.bfloat16))  # CPU tensors are rejected, no fallback
+
+
+def test_struct_layouts_match_header_order():
+    """field order of the ctypes structures == declaration order in the header"""
+    from ddpo_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "ddpo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    for cname, st in (("ddpo_ddim_common", _lib.DdimCommon), ("ddpo_igemm_args", _lib.IGemmArgs),
+                      ("ddpo_groupnorm_args", _lib.GroupNormArgs), ("ddpo_attention_args", _lib.AttentionArgs),
+                      ("ddpo_wgrad_args", _lib.WgradArgs), ("ddpo_attention_bwd_args", _lib.AttentionBwdArgs)):
+        body = re.search(r"typedef struct \{([^{}]*)\}\s*" + cname + ";", src, flags=re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                found = re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", part.strip())
+                if found:
+                    names.append(found[0])
+        assert names == [f[0] for f in st._fields_], (cname, names, [f[0] for f in st._fields_])
+
+
+def test_host_threefry_matches_oracle_lineage():
+    from ddpo_b200 import ops
+    from oracle import threefry as T
+    key = ops.prng_key(42)
+    assert list(key) == T.PRNGKey(42).tolist()
+    a = ops.threefry_split(key, 2)
+    assert [list(k) for k in a] == T.split(T.PRNGKey(42)).tolist()
+    b = ops.threefry_split(a[1], 8)
+    assert [list(k) for k in b] == T.split(np.array(a[1], np.uint32), 8).tolist()
+
+
+def test_stat_tracker_and_global_advantages():
+    from ddpo_b200.utils.stat_tracking import PerPromptStatTracker, global_advantages
+    tr = PerPromptStatTracker(4, 2)
+    prompts = np.array(["a", "a", "b"])
+    r = np.array([1.0, 3.0, 10.0])
+    adv = tr.update(prompts, r)
+    np.testing.assert_allclose(adv[:2], (r[:2] - 2.0) / (1.0 + 1e-6))           # own stats (count 2 >= min_count)
+    np.testing.assert_allclose(adv[2], (10.0 - r.mean()) / (r.std() + 1e-6))      # batch stats (count 1 < 2)
+    tr.update(np.array(["a"] * 4), np.array([5.0, 5.0, 5.0, 5.0]))
+    assert tr.get_stats()["a"]["count"] == 4 and tr.get_stats()["a"]["mean"] == 5.0  # ring buffer of 4
+    np.testing.assert_allclose(global_advantages(r), (r - r.mean()) / r.std())
+
+
+def test_parser_prompts_callbacks():
+    from ddpo_b200.training import callback_fns, evaluate_callbacks, make_prompts
+    from ddpo_b200.utils.parser import Parser
+    a = Parser().parse_args("pg", ["--dataset", "compressed-animals", "--ppo_clip_range", "2e-4", "--seed", "3"])
+    assert a.filter_field == "jpeg" and a.ppo_clip_range == 2e-4 and a.sample_batch_size == 8 and a.seed == 3
+    assert a.savepath.endswith("models/pg") and a.train_cfg is True and a.n_inference_steps == 50
+    inf, tr, meta = make_prompts(a.prompt_fn, 4, identical_batch=True)
+    assert len(set(inf)) == 1 and len(inf) == 4
+    imgs = np.random.default_rng(0).random((2, 32, 32, 3)).astype(np.float32)
+    out = evaluate_callbacks({"jpeg": callback_fns["jpeg"](), "neg": callback_fns["neg_jpeg"]()}, imgs, inf[:2], meta[:2])
+    assert out["jpeg"][0].shape == (2, 1) and np.all(out["jpeg"][0] < 0)
+    np.testing.assert_allclose(out["jpeg"][0], -out["neg"][0])
+    assert callback_fns["arange"]()(imgs, inf[:2], meta[:2])[0].tolist() == [0, 1]

@@ -104,3 +104,36 @@ def test_layernorm_bwd(m, c):
     assert (dx - 1.0 - xr.grad).abs().max().item() < 2e-3 * xr.grad.abs().max().item()
     assert (dsc - scr.grad).abs().max().item() < 2e-3 * scr.grad.abs().max().item()
     assert (dbi - bir.grad).abs().max().item() < 2e-3 * bir.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("b,heads,nq,nk", [(1, 1, 128, 128), (2, 2, 256, 256), (1, 2, 1024, 1024), (2, 2, 256, 77),
+                                           (2, 3, 64, 64), (2, 1, 64, 77)])
+def test_attention_bwd(b, heads, nq, nk):
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(4)
+    c = heads * 64
+    q = bf(torch.randn(b, nq, c, generator=g)).to(DEV)
+    kv = bf(torch.randn(b, nk, 2 * c, generator=g)).to(DEV)
+    do = bf(torch.randn(b, nq, c, generator=g)).to(DEV)
+    out = torch.zeros(b, nq, c, dtype=torch.bfloat16, device=DEV)
+    lse = torch.zeros(b, heads, nq, device=DEV)
+    ops.attention_fwd(q, kv, kv[:, :, c:], out, b, heads, nq, nk, c, 2 * c, 2 * c, c, lse=lse)
+    dq = torch.zeros(b, nq, c, dtype=torch.bfloat16, device=DEV)
+    dkv = torch.zeros(b, nk, 2 * c, dtype=torch.bfloat16, device=DEV)
+    delta = torch.zeros(b, heads, nq, device=DEV)
+    ops.attention_bwd(q, kv, kv[:, :, c:], out, do, lse, delta, dq, dkv, dkv[:, :, c:], b, heads, nq, nk, c, 2 * c, 2 * c,
+                      c, c, c, 2 * c, 2 * c)
+    torch.cuda.synchronize()
+    qr = q.float().requires_grad_(True)
+    kvr = kv.float().requires_grad_(True)
+    qh = qr.view(b, nq, heads, 64).permute(0, 2, 1, 3)
+    kh = kvr[:, :, :c].reshape(b, nk, heads, 64).permute(0, 2, 1, 3)
+    vh = kvr[:, :, c:].reshape(b, nk, heads, 64).permute(0, 2, 1, 3)
+    o = (torch.softmax((qh @ kh.transpose(-1, -2)) * 0.125, dim=-1) @ vh).permute(0, 2, 1, 3).reshape(b, nq, c)
+    o.backward(do.float())
+
+    def rel(a, r):
+        return ((a.float() - r).norm() / (r.norm() + 1e-12)).item()
+    assert rel(dq, qr.grad) < 2e-2, f"dq {rel(dq, qr.grad)}"
+    assert rel(dkv[:, :, :c], kvr.grad[:, :, :c]) < 2e-2, f"dk {rel(dkv[:, :, :c], kvr.grad[:, :, :c])}"
+    assert rel(dkv[:, :, c:], kvr.grad[:, :, c:]) < 2e-2, f"dv {rel(dkv[:, :, c:], kvr.grad[:, :, c:])}"
