@@ -38,44 +38,58 @@ __device__ __forceinline__ float2 gn_load2(const GnArgs& a, size_t pix, int c) {
   return *reinterpret_cast<const float2*>(a.x1 + pix * a.ld1 + (c - a.c0));
 }
 
-// grid (chunks, B).  thread -> (row r, channel pair); loops pixels r, r+R, ...
+// grid (chunks, B).  thread -> (row r, channel quad); loops pixels r, r+R, ... with 128-bit loads, 4 pixels in
+// flight.  Per-channel partial sums go to shared memory, then one warp per group reduces (rows x channels of
+// the group) in a fixed order -> chunk partials.  (A channel quad may straddle two groups: cpg = 10, 30.)
+__device__ __forceinline__ float4 gn_load4(const GnArgs& a, size_t pix, int c) {
+  if (c < a.c0) return *reinterpret_cast<const float4*>(a.x0 + pix * a.ld0 + c);
+  return *reinterpret_cast<const float4*>(a.x1 + pix * a.ld1 + (c - a.c0));
+}
+
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const GnArgs a) {
-  const int C = a.c0 + a.c1, C2 = C >> 1, cpg = C / GN_GROUPS;
-  const int cols = C2 < GN_THREADS ? C2 : GN_THREADS;
+  const int C = a.c0 + a.c1, C4 = C >> 2, cpg = C / GN_GROUPS;
+  const int cols = C4 < GN_THREADS ? C4 : GN_THREADS;
   const int R = GN_THREADS / cols;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int p_begin = chunk * a.pix_per_chunk;
   const int p_end = min(a.hw, p_begin + a.pix_per_chunk);
-  // per-group accumulation in shared memory in a fixed order:
-  // each thread owns a private slot per column pass; slots are then summed by one warp per group.
-  extern __shared__ float sm[];  // [passes][GN_THREADS][2]
-  const int passes = (C2 + cols - 1) / cols;
-  for (int ps = 0; ps < passes; ++ps) {
-    const int c2 = tc + ps * cols;
-    float s = 0.f, ss = 0.f;
-    if (tr < R && c2 < C2) {
-      for (int p = p_begin + tr; p < p_end; p += R) {
-        const float2 v = gn_load2(a, static_cast<size_t>(b) * a.hw + p, c2 * 2);
-        s += v.x + v.y;
-        ss += v.x * v.x + v.y * v.y;
+  extern __shared__ float sm[];  // [R][C][2]
+  const size_t base = static_cast<size_t>(b) * a.hw;
+  if (tr < R) {
+    for (int c4 = tc; c4 < C4; c4 += cols) {
+      const int c = c4 * 4;
+      float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+      int p = p_begin + tr;
+      for (; p + 3 * R < p_end; p += 4 * R) {
+        const float4 v0 = gn_load4(a, base + p, c), v1 = gn_load4(a, base + p + R, c);
+        const float4 v2 = gn_load4(a, base + p + 2 * R, c), v3 = gn_load4(a, base + p + 3 * R, c);
+        s[0] += (v0.x + v1.x) + (v2.x + v3.x), s[1] += (v0.y + v1.y) + (v2.y + v3.y);
+        s[2] += (v0.z + v1.z) + (v2.z + v3.z), s[3] += (v0.w + v1.w) + (v2.w + v3.w);
+        ss[0] += (v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x);
+        ss[1] += (v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y);
+        ss[2] += (v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z);
+        ss[3] += (v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w);
       }
+      for (; p < p_end; p += R) {
+        const float4 v = gn_load4(a, base + p, c);
+        s[0] += v.x, s[1] += v.y, s[2] += v.z, s[3] += v.w;
+        ss[0] += v.x * v.x, ss[1] += v.y * v.y, ss[2] += v.z * v.z, ss[3] += v.w * v.w;
+      }
+      float* o = sm + (static_cast<size_t>(tr) * C + c) * 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[2 * j] = s[j], o[2 * j + 1] = ss[j];
     }
-    sm[(ps * GN_THREADS + threadIdx.x) * 2 + 0] = s;
-    sm[(ps * GN_THREADS + threadIdx.x) * 2 + 1] = ss;
   }
   __syncthreads();
-  // group g owns channel pairs [g*cpg/2, (g+1)*cpg/2); each warp reduces groups warp, warp+16
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cp2 = cpg >> 1;
   for (int g = warp; g < GN_GROUPS; g += GN_THREADS / 32) {
     float s = 0.f, ss = 0.f;
-    const int n_items = cp2 * R;
+    const int n_items = cpg * R;
     for (int i = lane; i < n_items; i += 32) {
-      const int c2 = g * cp2 + i % cp2, r = i / cp2;
-      const int ps = c2 / cols, t = r * cols + (c2 - ps * cols);
-      s += sm[(ps * GN_THREADS + t) * 2 + 0];
-      ss += sm[(ps * GN_THREADS + t) * 2 + 1];
+      const int c = g * cpg + i % cpg, r = i / cpg;
+      s += sm[(static_cast<size_t>(r) * C + c) * 2];
+      ss += sm[(static_cast<size_t>(r) * C + c) * 2 + 1];
     }
     s = warp_sum(s), ss = warp_sum(ss);
     if (lane == 0) {
@@ -86,8 +100,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const GnArgs a) {
 }
 
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
-  const int C = a.c0 + a.c1, C2 = C >> 1, cpg = C / GN_GROUPS;
-  const int cols = C2 < GN_THREADS ? C2 : GN_THREADS;
+  const int C = a.c0 + a.c1, C4 = C >> 2, cpg = C / GN_GROUPS;
+  const int cols = C4 < GN_THREADS ? C4 : GN_THREADS;
   const int R = GN_THREADS / cols;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -108,21 +122,33 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
   }
   __syncthreads();
   if (tr >= R) return;
-  for (int c2 = tc; c2 < C2; c2 += cols) {
-    const int c = c2 * 2;
-    const int g = c / cpg;
-    const float mean = s_mean[g], rstd = s_rstd[g];
-    const float2 sc = *reinterpret_cast<const float2*>(a.scale + c);
-    const float2 bi = *reinterpret_cast<const float2*>(a.bias + c);
+  const size_t base = static_cast<size_t>(b) * a.hw;
+  for (int c4 = tc; c4 < C4; c4 += cols) {
+    const int c = c4 * 4;
+    const float4 sc = *reinterpret_cast<const float4*>(a.scale + c);
+    const float4 bi = *reinterpret_cast<const float4*>(a.bias + c);
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, biv[4] = {bi.x, bi.y, bi.z, bi.w};
+    float mu[4], rs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cpg;
+      mu[j] = s_mean[g], rs[j] = s_rstd[g];
+    }
     for (int p = p_begin + tr; p < p_end; p += R) {
-      const size_t pix = static_cast<size_t>(b) * a.hw + p;
-      const float2 v = gn_load2(a, pix, c);
-      float y0 = (v.x - mean) * rstd * sc.x + bi.x;
-      float y1 = (v.y - mean) * rstd * sc.y + bi.y;
-      if (a.silu) y0 = silu_f(y0), y1 = silu_f(y1);
-      if (a.y_bf16) *reinterpret_cast<uint32_t*>(a.y_bf16 + pix * C + c) = pack_bf16(y0, y1);
-      if (a.y_f32) *reinterpret_cast<float2*>(a.y_f32 + pix * C + c) = make_float2(y0, y1);
-      if (a.raw_bf16) *reinterpret_cast<uint32_t*>(a.raw_bf16 + pix * C + c) = pack_bf16(v.x, v.y);
+      const size_t pix = base + p;
+      const float4 v = gn_load4(a, pix, c);
+      const float xv[4] = {v.x, v.y, v.z, v.w};
+      float y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // same operation order as before the vectorisation: ((x - mean) * rstd) * scale + bias
+        y[j] = (xv[j] - mu[j]) * rs[j] * scv[j] + biv[j];
+        if (a.silu) y[j] = silu_f(y[j]);
+      }
+      if (a.y_bf16) *reinterpret_cast<uint2*>(a.y_bf16 + pix * C + c) = make_uint2(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]));
+      if (a.y_f32) *reinterpret_cast<float4*>(a.y_f32 + pix * C + c) = make_float4(y[0], y[1], y[2], y[3]);
+      if (a.raw_bf16)
+        *reinterpret_cast<uint2*>(a.raw_bf16 + pix * C + c) = make_uint2(pack_bf16(xv[0], xv[1]), pack_bf16(xv[2], xv[3]));
     }
   }
 }
@@ -419,6 +445,11 @@ static size_t gn_smem(int C, int per) {
   const int passes = (C2 + cols - 1) / cols;
   return static_cast<size_t>(passes) * GN_THREADS * per * sizeof(float);
 }
+static size_t gn_stats_smem(int C) {
+  const int C4 = C / 4, cols = C4 < GN_THREADS ? C4 : GN_THREADS;
+  const int R = GN_THREADS / cols;
+  return static_cast<size_t>(R) * C * 2 * sizeof(float);
+}
 
 }  // namespace ddpo
 
@@ -437,7 +468,9 @@ extern "C" int ddpo_groupnorm_fwd(const ddpo_groupnorm_args* a, void* stream_) {
   int rc = fill_gn(g, a);
   if (rc) return rc;
   dim3 grid(g.chunks, a->batch);
-  const size_t smem = gn_smem(a->c0 + a->c1, 2);
+  const size_t smem = gn_stats_smem(a->c0 + a->c1);
+  DDPO_REQUIRE(smem <= 48 * 1024, "groupnorm: too many channels (%d)", a->c0 + a->c1);
+  DDPO_REQUIRE(a->c0 % 4 == 0 && g.ld0 % 4 == 0 && g.ld1 % 4 == 0, "groupnorm: channel counts / pitches must be multiples of 4");
   if (!a->stats_only_skip) {
     gn_stats_kernel<<<grid, GN_THREADS, smem, stream>>>(g);
     DDPO_LAUNCH_OK();

@@ -530,6 +530,8 @@ class UNet:
         cin, hw, m = c0 + c1, h * w, b * h * w
         te = self.cfg.time_embed_dim
         dy = grads.pop(id(r["out"]))
+        if getattr(self, "_dbg", None) is not None:
+            self._dbg[name] = dy.clone()
         names = [name + "/conv2/bias"] + ([name + "/conv_shortcut/bias"] if r["has_sc"] else [])
         dyb = bias_grad_and_cast(dy, m, cout, names)
         ops.wgrad(dy=dyb, n=cout, x0=r["a2"], c0=cout, conv=(b, h, w), taps=9, dw=self.g(name + "/conv2/kernel"))
@@ -598,6 +600,8 @@ class UNet:
         L = self.ctx_len
         dctx = self.cfg.cross_attention_dim
         dy = grads.pop(id(t["out"]))
+        if getattr(self, "_dbg", None) is not None:
+            self._dbg[name] = dy.clone()
         # out = proj_out(h3b) + x
         dyb = bias_grad_and_cast(dy, m, c, [name + "/proj_out/bias"])
         ops.wgrad(dy=dyb, n=c, x0=t["h3b"], c0=c, m=m, dw=self.g(name + "/proj_out/kernel").view(c, c))
