@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 T_STEPS = 50
 SAMPLE_BATCH = 8
 TRAIN_BATCH = 2
+TRAIN_MACRO = 10  # timesteps of the same train batch evaluated in one U-Net pass (same parameters, see train_step doc)
 GUIDANCE, ETA, CLIP = 5.0, 1.0, 1e-4
 UNET_GFLOP = 804.3  # algorithmic GFLOP of one SD2-base U-Net application (SURVEY.md §8d / BASELINE.md §2)
 
@@ -286,23 +287,28 @@ def main():
                                          512, 512, GUIDANCE, ETA)
         adv = torch.tensor([1.0, -1.0], device=dev)
 
-        def make_batch(j, host=False):
-            bt = {"latents": lat[:, j].contiguous(), "next_latents": nxt[:, j].contiguous(), "ts": tss[:, j].contiguous(),
-                  "log_probs": lps[:, j].contiguous(), "advantages": adv, "prompt_embeds": emb[:Bt],
-                  "uncond_embeds": neg[:Bt]}
+        J = TRAIN_MACRO
+
+        def make_batch(j0, host=False):
+            """J consecutive (shuffled-order) timesteps of the Bt samples, stacked micro-batch major"""
+            js = [(j0 + i) % T_STEPS for i in range(J)]
+            st_ = lambda x: torch.stack([x[:, j] for j in js], 0).reshape(J * Bt, *x.shape[2:]).contiguous()
+            rep = lambda x: x.unsqueeze(0).expand(J, *x.shape).reshape(J * Bt, *x.shape[1:]).contiguous()
+            bt = {"latents": st_(lat), "next_latents": st_(nxt), "ts": st_(tss), "log_probs": st_(lps),
+                  "advantages": rep(adv), "prompt_embeds": rep(emb[:Bt]), "uncond_embeds": rep(neg[:Bt])}
             if host:
                 bt = {k: v.cpu().pin_memory() for k, v in bt.items()}
             return bt
 
-        batches = [make_batch(j % T_STEPS) for j in range(max(args.steps, 4))]
+        batches = [make_batch((j * J) % T_STEPS) for j in range(5)]
         lc0 = ops.LAUNCH_COUNT
         pg.USE_CUDA_GRAPH = False
-        pg.train_step(tstate, batches[0], st, sched, True, GUIDANCE, ETA, CLIP, False)
+        pg.train_step(tstate, batches[0], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
         torch.cuda.synchronize()
         train_launches = ops.LAUNCH_COUNT - lc0
         pg.USE_CUDA_GRAPH = True
         for i in range(max(3, args.warmup)):
-            _, info = pg.train_step(tstate, batches[i % len(batches)], st, sched, True, GUIDANCE, ETA, CLIP, False)
+            _, info = pg.train_step(tstate, batches[i % len(batches)], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
         first_pass_kl = float(info["approx_kl"].item())
         if world > 1:
             dist.barrier()
@@ -310,7 +316,7 @@ def main():
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record()
         for i in range(args.steps):
-            pg.train_step(tstate, batches[i % len(batches)], st, sched, True, GUIDANCE, ETA, CLIP, False)
+            pg.train_step(tstate, batches[i % len(batches)], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
         t1e.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -319,7 +325,7 @@ def main():
         # one optimizer update: NCCL all-reduce of the flat gradient + global norm + clip/AdamW + bf16 weight refresh
         u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         u0.record()
-        pg.train_step(tstate, batches[0], st, sched, True, GUIDANCE, ETA, CLIP, True)
+        pg.train_step(tstate, batches[0], st, sched, True, GUIDANCE, ETA, CLIP, True, micro_batch_size=Bt)
         u1.record()
         torch.cuda.synchronize()
         tu = torch.tensor([u0.elapsed_time(u1)], device=dev)
@@ -330,17 +336,17 @@ def main():
         ms_update = max(0.0, tu.item() - ms_train)
         # e2e train step: host-resident batch in, loss out
         hb = make_batch(1, host=True)
-        pg.train_step(tstate, hb, st, sched, True, GUIDANCE, ETA, CLIP, False)
+        pg.train_step(tstate, hb, st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
         torch.cuda.synchronize()
         te0 = time.perf_counter()
         for _ in range(3):
-            _, info = pg.train_step(tstate, hb, st, sched, True, GUIDANCE, ETA, CLIP, False)
+            _, info = pg.train_step(tstate, hb, st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
             _loss = float(info["loss"].item())
         ms_train_e2e = (time.perf_counter() - te0) / 3 * 1e3
         # profile one eager train step
         pg.USE_CUDA_GRAPH = False
         ops.PROFILE = []
-        pg.train_step(tstate, batches[1], st, sched, True, GUIDANCE, ETA, CLIP, False)
+        pg.train_step(tstate, batches[1], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
         torch.cuda.synchronize()
         tprof = ops.PROFILE
         ops.PROFILE = None
@@ -357,12 +363,14 @@ def main():
             if k in tagg and tagg[k][0] > 0:
                 tbreak[k]["tflops"] = round(tagg[k][1] / (tagg[k][0] * 1e-3) / 1e12, 1)
         # one PPO sample = T sampling steps (batch 8) + T train steps (batch 2) + its share of the update
-        s_per_sample = T_STEPS * (ms_per_step / B) + T_STEPS * (ms_train / Bt) + ms_update / Bt
-        s_per_sample_e2e = T_STEPS * (1e3 / (e2e_steps_per_s / world)) + T_STEPS * (ms_train_e2e / Bt) + ms_update / Bt
+        # (a macro train step covers J timesteps of Bt samples)
+        s_per_sample = T_STEPS * (ms_per_step / B) + (T_STEPS / J) * (ms_train / Bt) + ms_update / Bt
+        s_per_sample_e2e = T_STEPS * (1e3 / (e2e_steps_per_s / world)) + (T_STEPS / J) * (ms_train_e2e / Bt) + ms_update / Bt
         ppo = {"ms_per_train_step": ms_train, "ms_per_update": ms_update, "train_launches": train_launches,
                "samples_per_s": world * 1e3 / s_per_sample, "samples_per_s_e2e": world * 1e3 / s_per_sample_e2e,
                "ms_train_step_e2e": ms_train_e2e, "first_pass_approx_kl": first_pass_kl,
-               "train_tflops_per_gpu": 3 * 2 * Bt * UNET_GFLOP * 1e9 / (ms_train * 1e-3) / 1e12, "kernels": tbreak}
+               "train_tflops_per_gpu": 3 * 2 * Bt * J * UNET_GFLOP * 1e9 / (ms_train * 1e-3) / 1e12,
+               "train_batch": Bt, "timesteps_per_train_pass": J, "unet_batch_per_train_pass": 2 * Bt * J, "kernels": tbreak}
 
     if rank == 0:
         cpu = None
@@ -388,7 +396,7 @@ def main():
                        "cuda_graph": True, "per_gpu_steps_per_s": steps_per_s / world,
                        "unet_tflops_per_gpu": step_flops / (ms_per_step * 1e-3) / 1e12},
             "clocks": sampler.summary(),
-            "e2e": ({"value": ppo["samples_per_s_e2e"], "unit": "PPO samples/s", "h2d_bytes_per_step": h2d + 2 * 2 * 65536 + 2 * 2 * 77 * 1024 * 4,
+            "e2e": ({"value": ppo["samples_per_s_e2e"], "unit": "PPO samples/s", "h2d_bytes_per_step": h2d + TRAIN_MACRO * TRAIN_BATCH * (2 * 65536 + 2 * 77 * 1024 * 4 + 12),
                      "d2h_bytes_per_step": d2h + 12, "denoising_steps_per_sec": e2e_steps_per_s,
                      "what": "pipeline(...) from pinned host embeddings to host latents/log-probs + train_step(...) from a pinned host batch to host loss"}
                     if ppo is not None else

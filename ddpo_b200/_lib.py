@@ -63,7 +63,7 @@ SIGNATURES = {
     "ddpo_ddim_step_sample": (i32, [C.POINTER(DdimCommon), vp, vp, vp, vp]),
     "ddpo_ddim_logprob_fwd": (i32, [C.POINTER(DdimCommon), vp, vp, vp]),
     "ddpo_ddim_logprob_bwd": (i32, [C.POINTER(DdimCommon), vp, vp, vp, vp, vp]),
-    "ddpo_ppo_loss": (i32, [vp, vp, vp, i32, f32, vp, vp, vp]),
+    "ddpo_ppo_loss": (i32, [vp, vp, vp, i32, i32, f32, vp, vp, vp]),
     "ddpo_igemm": (i32, [C.POINTER(IGemmArgs), vp]),
     "ddpo_groupnorm_workspace_floats": (i64, [i32, i32, i32]),
     "ddpo_groupnorm_fwd": (i32, [C.POINTER(GroupNormArgs), vp]),
@@ -89,7 +89,8 @@ SIGNATURES = {
     "ddpo_colsum_cast": (i32, [vp, i32, vp, vp, i32, i32, vp, i32, i32, vp]),
     "ddpo_colsum_bf16": (i32, [vp, i32, vp, i32, vp, i32, i32, vp]),
     "ddpo_geglu_bwd": (i32, [vp, vp, vp, i64, i32, i32, vp]),
-    "ddpo_conv_out_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "ddpo_conv_out_bwd_workspace_floats": (i64, [i32]),
+    "ddpo_conv_out_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_conv_in_wgrad_workspace_floats": (i64, [i32, i32]),
     "ddpo_conv_in_wgrad": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "ddpo_dense_small_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),

@@ -9,23 +9,47 @@
 namespace ddpo {
 
 // ------------------------------------------------------------ colsum + cast ----
-// dy fp32 [M, N] -> optional bf16 copy; partial column sums per 256-row chunk -> part[chunk][N]
-constexpr int CS_ROWS = 256;
+// dy fp32 [M, N] -> optional bf16 copy; partial column sums per row chunk -> part[chunk][N].
+// CTA tile = chunk_rows x 128 columns: lane -> float4 column group, warp -> rows w, w+8, ... (4 loads in flight),
+// cross-warp reduction through shared memory in fixed order.
+constexpr int CS_ROWS = 64;
 __global__ void __launch_bounds__(256) colsum_cast_kernel(const float* __restrict__ dy, int ld, __nv_bfloat16* __restrict__ yb,
                                                           float* __restrict__ part, int M, int N, int chunk_rows) {
+  __shared__ float4 red[8][32];
   const int chunk = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = (blockIdx.y * 32 + lane) * 4;
   const int r0 = chunk * chunk_rows, r1 = min(M, r0 + chunk_rows);
-  for (int c = (blockIdx.y * 256 + threadIdx.x) * 2; c < N; c += gridDim.y * 512) {
-    float s0 = 0.f, s1 = 0.f;
-    for (int r = r0; r < r1; ++r) {
-      const float2 v = *reinterpret_cast<const float2*>(dy + static_cast<size_t>(r) * ld + c);
-      s0 += v.x, s1 += v.y;
-      if (yb != nullptr) *reinterpret_cast<uint32_t*>(yb + static_cast<size_t>(r) * N + c) = pack_bf16(v.x, v.y);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < N) {
+    int r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(dy + static_cast<size_t>(r + 8 * u) * ld + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc.x += v[u].x, acc.y += v[u].y, acc.z += v[u].z, acc.w += v[u].w;
+        if (yb != nullptr)
+          *reinterpret_cast<uint2*>(yb + static_cast<size_t>(r + 8 * u) * N + c) =
+              make_uint2(pack_bf16(v[u].x, v[u].y), pack_bf16(v[u].z, v[u].w));
+      }
     }
-    if (part != nullptr) {
-      part[static_cast<size_t>(chunk) * N + c] = s0;
-      part[static_cast<size_t>(chunk) * N + c + 1] = s1;
+    for (; r < r1; r += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(dy + static_cast<size_t>(r) * ld + c);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      if (yb != nullptr)
+        *reinterpret_cast<uint2*>(yb + static_cast<size_t>(r) * N + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
     }
+  }
+  if (part == nullptr) return;
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < N) {
+    float4 s = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s.x += red[w][lane].x, s.y += red[w][lane].y, s.z += red[w][lane].z, s.w += red[w][lane].w;
+    *reinterpret_cast<float4*>(part + static_cast<size_t>(chunk) * N + c) = s;
   }
 }
 // same for a bf16 input (no copy): partial column sums of x_bf16 [M, N]
@@ -103,15 +127,19 @@ __global__ void conv_out_dgrad_kernel(const float* __restrict__ dy, const float*
     dx[i] = acc;
   }
 }
-// dw[tap,c,n] += sum_p x[p+off, c] dy[n, p] ; grid (9, C/32), block 256 = 32 channels x 8 pixel lanes
+// dw[tap,c,n] = sum_p x[p+off, c] dy[n, p] ; grid (9, C/32, COW_SPLITS), block 256 = 32 channels x 8 pixel lanes;
+// partial sums per pixel split -> part[split][tap][C][4], reduced in split order by conv_out_wgrad_reduce_kernel
+constexpr int COW_SPLITS = 32;
 __global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                             float* __restrict__ dw, float* __restrict__ dbias, int B,
-                                                             int H, int W, int C) {
+                                                             float* __restrict__ part, int B, int H, int W, int C) {
   const int tap = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), pl = threadIdx.x >> 5;
   const int HW = H * W;
   const int oy = tap / 3 - 1, ox = tap % 3 - 1;
+  const int64_t P = static_cast<int64_t>(B) * HW;
+  const int64_t per = (P + COW_SPLITS - 1) / COW_SPLITS;
+  const int64_t p0 = blockIdx.z * per, p1 = min(P, p0 + per);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int64_t p = pl; p < static_cast<int64_t>(B) * HW; p += 8) {
+  for (int64_t p = p0 + pl; p < p1; p += 8) {
     const int b = p / HW, hw = p % HW, h = hw / W, xx0 = hw % W;
     const int yy = h + oy, xx = xx0 + ox;
     if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
@@ -127,15 +155,33 @@ __global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const float* __rest
     const int cl = threadIdx.x >> 2, n = threadIdx.x & 3;
     float s = 0.f;
     for (int q = 0; q < 8; ++q) s += sm[q][cl][n];
-    dw[(static_cast<size_t>(tap) * C + blockIdx.y * 32 + cl) * 4 + n] += s;
+    part[((static_cast<size_t>(blockIdx.z) * 9 + tap) * C + blockIdx.y * 32 + cl) * 4 + n] = s;
   }
-  if (dbias != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) {
+}
+__global__ void conv_out_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float s = 0.f;
+  for (int q = 0; q < COW_SPLITS; ++q) s += part[static_cast<size_t>(q) * total + i];
+  dw[i] += s;
+}
+// dbias[n] += sum_{b,p} dy[b,n,p] ; one CTA per output channel, fixed-order block reduction
+__global__ void __launch_bounds__(256) conv_out_dbias_kernel(const float* __restrict__ dy, float* __restrict__ dbias, int B,
+                                                             int HW) {
+  const int n = blockIdx.x;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* d = dy + (static_cast<size_t>(b) * 4 + n) * HW;
+    for (int p = threadIdx.x; p < HW; p += 256) acc += d[p];
+  }
+  __shared__ float sm[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
     float s = 0.f;
-    for (int64_t p = 0; p < static_cast<int64_t>(B) * HW; ++p) {
-      const int b = p / HW, hw = p % HW;
-      s += dy[(static_cast<size_t>(b) * 4 + threadIdx.x) * HW + hw];
-    }
-    dbias[threadIdx.x] += s;
+    for (int i = 0; i < 8; ++i) s += sm[i];
+    dbias[n] += s;
   }
 }
 
@@ -303,7 +349,8 @@ extern "C" int ddpo_colsum_cast(const float* dy, int ld, void* y_bf16, float* ou
     cpg = rows_per_group / cr;
   }
   DDPO_REQUIRE(out == nullptr || workspace != nullptr, "colsum_cast: workspace required");
-  dim3 grid(chunks, (n + 511) / 512);
+  DDPO_REQUIRE(n % 4 == 0 && (ld <= 0 || ld % 4 == 0), "colsum_cast: n and ld must be multiples of 4");
+  dim3 grid(chunks, (n + 127) / 128);
   colsum_cast_kernel<<<grid, 256, 0, stream>>>(dy, ld > 0 ? ld : n, static_cast<__nv_bfloat16*>(y_bf16),
                                               out ? workspace : nullptr, m, n, cr);
   DDPO_LAUNCH_OK();
@@ -339,16 +386,26 @@ extern "C" int ddpo_geglu_bwd(const void* pre_bf16, const float* dff, void* dpre
   return DDPO_OK;
 }
 
+extern "C" int64_t ddpo_conv_out_bwd_workspace_floats(int cin) { return static_cast<int64_t>(COW_SPLITS) * 9 * cin * 4; }
+
 extern "C" int ddpo_conv_out_bwd(const float* x_nhwc, const float* w_hwio, const float* dy_nchw, float* dx_nhwc,
-                                 float* dw, float* dbias, int batch, int h, int w, int cin, void* stream_) {
+                                 float* dw, float* dbias, float* workspace, int batch, int h, int w, int cin,
+                                 void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  DDPO_REQUIRE(x_nhwc && w_hwio && dy_nchw && dx_nhwc && dw && cin % 32 == 0, "conv_out_bwd: bad arguments");
+  DDPO_REQUIRE(x_nhwc && w_hwio && dy_nchw && dx_nhwc && dw && workspace && cin % 32 == 0, "conv_out_bwd: bad arguments");
   conv_out_dgrad_kernel<<<grid_for(static_cast<int64_t>(batch) * h * w * cin, 256), 256, 0, stream>>>(
       dy_nchw, w_hwio, dx_nhwc, batch, h, w, cin);
   DDPO_LAUNCH_OK();
-  dim3 grid(9, cin / 32);
-  conv_out_wgrad_kernel<<<grid, 256, 0, stream>>>(x_nhwc, dy_nchw, dw, dbias, batch, h, w, cin);
+  dim3 grid(9, cin / 32, COW_SPLITS);
+  conv_out_wgrad_kernel<<<grid, 256, 0, stream>>>(x_nhwc, dy_nchw, workspace, batch, h, w, cin);
   DDPO_LAUNCH_OK();
+  const int total = 9 * cin * 4;
+  conv_out_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(workspace, dw, total);
+  DDPO_LAUNCH_OK();
+  if (dbias != nullptr) {
+    conv_out_dbias_kernel<<<4, 256, 0, stream>>>(dy_nchw, dbias, batch, h * w);
+    DDPO_LAUNCH_OK();
+  }
   return DDPO_OK;
 }
 

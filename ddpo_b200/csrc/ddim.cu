@@ -225,8 +225,8 @@ __global__ void __launch_bounds__(DDIM_THREADS) ddim_logprob_bwd_kernel(const dd
 
 // ---------------------------------------------------------------------- PPO ----
 __global__ void ppo_loss_kernel(const float* __restrict__ lp, const float* __restrict__ old_lp,
-                                const float* __restrict__ adv, int n, float clip, float* __restrict__ info,
-                                float* __restrict__ dlogp) {
+                                const float* __restrict__ adv, int n, int grad_div, float clip,
+                                float* __restrict__ info, float* __restrict__ dlogp) {
   __shared__ float s_loss[32], s_kl[32], s_cf[32];
   float loss = 0.f, kl = 0.f, cf = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -238,7 +238,7 @@ __global__ void ppo_loss_kernel(const float* __restrict__ lp, const float* __res
     loss += fmaxf(unclipped, clipped);
     kl += d * d;
     cf += (fabsf(ratio - 1.0f) > clip) ? 1.0f : 0.0f;
-    if (dlogp != nullptr) dlogp[i] = (unclipped >= clipped) ? unclipped / static_cast<float>(n) : 0.0f;
+    if (dlogp != nullptr) dlogp[i] = (unclipped >= clipped) ? unclipped / static_cast<float>(grad_div) : 0.0f;
   }
   loss = warp_sum(loss), kl = warp_sum(kl), cf = warp_sum(cf);
   const int w = threadIdx.x >> 5;
@@ -330,11 +330,12 @@ extern "C" int ddpo_ddim_logprob_bwd(const ddpo_ddim_common* c, const float* pre
 }
 
 extern "C" int ddpo_ppo_loss(const float* log_prob, const float* old_log_prob, const float* advantages, int batch,
-                             float clip_range, float* info3, float* dlogp, void* stream) {
+                             int micro_batch, float clip_range, float* info3, float* dlogp, void* stream) {
   DDPO_REQUIRE(log_prob && old_log_prob && advantages && info3, "ppo_loss: null pointer");
   DDPO_REQUIRE(batch > 0 && batch <= 65536, "ppo_loss: batch=%d out of range", batch);
+  DDPO_REQUIRE(micro_batch > 0 && batch % micro_batch == 0, "ppo_loss: micro_batch must divide batch");
   ppo_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(log_prob, old_log_prob, advantages, batch,
-                                                                   clip_range, info3, dlogp);
+                                                                   micro_batch, clip_range, info3, dlogp);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }

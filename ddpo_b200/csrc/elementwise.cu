@@ -210,42 +210,55 @@ __global__ void timestep_sincos_kernel(const int32_t* __restrict__ t, int t_stri
 // 128-byte rows of w, each weight read exactly once), warp -> K slice, batch accumulators in registers,
 // cross-warp reduction through shared memory in fixed order (deterministic).
 constexpr int DS_MAXB = 32;
-__global__ void __launch_bounds__(256) dense_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                          const float* __restrict__ bias, float* __restrict__ y, int B,
-                                                          int K, int N, int silu_in, int silu_out) {
-  extern __shared__ float sm[];  // xs[B][K] then red[8][B][32]
+constexpr int DS_WARPS = 32;  // 1024 threads: warp -> K slice, lane -> output column
+template <int BMAX>
+__global__ void __launch_bounds__(DS_WARPS * 32) dense_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                    const float* __restrict__ bias, float* __restrict__ y,
+                                                                    int B, int K, int N, int silu_in, int silu_out) {
+  extern __shared__ float sm[];  // xs[B][K] then red[DS_WARPS][B][32]
   float* xs = sm;
   float* red = sm + static_cast<size_t>(B) * K;
-  for (int i = threadIdx.x; i < B * K; i += 256) {
+  for (int i = threadIdx.x; i < B * K; i += DS_WARPS * 32) {
     const float v = x[i];
     xs[i] = silu_in ? silu_f(v) : v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 32 + lane;
-  float acc[DS_MAXB];
+  float acc[BMAX];
 #pragma unroll
-  for (int b = 0; b < DS_MAXB; ++b) acc[b] = 0.f;
-  const int kper = (K + 7) / 8;
+  for (int b = 0; b < BMAX; ++b) acc[b] = 0.f;
+  const int kper = (K + DS_WARPS - 1) / DS_WARPS;
   const int k0 = warp * kper, k1 = min(K, k0 + kper);
   if (n < N) {
-    for (int k = k0; k < k1; ++k) {
+    int k = k0;
+    for (; k + 7 < k1; k += 8) {
+      float wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = w[static_cast<size_t>(k + u) * N + n];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int b = 0; b < BMAX; ++b)
+          if (b < B) acc[b] = fmaf(xs[b * K + k + u], wv[u], acc[b]);
+    }
+    for (; k < k1; ++k) {
       const float wv = w[static_cast<size_t>(k) * N + n];
 #pragma unroll
-      for (int b = 0; b < DS_MAXB; ++b)
+      for (int b = 0; b < BMAX; ++b)
         if (b < B) acc[b] = fmaf(xs[b * K + k], wv, acc[b]);
     }
   }
 #pragma unroll
-  for (int b = 0; b < DS_MAXB; ++b)
+  for (int b = 0; b < BMAX; ++b)
     if (b < B) red[(warp * B + b) * 32 + lane] = acc[b];
   __syncthreads();
-  for (int i = threadIdx.x; i < B * 32; i += 256) {
+  for (int i = threadIdx.x; i < B * 32; i += DS_WARPS * 32) {
     const int b = i >> 5, l = i & 31;
     const int nn = blockIdx.x * 32 + l;
     if (nn >= N) continue;
     float r = bias ? bias[nn] : 0.f;
-    for (int wq = 0; wq < 8; ++wq) r += red[(wq * B + b) * 32 + l];
+    for (int wq = 0; wq < DS_WARPS; ++wq) r += red[(wq * B + b) * 32 + l];
     y[static_cast<size_t>(b) * N + nn] = silu_out ? silu_f(r) : r;
   }
 }
@@ -341,17 +354,28 @@ extern "C" int ddpo_timestep_sincos(const int32_t* t, int t_stride, float* out, 
 }
 
 extern "C" int ddpo_dense_small(const float* x, const float* w, const float* bias, float* y, int batch, int k, int n,
-                                int silu_in, int silu_out, void* stream) {
-  DDPO_REQUIRE(x && w && y && k > 0 && n > 0 && batch > 0 && batch <= DS_MAXB, "dense_small: bad arguments (batch <= 32)");
-  const size_t smem = (static_cast<size_t>(batch) * k + 8 * batch * 32) * sizeof(float);
-  DDPO_REQUIRE(smem <= 200 * 1024, "dense_small: batch*k too large");
+                                int silu_in, int silu_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPO_REQUIRE(x && w && y && k > 0 && n > 0 && batch > 0, "dense_small: bad arguments");
+  // batches larger than 32 rows are processed in slabs of 32 (same per-row arithmetic -> batch invariant)
   static bool attr = false;
   if (!attr) {
-    DDPO_CUDA_OK(cudaFuncSetAttribute(dense_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DDPO_CUDA_OK(cudaFuncSetAttribute(dense_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DDPO_CUDA_OK(cudaFuncSetAttribute(dense_small_kernel<DS_MAXB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  dense_small_kernel<<<(n + 31) / 32, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, batch, k, n, silu_in,
-                                                                                     silu_out);
-  DDPO_LAUNCH_OK();
+  for (int b0 = 0; b0 < batch; b0 += DS_MAXB) {
+    const int bb = batch - b0 < DS_MAXB ? batch - b0 : DS_MAXB;
+    const size_t smem = (static_cast<size_t>(bb) * k + static_cast<size_t>(DS_WARPS) * bb * 32) * sizeof(float);
+    DDPO_REQUIRE(smem <= 200 * 1024, "dense_small: batch*k too large");
+    const float* xb = x + static_cast<size_t>(b0) * k;
+    float* yb = y + static_cast<size_t>(b0) * n;
+    if (bb <= 8)
+      dense_small_kernel<8><<<(n + 31) / 32, DS_WARPS * 32, smem, stream>>>(xb, w, bias, yb, bb, k, n, silu_in, silu_out);
+    else
+      dense_small_kernel<DS_MAXB><<<(n + 31) / 32, DS_WARPS * 32, smem, stream>>>(xb, w, bias, yb, bb, k, n, silu_in,
+                                                                                 silu_out);
+    DDPO_LAUNCH_OK();
+  }
   return DDPO_OK;
 }

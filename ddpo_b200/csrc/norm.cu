@@ -355,64 +355,92 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
 }
 
-// backward: dx (+)= rstd * (dy*scale - mean(dy*scale) - xhat * mean(dy*scale*xhat)); per-CTA dscale/dbias partials
+// backward: dx (+)= rstd * (dy*scale - mean(dy*scale) - xhat * mean(dy*scale*xhat)); per-CTA dscale/dbias partials.
+// One warp per row; a lane owns columns lane*4 + 128*i, so its dscale/dbias partial sums live in registers
+// (NC = ceil(C/128) column groups); cross-warp reduction through shared memory in fixed order.
 constexpr int LN_BWD_ROWS = 64;  // rows per CTA (8 warps x 8 rows)
+template <int NC>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                             const float* __restrict__ stats, const float* __restrict__ dy,
                                                             float* __restrict__ dx, float* __restrict__ dparam_part,
                                                             int M, int C, int accumulate) {
   extern __shared__ float sm[];  // [8 warps][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* my_ds = sm + static_cast<size_t>(warp) * 2 * C;
-  float* my_db = my_ds + C;
-  for (int c = lane; c < C; c += 32) my_ds[c] = 0.f, my_db[c] = 0.f;
-  __syncwarp();
-  for (int i = 0; i < LN_BWD_ROWS / 8; ++i) {
-    const int row = blockIdx.x * LN_BWD_ROWS + i * 8 + warp;
+  float ds[NC][4], db[NC][4];
+  float4 sc[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = lane * 4 + 128 * i;
+    sc[i] = c < C ? __ldg(reinterpret_cast<const float4*>(scale + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ds[i][j] = 0.f, db[i][j] = 0.f;
+  }
+  for (int it = 0; it < LN_BWD_ROWS / 8; ++it) {
+    const int row = blockIdx.x * LN_BWD_ROWS + it * 8 + warp;
     if (row >= M) break;
     const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
     const float* xr = x + static_cast<size_t>(row) * C;
     const float* dr = dy + static_cast<size_t>(row) * C;
+    float4 xv[NC], dv[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int c = lane * 4 + 128 * i;
+      if (c < C) {
+        xv[i] = *reinterpret_cast<const float4*>(xr + c);
+        dv[i] = *reinterpret_cast<const float4*>(dr + c);
+      } else {
+        xv[i] = make_float4(mean, mean, mean, mean);
+        dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     float m1 = 0.f, m2 = 0.f;
-    for (int c = lane * 4; c < C; c += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(xr + c);
-      const float4 d = *reinterpret_cast<const float4*>(dr + c);
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
-      const float xh[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
-      const float dd[4] = {d.x, d.y, d.z, d.w}, s4[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const float xh[4] = {(xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd, (xv[i].w - mean) * rstd};
+      const float dd[4] = {dv[i].x, dv[i].y, dv[i].z, dv[i].w}, s4[4] = {sc[i].x, sc[i].y, sc[i].z, sc[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         m1 += dd[j] * s4[j];
         m2 += dd[j] * s4[j] * xh[j];
-        my_ds[c + j] += dd[j] * xh[j];
-        my_db[c + j] += dd[j];
+        ds[i][j] += dd[j] * xh[j];
+        db[i][j] += dd[j];
       }
     }
     m1 = warp_sum(m1) / C, m2 = warp_sum(m2) / C;
     float* gr = dx + static_cast<size_t>(row) * C;
-    for (int c = lane * 4; c < C; c += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(xr + c);
-      const float4 d = *reinterpret_cast<const float4*>(dr + c);
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
-      float4 o;
-      o.x = rstd * (d.x * sc.x - m1 - (v.x - mean) * rstd * m2);
-      o.y = rstd * (d.y * sc.y - m1 - (v.y - mean) * rstd * m2);
-      o.z = rstd * (d.z * sc.z - m1 - (v.z - mean) * rstd * m2);
-      o.w = rstd * (d.w * sc.w - m1 - (v.w - mean) * rstd * m2);
-      if (accumulate) {
-        const float4 old = *reinterpret_cast<const float4*>(gr + c);
-        o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int c = lane * 4 + 128 * i;
+      if (c < C) {
+        float4 o;
+        o.x = rstd * (dv[i].x * sc[i].x - m1 - (xv[i].x - mean) * rstd * m2);
+        o.y = rstd * (dv[i].y * sc[i].y - m1 - (xv[i].y - mean) * rstd * m2);
+        o.z = rstd * (dv[i].z * sc[i].z - m1 - (xv[i].z - mean) * rstd * m2);
+        o.w = rstd * (dv[i].w * sc[i].w - m1 - (xv[i].w - mean) * rstd * m2);
+        if (accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(gr + c);
+          o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+        }
+        *reinterpret_cast<float4*>(gr + c) = o;
       }
-      *reinterpret_cast<float4*>(gr + c) = o;
+    }
+  }
+  float* my = sm + static_cast<size_t>(warp) * 2 * C;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = lane * 4 + 128 * i;
+    if (c < C) {
+      *reinterpret_cast<float4*>(my + c) = make_float4(ds[i][0], ds[i][1], ds[i][2], ds[i][3]);
+      *reinterpret_cast<float4*>(my + C + c) = make_float4(db[i][0], db[i][1], db[i][2], db[i][3]);
     }
   }
   __syncthreads();
   float* dp = dparam_part + static_cast<size_t>(blockIdx.x) * 2 * C;
   for (int c = threadIdx.x; c < C; c += 256) {
-    float ds = 0.f, db = 0.f;
-    for (int w = 0; w < 8; ++w) ds += sm[(w * 2) * C + c], db += sm[(w * 2 + 1) * C + c];
-    dp[c] = ds;
-    dp[C + c] = db;
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) a += sm[(w * 2) * C + c], b += sm[(w * 2 + 1) * C + c];
+    dp[c] = a;
+    dp[C + c] = b;
   }
 }
 
@@ -532,13 +560,21 @@ extern "C" int ddpo_layernorm_bwd(const float* x, const float* scale, const floa
                "layernorm_bwd: bad arguments");
   const int ctas = (m + LN_BWD_ROWS - 1) / LN_BWD_ROWS;
   const size_t smem = static_cast<size_t>(8) * 2 * c * sizeof(float);
+  DDPO_REQUIRE(c <= 1280 && smem <= 96 * 1024, "layernorm_bwd: C=%d too large (<= 1280)", c);
   static bool attr = false;
   if (!attr) {
-    DDPO_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    DDPO_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DDPO_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DDPO_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  DDPO_REQUIRE(smem <= 128 * 1024, "layernorm_bwd: C=%d too large", c);
-  layernorm_bwd_kernel<<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate);
+  const int nc = (c + 127) / 128;
+  if (nc <= 3)
+    layernorm_bwd_kernel<3><<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate);
+  else if (nc <= 5)
+    layernorm_bwd_kernel<5><<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate);
+  else
+    layernorm_bwd_kernel<10><<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate);
   DDPO_LAUNCH_OK();
   param_grad_reduce_kernel<<<(c + 127) / 128, 128, 0, stream>>>(workspace, ctas, c, dscale, dbias);
   DDPO_LAUNCH_OK();

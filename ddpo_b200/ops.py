@@ -119,10 +119,10 @@ def ddim_logprob_bwd(eps_u, eps_c, sample, prev, alphas_cumprod, timesteps, fina
     _run("ddim_logprob_bwd", lib().ddpo_ddim_logprob_bwd(C.byref(c), _p(prev), _p(dlogp), _p(d_eps_u), _p(d_eps_c), _stream()), 0.0, _e)
 
 
-def ppo_loss(logp, old_logp, adv, clip_range, info_out, dlogp_out):
+def ppo_loss(logp, old_logp, adv, clip_range, info_out, dlogp_out, micro_batch=None):
     _e = _ev()
-    _run("ppo_loss", lib().ddpo_ppo_loss(_p(logp), _p(old_logp), _p(adv), logp.numel(), float(clip_range), _p(info_out),
-                              _p(dlogp_out), _stream()), 0.0, _e)
+    _run("ppo_loss", lib().ddpo_ppo_loss(_p(logp), _p(old_logp), _p(adv), logp.numel(), int(micro_batch or logp.numel()),
+                                         float(clip_range), _p(info_out), _p(dlogp_out), _stream()), 0.0, _e)
 
 
 # ------------------------------------------------------------------ GEMM --------
@@ -295,7 +295,8 @@ def attention_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, batch, heads, nq, 
     _run("attention_bwd", lib().ddpo_attention_bwd(C.byref(a), _stream()), 14.0 * batch * heads * nq * nk * 64, _e)
 
 
-_KERNELS_PER_CALL.update({"attention_bwd": 3, "colsum_cast": 2, "conv_out_bwd": 2, "conv_in_wgrad": 2,
+_CIW_WS = {}
+_KERNELS_PER_CALL.update({"attention_bwd": 3, "colsum_cast": 2, "conv_out_bwd": 4, "conv_in_wgrad": 2,
                           "dense_small_bwd": 3, "grad_sumsq": 2, "wgrad": 2, "colsum_bf16": 2})
 _COLSUM_WS = {}
 
@@ -332,12 +333,14 @@ def geglu_bwd(pre, dff, dpre, m, n, bn=256):
 
 
 def conv_out_bwd(x_nhwc, w, dy_nchw, dx_nhwc, dw, dbias, batch, h, wd, cin):
+    need = int(lib().ddpo_conv_out_bwd_workspace_floats(cin))
+    ws = _CIW_WS.get(("cow", dw.device))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.float32, device=dw.device)
+        _CIW_WS[("cow", dw.device)] = ws
     _e = _ev()
-    _run("conv_out_bwd", lib().ddpo_conv_out_bwd(_p(x_nhwc), _p(w), _p(dy_nchw), _p(dx_nhwc), _p(dw), _p(dbias), batch, h,
-                                                 wd, cin, _stream()), 0.0, _e)
-
-
-_CIW_WS = {}
+    _run("conv_out_bwd", lib().ddpo_conv_out_bwd(_p(x_nhwc), _p(w), _p(dy_nchw), _p(dx_nhwc), _p(dw), _p(dbias), _p(ws),
+                                                 batch, h, wd, cin, _stream()), 0.0, _e)
 
 
 def conv_in_wgrad(lat, dx_nhwc, dw, batch, cin, h, wd, cout):

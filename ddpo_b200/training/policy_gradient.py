@@ -68,10 +68,11 @@ class AccumulatingTrainState:
     def create(cls, *, apply_fn, params=None, tx=None, **kw):
         return cls(step=0, apply_fn=apply_fn, params=params, tx=tx, **kw)
 
-    def apply_gradients(self, *, grads=None, do_update: bool, **kwargs):
+    def apply_gradients(self, *, grads=None, do_update: bool, n_micro: int = 1, **kwargs):
         """``grads`` is accepted for signature parity; the backward pass has already added this step's
-        gradient into ``grad_acc`` (fused accumulation), so only the bookkeeping happens here."""
-        self.n_acc += 1
+        gradient into ``grad_acc`` (fused accumulation), so only the bookkeeping happens here.
+        ``n_micro``: how many reference-sized train_step calls the just-finished pass stood for."""
+        self.n_acc += int(n_micro)
         if not do_update:
             return self
         world = 1
@@ -119,7 +120,8 @@ _GRAPHS: Dict[Any, _StepGraph] = {}
 USE_CUDA_GRAPH = True
 
 
-def _run_body(unet: UNet, G: _StepGraph, b, train_cfg, sched_state, ratio, guidance_scale, eta, clip_range):
+def _run_body(unet: UNet, G: _StepGraph, b, train_cfg, sched_state, ratio, guidance_scale, eta, clip_range,
+              micro_batch=None):
     n = G.lat[0].numel()
     if train_cfg:
         G.lat_in[:b].copy_(G.lat)
@@ -142,7 +144,7 @@ def _run_body(unet: UNet, G: _StepGraph, b, train_cfg, sched_state, ratio, guida
     ac = sched_state.common.alphas_cumprod
     fa = sched_state.final_alpha_cumprod
     ops.ddim_logprob_fwd(eu, ec, x, nx, ac, G.ts, fa, ratio, g, float(eta), G.logp, G.ws)
-    ops.ppo_loss(G.logp, G.old_logp, G.adv, float(clip_range), G.info, G.dlogp)
+    ops.ppo_loss(G.logp, G.old_logp, G.adv, float(clip_range), G.info, G.dlogp, micro_batch=micro_batch or b)
     if dc is None:
         scratch = unet.arena.alloc((b, n), torch.float32)
         ops.ddim_logprob_bwd(eu, ec, x, nx, ac, G.ts, fa, ratio, g, float(eta), G.dlogp, du, scratch, G.ws)
@@ -153,7 +155,12 @@ def _run_body(unet: UNet, G: _StepGraph, b, train_cfg, sched_state, ratio, guida
 
 
 def train_step(state: AccumulatingTrainState, batch, noise_scheduler_state, noise_scheduler, train_cfg,
-               guidance_scale, eta, clip_range, do_opt_update):
+               guidance_scale, eta, clip_range, do_opt_update, micro_batch_size=None):
+    """``micro_batch_size`` (extension, default = the batch size => exactly the reference call): the batch may
+    stack several reference micro-batches -- e.g. the same ``train_batch_size`` samples at several of their
+    timesteps, which the reference feeds through consecutive ``train_step`` calls at unchanged parameters
+    (``pipeline/policy_gradient.py:410-441``) -- and is then processed as ONE large U-Net batch.  Gradients,
+    ``n_acc`` and the averaged ``info`` equal those of the consecutive calls (up to fp32 summation order)."""
     assert isinstance(state, AccumulatingTrainState)
     unet = state.apply_fn
     lat = batch["latents"]
@@ -176,27 +183,29 @@ def train_step(state: AccumulatingTrainState, batch, noise_scheduler_state, nois
     else:
         G.ctx.copy_(emb)
     ratio = noise_scheduler.config.num_train_timesteps // noise_scheduler_state.num_inference_steps
-    sig = (float(guidance_scale), float(eta), float(clip_range), ratio, id(noise_scheduler_state.common.alphas_cumprod))
+    mb = int(micro_batch_size or b)
+    assert b % mb == 0
+    sig = (float(guidance_scale), float(eta), float(clip_range), ratio, id(noise_scheduler_state.common.alphas_cumprod), mb)
     if not USE_CUDA_GRAPH:
-        _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range)
+        _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range, mb)
     else:
         if G.graph is None or G.sig != sig:
             # warm-up outside capture (arena, workspaces, kernel attributes); undo its gradient contribution
             saved = state.grad_acc.clone()
-            _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range)
+            _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range, mb)
             torch.cuda.synchronize()
             state.grad_acc.copy_(saved)
             del saved
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range)
+                _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range, mb)
             G.graph, G.sig = g, sig
         G.graph.replay()
     info_t = G.info.clone()
     if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
         torch.distributed.all_reduce(info_t)                      # lax.pmean(info) (:142)
         info_t /= torch.distributed.get_world_size()
-    state.apply_gradients(grads=None, do_update=do_opt_update)
+    state.apply_gradients(grads=None, do_update=do_opt_update, n_micro=b // mb)
     info = {"approx_kl": info_t[0], "clipfrac": info_t[1], "loss": info_t[2]}
     return state, info
 

@@ -81,9 +81,12 @@ int ddpo_ddim_logprob_bwd(const ddpo_ddim_common* c, const float* prev_sample, c
 
 /* ------------------------------------------------------------------ PPO ------------
  * ddpo/training/policy_gradient.py:121-134 (clipped surrogate, info) and its gradient.
- * info = {approx_kl, clipfrac, loss}.  batch <= 1024. */
+ * info = {approx_kl, clipfrac, loss} averaged over `batch`.  `batch` may stack several reference-sized
+ * micro-batches (the reference's train_batch_size = micro_batch) evaluated at the same parameters: the gradient
+ * is d(sum over micro-batches of the micro-batch mean loss) = (dL_i/dlogp_i) / micro_batch, i.e. exactly what the
+ * reference accumulates over that many train_step calls. */
 int ddpo_ppo_loss(const float* log_prob, const float* old_log_prob, const float* advantages, int batch,
-                  float clip_range, float* info3, float* dlogp, void* stream);
+                  int micro_batch, float clip_range, float* info3, float* dlogp, void* stream);
 
 /* --------------------------------------------------------- dense contractions ------
  * nn.Conv / nn.Dense of 3P diffusers FlaxUNet2DConditionModel (reached from
@@ -216,8 +219,9 @@ int ddpo_colsum_cast(const float* dy, int ld, void* y_bf16, float* out, int rows
                      float* workspace, int m, int n, void* stream);
 int ddpo_colsum_bf16(const void* x_bf16, int ld, float* out, int accumulate, float* workspace, int m, int n, void* stream);
 int ddpo_geglu_bwd(const void* pre_bf16, const float* dff, void* dpre_bf16, int64_t m, int n, int bn, void* stream);
+int64_t ddpo_conv_out_bwd_workspace_floats(int cin);
 int ddpo_conv_out_bwd(const float* x_nhwc, const float* w_hwio, const float* dy_nchw, float* dx_nhwc, float* dw,
-                      float* dbias, int batch, int h, int w, int cin, void* stream);
+                      float* dbias, float* workspace, int batch, int h, int w, int cin, void* stream);
 int64_t ddpo_conv_in_wgrad_workspace_floats(int cin, int cout);
 int ddpo_conv_in_wgrad(const float* lat_nchw, const float* dx_nhwc, float* dw, float* workspace, int batch, int cin,
                        int h, int w, int cout, void* stream);

@@ -195,3 +195,32 @@ def test_train_step_clipped_branch_and_no_cfg():
     torch.cuda.synchronize()
     assert np.isfinite(info["loss"].item()) and float(net.grads.abs().max()) > 0.0
     assert torch.isfinite(net.grads).all()
+
+
+def test_macro_batched_train_step_equals_consecutive_calls():
+    """Stacking the same 2 samples at 3 timesteps into one pass (micro_batch_size=2) accumulates the same gradient,
+    n_acc and mean info as three reference-sized calls."""
+    from ddpo_b200.training import policy_gradient as pg
+    from ddpo_b200.unet import UNet
+    pg.USE_CUDA_GRAPH = False
+    pg._GRAPHS.clear()
+    cfg, flat, emb, neg, net, sched, st, out = _sample()
+    advs = [[1.0, -1.0], [0.3, 2.0], [-0.5, 0.5]]
+    state = pg.AccumulatingTrainState(apply_fn=net)
+    infos = []
+    for j in range(3):
+        _, info = pg.train_step(state, _batch(out, emb, neg, j, advs[j]), st, sched, True, 5.0, 1.0, 1e-4, False)
+        infos.append(info["loss"].item())
+    g_seq = net.grads.clone()
+    assert state.n_acc == 3
+    net2 = UNet(cfg, flat, "cuda")
+    state2 = pg.AccumulatingTrainState(apply_fn=net2)
+    bs = [_batch(out, emb, neg, j, advs[j]) for j in range(3)]
+    big = {k: torch.cat([b[k] for b in bs]) for k in bs[0]}
+    _, info = pg.train_step(state2, big, st, sched, True, 5.0, 1.0, 1e-4, False, micro_batch_size=2)
+    torch.cuda.synchronize()
+    assert state2.n_acc == 3
+    assert info["approx_kl"].item() == 0.0
+    np.testing.assert_allclose(info["loss"].item(), np.mean(infos), rtol=1e-5, atol=1e-6)
+    rel = ((net2.grads - g_seq).norm() / g_seq.norm()).item()
+    assert rel < 1e-3, f"macro-batched gradient differs from consecutive calls by {rel}"
