@@ -17,7 +17,8 @@
 //  * warp 1 = single-thread tcgen05.mma issuer, 128 x BN x 16 bf16 UMMAs, fp32
 //    accumulators in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i
 //    overlaps the main loop of tile i+1;
-//  * warps 4..7 = epilogue: tcgen05.ld 32x32b, fused bias / per-sample time-embedding
+//  * warps 4..11 = epilogue (two warps per TMEM lane quarter, alternating 32-column chunks):
+//    tcgen05.ld 32x32b, fused bias / per-sample time-embedding
 //    row vector / fp32 residual / GEGLU, 128-bit stores;
 //  * K order is fixed and independent of the batch size and of the position of a row in
 //    its tile -> results are batch-invariant and bit-reproducible (the PPO ratio of an
@@ -29,7 +30,7 @@ namespace ddpo {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int IGEMM_THREADS = 256;
+constexpr int IGEMM_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
 
 struct IGemmArgs {
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;
+    const int cgrp = (warp - 4) >> 2;  // 0/1: which alternating 32-column chunks this warp owns
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int tm = tile / tiles_n, tn = tile % tiles_n;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
       const float* rv = nullptr;
       if (p.rowvec != nullptr && row_ok) rv = p.rowvec + static_cast<size_t>(row / p.rows_per_sample) * p.rowvec_ld;
       if (!p.geglu) {
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = cgrp * 32; c0 < BN; c0 += 64) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c0, v);
           tmem_ld_wait();
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         // GEGLU: the weight rows of this N tile are [BN/2 linear | BN/2 gate] for the same
         // output channels (host-side row permutation), out = lin * gelu_tanh(gate)
         const int half = BN >> 1;
-        for (int c0 = 0; c0 < half; c0 += 32) {
+        for (int c0 = cgrp * 32; c0 < half; c0 += 64) {
           uint32_t a[32], g[32];
           tmem_ld_32x32(t_row + c0, a);
           tmem_ld_32x32(t_row + half + c0, g);

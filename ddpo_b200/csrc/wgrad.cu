@@ -17,7 +17,7 @@
 
 namespace ddpo {
 
-constexpr int WG_THREADS = 256;
+constexpr int WG_THREADS = 384;  // warps 4-11: epilogue (alternating 32-column chunks)
 constexpr int WG_BKP = 64;                         // pixels per pipeline stage
 constexpr int WG_BOX_BYTES = WG_BKP * 64 * 2;      // [64 pixels x 64 channels] bf16 = 8 KB
 constexpr int WG_A_BYTES = 2 * WG_BOX_BYTES;       // 128 input channels
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
+    const int cgrp = (warp - 4) >> 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int s, tap, src, blk, nt;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       const size_t rows_total = static_cast<size_t>(p.taps) * cin;
       float* dst = p.dst + (p.splits > 1 ? static_cast<size_t>(s) * rows_total * p.n : 0) + row * p.n + nt * 256;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
-      for (int c0 = 0; c0 < bn; c0 += 32) {
+      for (int c0 = cgrp * 32; c0 < bn; c0 += 64) {
         uint32_t v[32];
         tmem_ld_32x32(t_row + c0, v);
         tmem_ld_wait();
