@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
           if (c0 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
       }
       const float m_new = fmaxf(m_run, m_blk);
-      const float alpha = exp2f((m_run - m_new) * c);
+      const float alpha = ex2_mufu((m_run - m_new) * c);
       const float mc = m_new * c;
       float l_blk = 0.f;
       // pass 2: P = exp2(S*c - m*c) -> bf16 -> swizzled smem (K-major SW128, 2 sub-tiles of 64 keys)
@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
         float pr[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(__uint_as_float(v[i]) * c - mc);
+          const float xe = __uint_as_float(v[i]) * c - mc;
+          const float e = (i & 1) ? ex2_poly(xe) : ex2_mufu(xe);
           pr[i] = (c0 + i < valid) ? e : 0.f;
           l_blk += pr[i];
         }

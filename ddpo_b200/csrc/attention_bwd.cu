@@ -44,7 +44,8 @@ __device__ __forceinline__ void softmax_bwd_row(uint32_t t_s, uint32_t t_dp, uin
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const bool ok = row_ok && (c0 + i < valid_keys);
-      const float pv = ok ? exp2f(__uint_as_float(s[i]) * c - lse_l2) : 0.f;
+      const float xe = __uint_as_float(s[i]) * c - lse_l2;
+      const float pv = ok ? ((i & 1) ? ex2_poly(xe) : ex2_mufu(xe)) : 0.f;
       p[i] = pv;
       ds[i] = pv * (__uint_as_float(d[i]) - delta) * scale;
     }

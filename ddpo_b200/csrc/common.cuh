@@ -81,6 +81,23 @@ __device__ __forceinline__ float gelu_tanh_grad_f(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
 }
 
+// 2^x for x <= 0 two ways: the MUFU unit (16/clk/SM) and a Cody-Waite + degree-3 polynomial on the FMA/ALU pipes
+// (max relative error 8.8e-5, far below bf16 resolution).  The attention kernels alternate them by COLUMN
+// PARITY (a fixed function of the element position -> deterministic, batch-invariant) because the softmax
+// exponentials, not the tensor cores, bound the kernel when every element goes through MUFU.
+__device__ __forceinline__ float ex2_mufu(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float r = __fadd_rd(x, 12582912.0f);  // 1.5 * 2^23: low mantissa bits now hold floor(x)
+  const float f = x - (r - 12582912.0f);      // in [0, 1)
+  const float p = fmaf(fmaf(fmaf(0.0771190897f, f, 0.2275643945f), f, 0.6951461434f), f, 1.0f);
+  return __int_as_float(__float_as_int(p) + ((__float_as_int(r) - 0x4B400000) << 23));
+}
+
 // --------------------------------------------------------------- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

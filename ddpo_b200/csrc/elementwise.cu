@@ -364,10 +364,12 @@ extern "C" int ddpo_dense_small(const float* x, const float* w, const float* bia
     DDPO_CUDA_OK(cudaFuncSetAttribute(dense_small_kernel<DS_MAXB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  for (int b0 = 0; b0 < batch; b0 += DS_MAXB) {
-    const int bb = batch - b0 < DS_MAXB ? batch - b0 : DS_MAXB;
+  int slab = (200 * 1024) / (4 * k + 4 * DS_WARPS * 32);  // rows whose inputs + partials fit in shared memory
+  if (slab > DS_MAXB) slab = DS_MAXB;
+  DDPO_REQUIRE(slab >= 1, "dense_small: k=%d too large", k);
+  for (int b0 = 0; b0 < batch; b0 += slab) {
+    const int bb = batch - b0 < slab ? batch - b0 : slab;
     const size_t smem = (static_cast<size_t>(bb) * k + static_cast<size_t>(DS_WARPS) * bb * 32) * sizeof(float);
-    DDPO_REQUIRE(smem <= 200 * 1024, "dense_small: batch*k too large");
     const float* xb = x + static_cast<size_t>(b0) * k;
     float* yb = y + static_cast<size_t>(b0) * n;
     if (bb <= 8)
