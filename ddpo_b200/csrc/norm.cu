@@ -173,17 +173,18 @@ __device__ __forceinline__ float silu_grad_f(float z) {
   return s * (1.0f + z * (1.0f - s));
 }
 
-// pass 1: per-group sums of dyh = dy*act'(z)*scale and dyh*xhat ; also dscale/dbias partials
+// pass 1: per-group sums of dyh = dy*act'(z)*scale and dyh*xhat ; also dscale/dbias partials.
+// Same thread mapping as the forward (row r, channel quad, 128-bit loads); per-channel partials in shared memory.
 __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const GnBwdArgs a) {
   const GnArgs& f = a.f;
-  const int C = f.c0 + f.c1, C2 = C >> 1, cpg = C / GN_GROUPS;
-  const int cols = C2 < GN_THREADS ? C2 : GN_THREADS;
+  const int C = f.c0 + f.c1, C4 = C >> 2, cpg = C / GN_GROUPS;
+  const int cols = C4 < GN_THREADS ? C4 : GN_THREADS;
   const int R = GN_THREADS / cols;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int p_begin = chunk * f.pix_per_chunk;
   const int p_end = min(f.hw, p_begin + f.pix_per_chunk);
-  extern __shared__ float sm[];  // [passes][GN_THREADS][6]
+  extern __shared__ float sm[];  // [R][C][4] : a0, a1, dscale, dbias per channel
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
   if (threadIdx.x < GN_GROUPS) {
     float s = 0.f, ss = 0.f;
@@ -197,44 +198,46 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const GnBwdArg
     s_rstd[threadIdx.x] = rsqrtf(fmaxf(0.f, ss * inv_n - mean * mean) + f.eps);
   }
   __syncthreads();
-  const int passes = (C2 + cols - 1) / cols;
-  for (int ps = 0; ps < passes; ++ps) {
-    const int c2 = tc + ps * cols;
-    float a0 = 0.f, a1 = 0.f, ds0 = 0.f, ds1 = 0.f, db0 = 0.f, db1 = 0.f;
-    if (tr < R && c2 < C2) {
-      const int c = c2 * 2, g = c / cpg;
-      const float mean = s_mean[g], rstd = s_rstd[g];
-      const float2 sc = *reinterpret_cast<const float2*>(f.scale + c);
-      const float2 bi = *reinterpret_cast<const float2*>(f.bias + c);
+  const size_t base = static_cast<size_t>(b) * f.hw;
+  if (tr < R) {
+    for (int c4 = tc; c4 < C4; c4 += cols) {
+      const int c = c4 * 4;
+      const float4 sc4 = *reinterpret_cast<const float4*>(f.scale + c);
+      const float4 bi4 = *reinterpret_cast<const float4*>(f.bias + c);
+      const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, bi[4] = {bi4.x, bi4.y, bi4.z, bi4.w};
+      float mu[4], rs[4], a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, ds[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mu[j] = s_mean[(c + j) / cpg], rs[j] = s_rstd[(c + j) / cpg];
       for (int p = p_begin + tr; p < p_end; p += R) {
-        const size_t pix = static_cast<size_t>(b) * f.hw + p;
-        const float2 v = gn_load2(f, pix, c);
-        float2 d = *reinterpret_cast<const float2*>(a.dy + pix * C + c);
-        const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
-        if (f.silu) {
-          d.x *= silu_grad_f(xh0 * sc.x + bi.x);
-          d.y *= silu_grad_f(xh1 * sc.y + bi.y);
+        const size_t pix = base + p;
+        const float4 v = gn_load4(f, pix, c);
+        const float4 d4 = *reinterpret_cast<const float4*>(a.dy + pix * C + c);
+        const float xv[4] = {v.x, v.y, v.z, v.w};
+        float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xh = (xv[j] - mu[j]) * rs[j];
+          if (f.silu) d[j] *= silu_grad_f(xh * sc[j] + bi[j]);
+          ds[j] += d[j] * xh;
+          db[j] += d[j];
+          a0[j] += d[j] * sc[j];
+          a1[j] += d[j] * sc[j] * xh;
         }
-        ds0 += d.x * xh0, ds1 += d.y * xh1;
-        db0 += d.x, db1 += d.y;
-        a0 += d.x * sc.x + d.y * sc.y;
-        a1 += d.x * sc.x * xh0 + d.y * sc.y * xh1;
       }
+      float* o = sm + (static_cast<size_t>(tr) * C + c) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[4 * j] = a0[j], o[4 * j + 1] = a1[j], o[4 * j + 2] = ds[j], o[4 * j + 3] = db[j];
     }
-    float* s = sm + (ps * GN_THREADS + threadIdx.x) * 6;
-    s[0] = a0, s[1] = a1, s[2] = ds0, s[3] = ds1, s[4] = db0, s[5] = db1;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cp2 = cpg >> 1;
   for (int g = warp; g < GN_GROUPS; g += GN_THREADS / 32) {
     float s = 0.f, ss = 0.f;
-    const int n_items = cp2 * R;
+    const int n_items = cpg * R;
     for (int i = lane; i < n_items; i += 32) {
-      const int c2 = g * cp2 + i % cp2, r = i / cp2;
-      const int ps = c2 / cols, t = r * cols + (c2 - ps * cols);
-      s += sm[(ps * GN_THREADS + t) * 6 + 0];
-      ss += sm[(ps * GN_THREADS + t) * 6 + 1];
+      const int c = g * cpg + i % cpg, r = i / cpg;
+      s += sm[(static_cast<size_t>(r) * C + c) * 4];
+      ss += sm[(static_cast<size_t>(r) * C + c) * 4 + 1];
     }
     s = warp_sum(s), ss = warp_sum(ss);
     if (lane == 0) {
@@ -242,25 +245,23 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const GnBwdArg
       o[0] = s, o[1] = ss;
     }
   }
-  // dscale/dbias partials: sum over the R rows of this CTA for each channel pair
   float* dp = a.dparam_part + (static_cast<size_t>(b) * f.chunks + chunk) * 2 * C;
-  for (int c2 = threadIdx.x; c2 < C2; c2 += GN_THREADS) {
-    const int ps = c2 / cols, t0 = c2 - ps * cols;
-    float ds0 = 0.f, ds1 = 0.f, db0 = 0.f, db1 = 0.f;
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    float ds = 0.f, db = 0.f;
     for (int r = 0; r < R; ++r) {
-      const float* s = sm + (ps * GN_THREADS + r * cols + t0) * 6;
-      ds0 += s[2], ds1 += s[3], db0 += s[4], db1 += s[5];
+      ds += sm[(static_cast<size_t>(r) * C + c) * 4 + 2];
+      db += sm[(static_cast<size_t>(r) * C + c) * 4 + 3];
     }
-    dp[c2 * 2] = ds0, dp[c2 * 2 + 1] = ds1;
-    dp[C + c2 * 2] = db0, dp[C + c2 * 2 + 1] = db1;
+    dp[c] = ds;
+    dp[C + c] = db;
   }
 }
 
 // pass 2: dx
 __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const GnBwdArgs a) {
   const GnArgs& f = a.f;
-  const int C = f.c0 + f.c1, C2 = C >> 1, cpg = C / GN_GROUPS;
-  const int cols = C2 < GN_THREADS ? C2 : GN_THREADS;
+  const int C = f.c0 + f.c1, C4 = C >> 2, cpg = C / GN_GROUPS;
+  const int cols = C4 < GN_THREADS ? C4 : GN_THREADS;
   const int R = GN_THREADS / cols;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -283,29 +284,38 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const GnBwdArg
   }
   __syncthreads();
   if (tr >= R) return;
-  for (int c2 = tc; c2 < C2; c2 += cols) {
-    const int c = c2 * 2, g = c / cpg;
-    const float mean = s_mean[g], rstd = s_rstd[g], m1 = s_m1[g], m2 = s_m2[g];
-    const float2 sc = *reinterpret_cast<const float2*>(f.scale + c);
-    const float2 bi = *reinterpret_cast<const float2*>(f.bias + c);
+  const size_t base = static_cast<size_t>(b) * f.hw;
+  for (int c4 = tc; c4 < C4; c4 += cols) {
+    const int c = c4 * 4;
+    const float4 sc4 = *reinterpret_cast<const float4*>(f.scale + c);
+    const float4 bi4 = *reinterpret_cast<const float4*>(f.bias + c);
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, bi[4] = {bi4.x, bi4.y, bi4.z, bi4.w};
+    float mu[4], rs[4], m1[4], m2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cpg;
+      mu[j] = s_mean[g], rs[j] = s_rstd[g], m1[j] = s_m1[g], m2[j] = s_m2[g];
+    }
+    const bool src0 = c < f.c0;
     for (int p = p_begin + tr; p < p_end; p += R) {
-      const size_t pix = static_cast<size_t>(b) * f.hw + p;
-      const float2 v = gn_load2(f, pix, c);
-      float2 d = *reinterpret_cast<const float2*>(a.dy + pix * C + c);
-      const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
-      if (f.silu) {
-        d.x *= silu_grad_f(xh0 * sc.x + bi.x);
-        d.y *= silu_grad_f(xh1 * sc.y + bi.y);
+      const size_t pix = base + p;
+      const float4 v = gn_load4(f, pix, c);
+      const float4 d4 = *reinterpret_cast<const float4*>(a.dy + pix * C + c);
+      const float xv[4] = {v.x, v.y, v.z, v.w};
+      float d[4] = {d4.x, d4.y, d4.z, d4.w}, o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (xv[j] - mu[j]) * rs[j];
+        if (f.silu) d[j] *= silu_grad_f(xh * sc[j] + bi[j]);
+        o[j] = rs[j] * (d[j] * sc[j] - m1[j] - xh * m2[j]);
       }
-      const float g0 = rstd * (d.x * sc.x - m1 - xh0 * m2);
-      const float g1 = rstd * (d.y * sc.y - m1 - xh1 * m2);
-      float* dst = c < f.c0 ? a.dx0 + pix * a.ldd0 + c : a.dx1 + pix * a.ldd1 + (c - f.c0);
-      float2 o = make_float2(g0, g1);
+      float* dst = src0 ? a.dx0 + pix * a.ldd0 + c : a.dx1 + pix * a.ldd1 + (c - f.c0);
+      float4 out = make_float4(o[0], o[1], o[2], o[3]);
       if (a.accumulate) {
-        const float2 old = *reinterpret_cast<const float2*>(dst);
-        o.x += old.x, o.y += old.y;
+        const float4 old = *reinterpret_cast<const float4*>(dst);
+        out.x += old.x, out.y += old.y, out.z += old.z, out.w += old.w;
       }
-      *reinterpret_cast<float2*>(dst) = o;
+      *reinterpret_cast<float4*>(dst) = out;
     }
   }
 }
@@ -468,11 +478,6 @@ static int fill_gn(GnArgs& g, const ddpo_groupnorm_args* a) {
   return DDPO_OK;
 }
 
-static size_t gn_smem(int C, int per) {
-  const int C2 = C / 2, cols = C2 < GN_THREADS ? C2 : GN_THREADS;
-  const int passes = (C2 + cols - 1) / cols;
-  return static_cast<size_t>(passes) * GN_THREADS * per * sizeof(float);
-}
 static size_t gn_stats_smem(int C) {
   const int C4 = C / 4, cols = C4 < GN_THREADS ? C4 : GN_THREADS;
   const int R = GN_THREADS / cols;
@@ -523,13 +528,14 @@ extern "C" int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const float* dy,
   b.partial2 = a->workspace + static_cast<size_t>(a->batch) * b.f.chunks * GN_GROUPS * 2;
   b.dparam_part = b.partial2 + static_cast<size_t>(a->batch) * b.f.chunks * GN_GROUPS * 2;
   dim3 grid(b.f.chunks, a->batch);
-  const size_t smem = gn_smem(C, 6);
+  const size_t smem = 2 * gn_stats_smem(C);
   static bool attr = false;
   if (!attr) {
     DDPO_CUDA_OK(cudaFuncSetAttribute(gn_bwd_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
   DDPO_REQUIRE(smem <= 96 * 1024, "groupnorm_bwd: too many channels (%d)", C);
+  DDPO_REQUIRE(b.ldd0 % 4 == 0 && b.ldd1 % 4 == 0, "groupnorm_bwd: gradient pitches must be multiples of 4");
   gn_bwd_stats_kernel<<<grid, GN_THREADS, smem, stream>>>(b);
   DDPO_LAUNCH_OK();
   gn_bwd_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(b);
