@@ -411,7 +411,18 @@ def main():
             "kernels": breakdown,
             "cpu_baseline": cpu,
         }
+        line["gpu_mem_peak_gb"] = round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)
         print(json.dumps(line))
+    # orderly teardown: drop captured graphs and cached buffers before the process exits
+    torch.cuda.synchronize()
+    if ppo is not None:
+        pg._GRAPHS.clear()
+    pipe._graphs.clear()
+    del graph
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
     if world > 1:
         dist.destroy_process_group()
 

@@ -15,7 +15,7 @@
 
 namespace ddpo {
 
-constexpr int AB_THREADS = 192;  // warp0 TMA + TMEM alloc, warp1 MMA, warps 2..5 softmax/epilogue
+constexpr int AB_THREADS = 320;  // warp0 TMA + TMEM alloc, warp1 MMA, warps 2..9 softmax/epilogue (2 per TMEM lane quarter)
 constexpr int AB_T = 128 * 64 * 2;  // one [128 x 64] bf16 tile
 
 struct AttnBwdArgs {
@@ -33,9 +33,9 @@ struct AttnBwdArgs {
 // into [128 rows][64 keys] SW128 tiles.  `row_ok` false -> zeros.
 template <bool WRITE_P>
 __device__ __forceinline__ void softmax_bwd_row(uint32_t t_s, uint32_t t_dp, uint8_t* sP, uint8_t* sDS, int r, int valid_keys,
-                                                bool row_ok, float lse_l2, float delta, float c, float scale) {
+                                                bool row_ok, float lse_l2, float delta, float c, float scale, int col_begin) {
 #pragma unroll 1
-  for (int c0 = 0; c0 < 128; c0 += 32) {
+  for (int c0 = col_begin; c0 < col_begin + 64; c0 += 32) {
     uint32_t s[32], d[32];
     tmem_ld_32x32(t_s + c0, s);
     tmem_ld_32x32(t_dp + c0, d);
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
     prefetch_tmap(&p.tmQ), prefetch_tmap(&p.tmK), prefetch_tmap(&p.tmV), prefetch_tmap(&p.tmDO);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) mbar_init(&qdo_full[i], 1), mbar_init(&qdo_empty[i], 1);
-    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 4), mbar_init(pds_full, 4), mbar_init(pds_empty, 1);
+    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 8), mbar_init(pds_full, 8), mbar_init(pds_empty, 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
     }
   } else {
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;  // which 64 key columns of the 128-key block this warp handles
     const int r = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int valid_keys = min(128, p.nk - k0);
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
       mbar_wait(pds_empty, (i & 1) ^ 1);
       tc_fence_after();
       softmax_bwd_row<true>(T_S + lane_off, T_DP + lane_off, smem + KV_SMEM_P, smem + KV_SMEM_DS, r, valid_keys, row_ok,
-                            lse_l2, delta, p.scale_log2e, p.scale);
+                            lse_l2, delta, p.scale_log2e, p.scale, chalf * 64);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
     tc_fence_after();
     const int key = k0 + r;
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
+    for (int which = chalf; which < chalf + 1; ++which) {
       __nv_bfloat16* dst = which == 0 ? p.dv : p.dk;
       const int ld = which == 0 ? p.lddv : p.lddk;
       const uint32_t t = (which == 0 ? T_DV : T_DK) + lane_off;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dq_kernel(const _
     prefetch_tmap(&p.tmQ), prefetch_tmap(&p.tmK), prefetch_tmap(&p.tmV), prefetch_tmap(&p.tmDO);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
-    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 4), mbar_init(ds_full, 4), mbar_init(ds_empty, 1);
+    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 8), mbar_init(ds_full, 8), mbar_init(ds_empty, 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dq_kernel(const _
     }
   } else {
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int row = q0 + r;
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dq_kernel(const _
       mbar_wait(ds_empty, (j & 1) ^ 1);
       tc_fence_after();
       softmax_bwd_row<false>(T_S + lane_off, T_DP + lane_off, nullptr, smem + DQ_SMEM_DS, r, valid_keys, row_ok, lse_l2,
-                             delta, p.scale_log2e, p.scale);
+                             delta, p.scale_log2e, p.scale, chalf * 64);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
@@ -334,8 +336,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dq_kernel(const _
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
+    for (int c0 = chalf * 32; c0 < chalf * 32 + 32; c0 += 32) {
       uint32_t v[32];
       tmem_ld_32x32(T_DQ + lane_off + c0, v);
       tmem_ld_wait();

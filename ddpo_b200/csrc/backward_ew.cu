@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) conv_out_dbias_kernel(const float* __rest
 
 // ----------------------------------------------------------------- conv_in ----
 // dw[tap,ci,co] += sum_p lat[b,ci,p+off] dx[p,co]; two stage: part[split][36][Cout]
-constexpr int CIW_SPLITS = 32;
+constexpr int CIW_SPLITS = 256;
 __global__ void conv_in_wgrad_kernel(const float* __restrict__ lat, const float* __restrict__ dx, float* __restrict__ part,
                                      int B, int Cin, int H, int W, int Cout) {
   const int k = blockIdx.x;  // tap*Cin + ci

@@ -36,6 +36,7 @@ constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/
 struct IGemmArgs {
   CUtensorMap tmA0, tmA1, tmB;
   int M_total, N_total, BN, stages;
+  int MT;  // 128-row sub-tiles per CTA tile (1 or 2).  MT = 2: BM = 256 sharing one B tile -> 33% less operand traffic
   int taps, kc0, kc1;
   int is_conv, W, H, conv_stride, pad;
   const float* bias;      // [N] or null
@@ -57,7 +58,10 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
   const int BN = p.BN;
   const int stages = p.stages;
   const int b_tile_bytes = BN * BK * 2;
-  const int stage_bytes = A_TILE_BYTES + b_tile_bytes;
+  const int MT = p.MT;
+  const int a_bytes = MT * A_TILE_BYTES;
+  const int stage_bytes = a_bytes + b_tile_bytes;
+  const int nbuf = MT == 2 ? 1 : 2;  // MT = 2 uses all 512 TMEM columns for one tile (no accumulator double buffering)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full = empty_bar + stages;
@@ -67,7 +71,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = (p.M_total + BM - 1) / BM;
+  const int TM = BM * MT;
+  const int tiles_m = (p.M_total + TM - 1) / TM;
   const int tiles_n = p.N_total / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int kcs = p.kc0 + p.kc1;
@@ -106,32 +111,31 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
       const int HW = p.W * p.H;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / tiles_n, tn = tile % tiles_n;
-        const int m0 = tm * BM, n0 = tn * BN;
-        int b0 = 0, h0 = 0;
-        if (p.is_conv) {
-          b0 = m0 / HW;
-          h0 = (m0 % HW) / p.W;
-        }
+        const int m0 = tm * TM, n0 = tn * BN;
         for (int kit = 0; kit < kiters; ++kit) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * stage_bytes;
-          uint8_t* sB = sA + A_TILE_BYTES;
+          uint8_t* sB = sA + a_bytes;
           mbar_expect_tx(&full_bar[stage], stage_bytes);
-          if (p.is_conv) {
-            const int tap = kit / kcs, ch = kit - tap * kcs;
-            int dy = 0, dx = 0;
-            if (p.taps == 9) {
-              dy = tap / 3;
-              dx = tap - dy * 3;
+          for (int sub = 0; sub < MT; ++sub) {
+            const int ms = m0 + sub * BM;
+            if (p.is_conv) {
+              const int b0 = ms / HW, h0 = (ms % HW) / p.W;
+              const int tap = kit / kcs, ch = kit - tap * kcs;
+              int dy = 0, dx = 0;
+              if (p.taps == 9) {
+                dy = tap / 3;
+                dx = tap - dy * 3;
+              }
+              const int cx = dx - p.pad;
+              const int cy = h0 * p.conv_stride + dy - p.pad;
+              if (ch < p.kc0)
+                tma_load_4d(sA + sub * A_TILE_BYTES, &p.tmA0, &full_bar[stage], ch * BK, cx, cy, b0);
+              else
+                tma_load_4d(sA + sub * A_TILE_BYTES, &p.tmA1, &full_bar[stage], (ch - p.kc0) * BK, cx, cy, b0);
+            } else {
+              tma_load_2d(sA + sub * A_TILE_BYTES, &p.tmA0, &full_bar[stage], kit * BK, ms);
             }
-            const int cx = dx - p.pad;
-            const int cy = h0 * p.conv_stride + dy - p.pad;
-            if (ch < p.kc0)
-              tma_load_4d(sA, &p.tmA0, &full_bar[stage], ch * BK, cx, cy, b0);
-            else
-              tma_load_4d(sA, &p.tmA1, &full_bar[stage], (ch - p.kc0) * BK, cx, cy, b0);
-          } else {
-            tma_load_2d(sA, &p.tmA0, &full_bar[stage], kit * BK, m0);
           }
           tma_load_2d(sB, &p.tmB, &full_bar[stage], kit * BK, n0);
           if (++stage == stages) {
@@ -149,19 +153,21 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        const int buf = it % nbuf;
+        mbar_wait(&tmem_empty[buf], ((it / nbuf) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 256;
         for (int kit = 0; kit < kiters; ++kit) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_base = a_base + A_TILE_BYTES;
+          const uint32_t b_base = a_base + a_bytes;
+          for (int sub = 0; sub < MT; ++sub) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(d_tmem, umma_desc(a_base + k * 32, 16, 1024), umma_desc(b_base + k * 32, 16, 1024), idesc,
-                      (kit | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16(d_tmem + sub * 256, umma_desc(a_base + sub * A_TILE_BYTES + k * 32, 16, 1024),
+                        umma_desc(b_base + k * 32, 16, 1024), idesc, (kit | k) != 0);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == stages) {
@@ -175,21 +181,25 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;
-    const int cgrp = (warp - 4) >> 2;  // 0/1: which alternating 32-column chunks this warp owns
+    const int wgrp = (warp - 4) >> 2;
+    // MT = 1: the two warps of a lane quarter alternate 32-column chunks; MT = 2: one warp group per 128-row sub-tile
+    const int cgrp = MT == 2 ? 0 : wgrp;
+    const int cstep = MT == 2 ? 32 : 64;
+    const int sub = MT == 2 ? wgrp : 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int tm = tile / tiles_n, tn = tile % tiles_n;
-      const int m0 = tm * BM, n0 = tn * BN;
-      const int buf = it & 1;
-      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      const int m0 = tm * TM + sub * BM, n0 = tn * BN;
+      const int buf = it % nbuf;
+      mbar_wait(&tmem_full[buf], (it / nbuf) & 1);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M_total;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + sub * 256;
       const float* rv = nullptr;
       if (p.rowvec != nullptr && row_ok) rv = p.rowvec + static_cast<size_t>(row / p.rows_per_sample) * p.rowvec_ld;
       if (!p.geglu) {
-        for (int c0 = cgrp * 32; c0 < BN; c0 += 64) {
+        for (int c0 = cgrp * 32; c0 < BN; c0 += cstep) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c0, v);
           tmem_ld_wait();
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         // GEGLU: the weight rows of this N tile are [BN/2 linear | BN/2 gate] for the same
         // output channels (host-side row permutation), out = lin * gelu_tanh(gate)
         const int half = BN >> 1;
-        for (int c0 = cgrp * 32; c0 < half; c0 += 64) {
+        for (int c0 = cgrp * 32; c0 < half; c0 += cstep) {
           uint32_t a[32], g[32];
           tmem_ld_32x32(t_row + c0, a);
           tmem_ld_32x32(t_row + half + c0, g);
@@ -390,9 +400,16 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
   p.ld_out = a->ld_out > 0 ? a->ld_out : (a->geglu ? a->n / 2 : a->n);
   p.geglu = a->geglu, p.accumulate_out = a->accumulate_out;
   p.aux_bf16 = static_cast<__nv_bfloat16*>(a->aux_bf16);
-  const int stage_bytes = A_TILE_BYTES + BN * BK * 2;
+  // fat tiles (BM = 256) when there are still >= 2 waves of them and the main loop is long enough to amortise the
+  // non-overlapped epilogue: operand bytes per MMA cycle drop from 8192(1/128+1/BN) to 8192(1/256+1/BN)
+  const int kiters_h = a->taps * ((cin0 + cin1) / BK);
+  const long tiles2 = static_cast<long>((M_total + 2 * BM - 1) / (2 * BM)) * (a->n / BN);
+  int MT = (a->mt_override > 0) ? a->mt_override : ((tiles2 >= 2L * num_sms() && kiters_h >= 16 && !a->geglu) ? 2 : 1);
+  p.MT = MT;
+  const int stage_bytes = MT * A_TILE_BYTES + BN * BK * 2;
   int stages = SMEM_BUDGET / stage_bytes;
   if (stages > 8) stages = 8;
+  DDPO_REQUIRE(stages >= 2, "ddpo_igemm: not enough shared memory for BN=%d MT=%d", BN, MT);
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 256 + 1024;
   static bool attr_set = false;
@@ -400,7 +417,7 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
     DDPO_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int tiles = ((M_total + BM - 1) / BM) * (a->n / BN);
+  const int tiles = ((M_total + BM * MT - 1) / (BM * MT)) * (a->n / BN);
   int grid = num_sms();
   if (grid > tiles) grid = tiles;
   igemm_kernel<<<grid, IGEMM_THREADS, smem, stream>>>(p);

@@ -115,6 +115,7 @@ typedef struct {
   int accumulate_out;       /* out_f32 += */
   int bn_override;          /* 0 = auto */
   void* aux_bf16;           /* GEGLU only, optional: bf16 [M, n] pre-activation (tile-interleaved, bias included) */
+  int mt_override;          /* 0 = auto; 1 / 2 = force 128- / 256-row CTA tiles */
 } ddpo_igemm_args;
 int ddpo_igemm(const ddpo_igemm_args* a, void* stream);
 

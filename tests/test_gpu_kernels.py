@@ -323,3 +323,36 @@ def test_conv_in_out_dense_upsample():
     from oracle.unet import timestep_embedding
     refe = timestep_embedding(ts.cpu(), 320, torch.float32)
     assert (emb.cpu() - refe).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("b,h,c,n", [(2, 16, 64, 64), (3, 32, 128, 160), (5, 8, 128, 256), (1, 64, 320, 320)])
+def test_igemm_fat_tile_is_bit_identical(b, h, c, n):
+    """256-row CTA tiles (two 128-row UMMA streams sharing the B tile) must reproduce the 128-row tiling bit for
+    bit: tile shape is a scheduling choice, never an arithmetic one."""
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = bf(torch.randn(b, h, h, c, generator=g)).to(DEV)
+    w = (torch.randn(9 * c, n, generator=g) / math.sqrt(9 * c)).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV)
+    res = torch.randn(b * h * h, n, generator=g).to(DEV)
+    wt = _prep_w(w)
+    outs = []
+    for mt in (1, 2):
+        o = torch.zeros(b * h * h, n, device=DEV)
+        ob = torch.zeros(b * h * h, n, dtype=torch.bfloat16, device=DEV)
+        ops.igemm(a0=x, wt=wt, n=n, c0=c, conv=(b, h, h), taps=9, bias=bias, residual=res, out_f32=o, out_bf16=ob, mt=mt)
+        outs.append((o, ob))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    ref = _conv_ref(x.float(), bf(w.view(3, 3, c, n)).float(), bias, 1).reshape(b * h * h, n) + res
+    assert (outs[1][0] - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    # linear
+    m, k = b * h * h, c
+    a = bf(torch.randn(m, k, generator=g)).to(DEV)
+    w2 = (torch.randn(k, n, generator=g) / math.sqrt(k)).to(DEV)
+    wt2 = _prep_w(w2)
+    o1 = torch.zeros(m, n, device=DEV)
+    o2 = torch.zeros(m, n, device=DEV)
+    ops.igemm(a0=a, wt=wt2, n=n, c0=k, m=m, out_f32=o1, mt=1)
+    ops.igemm(a0=a, wt=wt2, n=n, c0=k, m=m, out_f32=o2, mt=2)
+    assert torch.equal(o1, o2)
