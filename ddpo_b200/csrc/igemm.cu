@@ -23,34 +23,9 @@
 //  * K order is fixed and independent of the batch size and of the position of a row in
 //    its tile -> results are batch-invariant and bit-reproducible (the PPO ratio of an
 //    unchanged policy must be exactly 1; reference config/base.py:88 clip 1e-4).
-#include "common.cuh"
+#include "igemm_common.cuh"
 
 namespace ddpo {
-
-constexpr int BM = 128;
-constexpr int BK = 64;
-constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int IGEMM_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
-constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
-
-struct IGemmArgs {
-  CUtensorMap tmA0, tmA1, tmB;
-  int M_total, N_total, BN, stages;
-  int MT;  // 128-row sub-tiles per CTA tile (1 or 2).  MT = 2: BM = 256 sharing one B tile -> 33% less operand traffic
-  int taps, kc0, kc1;
-  int is_conv, W, H, conv_stride, pad;
-  const float* bias;      // [N] or null
-  const float* rowvec;    // [B, rowvec_ld] or null: added per sample (time-embedding projection)
-  int rows_per_sample, rowvec_ld;
-  const float* residual;  // [M, ld_res] fp32 or null
-  int ld_res;
-  float* out_f32;         // [M, ld_out] or null
-  __nv_bfloat16* out_bf16;  // [M, ld_out] or null  (GEGLU: [M, ld_out] with N/2 useful columns)
-  int ld_out;
-  int geglu;
-  int accumulate_out;     // out_f32 += result (used by backward passes that sum two branches)
-  __nv_bfloat16* aux_bf16;  // GEGLU only: pre-activation [M, N] (tile-interleaved, bias included) kept for backward
-};
 
 __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_constant__ IGemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -196,116 +171,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M_total;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + sub * 256;
-      const float* rv = nullptr;
-      if (p.rowvec != nullptr && row_ok) rv = p.rowvec + static_cast<size_t>(row / p.rows_per_sample) * p.rowvec_ld;
-      if (!p.geglu) {
-        for (int c0 = cgrp * 32; c0 < BN; c0 += cstep) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_row + c0, v);
-          tmem_ld_wait();
-          if (row_ok) {
-            const int n = n0 + c0;
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
-              }
-            }
-            if (rv != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + n + j));
-                f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
-              }
-            }
-            if (p.residual != nullptr) {
-              const float* r = p.residual + static_cast<size_t>(row) * p.ld_res + n;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 b4 = *reinterpret_cast<const float4*>(r + j);
-                f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
-              }
-            }
-            if (p.out_f32 != nullptr) {
-              float* o = p.out_f32 + static_cast<size_t>(row) * p.ld_out + n;
-              if (p.accumulate_out) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 b4 = *reinterpret_cast<const float4*>(o + j);
-                  f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            }
-            if (p.out_bf16 != nullptr) {
-              __nv_bfloat16* o = p.out_bf16 + static_cast<size_t>(row) * p.ld_out + n;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                u.x = pack_bf16(f[j], f[j + 1]);
-                u.y = pack_bf16(f[j + 2], f[j + 3]);
-                u.z = pack_bf16(f[j + 4], f[j + 5]);
-                u.w = pack_bf16(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = u;
-              }
-            }
-          }
-        }
-      } else {
-        // GEGLU: the weight rows of this N tile are [BN/2 linear | BN/2 gate] for the same
-        // output channels (host-side row permutation), out = lin * gelu_tanh(gate)
-        const int half = BN >> 1;
-        for (int c0 = cgrp * 32; c0 < half; c0 += cstep) {
-          uint32_t a[32], g[32];
-          tmem_ld_32x32(t_row + c0, a);
-          tmem_ld_32x32(t_row + half + c0, g);
-          tmem_ld_wait();
-          if (row_ok) {
-            const int n = n0 + c0;
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float lin = __uint_as_float(a[j]) + __ldg(p.bias + n + j);
-              float gate = __uint_as_float(g[j]) + __ldg(p.bias + n + half + j);
-              f[j] = lin * gelu_tanh_f(gate);
-              a[j] = __float_as_uint(lin), g[j] = __float_as_uint(gate);
-            }
-            if (p.aux_bf16 != nullptr) {
-              __nv_bfloat16* ax = p.aux_bf16 + static_cast<size_t>(row) * p.N_total + n;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u, w;
-                u.x = pack_bf16(__uint_as_float(a[j]), __uint_as_float(a[j + 1]));
-                u.y = pack_bf16(__uint_as_float(a[j + 2]), __uint_as_float(a[j + 3]));
-                u.z = pack_bf16(__uint_as_float(a[j + 4]), __uint_as_float(a[j + 5]));
-                u.w = pack_bf16(__uint_as_float(a[j + 6]), __uint_as_float(a[j + 7]));
-                w.x = pack_bf16(__uint_as_float(g[j]), __uint_as_float(g[j + 1]));
-                w.y = pack_bf16(__uint_as_float(g[j + 2]), __uint_as_float(g[j + 3]));
-                w.z = pack_bf16(__uint_as_float(g[j + 4]), __uint_as_float(g[j + 5]));
-                w.w = pack_bf16(__uint_as_float(g[j + 6]), __uint_as_float(g[j + 7]));
-                *reinterpret_cast<uint4*>(ax + j) = u;
-                *reinterpret_cast<uint4*>(ax + half + j) = w;
-              }
-            }
-            __nv_bfloat16* o = p.out_bf16 + static_cast<size_t>(row) * p.ld_out + tn * half + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_bf16(f[j], f[j + 1]);
-              u.y = pack_bf16(f[j + 2], f[j + 3]);
-              u.z = pack_bf16(f[j + 4], f[j + 5]);
-              u.w = pack_bf16(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = u;
-            }
-          }
-        }
-      }
+      igemm_epilogue(p, t_row, row, row_ok, n0, tn, BN, cgrp, cstep);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -331,6 +197,8 @@ static int pick_bn(int N, int geglu) {
 }  // namespace ddpo
 
 using namespace ddpo;
+
+int ddpo_igemm2_launch(IGemmArgs& p, cudaStream_t stream);  // igemm2.cu
 
 extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -383,10 +251,12 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
     p.tmA1 = p.tmA0;
     p.W = 1, p.H = 1, p.conv_stride = 1, p.pad = 0;
   }
+  // CTA pairs (cta_group::2, 256 x BN tiles) whenever the problem has enough rows; see igemm2.cu
+  const bool use_pair = a->pair_override == 1 || (a->pair_override == 0 && a->mt_override == 0 && M_total >= 1024);
   {
     uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)a->n};
     uint64_t strides[1] = {(uint64_t)ktot * 2};
-    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)(use_pair ? BN / 2 : BN)};
     uint32_t es[2] = {1, 1};
     int rc = make_tensor_map(&p.tmB, a->wt, 2, 2, dims, strides, box, es, 1);
     if (rc) return rc;
@@ -400,11 +270,15 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
   p.ld_out = a->ld_out > 0 ? a->ld_out : (a->geglu ? a->n / 2 : a->n);
   p.geglu = a->geglu, p.accumulate_out = a->accumulate_out;
   p.aux_bf16 = static_cast<__nv_bfloat16*>(a->aux_bf16);
+  if (use_pair) {
+    p.MT = 1;
+    return ddpo_igemm2_launch(p, stream);
+  }
   // fat tiles (BM = 256) when there are still >= 2 waves of them and the main loop is long enough to amortise the
   // non-overlapped epilogue: operand bytes per MMA cycle drop from 8192(1/128+1/BN) to 8192(1/256+1/BN)
   const int kiters_h = a->taps * ((cin0 + cin1) / BK);
   const long tiles2 = static_cast<long>((M_total + 2 * BM - 1) / (2 * BM)) * (a->n / BN);
-  int MT = (a->mt_override > 0) ? a->mt_override : ((tiles2 >= 2L * num_sms() && kiters_h >= 16 && !a->geglu) ? 2 : 1);
+  int MT = (a->mt_override > 0) ? a->mt_override : 1;
   p.MT = MT;
   const int stage_bytes = MT * A_TILE_BYTES + BN * BK * 2;
   int stages = SMEM_BUDGET / stage_bytes;

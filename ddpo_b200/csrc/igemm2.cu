@@ -1,0 +1,199 @@
+// CTA-pair (tcgen05 cta_group::2) variant of the implicit-GEMM kernel: two CTAs of a cluster (one TPC) compute one
+// 256 x BN tile.  Each CTA stages ITS 128 activation rows and HALF of the weight tile; the leader CTA's single MMA
+// thread issues 256 x BN x 16 UMMAs that read both CTAs' shared memory and write both CTAs' TMEM.
+//
+// Why: with one CTA per tile the tensor core re-reads (128 + BN) x 32 B of shared memory per UMMA while TMA writes
+// the same amount -> ~230 B/clk/SM of shared-memory traffic against a 128 B/clk port: the 1-CTA kernel tops out
+// near 50 % of the tensor peak (measured, profiles/).  In a pair each CTA reads 128 x 32 B of A and only BN/2 x 32 B
+// of B per UMMA -> the shared-memory port is no longer the limiter.
+//
+// Protocol (all barriers live at identical offsets in both CTAs):
+//   full[s]  (leader's is used) : leader producer arrive.expect_tx(bytes of BOTH CTAs); both CTAs' TMA loads
+//                                 complete_tx on the leader's barrier (cp.async.bulk.tensor ... cta_group::2)
+//   empty[s] (one per CTA)      : tcgen05.commit.cta_group::2 multicast from the leader's MMA thread
+//   tmem_full[b] (one per CTA)  : multicast commit after the last k-block of a tile
+//   tmem_empty[b] (leader's)    : 8 epilogue warps of EACH CTA arrive (peer: mapa + remote arrive)
+// Everything else (TMA im2col-free operand fetch, fused epilogue, fixed K order => bit-identical results to the
+// 1-CTA kernel) is shared with igemm.cu.
+#include "igemm_common.cuh"
+
+namespace ddpo {
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
+    igemm2_kernel(const __grid_constant__ IGemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int BN = p.BN;
+  const int HB = BN >> 1;  // weight rows staged by each CTA
+  const int stages = p.stages;
+  const int stage_bytes = A_TILE_BYTES + HB * BK * 2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full = empty_bar + stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  const int tiles_m = (p.M_total + 2 * BM - 1) / (2 * BM);
+  const int tiles_n = p.N_total / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int kcs = p.kc0 + p.kc1;
+  const int kiters = p.taps * kcs;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA0);
+    prefetch_tmap(&p.tmA1);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 16);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // peer barriers initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int HW = p.W * p.H;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int tm = tile / tiles_n, tn = tile % tiles_n;
+        const int m0 = tm * 2 * BM + static_cast<int>(rank) * BM;  // this CTA's 128 rows
+        const int n0 = tn * BN + static_cast<int>(rank) * HB;       // this CTA's half of the weight tile
+        int b0 = 0, h0 = 0;
+        if (p.is_conv) {
+          b0 = m0 / HW;
+          h0 = (m0 % HW) / p.W;
+        }
+        for (int kit = 0; kit < kiters; ++kit) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * stage_bytes;
+          uint8_t* sB = sA + A_TILE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
+          if (p.is_conv) {
+            const int tap = kit / kcs, ch = kit - tap * kcs;
+            int dy = 0, dx = 0;
+            if (p.taps == 9) {
+              dy = tap / 3;
+              dx = tap - dy * 3;
+            }
+            const int cx = dx - p.pad;
+            const int cy = h0 * p.conv_stride + dy - p.pad;
+            if (ch < p.kc0)
+              tma_load_4d_2sm(sA, &p.tmA0, &full_bar[stage], ch * BK, cx, cy, b0);
+            else
+              tma_load_4d_2sm(sA, &p.tmA1, &full_bar[stage], (ch - p.kc0) * BK, cx, cy, b0);
+          } else {
+            tma_load_2d_2sm(sA, &p.tmA0, &full_bar[stage], kit * BK, m0);
+          }
+          tma_load_2d_2sm(sB, &p.tmB, &full_bar[stage], kit * BK, n0);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256;
+        for (int kit = 0; kit < kiters; ++kit) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_base = a_base + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16_2sm(d_tmem, umma_desc(a_base + k * 32, 16, 1024), umma_desc(b_base + k * 32, 16, 1024), idesc,
+                          (kit | k) != 0);
+          }
+          umma_commit_2sm(&empty_bar[stage], 0x3);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tmem_full[buf], 0x3);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    const int cgrp = (warp - 4) >> 2;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int tm = tile / tiles_n, tn = tile % tiles_n;
+      const int m0 = tm * 2 * BM + static_cast<int>(rank) * BM, n0 = tn * BN;
+      const int buf = it & 1;
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M_total;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
+      igemm_epilogue(p, t_row, row, row_ok, n0, tn, BN, cgrp, 64);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[buf], 0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair still reads its shared memory / barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+}  // namespace ddpo
+
+using namespace ddpo;
+
+// called by ddpo_igemm (igemm.cu) once the argument block is filled; tmB must have been encoded with box rows BN/2
+int ddpo_igemm2_launch(IGemmArgs& p, cudaStream_t stream) {
+  const int stage_bytes = A_TILE_BYTES + (p.BN / 2) * BK * 2;
+  int stages = SMEM_BUDGET / stage_bytes;
+  if (stages > 10) stages = 10;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DDPO_CUDA_OK(cudaFuncSetAttribute(igemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int tiles = ((p.M_total + 2 * BM - 1) / (2 * BM)) * (p.N_total / p.BN);
+  int pairs = num_sms() / 2;
+  if (pairs > tiles) pairs = tiles;
+  igemm2_kernel<<<2 * pairs, IGEMM_THREADS, smem, stream>>>(p);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}

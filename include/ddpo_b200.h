@@ -116,6 +116,7 @@ typedef struct {
   int bn_override;          /* 0 = auto */
   void* aux_bf16;           /* GEGLU only, optional: bf16 [M, n] pre-activation (tile-interleaved, bias included) */
   int mt_override;          /* 0 = auto; 1 / 2 = force 128- / 256-row CTA tiles */
+  int pair_override;        /* 0 = auto; 1 = force the CTA-pair (cta_group::2) kernel; 2 = force the 1-CTA kernel */
 } ddpo_igemm_args;
 int ddpo_igemm(const ddpo_igemm_args* a, void* stream);
 

@@ -356,3 +356,45 @@ def test_igemm_fat_tile_is_bit_identical(b, h, c, n):
     ops.igemm(a0=a, wt=wt2, n=n, c0=k, m=m, out_f32=o1, mt=1)
     ops.igemm(a0=a, wt=wt2, n=n, c0=k, m=m, out_f32=o2, mt=2)
     assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("b,h,c0,c1,n,taps,stride", [(2, 16, 64, 0, 64, 9, 1), (3, 32, 128, 64, 160, 9, 1), (5, 8, 128, 0, 256, 9, 1),
+                                                     (1, 64, 320, 0, 320, 9, 1), (2, 16, 64, 0, 128, 1, 1), (4, 8, 64, 0, 64, 9, 2)])
+def test_igemm_cta_pair_is_bit_identical(b, h, c0, c1, n, taps, stride):
+    """The cta_group::2 kernel (two CTAs per 256-row tile) must reproduce the 1-CTA kernel bit for bit."""
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(10)
+    hi = h * stride
+    x0 = bf(torch.randn(b, hi, hi, c0, generator=g)).to(DEV)
+    x1 = bf(torch.randn(b, hi, hi, c1, generator=g)).to(DEV) if c1 else None
+    cin = c0 + c1
+    w = (torch.randn(taps * cin, n, generator=g) / math.sqrt(taps * cin)).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV)
+    res = torch.randn(b * h * h, n, generator=g).to(DEV)
+    tv = torch.randn(b, n, generator=g).to(DEV)
+    wt = _prep_w(w)
+    outs = []
+    for pair in (2, 1):
+        o = torch.zeros(b * h * h, n, device=DEV)
+        ob = torch.zeros(b * h * h, n, dtype=torch.bfloat16, device=DEV)
+        ops.igemm(a0=x0, a1=x1, wt=wt, n=n, c0=c0, c1=c1, conv=(b, h, h), taps=taps, stride=stride, bias=bias,
+                  rowvec=tv, rows_per_sample=h * h, rowvec_ld=n, residual=res, out_f32=o, out_bf16=ob, pair=pair)
+        outs.append((o, ob))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    # linear + GEGLU through the pair kernel
+    m, k = 1000, 128
+    a = bf(torch.randn(m, k, generator=g)).to(DEV)
+    w2 = (torch.randn(k, 8 * k, generator=g) / math.sqrt(k)).to(DEV)
+    b2 = torch.randn(8 * k, generator=g).to(DEV)
+    wt2 = torch.empty(8 * k, k, dtype=torch.bfloat16, device=DEV)
+    ops.prep_weight(w2, wt2, k, 8 * k, geglu_bn=256)
+    bp = torch.empty_like(b2)
+    ops.permute_geglu_bias(b2, bp, 8 * k, 256)
+    r = []
+    for pair in (2, 1):
+        o = torch.zeros(m, 4 * k, dtype=torch.bfloat16, device=DEV)
+        ops.igemm(a0=a, wt=wt2, n=8 * k, c0=k, m=m, bias=bp, out_bf16=o, geglu=True, bn=256, pair=pair)
+        r.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(r[0], r[1])
