@@ -42,7 +42,6 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
   uint64_t* tmem_full = empty_bar + stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* epi_stage = reinterpret_cast<float*>(smem + stages * stage_bytes + 256);  // 8 x [32][33] floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -169,8 +168,10 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
       const int buf = it % nbuf;
       mbar_wait(&tmem_full[buf], (it / nbuf) & 1);
       tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M_total;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + sub * 256;
-      igemm_epilogue(p, t_row, m0 + q * 32, n0, tn, BN, cgrp, cstep, epi_stage + (warp - 4) * (32 * EPI_PITCH), lane);
+      igemm_epilogue(p, t_row, row, row_ok, n0, tn, BN, cgrp, cstep);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -282,7 +283,7 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
   if (stages > 8) stages = 8;
   DDPO_REQUIRE(stages >= 2, "ddpo_igemm: not enough shared memory for BN=%d MT=%d", BN, MT);
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 256 + EPI_SMEM_BYTES + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     DDPO_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -32,7 +32,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
   uint64_t* tmem_full = empty_bar + stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* epi_stage = reinterpret_cast<float*>(smem + stages * stage_bytes + 256);  // 8 x [32][33] floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader
@@ -156,8 +155,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
       const int buf = it & 1;
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M_total;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
-      igemm_epilogue(p, t_row, m0 + q * 32, n0, tn, BN, cgrp, 64, epi_stage + (warp - 4) * (32 * EPI_PITCH), lane);
+      igemm_epilogue(p, t_row, row, row_ok, n0, tn, BN, cgrp, 64);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[buf], 0);
@@ -183,7 +184,7 @@ int ddpo_igemm2_launch(IGemmArgs& p, cudaStream_t stream) {
   int stages = SMEM_BUDGET / stage_bytes;
   if (stages > 10) stages = 10;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 256 + EPI_SMEM_BYTES + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     DDPO_CUDA_OK(cudaFuncSetAttribute(igemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -10,7 +10,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int IGEMM_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
-constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - 8 * 32 * 33 * 4 /*epilogue staging*/;
+constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
 
 struct IGemmArgs {
   CUtensorMap tmA0, tmA1, tmB;
@@ -32,109 +32,120 @@ struct IGemmArgs {
 };
 
 
-constexpr int EPI_PITCH = 33;                                  // floats per staged row (conflict-free transposition)
-constexpr int EPI_STAGE_BYTES = 32 * EPI_PITCH * 4;            // per epilogue warp
-constexpr int EPI_SMEM_BYTES = 8 * EPI_STAGE_BYTES;            // 8 epilogue warps
-
-// Fused epilogue of one warp for its 32 accumulator rows (TMEM lane quarter) and its 32-column chunks.
-// tcgen05.ld hands each THREAD one ROW (32 consecutive columns): stored like that, a warp-wide store touches 32
-// different rows with 16 bytes each.  The chunk is therefore transposed through a per-warp shared-memory tile
-// ([32][33] floats, bank-conflict free both ways) so that 8 lanes cover 128 contiguous bytes of one output row:
-// bias / time-embedding row vector / residual loads and the fp32 / bf16 stores are fully coalesced.
-// t_row: TMEM address (lane quarter, buffer); row0: global output row of lane 0 of this warp.
-__device__ __forceinline__ void igemm_epilogue(const IGemmArgs& p, uint32_t t_row, int row0, int n0, int tn, int BN, int cgrp,
-                                               int cstep, float* stage, int lane) {
-  const int rsub = lane >> 3;        // row within a group of 4
-  const int c4 = (lane & 7) * 4;     // column quad within the 32-column chunk
-  if (!p.geglu) {
-    for (int c0 = cgrp * 32; c0 < BN; c0 += cstep) {
-      uint32_t v[32];
-      tmem_ld_32x32(t_row + c0, v);
-      tmem_ld_wait();
+// One epilogue warp: rows (row .. ) of TMEM lane quarter `q`, 32-column chunks c0 = cgrp*32, += cstep.
+// `t_row` = TMEM address of (lane quarter, accumulator buffer / sub-tile); row = global output row of this thread.
+__device__ __forceinline__ void igemm_epilogue(const IGemmArgs& p, uint32_t t_row, int row, bool row_ok, int n0, int tn,
+                                               int BN, int cgrp, int cstep) {
+  const float* rv = nullptr;
+      if (p.rowvec != nullptr && row_ok) rv = p.rowvec + static_cast<size_t>(row / p.rows_per_sample) * p.rowvec_ld;
+      if (!p.geglu) {
+        for (int c0 = cgrp * 32; c0 < BN; c0 += cstep) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c0, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int n = n0 + c0;
+            float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) stage[lane * EPI_PITCH + j] = __uint_as_float(v[j]);
-      __syncwarp();
-      const int n = n0 + c0 + c4;
-      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + rsub;
-        const int grow = row0 + r;
-        if (grow < p.M_total) {
-          const float* sp = stage + r * EPI_PITCH + c4;
-          float4 f = make_float4(sp[0] + bias4.x, sp[1] + bias4.y, sp[2] + bias4.z, sp[3] + bias4.w);
-          if (p.rowvec != nullptr) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(
-                p.rowvec + static_cast<size_t>(grow / p.rows_per_sample) * p.rowvec_ld + n));
-            f.x += t.x, f.y += t.y, f.z += t.z, f.w += t.w;
-          }
-          if (p.residual != nullptr) {
-            const float4 t = *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(grow) * p.ld_res + n);
-            f.x += t.x, f.y += t.y, f.z += t.z, f.w += t.w;
-          }
-          if (p.out_f32 != nullptr) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(grow) * p.ld_out + n);
-            if (p.accumulate_out) {
-              const float4 t = *o;
-              f.x += t.x, f.y += t.y, f.z += t.z, f.w += t.w;
+              for (int j = 0; j < 32; j += 4) {
+                float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+              }
             }
-            *o = f;
+            if (rv != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + n + j));
+                f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+              }
+            }
+            if (p.residual != nullptr) {
+              const float* r = p.residual + static_cast<size_t>(row) * p.ld_res + n;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 b4 = *reinterpret_cast<const float4*>(r + j);
+                f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+              }
+            }
+            if (p.out_f32 != nullptr) {
+              float* o = p.out_f32 + static_cast<size_t>(row) * p.ld_out + n;
+              if (p.accumulate_out) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 b4 = *reinterpret_cast<const float4*>(o + j);
+                  f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            }
+            if (p.out_bf16 != nullptr) {
+              __nv_bfloat16* o = p.out_bf16 + static_cast<size_t>(row) * p.ld_out + n;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u;
+                u.x = pack_bf16(f[j], f[j + 1]);
+                u.y = pack_bf16(f[j + 2], f[j + 3]);
+                u.z = pack_bf16(f[j + 4], f[j + 5]);
+                u.w = pack_bf16(f[j + 6], f[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = u;
+              }
+            }
           }
-          if (p.out_bf16 != nullptr)
-            *reinterpret_cast<uint2*>(p.out_bf16 + static_cast<size_t>(grow) * p.ld_out + n) =
-                make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+        }
+      } else {
+        // GEGLU: the weight rows of this N tile are [BN/2 linear | BN/2 gate] for the same
+        // output channels (host-side row permutation), out = lin * gelu_tanh(gate)
+        const int half = BN >> 1;
+        for (int c0 = cgrp * 32; c0 < half; c0 += cstep) {
+          uint32_t a[32], g[32];
+          tmem_ld_32x32(t_row + c0, a);
+          tmem_ld_32x32(t_row + half + c0, g);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int n = n0 + c0;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float lin = __uint_as_float(a[j]) + __ldg(p.bias + n + j);
+              float gate = __uint_as_float(g[j]) + __ldg(p.bias + n + half + j);
+              f[j] = lin * gelu_tanh_f(gate);
+              a[j] = __float_as_uint(lin), g[j] = __float_as_uint(gate);
+            }
+            if (p.aux_bf16 != nullptr) {
+              __nv_bfloat16* ax = p.aux_bf16 + static_cast<size_t>(row) * p.N_total + n;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u, w;
+                u.x = pack_bf16(__uint_as_float(a[j]), __uint_as_float(a[j + 1]));
+                u.y = pack_bf16(__uint_as_float(a[j + 2]), __uint_as_float(a[j + 3]));
+                u.z = pack_bf16(__uint_as_float(a[j + 4]), __uint_as_float(a[j + 5]));
+                u.w = pack_bf16(__uint_as_float(a[j + 6]), __uint_as_float(a[j + 7]));
+                w.x = pack_bf16(__uint_as_float(g[j]), __uint_as_float(g[j + 1]));
+                w.y = pack_bf16(__uint_as_float(g[j + 2]), __uint_as_float(g[j + 3]));
+                w.z = pack_bf16(__uint_as_float(g[j + 4]), __uint_as_float(g[j + 5]));
+                w.w = pack_bf16(__uint_as_float(g[j + 6]), __uint_as_float(g[j + 7]));
+                *reinterpret_cast<uint4*>(ax + j) = u;
+                *reinterpret_cast<uint4*>(ax + half + j) = w;
+              }
+            }
+            __nv_bfloat16* o = p.out_bf16 + static_cast<size_t>(row) * p.ld_out + tn * half + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16(f[j], f[j + 1]);
+              u.y = pack_bf16(f[j + 2], f[j + 3]);
+              u.z = pack_bf16(f[j + 4], f[j + 5]);
+              u.w = pack_bf16(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = u;
+            }
+          }
         }
       }
-      __syncwarp();
-    }
-  } else {
-    // GEGLU: the weight rows of this N tile are [BN/2 linear | BN/2 gate] for the same output channels
-    // (host-side row permutation), out = lin * gelu_tanh(gate)
-    const int half = BN >> 1;
-    for (int c0 = cgrp * 32; c0 < half; c0 += cstep) {
-      uint32_t v[32];
-      float4 lin[8];
-      tmem_ld_32x32(t_row + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) stage[lane * EPI_PITCH + j] = __uint_as_float(v[j]);
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float* sp = stage + (i * 4 + rsub) * EPI_PITCH + c4;
-        lin[i] = make_float4(sp[0], sp[1], sp[2], sp[3]);
-      }
-      __syncwarp();
-      tmem_ld_32x32(t_row + half + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) stage[lane * EPI_PITCH + j] = __uint_as_float(v[j]);
-      __syncwarp();
-      const int n = n0 + c0 + c4;
-      const float4 bl = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-      const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n + half));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + rsub;
-        const int grow = row0 + r;
-        if (grow < p.M_total) {
-          const float* sp = stage + r * EPI_PITCH + c4;
-          const float4 l = make_float4(lin[i].x + bl.x, lin[i].y + bl.y, lin[i].z + bl.z, lin[i].w + bl.w);
-          const float4 g = make_float4(sp[0] + bg.x, sp[1] + bg.y, sp[2] + bg.z, sp[3] + bg.w);
-          if (p.aux_bf16 != nullptr) {
-            __nv_bfloat16* ax = p.aux_bf16 + static_cast<size_t>(grow) * p.N_total + n;
-            *reinterpret_cast<uint2*>(ax) = make_uint2(pack_bf16(l.x, l.y), pack_bf16(l.z, l.w));
-            *reinterpret_cast<uint2*>(ax + half) = make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
-          }
-          *reinterpret_cast<uint2*>(p.out_bf16 + static_cast<size_t>(grow) * p.ld_out + tn * half + c0 + c4) =
-              make_uint2(pack_bf16(l.x * gelu_tanh_f(g.x), l.y * gelu_tanh_f(g.y)),
-                         pack_bf16(l.z * gelu_tanh_f(g.z), l.w * gelu_tanh_f(g.w)));
-        }
-      }
-      __syncwarp();
-    }
-  }
 }
 
 }  // namespace ddpo
