@@ -143,16 +143,22 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
       tc_fence_after();
       const int kbase = j * AT_BKV;
       const int valid = min(AT_BKV, p.nk - kbase);
-      // pass 1: row max
+      // pass 1: row max (full blocks take the predicate-free path: the softmax warps are instruction bound)
+      const bool full = valid == AT_BKV;
       float m_blk = -INFINITY;
 #pragma unroll 1
       for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(t_lane + xb * 128 + c0, v);
         tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+        }
       }
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = ex2_mufu((m_run - m_new) * c);
@@ -165,12 +171,21 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
         tmem_ld_32x32(t_lane + xb * 128 + c0, v);
         tmem_ld_wait();
         float pr[32];
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float xe = __uint_as_float(v[i]) * c - mc;
-          const float e = (i & 1) ? ex2_poly(xe) : ex2_mufu(xe);
-          pr[i] = (c0 + i < valid) ? e : 0.f;
-          l_blk += pr[i];
+          for (int i = 0; i < 32; ++i) {
+            const float xe = __uint_as_float(v[i]) * c - mc;
+            pr[i] = (i & 1) ? ex2_poly(xe) : ex2_mufu(xe);
+            l_blk += pr[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float xe = __uint_as_float(v[i]) * c - mc;
+            const float e = (i & 1) ? ex2_poly(xe) : ex2_mufu(xe);
+            pr[i] = (c0 + i < valid) ? e : 0.f;
+            l_blk += pr[i];
+          }
         }
         uint8_t* tile = sP + (c0 >> 6) * AT_TILE + r * 128;
 #pragma unroll

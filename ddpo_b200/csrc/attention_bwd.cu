@@ -41,13 +41,23 @@ __device__ __forceinline__ void softmax_bwd_row(uint32_t t_s, uint32_t t_dp, uin
     tmem_ld_32x32(t_dp + c0, d);
     tmem_ld_wait();
     float p[32], ds[32];
+    if (row_ok && valid_keys == 128) {  // predicate-free fast path (the softmax warps are instruction bound)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const bool ok = row_ok && (c0 + i < valid_keys);
-      const float xe = __uint_as_float(s[i]) * c - lse_l2;
-      const float pv = ok ? ((i & 1) ? ex2_poly(xe) : ex2_mufu(xe)) : 0.f;
-      p[i] = pv;
-      ds[i] = pv * (__uint_as_float(d[i]) - delta) * scale;
+      for (int i = 0; i < 32; ++i) {
+        const float xe = __uint_as_float(s[i]) * c - lse_l2;
+        const float pv = (i & 1) ? ex2_poly(xe) : ex2_mufu(xe);
+        p[i] = pv;
+        ds[i] = pv * (__uint_as_float(d[i]) - delta) * scale;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool ok = row_ok && (c0 + i < valid_keys);
+        const float xe = __uint_as_float(s[i]) * c - lse_l2;
+        const float pv = ok ? ((i & 1) ? ex2_poly(xe) : ex2_mufu(xe)) : 0.f;
+        p[i] = pv;
+        ds[i] = pv * (__uint_as_float(d[i]) - delta) * scale;
+      }
     }
     const int tile_off = (c0 >> 6) * AB_T + r * 128;
 #pragma unroll
