@@ -19,7 +19,7 @@ constexpr int AB_THREADS = 320;  // warp0 TMA + TMEM alloc, warp1 MMA, warps 2..
 constexpr int AB_T = 128 * 64 * 2;  // one [128 x 64] bf16 tile
 
 struct AttnBwdArgs {
-  CUtensorMap tmQ, tmK, tmV, tmDO;
+  CUtensorMap tmQ, tmK, tmV, tmDO, tmK64, tmV64;  // *64: 64-row boxes for the dQ kernel
   const float* lse;    // [B, heads, nq]
   const float* delta;  // [B, heads, nq]
   __nv_bfloat16* dq;
@@ -33,7 +33,7 @@ struct AttnBwdArgs {
 // into [128 rows][64 keys] SW128 tiles.  `row_ok` false -> zeros.
 template <bool WRITE_P>
 __device__ __forceinline__ void softmax_bwd_row(uint32_t t_s, uint32_t t_dp, uint8_t* sP, uint8_t* sDS, int r, int valid_keys,
-                                                bool row_ok, float lse_l2, float delta, float c, float scale, int col_begin) {
+                                                bool row_ok, float lse_l2, float delta, float c, float scale, int col_begin, bool full) {
 #pragma unroll 1
   for (int c0 = col_begin; c0 < col_begin + 64; c0 += 32) {
     uint32_t s[32], d[32];
@@ -41,7 +41,7 @@ __device__ __forceinline__ void softmax_bwd_row(uint32_t t_s, uint32_t t_dp, uin
     tmem_ld_32x32(t_dp + c0, d);
     tmem_ld_wait();
     float p[32], ds[32];
-    if (row_ok && valid_keys == 128) {  // predicate-free fast path (the softmax warps are instruction bound)
+    if (row_ok && full) {  // predicate-free fast path (the softmax warps are instruction bound)
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float xe = __uint_as_float(s[i]) * c - lse_l2;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
       mbar_wait(pds_empty, (i & 1) ^ 1);
       tc_fence_after();
       softmax_bwd_row<true>(T_S + lane_off, T_DP + lane_off, smem + KV_SMEM_P, smem + KV_SMEM_DS, r, valid_keys, row_ok,
-                            lse_l2, delta, p.scale_log2e, p.scale, chalf * 64);
+                            lse_l2, delta, p.scale_log2e, p.scale, chalf * 64, valid_keys == 128);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
@@ -232,70 +232,79 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
 }
 
 // ---------------------------------------------------------------------- dQ ----
-// smem: Q | dO | 2 x (K | V) | dS(2 tiles) | barriers
-constexpr int DQ_SMEM_Q = 0, DQ_SMEM_DO = AB_T, DQ_SMEM_RING = 2 * AB_T, DQ_SMEM_DS = 6 * AB_T, DQ_SMEM_BAR = 8 * AB_T,
-              DQ_SMEM_TOTAL = DQ_SMEM_BAR + 256;
+// 64-key blocks, 192 TMEM columns and 97 KB of shared memory per CTA -> TWO CTAs per SM, so that one CTA's
+// softmax/dS phase overlaps the other's MMAs (a single CTA alternates strictly between the two).
+// smem: Q | dO | 3 x (K | V) [64 keys each] | dS (1 tile) | barriers
+constexpr int DQ_BKV = 64;
+constexpr int DQ_KVT = DQ_BKV * 64 * 2;  // 8 KB
+constexpr int DQ_STAGES = 3;
+constexpr int DQ_THREADS = 192;          // warp0 TMA + TMEM alloc, warp1 MMA, warps 2..5 softmax/epilogue
+constexpr int DQ_SMEM_Q = 0, DQ_SMEM_DO = AB_T, DQ_SMEM_RING = 2 * AB_T, DQ_SMEM_DS = DQ_SMEM_RING + DQ_STAGES * 2 * DQ_KVT,
+              DQ_SMEM_BAR = DQ_SMEM_DS + AB_T, DQ_SMEM_TOTAL = DQ_SMEM_BAR + 256;
 
-__global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dq_kernel(const __grid_constant__ AttnBwdArgs p) {
+__global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const __grid_constant__ AttnBwdArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_SMEM_BAR);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* sdp_empty = bars + 6;  // count 4
-  uint64_t* ds_full = bars + 7;    // count 4
-  uint64_t* ds_empty = bars + 8;
-  uint64_t* acc_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* kv_full = bars + 1;    // [3]
+  uint64_t* kv_empty = bars + 4;   // [3]
+  uint64_t* sdp_full = bars + 7;
+  uint64_t* sdp_empty = bars + 8;  // count 4
+  uint64_t* ds_full = bars + 9;    // count 4
+  uint64_t* ds_empty = bars + 10;
+  uint64_t* acc_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
-  const int nkb = (p.nk + 127) / 128;
+  const int nkb = (p.nk + DQ_BKV - 1) / DQ_BKV;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
-    prefetch_tmap(&p.tmQ), prefetch_tmap(&p.tmK), prefetch_tmap(&p.tmV), prefetch_tmap(&p.tmDO);
+    prefetch_tmap(&p.tmQ), prefetch_tmap(&p.tmK64), prefetch_tmap(&p.tmV64), prefetch_tmap(&p.tmDO);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
-    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 8), mbar_init(ds_full, 8), mbar_init(ds_empty, 1);
+    for (int i = 0; i < DQ_STAGES; ++i) mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
+    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 4), mbar_init(ds_full, 4), mbar_init(ds_empty, 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t T_S = tmem_base, T_DP = tmem_base + 128, T_DQ = tmem_base + 256;
+  const uint32_t T_S = tmem_base, T_DP = tmem_base + 64, T_DQ = tmem_base + 128;
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(q_full, 2 * AB_T);
       tma_load_4d(smem + DQ_SMEM_Q, &p.tmQ, q_full, 0, head, q0, b);
       tma_load_4d(smem + DQ_SMEM_DO, &p.tmDO, q_full, 0, head, q0, b);
+      int st = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < nkb; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        uint8_t* sK = smem + DQ_SMEM_RING + st * 2 * AB_T;
-        mbar_expect_tx(&kv_full[st], 2 * AB_T);
-        tma_load_4d(sK, &p.tmK, &kv_full[st], 0, head, j * 128, b);
-        tma_load_4d(sK + AB_T, &p.tmV, &kv_full[st], 0, head, j * 128, b);
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        uint8_t* sK = smem + DQ_SMEM_RING + st * 2 * DQ_KVT;
+        mbar_expect_tx(&kv_full[st], 2 * DQ_KVT);
+        tma_load_4d(sK, &p.tmK64, &kv_full[st], 0, head, j * DQ_BKV, b);
+        tma_load_4d(sK + DQ_KVT, &p.tmV64, &kv_full[st], 0, head, j * DQ_BKV, b);
+        if (++st == DQ_STAGES) st = 0, ph ^= 1;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t id_s = umma_idesc_bf16(128, DQ_BKV, 0, 0);
       const uint32_t id_q = umma_idesc_bf16(128, 64, 0, 1);  // dQ = dS K : A K-major, B (K) MN-major
       const uint32_t q_addr = smem_u32(smem + DQ_SMEM_Q), do_addr = smem_u32(smem + DQ_SMEM_DO);
       const uint32_t ds_addr = smem_u32(smem + DQ_SMEM_DS);
       mbar_wait(q_full, 0);
+      int st = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < nkb; ++j) {
-        const int st = j & 1;
-        const uint32_t k_addr = smem_u32(smem + DQ_SMEM_RING + st * 2 * AB_T), v_addr = k_addr + AB_T;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        const uint32_t k_addr = smem_u32(smem + DQ_SMEM_RING + st * 2 * DQ_KVT), v_addr = k_addr + DQ_KVT;
+        mbar_wait(&kv_full[st], ph);
         mbar_wait(sdp_empty, (j & 1) ^ 1);
         tc_fence_after();
 #pragma unroll
@@ -308,17 +317,17 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dq_kernel(const _
         mbar_wait(ds_full, j & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // K = 128 keys: A sub-tile k>>2, 32-byte steps; B rows of 16 keys
-          umma_bf16(T_DQ, umma_desc(ds_addr + (k >> 2) * AB_T + (k & 3) * 32, 16, 1024),
-                    umma_desc(k_addr + k * 2048, AB_T, 1024), id_q, (j | k) != 0);
+        for (int k = 0; k < DQ_BKV / 16; ++k)  // A = dS [128 q x 64 keys] K-major; B = K_j rows of 16 keys (MN-major)
+          umma_bf16(T_DQ, umma_desc(ds_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 2048, DQ_KVT, 1024), id_q,
+                    (j | k) != 0);
         umma_commit(&kv_empty[st]);
         umma_commit(ds_empty);
+        if (++st == DQ_STAGES) st = 0, ph ^= 1;
       }
       umma_commit(acc_full);
     }
   } else {
     const int q = warp & 3;
-    const int chalf = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int row = q0 + r;
@@ -330,12 +339,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dq_kernel(const _
       delta = p.delta[o];
     }
     for (int j = 0; j < nkb; ++j) {
-      const int valid_keys = min(128, p.nk - j * 128);
+      const int valid_keys = min(DQ_BKV, p.nk - j * DQ_BKV);
       mbar_wait(sdp_full, j & 1);
       mbar_wait(ds_empty, (j & 1) ^ 1);
       tc_fence_after();
       softmax_bwd_row<false>(T_S + lane_off, T_DP + lane_off, nullptr, smem + DQ_SMEM_DS, r, valid_keys, row_ok, lse_l2,
-                             delta, p.scale_log2e, p.scale, chalf * 64);
+                             delta, p.scale_log2e, p.scale, 0, valid_keys == DQ_BKV);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
@@ -346,7 +355,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dq_kernel(const _
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    for (int c0 = chalf * 32; c0 < chalf * 32 + 32; c0 += 32) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 32) {
       uint32_t v[32];
       tmem_ld_32x32(T_DQ + lane_off + c0, v);
       tmem_ld_wait();
@@ -368,7 +378,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dq_kernel(const _
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -400,10 +410,10 @@ __global__ void attention_delta_kernel(const __nv_bfloat16* __restrict__ o, int 
   }
 }
 
-static int make_map(CUtensorMap* m, const void* base, int heads, int n, int batch, int ld) {
+static int make_map(CUtensorMap* m, const void* base, int heads, int n, int batch, int ld, int box_rows = 128) {
   uint64_t dims[4] = {64, (uint64_t)heads, (uint64_t)n, (uint64_t)batch};
   uint64_t strides[3] = {128, (uint64_t)ld * 2, (uint64_t)ld * 2 * n};
-  uint32_t box[4] = {64, 1, 128, 1};
+  uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
   uint32_t es[4] = {1, 1, 1, 1};
   return make_tensor_map(m, base, 2, 4, dims, strides, box, es, 1);
 }
@@ -424,6 +434,8 @@ extern "C" int ddpo_attention_bwd(const ddpo_attention_bwd_args* a, void* stream
   if ((rc = make_map(&p.tmK, a->k, a->heads, a->nk, a->batch, a->ldk))) return rc;
   if ((rc = make_map(&p.tmV, a->v, a->heads, a->nk, a->batch, a->ldv))) return rc;
   if ((rc = make_map(&p.tmDO, a->dout, a->heads, a->nq, a->batch, a->lddo))) return rc;
+  if ((rc = make_map(&p.tmK64, a->k, a->heads, a->nk, a->batch, a->ldk, DQ_BKV))) return rc;
+  if ((rc = make_map(&p.tmV64, a->v, a->heads, a->nk, a->batch, a->ldv, DQ_BKV))) return rc;
   p.lse = a->lse, p.delta = a->delta;
   p.dq = static_cast<__nv_bfloat16*>(a->dq), p.dk = static_cast<__nv_bfloat16*>(a->dk);
   p.dv = static_cast<__nv_bfloat16*>(a->dv);
@@ -445,7 +457,7 @@ extern "C" int ddpo_attention_bwd(const ddpo_attention_bwd_args* a, void* stream
   attention_bwd_dkdv_kernel<<<g1, AB_THREADS, KV_SMEM_TOTAL, stream>>>(p);
   DDPO_LAUNCH_OK();
   dim3 g2((a->nq + 127) / 128, a->heads, a->batch);
-  attention_bwd_dq_kernel<<<g2, AB_THREADS, DQ_SMEM_TOTAL, stream>>>(p);
+  attention_bwd_dq_kernel<<<g2, DQ_THREADS, DQ_SMEM_TOTAL, stream>>>(p);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }
