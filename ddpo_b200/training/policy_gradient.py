@@ -25,6 +25,7 @@ from typing import Any, Dict, Optional
 import torch
 
 from .. import ops
+from . import distributed
 from ..unet import UNet
 
 ADV_CLIP_MAX = 10.0  # applied inside the CUDA PPO kernel (reference :60,121)
@@ -75,16 +76,12 @@ class AccumulatingTrainState:
         self.n_acc += int(n_micro)
         if not do_update:
             return self
-        world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            world = torch.distributed.get_world_size()
-            if world > 1:
-                torch.distributed.all_reduce(self.grad_acc)  # sum over ranks (NCCL over NVLink)
+        world = distributed.allreduce_sum_(self.grad_acc)  # ONE sum over ranks (NCCL over NVLink) per update
         ops.grad_sumsq(self.grad_acc, self._ws, self._sumsq)
         self.opt_state["count"] += 1
         c = self.tx
         ops.clip_adamw(self.params, self.grad_acc, self.opt_state["mu"], self.opt_state["nu"], self._sumsq,
-                       1.0 / (self.n_acc * world), c.max_grad_norm, c.learning_rate, c.b1, c.b2, c.eps, c.weight_decay,
+                       distributed.grad_scale(self.n_acc, world), c.max_grad_norm, c.learning_rate, c.b1, c.b2, c.eps, c.weight_decay,
                        self.opt_state["count"], norm_out=self.last_grad_norm)
         self.apply_fn.refresh_weights()
         self.step += 1
@@ -202,9 +199,7 @@ def train_step(state: AccumulatingTrainState, batch, noise_scheduler_state, nois
             G.graph, G.sig = g, sig
         G.graph.replay()
     info_t = G.info.clone()
-    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-        torch.distributed.all_reduce(info_t)                      # lax.pmean(info) (:142)
-        info_t /= torch.distributed.get_world_size()
+    distributed.pmean_(info_t)                                    # lax.pmean(info) (:142)
     state.apply_gradients(grads=None, do_update=do_opt_update, n_micro=b // mb)
     info = {"approx_kl": info_t[0], "clipfrac": info_t[1], "loss": info_t[2]}
     return state, info

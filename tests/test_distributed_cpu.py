@@ -1,0 +1,99 @@
+"""N>1 host logic on CPU: two gloo processes on 127.0.0.1 run the data-parallel plumbing
+(`ddpo_b200/training/distributed.py`) that wraps the one gradient all-reduce of the PPO update.
+
+Checked against the oracle's AccumulatingTrainState (reference pipeline/policy_gradient.py:13-57, :137-142):
+two ranks x two accumulated micro-gradients each, reduced with `allreduce_sum_` and scaled by `grad_scale`,
+must give the same AdamW update on both ranks as ONE process that saw all four micro-gradients.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ddpo_b200.training import distributed as D
+from oracle import optim as O
+
+N_PARAMS = 4099
+N_ACC = 2
+WORLD = 2
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _micro_grads():
+    rng = np.random.default_rng(7)
+    return rng.standard_normal((WORLD, N_ACC, N_PARAMS)).astype(np.float32) * 0.02
+
+
+def _worker(rank, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        assert D.is_distributed() and D.world_size() == WORLD and D.rank() == rank
+        g = _micro_grads()
+        # fused accumulation: the backward pass adds every micro-gradient into grad_acc
+        grad_acc = torch.zeros(N_PARAMS)
+        for i in range(N_ACC):
+            grad_acc += torch.from_numpy(g[rank, i])
+        world = D.allreduce_sum_(grad_acc)
+        scale = D.grad_scale(N_ACC, world)
+        mean_grad = (grad_acc * scale).numpy()
+        # PPO info: lax.pmean over ranks
+        info = torch.tensor([0.1 * (rank + 1), 0.5 * rank, -1.0 + rank], dtype=torch.float32)
+        D.pmean_(info)
+        lo, hi = D.shard_bounds(16)
+        t = D.max_over_ranks(10.0 + rank)
+        # optimizer update every rank applies to its replica
+        params = np.linspace(-1, 1, N_PARAMS, dtype=np.float32)
+        st = O.AdamWState(N_PARAMS)
+        new_p, gn = O.clip_adamw_update(params, mean_grad, st, max_norm=1.0)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), mean_grad=mean_grad, info=info.numpy(), lo=lo, hi=hi, t=t,
+                 new_p=new_p, gn=gn, world=world)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_gradient_reduction_matches_single_process(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    r = [np.load(tmp_path / f"rank{i}.npz") for i in range(WORLD)]
+    g = _micro_grads()
+    # single process that accumulated all WORLD * N_ACC micro-gradients (reference :33-41)
+    ref = O.AccumulatingTrainState(np.linspace(-1, 1, N_PARAMS, dtype=np.float32), max_norm=1.0)
+    flat = g.reshape(-1, N_PARAMS)
+    for i, gi in enumerate(flat):
+        ref.apply_gradients(gi, do_update=(i == len(flat) - 1))
+    for i in range(WORLD):
+        assert int(r[i]["world"]) == WORLD
+        np.testing.assert_allclose(r[i]["mean_grad"], flat.mean(0), rtol=0, atol=2e-8)
+        np.testing.assert_allclose(r[i]["new_p"], ref.params, rtol=0, atol=2e-7)
+        np.testing.assert_allclose(r[i]["info"], [0.15, 0.25, -0.5], rtol=0, atol=1e-7)
+        assert (int(r[i]["lo"]), int(r[i]["hi"])) == (8 * i, 8 * i + 8)
+        assert float(r[i]["t"]) == 11.0
+    # replicas stay bit-identical: same reduced gradient -> same update on every rank
+    assert np.array_equal(r[0]["mean_grad"], r[1]["mean_grad"])
+    assert np.array_equal(r[0]["new_p"], r[1]["new_p"])
+
+
+def test_single_process_helpers_are_identity():
+    assert not D.is_distributed() and D.world_size() == 1 and D.rank() == 0
+    t = torch.arange(5, dtype=torch.float32)
+    assert D.allreduce_sum_(t) == 1 and torch.equal(t, torch.arange(5, dtype=torch.float32))
+    assert torch.equal(D.pmean_(t.clone()), t)
+    assert D.shard_bounds(8) == (0, 8)
+    assert D.shard_bounds(8, 1, 4) == (2, 4)
+    assert D.max_over_ranks(3.5) == 3.5
+    assert D.grad_scale(4, 2) == 0.125
+    with pytest.raises(ValueError):
+        D.shard_bounds(7, 0, 2)
+    with pytest.raises(ValueError):
+        D.grad_scale(0, 1)
