@@ -108,6 +108,23 @@ def cpu_step_seconds(n_steps, threads=None):
     return float(np.mean(times)), torch.get_num_threads()
 
 
+def _dump_shapes(prof, tags, path):
+    """Per-(kernel, shape) table of the eager CUDA-event profile: which GEMM shapes the time goes to."""
+    agg = {}
+    for (name, work, a, b), tag in zip(prof, tags):
+        d = agg.setdefault((name, tag), [0.0, 0.0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += work
+        d[2] += 1
+    tot = sum(v[0] for v in agg.values())
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        f.write(f"total {tot:.3f} ms\n")
+        for (name, tag), v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            tf = f"{v[1] / (v[0] * 1e-3) / 1e12:7.1f} TF/s" if v[1] > 0 else ""
+            f.write(f"{v[0]:8.3f} ms {100 * v[0] / tot:5.1f}%  n={v[2]:3d}  {v[0] / v[2] * 1e3:8.1f} us/launch  {name:16s} {tag}  {tf}\n")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -135,6 +152,7 @@ def main():
     ap.add_argument("--phase", default="auto", choices=["auto", "sample", "ppo"])
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--shapes", action="store_true", help="also write per-shape kernel tables to gpurun_out/shapes_*.txt")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -233,11 +251,13 @@ def main():
     steps_per_s = world * B * args.steps / (ms / 1e3)  # denoising steps of one sample, whole job
 
     # ---------------- kernel profile (eager, CUDA events per launch) ----------------
-    ops.PROFILE = []
+    ops.PROFILE, ops.PROFILE_TAGS = [], []
     one_step()
     torch.cuda.synchronize()
     prof = ops.PROFILE
     ops.PROFILE = None
+    if args.shapes and rank == 0:
+        _dump_shapes(prof, ops.PROFILE_TAGS, "gpurun_out/shapes_sample.txt")
     agg = {}
     for name, work, a, b in prof:
         d = agg.setdefault(name, [0.0, 0.0, 0])
@@ -346,11 +366,13 @@ def main():
         ms_train_e2e = (time.perf_counter() - te0) / 3 * 1e3
         # profile one eager train step
         pg.USE_CUDA_GRAPH = False
-        ops.PROFILE = []
+        ops.PROFILE, ops.PROFILE_TAGS = [], []
         pg.train_step(tstate, batches[1], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
         torch.cuda.synchronize()
         tprof = ops.PROFILE
         ops.PROFILE = None
+        if args.shapes and rank == 0:
+            _dump_shapes(tprof, ops.PROFILE_TAGS, "gpurun_out/shapes_train.txt")
         pg.USE_CUDA_GRAPH = True
         tagg = {}
         for name, work, a, b in tprof:

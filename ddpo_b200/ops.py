@@ -18,13 +18,17 @@ PROFILE = None             # list of (name, work, event0, event1) while profilin
 _KERNELS_PER_CALL = {"groupnorm_fwd": 2, "groupnorm_bwd": 3, "layernorm_bwd": 2}
 
 
-def _run(name, status, work=0.0, ev=None):
+PROFILE_TAGS = []          # parallel to PROFILE: a shape tag per entry (bench.py --shapes)
+
+
+def _run(name, status, work=0.0, ev=None, tag=""):
     global LAUNCH_COUNT
     LAUNCH_COUNT += _KERNELS_PER_CALL.get(name, 1)
     if ev is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         PROFILE.append((name, work, ev, e1))
+        PROFILE_TAGS.append(tag)
     check(status, name)
 
 
@@ -153,7 +157,10 @@ def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None,
     a.pair_override = int(pair)
     rows = a.batch * a.h * a.w if a.is_conv else a.m
     _e = _ev()
-    _run("igemm", lib().ddpo_igemm(C.byref(a), _stream()), 2.0 * rows * a.n * a.taps * (a.c0 + a.c1), _e)
+    _run("igemm", lib().ddpo_igemm(C.byref(a), _stream()), 2.0 * rows * a.n * a.taps * (a.c0 + a.c1), _e,
+         f"M{rows} N{a.n} K{a.taps * (a.c0 + a.c1)} taps{a.taps} s{a.conv_stride}"
+         f"{' geglu' if geglu else ''}{' res' if residual is not None else ''}{' f32' if out_f32 is not None else ''}"
+         f"{' bf16' if out_bf16 is not None else ''}{' acc' if accumulate else ''}" if _e is not None else "")
 
 
 # ------------------------------------------------------------------ norms -------
@@ -253,7 +260,8 @@ def dense_small(x, w, bias, y, batch, k, n, silu_in=False, silu_out=False):
 def attention_fwd(q, k, v, out, batch, heads, nq, nk, ldq, ldk, ldv, ldo, lse=None):
     a = AttentionArgs(_p(q), _p(k), _p(v), _p(out), _p(lse), batch, heads, nq, nk, 64, ldq, ldk, ldv, ldo)
     _e = _ev()
-    _run("attention_fwd", lib().ddpo_attention_fwd(C.byref(a), _stream()), 4.0 * batch * heads * nq * nk * 64, _e)
+    _run("attention_fwd", lib().ddpo_attention_fwd(C.byref(a), _stream()), 4.0 * batch * heads * nq * nk * 64, _e,
+         f"B{batch} H{heads} nq{nq} nk{nk}")
 
 
 # ------------------------------------------------------------------ wgrad -------
@@ -284,7 +292,8 @@ def wgrad(*, dy, n, x0, dw, x1=None, c0=None, c1=0, ldy=0, ldx0=0, ldx1=0, conv=
     a.workspace_floats = ws.numel() if (need > 0) else 0
     rows = a.batch * a.h * a.w if a.is_conv else a.m
     _e = _ev()
-    _run("wgrad", lib().ddpo_wgrad(C.byref(a), _stream()), 2.0 * rows * a.n * a.taps * (a.c0 + a.c1), _e)
+    _run("wgrad", lib().ddpo_wgrad(C.byref(a), _stream()), 2.0 * rows * a.n * a.taps * (a.c0 + a.c1), _e,
+         f"M{rows} N{a.n} K{a.taps * (a.c0 + a.c1)} taps{a.taps} s{a.conv_stride}")
 
 
 # ------------------------------------------------------- backward wrappers -------
@@ -294,7 +303,8 @@ def attention_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, batch, heads, nq, 
     a = AttentionBwdArgs(_p(q), _p(k), _p(v), _p(out), _p(dout), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), batch,
                          heads, nq, nk, 64, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, None)
     _e = _ev()
-    _run("attention_bwd", lib().ddpo_attention_bwd(C.byref(a), _stream()), 14.0 * batch * heads * nq * nk * 64, _e)
+    _run("attention_bwd", lib().ddpo_attention_bwd(C.byref(a), _stream()), 14.0 * batch * heads * nq * nk * 64, _e,
+         f"B{batch} H{heads} nq{nq} nk{nk}")
 
 
 _CIW_WS = {}
