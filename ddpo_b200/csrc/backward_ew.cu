@@ -103,66 +103,90 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const fl
   }
 }
 
-// ---------------------------------------------------------------- conv_out ----
-// forward: y[b,n,q] = bias[n] + sum_{tap,c} x[b, q+off(tap), c] w[tap,c,n]   (x NHWC fp32, y NCHW)
-// dx[b,p,c] = sum_{tap,n} dy[b,n,p-off(tap)] w[tap,c,n]
-__global__ void conv_out_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
-                                      int B, int H, int W, int C) {
-  const int64_t total = static_cast<int64_t>(B) * H * W * C;
+// ------------------------------------------------- conv_in / conv_out backward ----
+// Both stem convolutions pair a 4-channel NCHW tensor `s` (latents / d_eps) with a C-channel NHWC tensor `g`
+// (d conv_in output / conv_out input).  One kernel serves both: thread = channel c of `g`, a CTA walks a contiguous
+// pixel range in chunks of STEM_PC pixels whose 9x4 `s` patches are staged in shared memory (zero outside the image):
+//   patch[k = tap*4 + n] = s[b, n, y + sign*oy(tap), x + sign*ox(tap)]
+//   wgrad:  acc[k] += g[p, c] * patch[k]          -> part[split][...]   (fixed order, reduced in split order)
+//   dgrad:  dx[p, c] = sum_k patch[k] * w[k][c]   (conv_out only; w = [tap][C][4] held in 36 registers)
+// conv_out (forward y[b,n,q] = bias[n] + sum_{tap,c} x[b,q+off,c] w[tap,c,n]): sign = -1, part index (tap*C + c)*4 + n.
+// conv_in  (dw[tap,ci,co] += sum_p lat[b,ci,p+off] dx[p,co]):                 sign = +1, part index (tap*4 + ci)*C + co.
+// `g` is read exactly once (coalesced); the old per-tap kernels re-read it 9-36 times.
+constexpr int STEM_SPLITS = 256;
+constexpr int STEM_PC = 32;
+constexpr int COW_SPLITS = STEM_SPLITS, CIW_SPLITS = STEM_SPLITS;
+template <bool CONV_OUT>
+__global__ void __launch_bounds__(512) stem_bwd_kernel(const float* __restrict__ s, const float* __restrict__ g,
+                                                        const float* __restrict__ w, float* __restrict__ dx,
+                                                        float* __restrict__ part, int B, int H, int W, int C) {
+  __shared__ __align__(16) float patch[STEM_PC][36];
+  const int c = threadIdx.x;
+  const bool c_ok = c < C;
   const int HW = H * W;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c = i % C;
-    const int64_t pix = i / C;
-    const int b = pix / HW, hw = pix % HW, h = hw / W, x = hw % W;
-    float acc = 0.f;
+  const int64_t P = static_cast<int64_t>(B) * HW;
+  int64_t per = (P + STEM_SPLITS - 1) / STEM_SPLITS;
+  per = (per + STEM_PC - 1) / STEM_PC * STEM_PC;
+  const int64_t p0 = blockIdx.x * per, p1 = min(P, p0 + per);
+  constexpr int sign = CONV_OUT ? -1 : 1;
+  float acc[36], wr[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.f, wr[k] = 0.f;
+  if (CONV_OUT && c_ok) {
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-      const int yy = h - (tap / 3 - 1), xx = x - (tap % 3 - 1);
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
       const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (static_cast<size_t>(tap) * C + c) * 4));
-      const float* d = dy + static_cast<size_t>(b) * 4 * HW + yy * W + xx;
-      acc += d[0] * wv.x + d[HW] * wv.y + d[2 * HW] * wv.z + d[3 * HW] * wv.w;
+      wr[tap * 4] = wv.x, wr[tap * 4 + 1] = wv.y, wr[tap * 4 + 2] = wv.z, wr[tap * 4 + 3] = wv.w;
     }
-    dx[i] = acc;
+  }
+  for (int64_t pc = p0; pc < p1; pc += STEM_PC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < STEM_PC * 36; i += blockDim.x) {
+      const int j = i / 36, k = i % 36, tap = k >> 2, n = k & 3;
+      const int64_t p = pc + j;
+      float v = 0.f;
+      if (p < p1) {
+        const int b = p / HW, hw = p % HW, y = hw / W + sign * (tap / 3 - 1), x = hw % W + sign * (tap % 3 - 1);
+        if (y >= 0 && y < H && x >= 0 && x < W) v = s[((static_cast<size_t>(b) * 4 + n) * H + y) * W + x];
+      }
+      patch[j][k] = v;
+    }
+    __syncthreads();
+    if (!c_ok) continue;
+    const int np = static_cast<int>(min(static_cast<int64_t>(STEM_PC), p1 - pc));
+#pragma unroll 1
+    for (int j0 = 0; j0 < np; j0 += 8) {
+      float gv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = (j0 + j < np) ? g[(pc + j0 + j) * C + c] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4* pt = reinterpret_cast<const float4*>(patch[j0 + j]);
+        float d = 0.f;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          const float4 pv = pt[q];
+          acc[4 * q] += gv[j] * pv.x, acc[4 * q + 1] += gv[j] * pv.y, acc[4 * q + 2] += gv[j] * pv.z,
+              acc[4 * q + 3] += gv[j] * pv.w;
+          if (CONV_OUT) d += pv.x * wr[4 * q] + pv.y * wr[4 * q + 1] + pv.z * wr[4 * q + 2] + pv.w * wr[4 * q + 3];
+        }
+        if (CONV_OUT && j0 + j < np) dx[(pc + j0 + j) * C + c] = d;
+      }
+    }
+  }
+  if (!c_ok) return;
+  float* o = part + static_cast<size_t>(blockIdx.x) * 36 * C;
+#pragma unroll
+  for (int k = 0; k < 36; ++k) {
+    if (CONV_OUT) o[(static_cast<size_t>(k >> 2) * C + c) * 4 + (k & 3)] = acc[k];
+    else o[static_cast<size_t>(k) * C + c] = acc[k];
   }
 }
-// dw[tap,c,n] = sum_p x[p+off, c] dy[n, p] ; grid (9, C/32, COW_SPLITS), block 256 = 32 channels x 8 pixel lanes;
-// partial sums per pixel split -> part[split][tap][C][4], reduced in split order by conv_out_wgrad_reduce_kernel
-constexpr int COW_SPLITS = 32;
-__global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                             float* __restrict__ part, int B, int H, int W, int C) {
-  const int tap = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), pl = threadIdx.x >> 5;
-  const int HW = H * W;
-  const int oy = tap / 3 - 1, ox = tap % 3 - 1;
-  const int64_t P = static_cast<int64_t>(B) * HW;
-  const int64_t per = (P + COW_SPLITS - 1) / COW_SPLITS;
-  const int64_t p0 = blockIdx.z * per, p1 = min(P, p0 + per);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int64_t p = p0 + pl; p < p1; p += 8) {
-    const int b = p / HW, hw = p % HW, h = hw / W, xx0 = hw % W;
-    const int yy = h + oy, xx = xx0 + ox;
-    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-    const float v = x[((static_cast<size_t>(b) * H + yy) * W + xx) * C + c];
-    const float* d = dy + static_cast<size_t>(b) * 4 * HW + hw;
-    a0 += v * d[0], a1 += v * d[HW], a2 += v * d[2 * HW], a3 += v * d[3 * HW];
-  }
-  __shared__ float sm[8][32][4];
-  sm[pl][threadIdx.x & 31][0] = a0, sm[pl][threadIdx.x & 31][1] = a1, sm[pl][threadIdx.x & 31][2] = a2,
-  sm[pl][threadIdx.x & 31][3] = a3;
-  __syncthreads();
-  if (threadIdx.x < 128) {
-    const int cl = threadIdx.x >> 2, n = threadIdx.x & 3;
-    float s = 0.f;
-    for (int q = 0; q < 8; ++q) s += sm[q][cl][n];
-    part[((static_cast<size_t>(blockIdx.z) * 9 + tap) * C + blockIdx.y * 32 + cl) * 4 + n] = s;
-  }
-}
-__global__ void conv_out_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int total) {
+__global__ void stem_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   float s = 0.f;
-  for (int q = 0; q < COW_SPLITS; ++q) s += part[static_cast<size_t>(q) * total + i];
+  for (int q = 0; q < STEM_SPLITS; ++q) s += part[static_cast<size_t>(q) * total + i];
   dw[i] += s;
 }
 // dbias[n] += sum_{b,p} dy[b,n,p] ; one CTA per output channel, fixed-order block reduction
@@ -183,38 +207,6 @@ __global__ void __launch_bounds__(256) conv_out_dbias_kernel(const float* __rest
     for (int i = 0; i < 8; ++i) s += sm[i];
     dbias[n] += s;
   }
-}
-
-// ----------------------------------------------------------------- conv_in ----
-// dw[tap,ci,co] += sum_p lat[b,ci,p+off] dx[p,co]; two stage: part[split][36][Cout]
-constexpr int CIW_SPLITS = 256;
-__global__ void conv_in_wgrad_kernel(const float* __restrict__ lat, const float* __restrict__ dx, float* __restrict__ part,
-                                     int B, int Cin, int H, int W, int Cout) {
-  const int k = blockIdx.x;  // tap*Cin + ci
-  const int split = blockIdx.y;
-  const int tap = k / Cin, ci = k % Cin;
-  const int oy = tap / 3 - 1, ox = tap % 3 - 1;
-  const int HW = H * W;
-  const int64_t P = static_cast<int64_t>(B) * HW;
-  const int64_t per = (P + CIW_SPLITS - 1) / CIW_SPLITS;
-  const int64_t p0 = split * per, p1 = min(P, p0 + per);
-  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-    float acc = 0.f;
-    for (int64_t p = p0; p < p1; ++p) {
-      const int b = p / HW, hw = p % HW, h = hw / W, x = hw % W;
-      const int yy = h + oy, xx = x + ox;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      acc += lat[((static_cast<size_t>(b) * Cin + ci) * H + yy) * W + xx] * dx[p * Cout + co];
-    }
-    part[(static_cast<size_t>(split) * gridDim.x + k) * Cout + co] = acc;
-  }
-}
-__global__ void conv_in_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int total) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  float s = 0.f;
-  for (int q = 0; q < CIW_SPLITS; ++q) s += part[static_cast<size_t>(q) * total + i];
-  dw[i] += s;
 }
 
 // ------------------------------------------------------------- dense (M = B) ----
@@ -392,15 +384,12 @@ extern "C" int ddpo_conv_out_bwd(const float* x_nhwc, const float* w_hwio, const
                                  float* dw, float* dbias, float* workspace, int batch, int h, int w, int cin,
                                  void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  DDPO_REQUIRE(x_nhwc && w_hwio && dy_nchw && dx_nhwc && dw && workspace && cin % 32 == 0, "conv_out_bwd: bad arguments");
-  conv_out_dgrad_kernel<<<grid_for(static_cast<int64_t>(batch) * h * w * cin, 256), 256, 0, stream>>>(
-      dy_nchw, w_hwio, dx_nhwc, batch, h, w, cin);
-  DDPO_LAUNCH_OK();
-  dim3 grid(9, cin / 32, COW_SPLITS);
-  conv_out_wgrad_kernel<<<grid, 256, 0, stream>>>(x_nhwc, dy_nchw, workspace, batch, h, w, cin);
+  DDPO_REQUIRE(x_nhwc && w_hwio && dy_nchw && dx_nhwc && dw && workspace && cin % 32 == 0 && cin <= 512,
+               "conv_out_bwd: bad arguments");
+  stem_bwd_kernel<true><<<STEM_SPLITS, cin, 0, stream>>>(dy_nchw, x_nhwc, w_hwio, dx_nhwc, workspace, batch, h, w, cin);
   DDPO_LAUNCH_OK();
   const int total = 9 * cin * 4;
-  conv_out_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(workspace, dw, total);
+  stem_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(workspace, dw, total);
   DDPO_LAUNCH_OK();
   if (dbias != nullptr) {
     conv_out_dbias_kernel<<<4, 256, 0, stream>>>(dy_nchw, dbias, batch, h * w);
@@ -417,11 +406,12 @@ extern "C" int ddpo_conv_in_wgrad(const float* lat_nchw, const float* dx_nhwc, f
                                   int cin, int h, int w, int cout, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DDPO_REQUIRE(lat_nchw && dx_nhwc && dw && workspace, "conv_in_wgrad: null pointer");
-  dim3 grid(9 * cin, CIW_SPLITS);
-  conv_in_wgrad_kernel<<<grid, 320, 0, stream>>>(lat_nchw, dx_nhwc, workspace, batch, cin, h, w, cout);
+  DDPO_REQUIRE(cin == 4 && cout <= 512, "conv_in_wgrad: needs 4 latent channels and <= 512 output channels");
+  stem_bwd_kernel<false><<<STEM_SPLITS, (cout + 31) / 32 * 32, 0, stream>>>(lat_nchw, dx_nhwc, nullptr, nullptr, workspace,
+                                                                           batch, h, w, cout);
   DDPO_LAUNCH_OK();
   const int total = 9 * cin * cout;
-  conv_in_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(workspace, dw, total);
+  stem_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(workspace, dw, total);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }

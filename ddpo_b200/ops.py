@@ -308,7 +308,7 @@ def attention_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, batch, heads, nq, 
 
 
 _CIW_WS = {}
-_KERNELS_PER_CALL.update({"attention_bwd": 3, "colsum_cast": 2, "conv_out_bwd": 4, "conv_in_wgrad": 2,
+_KERNELS_PER_CALL.update({"attention_bwd": 3, "colsum_cast": 2, "conv_out_bwd": 3, "conv_in_wgrad": 2,
                           "dense_small_bwd": 3, "grad_sumsq": 2, "wgrad": 2, "colsum_bf16": 2})
 _COLSUM_WS = {}
 

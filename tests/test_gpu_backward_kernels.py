@@ -137,3 +137,43 @@ def test_attention_bwd(b, heads, nq, nk):
     assert rel(dq, qr.grad) < 2e-2, f"dq {rel(dq, qr.grad)}"
     assert rel(dkv[:, :, :c], kvr.grad[:, :, :c]) < 2e-2, f"dk {rel(dkv[:, :, :c], kvr.grad[:, :, :c])}"
     assert rel(dkv[:, :, c:], kvr.grad[:, :, c:]) < 2e-2, f"dv {rel(dkv[:, :, c:], kvr.grad[:, :, c:])}"
+
+
+# ---- stem convolutions (conv_in weight grad; conv_out dgrad + wgrad + dbias) vs torch autograd on the CPU ----
+@pytest.mark.parametrize("b,h,w,c", [(2, 16, 16, 64), (3, 8, 24, 320), (1, 5, 7, 96)])
+def test_conv_out_bwd(b, h, w, c):
+    from ddpo_b200 import ops
+    g = torch.Generator().manual_seed(b * 100 + c)
+    x = torch.randn(b, h, w, c, generator=g)                 # NHWC fp32 (conv_out input)
+    wt = torch.randn(3, 3, c, 4, generator=g) * 0.1          # HWIO
+    dy = torch.randn(b, 4, h, w, generator=g)                # NCHW
+    xr, wr = x.clone().requires_grad_(), wt.clone().requires_grad_()
+    bias = torch.zeros(4, requires_grad=True)
+    y = torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), bias, padding=1)
+    y.backward(dy)
+    dx = torch.empty(b, h, w, c, device=DEV)
+    dw = torch.ones(3, 3, c, 4, device=DEV)                  # kernels accumulate into the gradient buffers
+    db = torch.ones(4, device=DEV)
+    ops.conv_out_bwd(x.to(DEV), wt.to(DEV), dy.to(DEV), dx, dw, db, b, h, w, c)
+    torch.cuda.synchronize()
+    assert torch.allclose(dx.cpu(), xr.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(dw.cpu() - 1, wr.grad, rtol=1e-4, atol=2e-3)
+    assert torch.allclose(db.cpu() - 1, bias.grad, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("b,h,w,c", [(2, 16, 16, 64), (3, 8, 24, 320), (1, 5, 7, 96)])
+def test_conv_in_wgrad(b, h, w, c):
+    from ddpo_b200 import ops
+    g = torch.Generator().manual_seed(b * 10 + c)
+    lat = torch.randn(b, 4, h, w, generator=g)               # NCHW latents
+    dx = torch.randn(b, h, w, c, generator=g)                # NHWC gradient of the conv_in output
+    wr = torch.zeros(3, 3, 4, c, requires_grad=True)         # HWIO
+    y = torch.nn.functional.conv2d(lat, wr.permute(3, 2, 0, 1), None, padding=1)
+    y.backward(dx.permute(0, 3, 1, 2))
+    dw = torch.full((3, 3, 4, c), 2.0, device=DEV)
+    ops.conv_in_wgrad(lat.to(DEV), dx.to(DEV), dw, b, 4, h, w, c)
+    dw2 = torch.full((3, 3, 4, c), 2.0, device=DEV)
+    ops.conv_in_wgrad(lat.to(DEV), dx.to(DEV), dw2, b, 4, h, w, c)
+    torch.cuda.synchronize()
+    assert torch.allclose(dw.cpu() - 2, wr.grad, rtol=1e-4, atol=2e-3)
+    assert torch.equal(dw, dw2)                              # fixed reduction order -> bit-reproducible
