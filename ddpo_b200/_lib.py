@@ -23,7 +23,7 @@ class IGemmArgs(C.Structure):
                 ("is_conv", i32), ("batch", i32), ("h", i32), ("w", i32), ("conv_stride", i32), ("taps", i32),
                 ("m", i32), ("n", i32), ("wt", vp), ("bias", vp), ("rowvec", vp), ("rows_per_sample", i32),
                 ("rowvec_ld", i32), ("residual", vp), ("ld_res", i32), ("out_f32", vp), ("out_bf16", vp),
-                ("ld_out", i32), ("geglu", i32), ("accumulate_out", i32), ("bn_override", i32), ("aux_bf16", vp), ("mt_override", i32), ("pair_override", i32)]
+                ("ld_out", i32), ("geglu", i32), ("accumulate_out", i32), ("bn_override", i32), ("aux_bf16", vp), ("mt_override", i32), ("pair_override", i32), ("epi_override", i32)]
 
 
 class GroupNormArgs(C.Structure):

@@ -68,17 +68,32 @@ __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcpf_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float k = 0.7978845608028654f;  // sqrt(2/pi)
   float u = k * (x + 0.044715f * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(u));
+  // 0.5 (1 + tanh u) == 1 / (1 + e^{-2u}): two MUFU ops (ex2, rcp) instead of libm tanhf's ~25 instructions;
+  // relative error ~2e-7, exact limits at +-inf
+  const float e = exp2f_approx(-2.885390081777927f * u);  // e^{-2u}
+  return x * rcpf_approx(1.0f + e);
 }
 __device__ __forceinline__ float gelu_tanh_grad_f(float x) {
   const float k = 0.7978845608028654f;
   float u = k * (x + 0.044715f * x * x * x);
-  float t = tanhf(u);
+  const float e = exp2f_approx(fminf(-2.885390081777927f * u, 80.0f));  // e^{-2u}, clamped so that e * sg stays finite
+  const float sg = rcpf_approx(1.0f + e);  // (1 + tanh u) / 2
   float du = k * (1.0f + 3.0f * 0.044715f * x * x);
-  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+  // d/dx [x sg] with 1 - tanh^2 u = 4 e sg^2 (no cancellation near |tanh| = 1)
+  return sg + 2.0f * x * du * (e * sg) * sg;
 }
 
 // 2^x for x <= 0 two ways: the MUFU unit (16/clk/SM) and a Cody-Waite + degree-3 polynomial on the FMA/ALU pipes
@@ -156,6 +171,20 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+
+// TMA store (shared -> global, bulk async-group completion); rows/columns outside the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // all but the N most recent groups have finished READING smem
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------- tcgen05 ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {

@@ -27,11 +27,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
   const int HB = BN >> 1;  // weight rows staged by each CTA
   const int stages = p.stages;
   const int stage_bytes = A_TILE_BYTES + HB * BK * 2;
+  uint8_t* epi_base = smem;  // [EPI_BYTES] staging of the TMA epilogue (absent in register-epilogue mode)
+  if (p.epi_tma) smem += EPI_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full = empty_bar + stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* epi_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes + 256);  // [8 warps][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader
@@ -57,6 +60,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 16);
     }
+    if (p.epi_tma)
+      for (int i = 0; i < 16; ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -149,6 +154,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
     const int q = warp & 3;
     const int cgrp = (warp - 4) >> 2;
     int it = 0;
+    if (p.epi_tma) {
+      if (lane == 0) {
+        prefetch_tmap(&p.tmIn);
+        prefetch_tmap(&p.tmOutF);
+        prefetch_tmap(&p.tmOutB);
+      }
+      EpiWarp e{epi_base + (warp - 4) * EPI_WARP_BYTES, epi_bar + (warp - 4) * 2, 0u};
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int tm = tile / tiles_n, tn = tile % tiles_n;
+        const int m_slab = tm * 2 * BM + static_cast<int>(rank) * BM + q * 32, n0 = tn * BN;
+        const int buf = it & 1;
+        const bool slab_ok = m_slab < p.M_total;  // warp-uniform; a slab entirely below the matrix has nothing to do
+        if (slab_ok && p.epi_in && lane == 0) epi_request(p, e, e.g, n0 + cgrp * 32, m_slab);
+        mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
+        if (slab_ok) igemm_epilogue_tma(p, e, t_row, m_slab, lane, n0, BN, cgrp, 64);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tmem_empty[buf], 0);
+      }
+      if (lane == 0) bulk_wait_all();
+    } else
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int tm = tile / tiles_n, tn = tile % tiles_n;
       const int m0 = tm * 2 * BM + static_cast<int>(rank) * BM, n0 = tn * BN;
@@ -181,10 +209,11 @@ using namespace ddpo;
 // called by ddpo_igemm (igemm.cu) once the argument block is filled; tmB must have been encoded with box rows BN/2
 int ddpo_igemm2_launch(IGemmArgs& p, cudaStream_t stream) {
   const int stage_bytes = A_TILE_BYTES + (p.BN / 2) * BK * 2;
-  int stages = SMEM_BUDGET / stage_bytes;
+  const int epi = p.epi_tma ? EPI_BYTES + EPI_BAR_BYTES : 0;
+  int stages = (SMEM_BUDGET - epi) / stage_bytes;
   if (stages > 10) stages = 10;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 256 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 256 + 1024 + epi;
   static bool attr_set = false;
   if (!attr_set) {
     DDPO_CUDA_OK(cudaFuncSetAttribute(igemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

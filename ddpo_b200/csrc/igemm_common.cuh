@@ -29,7 +29,104 @@ struct IGemmArgs {
   int geglu;
   int accumulate_out;     // out_f32 += result (used by backward passes that sum two branches)
   __nv_bfloat16* aux_bf16;  // GEGLU only: pre-activation [M, N] (tile-interleaved, bias included) kept for backward
+  // TMA epilogue (CTA-pair kernel): residual / previous output fetched and results written as 32 x 32 boxes through
+  // per-warp shared-memory staging, so that every global access is a full 128-byte (fp32) / 64-byte (bf16) row
+  // segment issued by the TMA engine instead of 16-byte pieces of 32 different rows per LSU instruction.
+  int epi_tma;               // 0 = register epilogue (igemm_epilogue), 1 = igemm_epilogue_tma
+  int epi_in;                // epi_tma: an fp32 input tile (residual, or the old output when accumulate_out) is added
+  CUtensorMap tmIn, tmOutF, tmOutB;
 };
+
+constexpr int EPI_F32_TILE = 32 * 32 * 4;   // 4 KB, SWIZZLE_128B (rows of 128 B)
+constexpr int EPI_BF16_TILE = 32 * 32 * 2;  // 2 KB, SWIZZLE_64B  (rows of 64 B)
+constexpr int EPI_WARP_BYTES = 2 * EPI_F32_TILE + 2 * EPI_BF16_TILE;  // double-buffered per epilogue warp
+constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;                         // 96 KB
+constexpr int EPI_BAR_BYTES = 8 * 2 * 8;
+
+struct EpiWarp {
+  uint8_t* buf;   // this warp's EPI_WARP_BYTES
+  uint64_t* bar;  // [2] input-tile barriers
+  uint32_t g;     // chunks processed so far (selects buffer / barrier parity)
+};
+
+// lane 0: fetch the fp32 input tile (rows m.., columns n..) of chunk number g into its staging buffer
+__device__ __forceinline__ void epi_request(const IGemmArgs& p, const EpiWarp& e, uint32_t g, int n, int m) {
+  mbar_expect_tx(&e.bar[g & 1], EPI_F32_TILE);
+  tma_load_2d(e.buf + (g & 1) * EPI_F32_TILE, &p.tmIn, &e.bar[g & 1], n, m);
+}
+
+// One epilogue warp, one tile: 32 rows (TMEM lane quarter; global rows m_slab..m_slab+31) x the 32-column chunks
+// c0 = cgrp*32, += cstep.  The caller has already issued epi_request for the first chunk (before waiting for the
+// accumulator) when p.epi_in.  Arithmetic order is the register epilogue's: acc + bias + rowvec + input.
+__device__ __forceinline__ void igemm_epilogue_tma(const IGemmArgs& p, EpiWarp& e, uint32_t t_row, int m_slab, int lane,
+                                                   int n0, int BN, int cgrp, int cstep) {
+  const int row = m_slab + lane;
+  const float* rv = nullptr;
+  if (p.rowvec != nullptr && row < p.M_total) rv = p.rowvec + static_cast<size_t>(row / p.rows_per_sample) * p.rowvec_ld;
+  const uint32_t sw128 = static_cast<uint32_t>(lane & 7), sw64 = static_cast<uint32_t>((lane >> 1) & 3);
+  for (int c0 = cgrp * 32; c0 < BN; c0 += cstep) {
+    const uint32_t s = e.g & 1;
+    uint8_t* fb = e.buf + s * EPI_F32_TILE;
+    uint8_t* bb = e.buf + 2 * EPI_F32_TILE + s * EPI_BF16_TILE;
+    const int n = n0 + c0;
+    uint32_t v[32];
+    tmem_ld_32x32(t_row + c0, v);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+      }
+    }
+    if (rv != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + n + j));
+        f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+      }
+    }
+    if (p.epi_in) {
+      mbar_wait(&e.bar[s], (e.g >> 1) & 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = *reinterpret_cast<const float4*>(fb + lane * 128 + ((j ^ sw128) << 4));
+        f[4 * j] += b4.x, f[4 * j + 1] += b4.y, f[4 * j + 2] += b4.z, f[4 * j + 3] += b4.w;
+      }
+    }
+    if (p.out_f32 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(fb + lane * 128 + ((j ^ sw128) << 4)) =
+            make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    }
+    if (p.out_bf16 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16(f[8 * j], f[8 * j + 1]);
+        u.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+        u.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+        u.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+        *reinterpret_cast<uint4*>(bb + lane * 64 + ((j ^ sw64) << 4)) = u;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (p.out_f32 != nullptr) tma_store_2d(&p.tmOutF, fb, n, m_slab);
+      if (p.out_bf16 != nullptr) tma_store_2d(&p.tmOutB, bb, n, m_slab);
+      bulk_commit();
+      bulk_wait_read<1>();  // the stores of the previous chunk have left their buffers -> the other buffer pair is free
+      if (p.epi_in && c0 + cstep < BN) epi_request(p, e, e.g + 1, n + cstep, m_slab);
+    }
+    __syncwarp();
+    ++e.g;
+  }
+}
 
 
 // One epilogue warp: rows (row .. ) of TMEM lane quarter `q`, 32-column chunks c0 = cgrp*32, += cstep.

@@ -132,7 +132,7 @@ def ppo_loss(logp, old_logp, adv, clip_range, info_out, dlogp_out, micro_batch=N
 # ------------------------------------------------------------------ GEMM --------
 def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None, m=None, taps=1, stride=1,
           bias=None, rowvec=None, rows_per_sample=0, rowvec_ld=0, residual=None, ld_res=0, out_f32=None,
-          out_bf16=None, ld_out=0, geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0):
+          out_bf16=None, ld_out=0, geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0):
     """conv=(batch, h_out, w_out) for convolutions, else linear with m rows."""
     a = IGemmArgs()
     a.a0, a.a1 = _p(a0), _p(a1)
@@ -155,6 +155,7 @@ def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None,
     a.aux_bf16 = _p(aux_bf16)
     a.mt_override = int(mt)
     a.pair_override = int(pair)
+    a.epi_override = int(epi)
     rows = a.batch * a.h * a.w if a.is_conv else a.m
     _e = _ev()
     _run("igemm", lib().ddpo_igemm(C.byref(a), _stream()), 2.0 * rows * a.n * a.taps * (a.c0 + a.c1), _e,

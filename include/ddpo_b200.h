@@ -117,6 +117,7 @@ typedef struct {
   void* aux_bf16;           /* GEGLU only, optional: bf16 [M, n] pre-activation (tile-interleaved, bias included) */
   int mt_override;          /* 0 = auto; 1 / 2 = force 128- / 256-row CTA tiles */
   int pair_override;        /* 0 = auto; 1 = force the CTA-pair (cta_group::2) kernel; 2 = force the 1-CTA kernel */
+  int epi_override;         /* 0 = auto; 1 = force the TMA-staged epilogue (pair kernel); 2 = force the register epilogue */
 } ddpo_igemm_args;
 int ddpo_igemm(const ddpo_igemm_args* a, void* stream);
 

@@ -398,3 +398,45 @@ def test_igemm_cta_pair_is_bit_identical(b, h, c0, c1, n, taps, stride):
         r.append(o)
     torch.cuda.synchronize()
     assert torch.equal(r[0], r[1])
+
+
+@pytest.mark.parametrize("m,k,n", [(4096, 320, 320), (1000, 128, 640), (2048 + 37, 64, 96), (8192, 640, 1280)])
+@pytest.mark.parametrize("mode", ["res_f32", "bf16", "res_f32_bf16", "f32", "acc_f32", "rowvec_f32"])
+def test_igemm_tma_epilogue_is_bit_identical(m, k, n, mode):
+    """The TMA-staged epilogue of the CTA-pair kernel (32x32 boxes through swizzled shared memory, TMA loads of the
+    residual / old output, TMA stores of fp32 and bf16 results) must reproduce the register epilogue bit for bit,
+    including ragged M (boxes clipped by the tensor map) and outputs narrower than their row pitch."""
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(11)
+    a = bf(torch.randn(m, k, generator=g)).to(DEV)
+    w = (torch.randn(k, n, generator=g) / math.sqrt(k)).to(DEV)
+    wt = _prep_w(w)
+    bias = torch.randn(n, generator=g).to(DEV)
+    res = torch.randn(m, n, generator=g).to(DEV) if "res" in mode else None
+    rows_per = 64
+    tv = torch.randn((m + rows_per - 1) // rows_per, n, generator=g).to(DEV) if "rowvec" in mode else None
+    init = torch.randn(m, n + 32, generator=g).to(DEV)    # row pitch wider than N: columns n.. must stay untouched
+    outs = []
+    for epi in (2, 1):
+        o = init.clone() if ("f32" in mode) else None
+        ob = torch.full((m, n + 32), 7.0, dtype=torch.bfloat16, device=DEV) if "bf16" in mode else None
+        ops.igemm(a0=a, wt=wt, n=n, c0=k, m=m, bias=bias, residual=res, ld_res=n if res is not None else 0,
+                  rowvec=tv, rows_per_sample=rows_per if tv is not None else 0, rowvec_ld=n if tv is not None else 0,
+                  out_f32=o, out_bf16=ob, ld_out=n + 32, accumulate=(mode == "acc_f32"), pair=1, epi=epi)
+        outs.append((o, ob))
+    torch.cuda.synchronize()
+    for x, y in zip(outs[0], outs[1]):
+        if x is not None:
+            assert torch.equal(x, y)
+    if outs[1][0] is not None:
+        assert torch.equal(outs[1][0][:, n:], init[:, n:])
+        ref = a.float() @ bf(w).float() + bias
+        if res is not None:
+            ref = ref + res
+        if tv is not None:
+            ref = ref + tv.repeat_interleave(rows_per, 0)[:m]
+        if mode == "acc_f32":
+            ref = ref + init[:, :n]
+        assert (outs[1][0][:, :n] - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    if outs[1][1] is not None:
+        assert (outs[1][1][:, n:].float() == 7.0).all()
