@@ -284,11 +284,14 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
-// arrive on the mbarrier at the same offset in CTA `cta` of the cluster
+// arrive on the mbarrier at the same offset in CTA `cta` of the cluster.  RELAXED: the only data the waiter depends on
+// are TMEM reads, ordered by tcgen05.fence::before_thread_sync; a .release.cluster arrive compiles to
+// MEMBAR.ALL.GPU + ERRBAR and stalls the epilogue warp until all of its global stores are acknowledged
+// (16 % of the stall samples of the GEGLU linear, profiles/r1_linear_epilogue.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
 }

@@ -61,7 +61,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
       mbar_init(&tmem_empty[i], 16);
     }
     if (p.epi_tma)
-      for (int i = 0; i < 16; ++i) mbar_init(&epi_bar[i], 1);
+      for (int i = 0; i < 8 * EPI_RING; ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -160,13 +160,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
         prefetch_tmap(&p.tmOutF);
         prefetch_tmap(&p.tmOutB);
       }
-      EpiWarp e{epi_base + (warp - 4) * EPI_WARP_BYTES, epi_bar + (warp - 4) * 2, 0u};
+      EpiWarp e{epi_base + (warp - 4) * EPI_WARP_BYTES, epi_bar + (warp - 4) * EPI_RING, 0u, 0u};
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
         const int tm = tile / tiles_n, tn = tile % tiles_n;
         const int m_slab = tm * 2 * BM + static_cast<int>(rank) * BM + q * 32, n0 = tn * BN;
         const int buf = it & 1;
         const bool slab_ok = m_slab < p.M_total;  // warp-uniform; a slab entirely below the matrix has nothing to do
-        if (slab_ok && p.epi_in && lane == 0) epi_request(p, e, e.g, n0 + cgrp * 32, m_slab);
+        if (slab_ok && p.epi_in && lane == 0)
+          epi_request(p, e, e.g, (BN - cgrp * 32 + 63) / 64, e.g, n0 + cgrp * 32, 64, m_slab);
         mbar_wait(&tmem_full[buf], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;

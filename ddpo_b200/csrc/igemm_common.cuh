@@ -39,24 +39,33 @@ struct IGemmArgs {
 
 constexpr int EPI_F32_TILE = 32 * 32 * 4;   // 4 KB, SWIZZLE_128B (rows of 128 B)
 constexpr int EPI_BF16_TILE = 32 * 32 * 2;  // 2 KB, SWIZZLE_64B  (rows of 64 B)
-constexpr int EPI_WARP_BYTES = 2 * EPI_F32_TILE + 2 * EPI_BF16_TILE;  // double-buffered per epilogue warp
-constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;                         // 96 KB
-constexpr int EPI_BAR_BYTES = 8 * 2 * 8;
+constexpr int EPI_RING = 3;                 // fp32 tiles per warp: input fetched up to two chunks ahead, in-place output
+constexpr int EPI_WARP_BYTES = EPI_RING * EPI_F32_TILE + 2 * EPI_BF16_TILE;
+constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;  // 128 KB
+constexpr int EPI_BAR_BYTES = 256;             // 8 warps x EPI_RING barriers
 
 struct EpiWarp {
   uint8_t* buf;   // this warp's EPI_WARP_BYTES
-  uint64_t* bar;  // [2] input-tile barriers
-  uint32_t g;     // chunks processed so far (selects buffer / barrier parity)
+  uint64_t* bar;  // [EPI_RING] input-tile barriers
+  uint32_t g;     // chunks processed so far (chunk g uses fp32 buffer g % EPI_RING, bf16 buffer g & 1)
+  uint32_t req;   // input tiles requested so far
 };
 
-// lane 0: fetch the fp32 input tile (rows m.., columns n..) of chunk number g into its staging buffer
-__device__ __forceinline__ void epi_request(const IGemmArgs& p, const EpiWarp& e, uint32_t g, int n, int m) {
-  mbar_expect_tx(&e.bar[g & 1], EPI_F32_TILE);
-  tma_load_2d(e.buf + (g & 1) * EPI_F32_TILE, &p.tmIn, &e.bar[g & 1], n, m);
+// lane 0: fetch the fp32 input tiles of this tile's chunks [req - g0, nch) as far as the ring allows: chunk r may be
+// requested once the store of chunk r - EPI_RING has left its buffer, i.e. (bulk_wait_read<1> after every commit)
+// once chunk r - EPI_RING + 1 has been committed: r <= done + EPI_RING - 2 where done = chunks committed so far.
+__device__ __forceinline__ void epi_request(const IGemmArgs& p, EpiWarp& e, uint32_t g0, int nch, uint32_t done, int n_first,
+                                            int cstep, int m) {
+  while (e.req < g0 + nch && e.req + 2 <= done + EPI_RING) {
+    const uint32_t b = e.req % EPI_RING;
+    mbar_expect_tx(&e.bar[b], EPI_F32_TILE);
+    tma_load_2d(e.buf + b * EPI_F32_TILE, &p.tmIn, &e.bar[b], n_first + static_cast<int>(e.req - g0) * cstep, m);
+    ++e.req;
+  }
 }
 
 // One epilogue warp, one tile: 32 rows (TMEM lane quarter; global rows m_slab..m_slab+31) x the 32-column chunks
-// c0 = cgrp*32, += cstep.  The caller has already issued epi_request for the first chunk (before waiting for the
+// c0 = cgrp*32, += cstep.  The caller has already called epi_request for this tile (before waiting for the
 // accumulator) when p.epi_in.  Arithmetic order is the register epilogue's: acc + bias + rowvec + input.
 __device__ __forceinline__ void igemm_epilogue_tma(const IGemmArgs& p, EpiWarp& e, uint32_t t_row, int m_slab, int lane,
                                                    int n0, int BN, int cgrp, int cstep) {
@@ -64,10 +73,12 @@ __device__ __forceinline__ void igemm_epilogue_tma(const IGemmArgs& p, EpiWarp& 
   const float* rv = nullptr;
   if (p.rowvec != nullptr && row < p.M_total) rv = p.rowvec + static_cast<size_t>(row / p.rows_per_sample) * p.rowvec_ld;
   const uint32_t sw128 = static_cast<uint32_t>(lane & 7), sw64 = static_cast<uint32_t>((lane >> 1) & 3);
+  const uint32_t g0 = e.g;
+  const int nch = (BN - cgrp * 32 + cstep - 1) / cstep;
   for (int c0 = cgrp * 32; c0 < BN; c0 += cstep) {
-    const uint32_t s = e.g & 1;
-    uint8_t* fb = e.buf + s * EPI_F32_TILE;
-    uint8_t* bb = e.buf + 2 * EPI_F32_TILE + s * EPI_BF16_TILE;
+    const uint32_t b = e.g % EPI_RING;
+    uint8_t* fb = e.buf + b * EPI_F32_TILE;
+    uint8_t* bb = e.buf + EPI_RING * EPI_F32_TILE + (e.g & 1) * EPI_BF16_TILE;
     const int n = n0 + c0;
     uint32_t v[32];
     tmem_ld_32x32(t_row + c0, v);
@@ -90,7 +101,7 @@ __device__ __forceinline__ void igemm_epilogue_tma(const IGemmArgs& p, EpiWarp& 
       }
     }
     if (p.epi_in) {
-      mbar_wait(&e.bar[s], (e.g >> 1) & 1);
+      mbar_wait(&e.bar[b], (e.g / EPI_RING) & 1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b4 = *reinterpret_cast<const float4*>(fb + lane * 128 + ((j ^ sw128) << 4));
@@ -116,18 +127,18 @@ __device__ __forceinline__ void igemm_epilogue_tma(const IGemmArgs& p, EpiWarp& 
     }
     fence_proxy_async_smem();
     __syncwarp();
+    ++e.g;
     if (lane == 0) {
       if (p.out_f32 != nullptr) tma_store_2d(&p.tmOutF, fb, n, m_slab);
       if (p.out_bf16 != nullptr) tma_store_2d(&p.tmOutB, bb, n, m_slab);
       bulk_commit();
-      bulk_wait_read<1>();  // the stores of the previous chunk have left their buffers -> the other buffer pair is free
-      if (p.epi_in && c0 + cstep < BN) epi_request(p, e, e.g + 1, n + cstep, m_slab);
+      bulk_wait_read<1>();  // every store but the one just issued has left its buffers
+      if (p.epi_in) epi_request(p, e, g0, nch, e.g, n0 + cgrp * 32, cstep, m_slab);
     }
     __syncwarp();
-    ++e.g;
   }
+  e.req = e.g > e.req ? e.g : e.req;  // keeps lanes other than 0 (which never request) and the no-input mode consistent
 }
-
 
 // One epilogue warp: rows (row .. ) of TMEM lane quarter `q`, 32-column chunks c0 = cgrp*32, += cstep.
 // `t_row` = TMEM address of (lane quarter, accumulator buffer / sub-tile); row = global output row of this thread.
@@ -207,11 +218,17 @@ __device__ __forceinline__ void igemm_epilogue(const IGemmArgs& p, uint32_t t_ro
             const int n = n0 + c0;
             float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float lin = __uint_as_float(a[j]) + __ldg(p.bias + n + j);
-              float gate = __uint_as_float(g[j]) + __ldg(p.bias + n + half + j);
-              f[j] = lin * gelu_tanh_f(gate);
-              a[j] = __float_as_uint(lin), g[j] = __float_as_uint(gate);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bl = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+              const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n + half + j));
+              const float blv[4] = {bl.x, bl.y, bl.z, bl.w}, bgv[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float lin = __uint_as_float(a[j + q]) + blv[q];
+                float gate = __uint_as_float(g[j + q]) + bgv[q];
+                f[j + q] = lin * gelu_tanh_f(gate);
+                a[j + q] = __float_as_uint(lin), g[j + q] = __float_as_uint(gate);
+              }
             }
             if (p.aux_bf16 != nullptr) {
               __nv_bfloat16* ax = p.aux_bf16 + static_cast<size_t>(row) * p.N_total + n;
