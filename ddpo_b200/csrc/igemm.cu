@@ -186,12 +186,29 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
   }
 }
 
-static int pick_bn(int N, int geglu) {
-  // widest UMMA N (multiple of 32, <=256) that divides N exactly; GEGLU needs BN/2 % 32 == 0
+// UMMA N of the CTA tile (multiple of 32, <= 256, divides N; GEGLU needs BN/2 % 32 == 0).  Tile shape is a pure
+// scheduling choice (the K order of every output element is fixed), so it is picked by a small cost model:
+//   time ~ waves x (k-blocks x clks per k-block + fixed tile overhead)
+// with, per 64-deep k-block, the tensor pipe needing 2*BN clks (4096 MAC/clk/SM) and the shared-memory port
+// (128 B/clk, written once by TMA and read once by the MMA) needing 256 + BN clks in a CTA pair (128 A rows + BN/2
+// weight rows per CTA) or 256 + 2*BN clks for a single CTA.  Wide tiles win when there are many waves; narrower
+// tiles win when the widest tiling leaves most SMs idle in the last wave (e.g. 80 tiles on 74 CTA pairs).
+static int pick_bn(int N, int geglu, int M_total, int kiters, bool pair) {
   const int step = geglu ? 64 : 32;
-  for (int bn = 256; bn >= step; bn -= step)
-    if (N % bn == 0) return bn;
-  return 0;
+  const int workers = pair ? num_sms() / 2 : num_sms();
+  const int rows = pair ? 2 * BM : BM;
+  const long tiles_m = (M_total + rows - 1) / rows;
+  int best = 0;
+  long best_cost = 0;
+  for (int bn = 256; bn >= step; bn -= step) {
+    if (N % bn != 0) continue;
+    const long tiles = tiles_m * (N / bn);
+    const long waves = (tiles + workers - 1) / workers;
+    const long mma = 2L * bn, port = pair ? 256L + bn : 256L + 2L * bn;
+    const long cost = waves * ((mma > port ? mma : port) * kiters + 1000);
+    if (best == 0 || cost < best_cost) best = bn, best_cost = cost;
+  }
+  return best;
 }
 
 }  // namespace ddpo
@@ -208,7 +225,11 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
   DDPO_REQUIRE(a->taps == 1 || a->taps == 9, "ddpo_igemm: taps must be 1 or 9");
   DDPO_REQUIRE(a->n % 32 == 0, "ddpo_igemm: N=%d must be a multiple of 32", a->n);
   DDPO_REQUIRE(a->out_f32 != nullptr || a->out_bf16 != nullptr, "ddpo_igemm: no output");
-  int BN = a->bn_override > 0 ? a->bn_override : pick_bn(a->n, a->geglu);
+  const int m_rows = a->is_conv ? a->batch * a->w * a->h : a->m;
+  // CTA pairs (cta_group::2, 256 x BN tiles) whenever the problem has enough rows; see igemm2.cu
+  const bool use_pair = a->pair_override == 1 || (a->pair_override == 0 && a->mt_override == 0 && m_rows >= 1024);
+  int BN = a->bn_override > 0 ? a->bn_override
+                              : pick_bn(a->n, a->geglu, m_rows, a->taps * (cin0 + cin1) / BK, use_pair);
   DDPO_REQUIRE(BN > 0 && a->n % BN == 0 && BN % 32 == 0 && BN <= 256, "ddpo_igemm: no valid BN for N=%d", a->n);
   if (a->geglu) DDPO_REQUIRE(BN % 64 == 0 && a->out_bf16 != nullptr && a->bias != nullptr, "ddpo_igemm: bad GEGLU config");
 
@@ -251,8 +272,6 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
     p.tmA1 = p.tmA0;
     p.W = 1, p.H = 1, p.conv_stride = 1, p.pad = 0;
   }
-  // CTA pairs (cta_group::2, 256 x BN tiles) whenever the problem has enough rows; see igemm2.cu
-  const bool use_pair = a->pair_override == 1 || (a->pair_override == 0 && a->mt_override == 0 && M_total >= 1024);
   {
     uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)a->n};
     uint64_t strides[1] = {(uint64_t)ktot * 2};
