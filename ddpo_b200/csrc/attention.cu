@@ -137,13 +137,13 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
     float m_run = -INFINITY, l_run = 0.f;
     const float c = p.scale_log2e;
     uint8_t* sP = smem + AT_SMEM_P;
-    for (int j = 0; j < nkb; ++j) {
+    // pass 1 of a block: row max over the 128 scores in X[j & 1] (full blocks take the predicate-free path: the
+    // softmax warps are instruction bound)
+    auto row_max = [&](int j) {
       const int xb = j & 1;
       mbar_wait(&s_full[xb], (j >> 1) & 1);
       tc_fence_after();
-      const int kbase = j * AT_BKV;
-      const int valid = min(AT_BKV, p.nk - kbase);
-      // pass 1: row max (full blocks take the predicate-free path: the softmax warps are instruction bound)
+      const int valid = min(AT_BKV, p.nk - j * AT_BKV);
       const bool full = valid == AT_BKV;
       float m_blk = -INFINITY;
 #pragma unroll 1
@@ -160,6 +160,17 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
             if (c0 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
         }
       }
+      return m_blk;
+    };
+    // The row max of block j+1 is taken while the tensor core computes P_j V_j, so the wait for O_j is hidden
+    // (it was 14 % of the stall samples when O_j was awaited right after P_j was published).
+    float m_next = row_max(0);
+    for (int j = 0; j < nkb; ++j) {
+      const int xb = j & 1;
+      const int kbase = j * AT_BKV;
+      const int valid = min(AT_BKV, p.nk - kbase);
+      const bool full = valid == AT_BKV;
+      const float m_blk = m_next;
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = ex2_mufu((m_run - m_new) * c);
       const float mc = m_new * c;
@@ -206,6 +217,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (j + 1 < nkb) m_next = row_max(j + 1);
       // O_j
       mbar_wait(&o_full[xb], (j >> 1) & 1);
       tc_fence_after();

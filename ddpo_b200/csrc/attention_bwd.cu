@@ -139,7 +139,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
       const uint32_t k_addr = smem_u32(smem + KV_SMEM_K), v_addr = smem_u32(smem + KV_SMEM_V);
       const uint32_t p_addr = smem_u32(smem + KV_SMEM_P), ds_addr = smem_u32(smem + KV_SMEM_DS);
       mbar_wait(kv_full, 0);
-      for (int i = 0; i < nqb; ++i) {
+      // Software-pipelined issue order: S/dP of query block i+1 go to the tensor pipe BEFORE dV/dK of block i.  The
+      // softmax warps wait only for S/dP; queueing them behind the two gradient GEMMs of the previous block (the
+      // tensor pipe executes in order) left those warps idle for ~30 % of their time (profiles/r1_attention.md).
+      auto issue_sdp = [&](int i) {
         const int st = i & 1;
         const uint32_t q_addr = smem_u32(smem + KV_SMEM_RING + st * 2 * AB_T), do_addr = q_addr + AB_T;
         mbar_wait(&qdo_full[st], (i >> 1) & 1);
@@ -152,7 +155,13 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
         for (int k = 0; k < 4; ++k)
           umma_bf16(T_DP, umma_desc(do_addr + k * 32, 16, 1024), umma_desc(v_addr + k * 32, 16, 1024), id_s, k != 0);
         umma_commit(sdp_full);
+      };
+      issue_sdp(0);
+      for (int i = 0; i < nqb; ++i) {
+        const int st = i & 1;
+        const uint32_t q_addr = smem_u32(smem + KV_SMEM_RING + st * 2 * AB_T), do_addr = q_addr + AB_T;
         mbar_wait(pds_full, i & 1);
+        if (i + 1 < nqb) issue_sdp(i + 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // K = 128 query rows, 16 per instruction
@@ -300,11 +309,11 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
       const uint32_t q_addr = smem_u32(smem + DQ_SMEM_Q), do_addr = smem_u32(smem + DQ_SMEM_DO);
       const uint32_t ds_addr = smem_u32(smem + DQ_SMEM_DS);
       mbar_wait(q_full, 0);
-      int st = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nkb; ++j) {
+      // same issue order as the dK/dV kernel: S/dP of key block j+1 before dQ of block j
+      auto issue_sdp = [&](int j) {
+        const int st = j % DQ_STAGES;
         const uint32_t k_addr = smem_u32(smem + DQ_SMEM_RING + st * 2 * DQ_KVT), v_addr = k_addr + DQ_KVT;
-        mbar_wait(&kv_full[st], ph);
+        mbar_wait(&kv_full[st], (j / DQ_STAGES) & 1);
         mbar_wait(sdp_empty, (j & 1) ^ 1);
         tc_fence_after();
 #pragma unroll
@@ -314,7 +323,13 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
         for (int k = 0; k < 4; ++k)
           umma_bf16(T_DP, umma_desc(do_addr + k * 32, 16, 1024), umma_desc(v_addr + k * 32, 16, 1024), id_s, k != 0);
         umma_commit(sdp_full);
+      };
+      issue_sdp(0);
+      for (int j = 0; j < nkb; ++j) {
+        const int st = j % DQ_STAGES;
+        const uint32_t k_addr = smem_u32(smem + DQ_SMEM_RING + st * 2 * DQ_KVT);
         mbar_wait(ds_full, j & 1);
+        if (j + 1 < nkb) issue_sdp(j + 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < DQ_BKV / 16; ++k)  // A = dS [128 q x 64 keys] K-major; B = K_j rows of 16 keys (MN-major)
@@ -322,7 +337,6 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
                     (j | k) != 0);
         umma_commit(&kv_empty[st]);
         umma_commit(ds_empty);
-        if (++st == DQ_STAGES) st = 0, ph ^= 1;
       }
       umma_commit(acc_full);
     }
