@@ -41,7 +41,7 @@ class WgradArgs(C.Structure):
     _fields_ = [("dy", vp), ("ldy", i32), ("n", i32), ("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32),
                 ("ldx0", i32), ("ldx1", i32), ("is_conv", i32), ("batch", i32), ("h", i32), ("w", i32),
                 ("conv_stride", i32), ("taps", i32), ("m", i32), ("dw", vp), ("workspace", vp),
-                ("workspace_floats", i64)]
+                ("workspace_floats", i64), ("kernel_override", i32)]
 
 
 class AttentionBwdArgs(C.Structure):

@@ -229,17 +229,41 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
 
 using namespace ddpo;
 
+int ddpo_wgrad2_tiles(int taps, int cin, int n);  // wgrad2.cu
+int ddpo_wgrad2_launch(const CUtensorMap& tmX0, const CUtensorMap& tmX1, const CUtensorMap& tmDY, int c0, int c1, int n,
+                       int taps, int is_conv, int W, int H, int conv_stride, int splits, int pblocks, float* dst,
+                       cudaStream_t stream);
+
+static bool wgrad_use_pair(const ddpo_wgrad_args* a) { return a->kernel_override != 2; }
+
 static int wgrad_plan(const ddpo_wgrad_args* a, int* splits, int* pblocks) {
   const int m = a->is_conv ? a->batch * a->h * a->w : a->m;
   const int pb = (m + WG_BKP - 1) / WG_BKP;
   const int cin = a->c0 + a->c1;
-  const int mt = a->taps * ((a->c0 + 127) / 128 + (a->c1 + 127) / 128);
-  const int nt = (a->n + 255) / 256;
-  const int tiles = mt * nt;
-  // fill ~2 waves of 148 CTAs, keep >= 8 pixel blocks per split, bound the workspace
-  int s = (2 * 148 + tiles - 1) / tiles;
-  if (s > pb / 8) s = pb / 8;
-  if (s < 1) s = 1;
+  int s;
+  if (wgrad_use_pair(a)) {
+    // CTA-pair kernel: 74 pairs; among 2..4 waves' worth of splits take the one whose last wave is fullest
+    const int tiles = ddpo_wgrad2_tiles(a->taps, cin, a->n);
+    const int workers = num_sms() / 2;
+    s = 1;
+    double best = -1.0;
+    for (int k = 2; k <= 4; ++k) {
+      int sk = (k * workers + tiles - 1) / tiles;
+      if (sk > pb / 8) sk = pb / 8;
+      if (sk < 1) sk = 1;
+      const int units = sk * tiles;
+      const double eff = static_cast<double>(units) / (((units + workers - 1) / workers) * workers);
+      if (eff > best + 1e-9) best = eff, s = sk;
+    }
+  } else {
+    const int mt = a->taps * ((a->c0 + 127) / 128 + (a->c1 + 127) / 128);
+    const int nt = (a->n + 255) / 256;
+    const int tiles = mt * nt;
+    // fill ~2 waves of 148 CTAs, keep >= 8 pixel blocks per split, bound the workspace
+    s = (2 * 148 + tiles - 1) / tiles;
+    if (s > pb / 8) s = pb / 8;
+    if (s < 1) s = 1;
+  }
   const int64_t wsz = static_cast<int64_t>(a->taps) * cin * a->n;
   while (s > 1 && wsz * s > (int64_t(48) << 20)) --s;  // <= 48M floats of partials
   *splits = s;
@@ -311,19 +335,25 @@ extern "C" int ddpo_wgrad(const ddpo_wgrad_args* a, void* stream_) {
   p.mt_per_tap0 = (a->c0 + 127) / 128, p.mt_per_tap1 = (a->c1 + 127) / 128;
   p.dst = splits > 1 ? a->workspace : a->dw;
   p.accumulate = 1;
-  const int stage_bytes = WG_A_BYTES + 4 * WG_BOX_BYTES;
-  p.stages = WG_SMEM_BUDGET / stage_bytes;
-  const size_t smem = (size_t)p.stages * stage_bytes + 256 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    DDPO_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+  if (wgrad_use_pair(a)) {
+    int rc = ddpo_wgrad2_launch(p.tmX0, p.tmX1, p.tmDY, a->c0, a->c1, a->n, a->taps, a->is_conv, p.W, p.H, p.conv_stride,
+                                splits, pblocks, p.dst, stream);
+    if (rc) return rc;
+  } else {
+    const int stage_bytes = WG_A_BYTES + 4 * WG_BOX_BYTES;
+    p.stages = WG_SMEM_BUDGET / stage_bytes;
+    const size_t smem = (size_t)p.stages * stage_bytes + 256 + 1024;
+    static bool attr = false;
+    if (!attr) {
+      DDPO_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr = true;
+    }
+    const int tiles = splits * p.taps * (p.mt_per_tap0 + p.mt_per_tap1) * ((a->n + 255) / 256);
+    int grid = num_sms();
+    if (grid > tiles) grid = tiles;
+    wgrad_kernel<<<grid, WG_THREADS, smem, stream>>>(p);
+    DDPO_LAUNCH_OK();
   }
-  const int tiles = splits * p.taps * (p.mt_per_tap0 + p.mt_per_tap1) * ((a->n + 255) / 256);
-  int grid = num_sms();
-  if (grid > tiles) grid = tiles;
-  wgrad_kernel<<<grid, WG_THREADS, smem, stream>>>(p);
-  DDPO_LAUNCH_OK();
   if (splits > 1) {
     const int64_t n4 = static_cast<int64_t>(a->taps) * (a->c0 + a->c1) * a->n / 4;
     int blocks = static_cast<int>((n4 + 255) / 256);

@@ -269,7 +269,7 @@ def attention_fwd(q, k, v, out, batch, heads, nq, nk, ldq, ldk, ldv, ldo, lse=No
 _WGRAD_WS = {}
 
 
-def wgrad(*, dy, n, x0, dw, x1=None, c0=None, c1=0, ldy=0, ldx0=0, ldx1=0, conv=None, m=None, taps=1, stride=1):
+def wgrad(*, dy, n, x0, dw, x1=None, c0=None, c1=0, ldy=0, ldx0=0, ldx1=0, conv=None, m=None, taps=1, stride=1, kernel=0):
     """dw[(tap, cin), n] += X^T dY (fp32, Flax layout).  conv=(batch, h_out, w_out) or linear with m rows."""
     from ._lib import WgradArgs
     a = WgradArgs()
@@ -283,6 +283,7 @@ def wgrad(*, dy, n, x0, dw, x1=None, c0=None, c1=0, ldy=0, ldx0=0, ldx1=0, conv=
         a.is_conv, a.batch, a.h, a.w, a.m = 0, 0, 0, 0, int(m)
     a.conv_stride, a.taps = int(stride), int(taps)
     a.dw = _p(dw)
+    a.kernel_override = int(kernel)
     need = int(lib().ddpo_wgrad_workspace_floats(C.byref(a)))
     dev = dw.device
     ws = _WGRAD_WS.get(dev)

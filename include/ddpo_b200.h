@@ -198,6 +198,7 @@ typedef struct {
   float* dw;       /* fp32 [taps*(c0+c1), n], accumulated */
   float* workspace;
   int64_t workspace_floats;
+  int kernel_override; /* 0 = auto (CTA-pair kernel, wgrad2.cu); 2 = force the 1-CTA kernel (wgrad.cu) */
 } ddpo_wgrad_args;
 int64_t ddpo_wgrad_workspace_floats(const ddpo_wgrad_args* a);
 int ddpo_wgrad(const ddpo_wgrad_args* a, void* stream);

@@ -12,14 +12,18 @@ def bf(x):
     return x.to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("m,k,n", [(256, 64, 64), (1000, 320, 320), (4096, 1280, 640), (154, 1024, 1280), (8192, 128, 960)])
-def test_wgrad_linear(m, k, n):
+@pytest.mark.parametrize("kernel", [0, 2])  # 0 = CTA-pair kernel (wgrad2.cu), 2 = 1-CTA kernel (wgrad.cu)
+@pytest.mark.parametrize("m,k,n", [(256, 64, 64), (1000, 320, 320), (4096, 1280, 640), (154, 1024, 1280), (8192, 128, 960),
+                                   (5000, 192, 192), (40960, 320, 2560)])
+def test_wgrad_linear(m, k, n, kernel):
     from ddpo_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(0)
     x = bf(torch.randn(m, k, generator=g)).to(DEV)
-    dy = bf(torch.randn(m, n, generator=g)).to(DEV)
+    # dY is a column slice of a wider buffer (as the q/k/v gradients are): columns beyond n must not leak in
+    dyw = bf(torch.randn(m, n + 64, generator=g)).to(DEV)
+    dy = dyw[:, :n]
     dw = torch.ones(k, n, device=DEV)
-    ops.wgrad(dy=dy, n=n, x0=x, c0=k, m=m, dw=dw)
+    ops.wgrad(dy=dy, ldy=n + 64, n=n, x0=x, c0=k, m=m, dw=dw, kernel=kernel)
     torch.cuda.synchronize()
     ref = 1.0 + x.float().t() @ dy.float()
     err = (dw - ref).abs().max().item()
@@ -28,8 +32,10 @@ def test_wgrad_linear(m, k, n):
 
 @pytest.mark.parametrize("b,h,c0,c1,n,ks,stride", [(2, 8, 64, 0, 64, 3, 1), (2, 16, 128, 64, 128, 3, 1), (4, 64, 64, 0, 64, 3, 1),
                                                    (2, 32, 320, 0, 320, 3, 1), (2, 16, 64, 64, 128, 1, 1),
-                                                   (2, 8, 64, 0, 64, 3, 2), (3, 4, 64, 0, 64, 3, 1)])
-def test_wgrad_conv(b, h, c0, c1, n, ks, stride):
+                                                   (2, 8, 64, 0, 64, 3, 2), (3, 4, 64, 0, 64, 3, 1),
+                                                   (2, 16, 320, 640, 320, 3, 1), (1, 8, 192, 0, 448, 3, 1)])
+@pytest.mark.parametrize("kernel", [0, 2])
+def test_wgrad_conv(b, h, c0, c1, n, ks, stride, kernel):
     from ddpo_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(1)
     hi = h * stride
@@ -38,7 +44,7 @@ def test_wgrad_conv(b, h, c0, c1, n, ks, stride):
     dy = bf(torch.randn(b * h * h, n, generator=g)).to(DEV)
     cin = c0 + c1
     dw = torch.zeros(ks * ks * cin, n, device=DEV)
-    ops.wgrad(dy=dy, n=n, x0=x0, x1=x1, c0=c0, c1=c1, conv=(b, h, h), taps=ks * ks, stride=stride, dw=dw)
+    ops.wgrad(dy=dy, n=n, x0=x0, x1=x1, c0=c0, c1=c1, conv=(b, h, h), taps=ks * ks, stride=stride, dw=dw, kernel=kernel)
     torch.cuda.synchronize()
     xin = (x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], -1)).permute(0, 3, 1, 2).requires_grad_(False)
     w = torch.zeros(n, cin, ks, ks, device=DEV, requires_grad=True)
