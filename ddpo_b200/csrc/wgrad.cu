@@ -242,18 +242,26 @@ static int wgrad_plan(const ddpo_wgrad_args* a, int* splits, int* pblocks) {
   const int cin = a->c0 + a->c1;
   int s;
   if (wgrad_use_pair(a)) {
-    // CTA-pair kernel: 74 pairs; among 2..4 waves' worth of splits take the one whose last wave is fullest
+    // CTA-pair kernel, 74 pairs.  Number of pixel splits from a small cost model (microseconds):
+    //   main loop  = rounds x pixel blocks per split x 0.42 us per 256-wide 64-pixel stage (measured; 0.6 of that for
+    //                the 128-wide padded remainder tile)
+    //   reduction  = (splits + 2) x |dW| x 4 B at ~4 TB/s (partials written, read back, dW read-modify-written)
     const int tiles = ddpo_wgrad2_tiles(a->taps, cin, a->n);
     const int workers = num_sms() / 2;
+    const int nt = (a->n + 255) / 256;
+    const double wide = (a->n - (nt - 1) * 256) > 128 ? 1.0 : 0.6;
+    const double stage_us = 0.42 * ((nt - 1) + wide) / nt;
+    const double dw_mb = static_cast<double>(a->taps) * cin * a->n * 4.0 / 1e6;
+    int hi = pb / 4;
+    if (hi < 1) hi = 1;
+    if (hi > 64) hi = 64;
     s = 1;
-    double best = -1.0;
-    for (int k = 2; k <= 4; ++k) {
-      int sk = (k * workers + tiles - 1) / tiles;
-      if (sk > pb / 8) sk = pb / 8;
-      if (sk < 1) sk = 1;
+    double best = 1e30;
+    for (int sk = 1; sk <= hi; ++sk) {
       const int units = sk * tiles;
-      const double eff = static_cast<double>(units) / (((units + workers - 1) / workers) * workers);
-      if (eff > best + 1e-9) best = eff, s = sk;
+      const int rounds = (units + workers - 1) / workers;
+      const double t = rounds * ((pb + sk - 1) / sk) * stage_us + (sk > 1 ? (sk + 2) * dw_mb / 4.0 : 0.0);
+      if (t < best - 1e-9) best = t, s = sk;
     }
   } else {
     const int mt = a->taps * ((a->c0 + 127) / 128 + (a->c1 + 127) / 128);

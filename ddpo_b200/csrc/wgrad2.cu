@@ -82,9 +82,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile -> (split, row tile, column tile)
+  // tile -> (split, row tile, column tile).  Column tiles differ in cost (256 wide vs a padded remainder); when the
+  // number of pairs is a multiple of NT a pair would see the same column tile in every round (even pairs all the
+  // 256-wide tiles of N = 320, odd pairs all the narrow ones), so the column index is rotated by the round number.
+  const bool skew = (num_pairs % p.NT) == 0;
   auto decode = [&](int tile, int& s, int& mt, int& nt) {
     nt = tile % p.NT;
+    if (skew) nt = (nt + tile / num_pairs) % p.NT;
     const int r = tile / p.NT;
     mt = r % p.MT;
     s = r / p.MT;
