@@ -108,6 +108,16 @@ def cpu_step_seconds(n_steps, threads=None):
     return float(np.mean(times)), torch.get_num_threads()
 
 
+def _ncu_traffic():
+    """Average DRAM bytes (read + write) per igemm launch of one denoising step, from the committed ncu capture of
+    `bench.py --ncu sample` (profiles/r1_traffic.json, written by profiles/make_launch_summary.py); None if absent."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
+            return json.load(f)["sample"]["igemm"]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def _dump_shapes(prof, tags, path):
     """Per-(kernel, shape) table of the eager CUDA-event profile: which GEMM shapes the time goes to."""
     agg = {}
@@ -152,6 +162,9 @@ def main():
     ap.add_argument("--phase", default="auto", choices=["auto", "sample", "ppo"])
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ncu", default="", choices=["", "sample", "train"],
+                    help="run under `ncu --profile-from-start off`: bracket ONE eager denoising step / train pass with "
+                         "cudaProfilerStart/Stop, print nothing, exit (profiles/README.md has the command lines)")
     ap.add_argument("--shapes", action="store_true", help="also write per-shape kernel tables to gpurun_out/shapes_*.txt")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -250,6 +263,13 @@ def main():
     ms_per_step = ms / args.steps
     steps_per_s = world * B * args.steps / (ms / 1e3)  # denoising steps of one sample, whole job
 
+    if args.ncu == "sample":
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        one_step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     # ---------------- kernel profile (eager, CUDA events per launch) ----------------
     ops.PROFILE, ops.PROFILE_TAGS = [], []
     one_step()
@@ -331,6 +351,14 @@ def main():
         for i in range(max(3, args.warmup)):
             _, info = pg.train_step(tstate, batches[i % len(batches)], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
         first_pass_kl = float(info["approx_kl"].item())
+        if args.ncu == "train":
+            pg.USE_CUDA_GRAPH = False
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            pg.train_step(tstate, batches[1], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            return
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -428,7 +456,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps + (ppo["train_launches"] * args.steps if ppo else 0),
             "ppo": ppo,
             "roofline": {"bound": "tensor", "achieved": igemm_tflops, "peak": sus_tf, "unit": "TFLOP/s",
-                         "frac": igemm_tflops / sus_tf, "traffic": None, "kernel": "igemm_kernel",
+                         "frac": igemm_tflops / sus_tf, "traffic": _ncu_traffic(), "kernel": "igemm2_kernel (CTA-pair implicit GEMM; igemm_kernel below 1024 rows)",
                          "peak_source": f"{peak_src} bf16_tflops_sustained",
                          "how": "sum of algorithmic 2MNK over the igemm launches of one step / sum of their CUDA-event durations"},
             "kernels": breakdown,

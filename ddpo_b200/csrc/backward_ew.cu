@@ -5,6 +5,7 @@
 // the time embedding, zero-dilation for the stride-2 conv's data gradient, strided accumulate.
 // All reductions are two-stage with fixed order (deterministic).
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace ddpo {
 
@@ -67,18 +68,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
     part[static_cast<size_t>(chunk) * N + c + 1] = s1;
   }
 }
-// out[g][n] (+)= sum over the chunks of group g (chunks_per_group consecutive chunks), fixed order
-__global__ void colsum_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int N, int groups,
-                                     int chunks_per_group, int accumulate, float* __restrict__ out2) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = blockIdx.y;
-  if (n >= N) return;
-  float s = 0.f;
-  for (int c = 0; c < chunks_per_group; ++c) s += part[(static_cast<size_t>(g) * chunks_per_group + c) * N + n];
-  float* o = out + static_cast<size_t>(g) * N + n;
-  *o = accumulate ? *o + s : s;
-  (void)out2;
-}
+// second stage (out[g][n] (+)= sum over the chunks of group g, fixed order): reduce_rows_kernel, reduce.cuh
 
 // ------------------------------------------------------------------- GEGLU ----
 // pre: bf16 [M, N] tile-interleaved ([bn/2 lin | bn/2 gate] per bn columns, bias included)
@@ -347,8 +337,7 @@ extern "C" int ddpo_colsum_cast(const float* dy, int ld, void* y_bf16, float* ou
                                               out ? workspace : nullptr, m, n, cr);
   DDPO_LAUNCH_OK();
   if (out != nullptr) {
-    dim3 g2((n + 127) / 128, groups);
-    colsum_reduce_kernel<<<g2, 128, 0, stream>>>(workspace, out, n, groups, cpg, accumulate, nullptr);
+    launch_reduce_rows(workspace, groups, cpg, n, n, out, nullptr, accumulate, stream);
     DDPO_LAUNCH_OK();
   }
   return DDPO_OK;
@@ -363,8 +352,7 @@ extern "C" int ddpo_colsum_bf16(const void* x_bf16, int ld, float* out, int accu
   colsum_bf16_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x_bf16), ld > 0 ? ld : n, workspace, m, n,
                                               CS_ROWS);
   DDPO_LAUNCH_OK();
-  dim3 g2((n + 127) / 128, 1);
-  colsum_reduce_kernel<<<g2, 128, 0, stream>>>(workspace, out, n, 1, chunks, accumulate, nullptr);
+  launch_reduce_rows(workspace, 1, chunks, n, n, out, nullptr, accumulate, stream);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }

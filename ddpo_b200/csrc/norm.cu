@@ -12,6 +12,7 @@
 // sums written by the stats kernel, summed in chunk order by the apply kernel.  The
 // chunking depends only on HW, never on the batch size -> batch-invariant results.
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace ddpo {
 
@@ -320,19 +321,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const GnBwdArg
   }
 }
 
-// dscale/dbias: sum partial [rows, 2, C] over rows in fixed order, accumulate into grads
-__global__ void param_grad_reduce_kernel(const float* __restrict__ part, int rows, int C, float* __restrict__ dscale,
-                                         float* __restrict__ dbias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float ds = 0.f, db = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    ds += part[(static_cast<size_t>(r) * 2) * C + c];
-    db += part[(static_cast<size_t>(r) * 2 + 1) * C + c];
-  }
-  dscale[c] += ds;
-  dbias[c] += db;
-}
+// dscale/dbias: partial [rows, 2, C] summed over rows in fixed order into the gradients: reduce_rows_kernel (reduce.cuh)
 
 // ------------------------------------------------------------------ LayerNorm ----
 // one warp per row; x fp32 [M, C] -> y bf16 [M, C]
@@ -540,7 +529,7 @@ extern "C" int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const float* dy,
   DDPO_LAUNCH_OK();
   gn_bwd_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(b);
   DDPO_LAUNCH_OK();
-  param_grad_reduce_kernel<<<(C + 127) / 128, 128, 0, stream>>>(b.dparam_part, a->batch * b.f.chunks, C, dscale, dbias);
+  launch_reduce_rows(b.dparam_part, 1, a->batch * b.f.chunks, 2 * C, C, dscale, dbias, 1, stream);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }
@@ -582,7 +571,7 @@ extern "C" int ddpo_layernorm_bwd(const float* x, const float* scale, const floa
   else
     layernorm_bwd_kernel<10><<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate);
   DDPO_LAUNCH_OK();
-  param_grad_reduce_kernel<<<(c + 127) / 128, 128, 0, stream>>>(workspace, ctas, c, dscale, dbias);
+  launch_reduce_rows(workspace, 1, ctas, 2 * c, c, dscale, dbias, 1, stream);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }
