@@ -135,9 +135,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
       const int g = (c + j) / cpg;
       mu[j] = s_mean[g], rs[j] = s_rstd[g];
     }
-    for (int p = p_begin + tr; p < p_end; p += R) {
-      const size_t pix = base + p;
-      const float4 v = gn_load4(a, pix, c);
+    auto emit = [&](size_t pix, const float4& v) {
       const float xv[4] = {v.x, v.y, v.z, v.w};
       float y[4];
 #pragma unroll
@@ -150,7 +148,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
       if (a.y_f32) *reinterpret_cast<float4*>(a.y_f32 + pix * C + c) = make_float4(y[0], y[1], y[2], y[3]);
       if (a.raw_bf16)
         *reinterpret_cast<uint2*>(a.raw_bf16 + pix * C + c) = make_uint2(pack_bf16(xv[0], xv[1]), pack_bf16(xv[2], xv[3]));
+    };
+    int p = p_begin + tr;
+    for (; p + 3 * R < p_end; p += 4 * R) {  // four independent 16-byte loads in flight per thread
+      const float4 v0 = gn_load4(a, base + p, c), v1 = gn_load4(a, base + p + R, c);
+      const float4 v2 = gn_load4(a, base + p + 2 * R, c), v3 = gn_load4(a, base + p + 3 * R, c);
+      emit(base + p, v0), emit(base + p + R, v1), emit(base + p + 2 * R, v2), emit(base + p + 3 * R, v3);
     }
+    for (; p < p_end; p += R) emit(base + p, gn_load4(a, base + p, c));
   }
 }
 
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const GnBwdArg
 }
 
 // pass 2: dx
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const GnBwdArgs a) {
+__global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(const GnBwdArgs a) {
   const GnArgs& f = a.f;
   const int C = f.c0 + f.c1, C4 = C >> 2, cpg = C / GN_GROUPS;
   const int cols = C4 < GN_THREADS ? C4 : GN_THREADS;
@@ -298,10 +303,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const GnBwdArg
       mu[j] = s_mean[g], rs[j] = s_rstd[g], m1[j] = s_m1[g], m2[j] = s_m2[g];
     }
     const bool src0 = c < f.c0;
-    for (int p = p_begin + tr; p < p_end; p += R) {
-      const size_t pix = base + p;
-      const float4 v = gn_load4(f, pix, c);
-      const float4 d4 = *reinterpret_cast<const float4*>(a.dy + pix * C + c);
+    auto emit = [&](size_t pix, const float4& v, const float4& d4, const float4& old) {
       const float xv[4] = {v.x, v.y, v.z, v.w};
       float d[4] = {d4.x, d4.y, d4.z, d4.w}, o[4];
 #pragma unroll
@@ -312,11 +314,26 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const GnBwdArg
       }
       float* dst = src0 ? a.dx0 + pix * a.ldd0 + c : a.dx1 + pix * a.ldd1 + (c - f.c0);
       float4 out = make_float4(o[0], o[1], o[2], o[3]);
-      if (a.accumulate) {
-        const float4 old = *reinterpret_cast<const float4*>(dst);
-        out.x += old.x, out.y += old.y, out.z += old.z, out.w += old.w;
-      }
+      if (a.accumulate) out.x += old.x, out.y += old.y, out.z += old.z, out.w += old.w;
       *reinterpret_cast<float4*>(dst) = out;
+    };
+    auto load_old = [&](size_t pix) {
+      if (!a.accumulate) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* dst = src0 ? a.dx0 + pix * a.ldd0 + c : a.dx1 + pix * a.ldd1 + (c - f.c0);
+      return *reinterpret_cast<const float4*>(dst);
+    };
+    int p = p_begin + tr;
+    for (; p + R < p_end; p += 2 * R) {  // two pixels = up to six independent 16-byte loads in flight per thread
+      const size_t q0 = base + p, q1 = base + p + R;
+      const float4 v0 = gn_load4(f, q0, c), v1 = gn_load4(f, q1, c);
+      const float4 d0 = *reinterpret_cast<const float4*>(a.dy + q0 * C + c);
+      const float4 d1 = *reinterpret_cast<const float4*>(a.dy + q1 * C + c);
+      const float4 o0 = load_old(q0), o1 = load_old(q1);
+      emit(q0, v0, d0, o0), emit(q1, v1, d1, o1);
+    }
+    for (; p < p_end; p += R) {
+      const size_t q0 = base + p;
+      emit(q0, gn_load4(f, q0, c), *reinterpret_cast<const float4*>(a.dy + q0 * C + c), load_old(q0));
     }
   }
 }
