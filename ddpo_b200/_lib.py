@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libddpo_b200.so")
+# DDPO_B200_LIB: developer override used for A/B timing of kernel variants (another build of the same C ABI)
+LIB_PATH = os.environ.get("DDPO_B200_LIB") or os.path.join(_HERE, "libddpo_b200.so")
 
 vp, i32, i64, f32, u32p, f32p = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_void_p
 

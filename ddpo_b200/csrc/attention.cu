@@ -186,14 +186,14 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float xe = __uint_as_float(v[i]) * c - mc;
-            pr[i] = (i & 1) ? ex2_poly(xe) : ex2_mufu(xe);
+            pr[i] = ex2_sel<DDPO_EXP_POLY_FWD>(i, xe);
             l_blk += pr[i];
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float xe = __uint_as_float(v[i]) * c - mc;
-            const float e = (i & 1) ? ex2_poly(xe) : ex2_mufu(xe);
+            const float e = ex2_sel<DDPO_EXP_POLY_FWD>(i, xe);
             pr[i] = (c0 + i < valid) ? e : 0.f;
             l_blk += pr[i];
           }

@@ -34,6 +34,7 @@ struct AttnBwdArgs {
 template <bool WRITE_P>
 __device__ __forceinline__ void softmax_bwd_row(uint32_t t_s, uint32_t t_dp, uint8_t* sP, uint8_t* sDS, int r, int valid_keys,
                                                 bool row_ok, float lse_l2, float delta, float c, float scale, int col_begin, bool full) {
+  const float delta_s = delta * scale;  // dS = P (dP - delta) scale = P (dP scale - delta scale): one FFMA + one FMUL
 #pragma unroll 1
   for (int c0 = col_begin; c0 < col_begin + 64; c0 += 32) {
     uint32_t s[32], d[32];
@@ -45,18 +46,18 @@ __device__ __forceinline__ void softmax_bwd_row(uint32_t t_s, uint32_t t_dp, uin
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float xe = __uint_as_float(s[i]) * c - lse_l2;
-        const float pv = (i & 1) ? ex2_poly(xe) : ex2_mufu(xe);
+        const float pv = ex2_sel<DDPO_EXP_POLY_BWD>(i, xe);
         p[i] = pv;
-        ds[i] = pv * (__uint_as_float(d[i]) - delta) * scale;
+        ds[i] = pv * fmaf(__uint_as_float(d[i]), scale, -delta_s);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const bool ok = row_ok && (c0 + i < valid_keys);
         const float xe = __uint_as_float(s[i]) * c - lse_l2;
-        const float pv = ok ? ((i & 1) ? ex2_poly(xe) : ex2_mufu(xe)) : 0.f;
+        const float pv = ok ? ex2_sel<DDPO_EXP_POLY_BWD>(i, xe) : 0.f;
         p[i] = pv;
-        ds[i] = pv * (__uint_as_float(d[i]) - delta) * scale;
+        ds[i] = pv * fmaf(__uint_as_float(d[i]), scale, -delta_s);
       }
     }
     const int tile_off = (c0 >> 6) * AB_T + r * 128;
