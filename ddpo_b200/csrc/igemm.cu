@@ -294,30 +294,41 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
     // TMA epilogue where the epilogue, not the main loop, bounds the tile: short K (the 1x1 / linear layers).
     // Long-K convolutions hide the register epilogue behind the next tile's MMAs and keep every stage for operands.
     const int kiters = a->taps * (cin0 + cin1) / BK;
-    const bool can_tma = !a->geglu && !(a->residual != nullptr && a->accumulate_out) &&
-                         (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0 &&
+    const bool aligned = (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 &&
-                         (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0 && p.ld_out % 8 == 0 && p.ld_res % 4 == 0;
+                         (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a->aux_bf16) & 15) == 0 && p.ld_out % 8 == 0 && p.ld_res % 4 == 0;
+    const bool can_tma = aligned && !(a->residual != nullptr && a->accumulate_out) &&
+                         (!a->geglu || (a->residual == nullptr && !a->accumulate_out && a->out_f32 == nullptr));
     const bool want_tma = a->epi_override == 1 || (a->epi_override == 0 && kiters <= 24);
     if (can_tma && want_tma) {
       p.epi_tma = 1;
-      const float* in = a->residual != nullptr ? a->residual : (a->accumulate_out ? a->out_f32 : nullptr);
-      const int ld_in = a->residual != nullptr ? p.ld_res : p.ld_out;
-      p.epi_in = in != nullptr;
       uint32_t box[2] = {32, 32}, es[2] = {1, 1};
-      uint64_t dims[2] = {(uint64_t)a->n, (uint64_t)M_total};
       int rc;
-      if (in != nullptr) {
-        uint64_t st[1] = {(uint64_t)ld_in * 4};
-        if ((rc = make_tensor_map(&p.tmIn, in, 4, 2, dims, st, box, es, 1))) return rc;
-      }
-      if (a->out_f32 != nullptr) {
-        uint64_t st[1] = {(uint64_t)p.ld_out * 4};
-        if ((rc = make_tensor_map(&p.tmOutF, a->out_f32, 4, 2, dims, st, box, es, 1))) return rc;
-      }
-      if (a->out_bf16 != nullptr) {
-        uint64_t st[1] = {(uint64_t)p.ld_out * 2};
-        if ((rc = make_tensor_map(&p.tmOutB, a->out_bf16, 2, 2, dims, st, box, es, 2))) return rc;
+      if (a->geglu) {
+        uint64_t dims_o[2] = {(uint64_t)a->n / 2, (uint64_t)M_total}, st_o[1] = {(uint64_t)p.ld_out * 2};
+        if ((rc = make_tensor_map(&p.tmOutB, a->out_bf16, 2, 2, dims_o, st_o, box, es, 2))) return rc;
+        if (a->aux_bf16 != nullptr) {
+          uint64_t dims_a[2] = {(uint64_t)a->n, (uint64_t)M_total}, st_a[1] = {(uint64_t)a->n * 2};
+          if ((rc = make_tensor_map(&p.tmIn, a->aux_bf16, 2, 2, dims_a, st_a, box, es, 2))) return rc;
+        }
+      } else {
+        const float* in = a->residual != nullptr ? a->residual : (a->accumulate_out ? a->out_f32 : nullptr);
+        const int ld_in = a->residual != nullptr ? p.ld_res : p.ld_out;
+        p.epi_in = in != nullptr;
+        uint64_t dims[2] = {(uint64_t)a->n, (uint64_t)M_total};
+        if (in != nullptr) {
+          uint64_t st[1] = {(uint64_t)ld_in * 4};
+          if ((rc = make_tensor_map(&p.tmIn, in, 4, 2, dims, st, box, es, 1))) return rc;
+        }
+        if (a->out_f32 != nullptr) {
+          uint64_t st[1] = {(uint64_t)p.ld_out * 4};
+          if ((rc = make_tensor_map(&p.tmOutF, a->out_f32, 4, 2, dims, st, box, es, 1))) return rc;
+        }
+        if (a->out_bf16 != nullptr) {
+          uint64_t st[1] = {(uint64_t)p.ld_out * 2};
+          if ((rc = make_tensor_map(&p.tmOutB, a->out_bf16, 2, 2, dims, st, box, es, 2))) return rc;
+        }
       }
     }
     return ddpo_igemm2_launch(p, stream);

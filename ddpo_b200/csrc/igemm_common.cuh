@@ -34,7 +34,7 @@ struct IGemmArgs {
   // segment issued by the TMA engine instead of 16-byte pieces of 32 different rows per LSU instruction.
   int epi_tma;               // 0 = register epilogue (igemm_epilogue), 1 = igemm_epilogue_tma
   int epi_in;                // epi_tma: an fp32 input tile (residual, or the old output when accumulate_out) is added
-  CUtensorMap tmIn, tmOutF, tmOutB;
+  CUtensorMap tmIn, tmOutF, tmOutB;  // GEGLU: tmIn = bf16 map of the pre-activation buffer (aux), tmOutB = [M, N/2]
 };
 
 constexpr int EPI_F32_TILE = 32 * 32 * 4;   // 4 KB, SWIZZLE_128B (rows of 128 B)
@@ -73,6 +73,74 @@ __device__ __forceinline__ void igemm_epilogue_tma(const IGemmArgs& p, EpiWarp& 
   const float* rv = nullptr;
   if (p.rowvec != nullptr && row < p.M_total) rv = p.rowvec + static_cast<size_t>(row / p.rows_per_sample) * p.rowvec_ld;
   const uint32_t sw128 = static_cast<uint32_t>(lane & 7), sw64 = static_cast<uint32_t>((lane >> 1) & 3);
+  if (p.geglu) {
+    // GEGLU: this N tile is [BN/2 linear | BN/2 gate] columns of the same output channels.  Per 32-channel chunk three
+    // bf16 tiles leave through TMA: out = lin * gelu(gate) -> out_bf16[:, tn*BN/2 + c0], and (training) the
+    // pre-activations lin / gate -> aux[:, n0 + c0] / aux[:, n0 + BN/2 + c0].  Same arithmetic as igemm_epilogue.
+    const int half = BN >> 1;
+    const int tn = n0 / BN;
+    for (int c0 = cgrp * 32; c0 < half; c0 += cstep) {
+      const uint32_t sl = e.g & 1;
+      uint8_t* ob = e.buf + EPI_RING * EPI_F32_TILE + sl * EPI_BF16_TILE;
+      uint8_t* lb = e.buf + sl * EPI_F32_TILE;
+      uint8_t* gb = lb + EPI_BF16_TILE;
+      const int n = n0 + c0;
+      uint32_t a[32], g[32];
+      tmem_ld_32x32(t_row + c0, a);
+      tmem_ld_32x32(t_row + half + c0, g);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bl = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n + half + j));
+        const float blv[4] = {bl.x, bl.y, bl.z, bl.w}, bgv[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float lin = __uint_as_float(a[j + q]) + blv[q];
+          float gate = __uint_as_float(g[j + q]) + bgv[q];
+          f[j + q] = lin * gelu_tanh_f(gate);
+          a[j + q] = __float_as_uint(lin), g[j + q] = __float_as_uint(gate);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t off = lane * 64 + ((j ^ sw64) << 4);
+        uint4 u;
+        u.x = pack_bf16(f[8 * j], f[8 * j + 1]), u.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+        u.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]), u.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+        *reinterpret_cast<uint4*>(ob + off) = u;
+        if (p.aux_bf16 != nullptr) {
+          uint4 v, w;
+          v.x = pack_bf16(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1]));
+          v.y = pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3]));
+          v.z = pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5]));
+          v.w = pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7]));
+          w.x = pack_bf16(__uint_as_float(g[8 * j]), __uint_as_float(g[8 * j + 1]));
+          w.y = pack_bf16(__uint_as_float(g[8 * j + 2]), __uint_as_float(g[8 * j + 3]));
+          w.z = pack_bf16(__uint_as_float(g[8 * j + 4]), __uint_as_float(g[8 * j + 5]));
+          w.w = pack_bf16(__uint_as_float(g[8 * j + 6]), __uint_as_float(g[8 * j + 7]));
+          *reinterpret_cast<uint4*>(lb + off) = v;
+          *reinterpret_cast<uint4*>(gb + off) = w;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      ++e.g;
+      if (lane == 0) {
+        tma_store_2d(&p.tmOutB, ob, tn * half + c0, m_slab);
+        if (p.aux_bf16 != nullptr) {
+          tma_store_2d(&p.tmIn, lb, n, m_slab);
+          tma_store_2d(&p.tmIn, gb, n + half, m_slab);
+        }
+        bulk_commit();
+        bulk_wait_read<1>();
+      }
+      __syncwarp();
+    }
+    e.req = e.g;
+    return;
+  }
   const uint32_t g0 = e.g;
   const int nch = (BN - cgrp * 32 + cstep - 1) / cstep;
   for (int c0 = cgrp * 32; c0 < BN; c0 += cstep) {

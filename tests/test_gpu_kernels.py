@@ -440,3 +440,33 @@ def test_igemm_tma_epilogue_is_bit_identical(m, k, n, mode):
         assert (outs[1][0][:, :n] - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
     if outs[1][1] is not None:
         assert (outs[1][1][:, n:].float() == 7.0).all()
+
+
+@pytest.mark.parametrize("m,k", [(1000, 128), (4096 + 77, 320)])
+@pytest.mark.parametrize("with_aux", [False, True])
+def test_igemm_geglu_tma_epilogue_is_bit_identical(m, k, with_aux):
+    """GEGLU through the TMA-staged epilogue (activation tile + the two pre-activation tiles per chunk) == register
+    epilogue, bit for bit; training keeps the pre-activations (aux), sampling does not."""
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(12)
+    a = bf(torch.randn(m, k, generator=g)).to(DEV)
+    w2 = (torch.randn(k, 8 * k, generator=g) / math.sqrt(k)).to(DEV)
+    b2 = torch.randn(8 * k, generator=g).to(DEV)
+    wt2 = torch.empty(8 * k, k, dtype=torch.bfloat16, device=DEV)
+    ops.prep_weight(w2, wt2, k, 8 * k, geglu_bn=256)
+    bp = torch.empty_like(b2)
+    ops.permute_geglu_bias(b2, bp, 8 * k, 256)
+    r = []
+    for epi in (2, 1):
+        o = torch.full((m, 4 * k), 3.0, dtype=torch.bfloat16, device=DEV)
+        aux = torch.full((m, 8 * k), 5.0, dtype=torch.bfloat16, device=DEV) if with_aux else None
+        ops.igemm(a0=a, wt=wt2, n=8 * k, c0=k, m=m, bias=bp, out_bf16=o, geglu=True, bn=256, aux_bf16=aux, pair=1, epi=epi)
+        r.append((o, aux))
+    torch.cuda.synchronize()
+    assert torch.equal(r[0][0], r[1][0])
+    if with_aux:
+        assert torch.equal(r[0][1], r[1][1])
+    lin = a.float() @ bf(w2[:, :4 * k]).float() + b2[:4 * k]
+    gate = a.float() @ bf(w2[:, 4 * k:]).float() + b2[4 * k:]
+    ref = lin * torch.nn.functional.gelu(gate, approximate="tanh")
+    assert (r[1][0].float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
