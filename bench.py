@@ -8,8 +8,9 @@ DDIM, CFG 5.0, eta 1.0, per-GPU sample batch 8 (global batch 64 on 8 GPUs), synt
 embeddings, random-init U-Net weights.  One bench "step" is one pass of the hot path over one batch:
   phase=sample : one denoising step of the 8-sample batch (U-Net on the 2x8 CFG batch + fused
                  CFG/DDIM/log-prob/noise kernel)                          -> denoising steps/s
-  phase=ppo    : one PPO minibatch step (train batch 2, train_cfg: fwd+bwd of the 4-sample CFG batch,
-                 log-prob, PPO loss, gradient accumulate)                 -> counted into PPO samples/s
+  phase=ppo    : one PPO train pass: 10 timesteps of the train batch of 2 (reference micro-batch, train_cfg) stacked
+                 into one U-Net fwd+bwd of batch 40, log-prob, PPO loss (per-micro-batch means), gradient accumulate;
+                 plus the optimizer update (all-reduce + clip + AdamW) timed separately  -> PPO samples/s
 The headline `value` is PPO samples/s when the training path is available (a PPO sample = 50 sampling
 steps + 50 train steps of one trajectory), else denoising steps/s.
 One process per GPU (torchrun for N>1), max-over-ranks CUDA-event timing.
