@@ -73,23 +73,33 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // ------------------------------------------------------------------- GEGLU ----
 // pre: bf16 [M, N] tile-interleaved ([bn/2 lin | bn/2 gate] per bn columns, bias included)
 // dff: fp32 [M, N/2] gradient w.r.t. lin*gelu(gate);  dpre: bf16 [M, N] in PLAIN order [lin(N/2) | gate(N/2)]
-__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const float* __restrict__ dff,
-                                 __nv_bfloat16* __restrict__ dpre, int64_t M, int N, int bn) {
-  const int half = bn >> 1, hn = N >> 1;
-  const int64_t total = M * (hn >> 1);
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const float* __restrict__ dff,
+                                                        __nv_bfloat16* __restrict__ dpre, int64_t M, int N, int bn) {
+  // 8 output channels per thread: 16-byte loads of lin / gate, 2 x 16 bytes of dff, two 16-byte stores
+  const int half = bn >> 1, hn = N >> 1, groups = hn >> 3;
+  const int64_t total = M * groups;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / (hn >> 1);
-    const int j = static_cast<int>(i % (hn >> 1)) * 2;  // output channel pair j, j+1
+    const int64_t r = i / groups;
+    const int j = static_cast<int>(i % groups) * 8;  // output channels j .. j+7 (never straddle a tile: half % 8 == 0)
     const int tile = j / half, pos = j % half;
     const __nv_bfloat16* pr = pre + r * N + tile * bn + pos;
-    const uint32_t lin2 = *reinterpret_cast<const uint32_t*>(pr);
-    const uint32_t gate2 = *reinterpret_cast<const uint32_t*>(pr + half);
-    const float2 d = *reinterpret_cast<const float2*>(dff + r * hn + j);
-    const float l0 = bf16_lo(lin2), l1 = bf16_hi(lin2), g0 = bf16_lo(gate2), g1 = bf16_hi(gate2);
-    *reinterpret_cast<uint32_t*>(dpre + r * N + j) = pack_bf16(d.x * gelu_tanh_f(g0), d.y * gelu_tanh_f(g1));
-    *reinterpret_cast<uint32_t*>(dpre + r * N + hn + j) =
-        pack_bf16(d.x * l0 * gelu_tanh_grad_f(g0), d.y * l1 * gelu_tanh_grad_f(g1));
+    const uint4 lin8 = *reinterpret_cast<const uint4*>(pr);
+    const uint4 gate8 = *reinterpret_cast<const uint4*>(pr + half);
+    const float4 d0 = *reinterpret_cast<const float4*>(dff + r * hn + j);
+    const float4 d1 = *reinterpret_cast<const float4*>(dff + r * hn + j + 4);
+    const uint32_t lw[4] = {lin8.x, lin8.y, lin8.z, lin8.w}, gw[4] = {gate8.x, gate8.y, gate8.z, gate8.w};
+    const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    uint32_t ol[4], og[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float l0 = bf16_lo(lw[q]), l1 = bf16_hi(lw[q]), g0 = bf16_lo(gw[q]), g1 = bf16_hi(gw[q]);
+      const float e0 = dv[2 * q], e1 = dv[2 * q + 1];
+      ol[q] = pack_bf16(e0 * gelu_tanh_f(g0), e1 * gelu_tanh_f(g1));
+      og[q] = pack_bf16(e0 * l0 * gelu_tanh_grad_f(g0), e1 * l1 * gelu_tanh_grad_f(g1));
+    }
+    *reinterpret_cast<uint4*>(dpre + r * N + j) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    *reinterpret_cast<uint4*>(dpre + r * N + hn + j) = make_uint4(og[0], og[1], og[2], og[3]);
   }
 }
 
@@ -359,8 +369,8 @@ extern "C" int ddpo_colsum_bf16(const void* x_bf16, int ld, float* out, int accu
 
 extern "C" int ddpo_geglu_bwd(const void* pre_bf16, const float* dff, void* dpre_bf16, int64_t m, int n, int bn,
                               void* stream) {
-  DDPO_REQUIRE(pre_bf16 && dff && dpre_bf16 && n % bn == 0 && bn % 4 == 0, "geglu_bwd: bad arguments");
-  geglu_bwd_kernel<<<grid_for(m * (n / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  DDPO_REQUIRE(pre_bf16 && dff && dpre_bf16 && n % bn == 0 && bn % 16 == 0, "geglu_bwd: bad arguments");
+  geglu_bwd_kernel<<<grid_for(m * (n / 16), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(pre_bf16), dff, static_cast<__nv_bfloat16*>(dpre_bf16), m, n, bn);
   DDPO_LAUNCH_OK();
   return DDPO_OK;

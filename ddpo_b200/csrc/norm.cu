@@ -397,13 +397,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
     const float* xr = x + static_cast<size_t>(row) * C;
     const float* dr = dy + static_cast<size_t>(row) * C;
-    float4 xv[NC], dv[NC];
+    float* gr = dx + static_cast<size_t>(row) * C;
+    float4 xv[NC], dv[NC], ov[NC];  // the old gradient (accumulate mode) is fetched with x and dy: 3 streams in flight
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const int c = lane * 4 + 128 * i;
+      ov[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < C) {
         xv[i] = *reinterpret_cast<const float4*>(xr + c);
         dv[i] = *reinterpret_cast<const float4*>(dr + c);
+        if (accumulate) ov[i] = *reinterpret_cast<const float4*>(gr + c);
       } else {
         xv[i] = make_float4(mean, mean, mean, mean);
         dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -423,7 +426,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       }
     }
     m1 = warp_sum(m1) / C, m2 = warp_sum(m2) / C;
-    float* gr = dx + static_cast<size_t>(row) * C;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const int c = lane * 4 + 128 * i;
@@ -433,10 +435,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.y = rstd * (dv[i].y * sc[i].y - m1 - (xv[i].y - mean) * rstd * m2);
         o.z = rstd * (dv[i].z * sc[i].z - m1 - (xv[i].z - mean) * rstd * m2);
         o.w = rstd * (dv[i].w * sc[i].w - m1 - (xv[i].w - mean) * rstd * m2);
-        if (accumulate) {
-          const float4 old = *reinterpret_cast<const float4*>(gr + c);
-          o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
-        }
+        o.x += ov[i].x, o.y += ov[i].y, o.z += ov[i].z, o.w += ov[i].w;
         *reinterpret_cast<float4*>(gr + c) = o;
       }
     }

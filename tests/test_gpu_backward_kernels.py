@@ -183,3 +183,27 @@ def test_conv_in_wgrad(b, h, w, c):
     torch.cuda.synchronize()
     assert torch.allclose(dw.cpu() - 2, wr.grad, rtol=1e-4, atol=2e-3)
     assert torch.equal(dw, dw2)                              # fixed reduction order -> bit-reproducible
+
+
+@pytest.mark.parametrize("m,c", [(300, 64), (4096, 320)])
+def test_geglu_bwd(m, c):
+    """d(lin * gelu_tanh(gate)) from the tile-interleaved bf16 pre-activation the forward GEMM saved (bn = 256:
+    [128 lin | 128 gate] per 256 columns) -> plain [lin(4c) | gate(4c)] bf16 gradient."""
+    from ddpo_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n = 8 * c
+    lin = bf(torch.randn(m, 4 * c, generator=g))
+    gate = bf(torch.randn(m, 4 * c, generator=g))
+    dff = torch.randn(m, 4 * c, generator=g)
+    pre = torch.empty(m, n, dtype=torch.bfloat16)
+    for t in range(n // 256):
+        pre[:, t * 256:t * 256 + 128] = lin[:, t * 128:(t + 1) * 128]
+        pre[:, t * 256 + 128:(t + 1) * 256] = gate[:, t * 128:(t + 1) * 128]
+    lr, gr = lin.float().requires_grad_(), gate.float().requires_grad_()
+    (lr * torch.nn.functional.gelu(gr, approximate="tanh")).backward(dff)
+    dpre = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
+    ops.geglu_bwd(pre.to(DEV), dff.to(DEV), dpre, m, n, 256)
+    torch.cuda.synchronize()
+    out = dpre.float().cpu()
+    assert torch.allclose(out[:, :4 * c], lr.grad, rtol=1e-2, atol=1e-2)
+    assert torch.allclose(out[:, 4 * c:], gr.grad, rtol=1e-2, atol=1e-2)
