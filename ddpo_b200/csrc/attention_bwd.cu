@@ -31,12 +31,12 @@ struct AttnBwdArgs {
 
 // one query row (thread r) x 128 keys: read S and dP from TMEM, write P (optional) and dS as bf16
 // into [128 rows][64 keys] SW128 tiles.  `row_ok` false -> zeros.
-template <bool WRITE_P>
+template <bool WRITE_P, int NCOLS = 64>
 __device__ __forceinline__ void softmax_bwd_row(uint32_t t_s, uint32_t t_dp, uint8_t* sP, uint8_t* sDS, int r, int valid_keys,
                                                 bool row_ok, float lse_l2, float delta, float c, float scale, int col_begin, bool full) {
   const float delta_s = delta * scale;  // dS = P (dP - delta) scale = P (dP scale - delta scale): one FFMA + one FMUL
 #pragma unroll 1
-  for (int c0 = col_begin; c0 < col_begin + 64; c0 += 32) {
+  for (int c0 = col_begin; c0 < col_begin + NCOLS; c0 += 32) {
     uint32_t s[32], d[32];
     tmem_ld_32x32(t_s + c0, s);
     tmem_ld_32x32(t_dp + c0, d);
@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
 constexpr int DQ_BKV = 64;
 constexpr int DQ_KVT = DQ_BKV * 64 * 2;  // 8 KB
 constexpr int DQ_STAGES = 3;
-constexpr int DQ_THREADS = 192;          // warp0 TMA + TMEM alloc, warp1 MMA, warps 2..5 softmax/epilogue
+constexpr int DQ_THREADS = 320;          // warp0 TMA + TMEM alloc, warp1 MMA, warps 2..9 softmax/epilogue:
+                                         // 4 TMEM lane quarters x 2 halves of 32 key columns -> with 2 CTAs/SM four
+                                         // latency-bound softmax warps per scheduler instead of two
 constexpr int DQ_SMEM_Q = 0, DQ_SMEM_DO = AB_T, DQ_SMEM_RING = 2 * AB_T, DQ_SMEM_DS = DQ_SMEM_RING + DQ_STAGES * 2 * DQ_KVT,
               DQ_SMEM_BAR = DQ_SMEM_DS + AB_T, DQ_SMEM_TOTAL = DQ_SMEM_BAR + 256;
 
@@ -259,8 +261,8 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
   uint64_t* kv_full = bars + 1;    // [3]
   uint64_t* kv_empty = bars + 4;   // [3]
   uint64_t* sdp_full = bars + 7;
-  uint64_t* sdp_empty = bars + 8;  // count 4
-  uint64_t* ds_full = bars + 9;    // count 4
+  uint64_t* sdp_empty = bars + 8;  // count 8
+  uint64_t* ds_full = bars + 9;    // count 8
   uint64_t* ds_empty = bars + 10;
   uint64_t* acc_full = bars + 11;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
     prefetch_tmap(&p.tmQ), prefetch_tmap(&p.tmK64), prefetch_tmap(&p.tmV64), prefetch_tmap(&p.tmDO);
     mbar_init(q_full, 1);
     for (int i = 0; i < DQ_STAGES; ++i) mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
-    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 4), mbar_init(ds_full, 4), mbar_init(ds_empty, 1);
+    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 8), mbar_init(ds_full, 8), mbar_init(ds_empty, 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -343,6 +345,7 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
     }
   } else {
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;  // which 32 of the 64 key columns (and of the 64 dQ columns in the epilogue)
     const int r = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int row = q0 + r;
@@ -358,8 +361,8 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
       mbar_wait(sdp_full, j & 1);
       mbar_wait(ds_empty, (j & 1) ^ 1);
       tc_fence_after();
-      softmax_bwd_row<false>(T_S + lane_off, T_DP + lane_off, nullptr, smem + DQ_SMEM_DS, r, valid_keys, row_ok, lse_l2,
-                             delta, p.scale_log2e, p.scale, 0, valid_keys == DQ_BKV);
+      softmax_bwd_row<false, 32>(T_S + lane_off, T_DP + lane_off, nullptr, smem + DQ_SMEM_DS, r, valid_keys, row_ok,
+                                 lse_l2, delta, p.scale_log2e, p.scale, chalf * 32, valid_keys == DQ_BKV);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
     mbar_wait(acc_full, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 32) {
+    for (int c0 = chalf * 32; c0 < chalf * 32 + 32; c0 += 32) {
       uint32_t v[32];
       tmem_ld_32x32(T_DQ + lane_off + c0, v);
       tmem_ld_wait();
