@@ -69,6 +69,14 @@ def threefry_split(key, num=2):
     return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(num)]
 
 
+def threefry_randint(key, n, minval, maxval):
+    """jax.random.randint(key, (n,), minval, maxval) on the host -> list of ints."""
+    k = (C.c_uint32 * 2)(key[0], key[1])
+    out = (C.c_int32 * int(n))()
+    check(lib().ddpo_threefry_randint_host(k, int(n), int(minval), int(maxval), out), "threefry_randint")
+    return [int(v) for v in out]
+
+
 def key_tensor(keys, device):
     """[(k0,k1), ...] -> int64-free uint32 storage as int32 tensor [len, 2] on device."""
     flat = []
@@ -401,3 +409,39 @@ def clip_adamw(params, grad_acc, mu, nu, sumsq, grad_scale, max_norm, lr, b1, b2
                                              float(grad_scale), float(max_norm), float(lr), float(b1), float(b2),
                                              float(eps), float(wd), int(step), _p(norm_out), _stream()),
          float(params.numel()) * 24, _e)
+
+
+# --------------------------------------------------------------------- RWR -------
+def rwr_workspace(batch, device):
+    return torch.zeros(int(lib().ddpo_rwr_workspace_floats(int(batch))), dtype=torch.float32, device=device)
+
+
+def rwr_noisy_latents(moments_nhwc, key_sample_dev, key_noise_dev, timesteps, alphas_cumprod, noise_out, noisy_out,
+                      latents_out=None, scaling=0.18215):
+    """moments [B,h,w,2C] fp32 -> noise / noisy latents [B,C,h,w] (reference ddpo/training/diffusion.py:16-43)."""
+    _chk(moments_nhwc, torch.float32, "moments")
+    _chk(timesteps, torch.int32, "timesteps")
+    _chk(noise_out, torch.float32, "noise_out")
+    _chk(noisy_out, torch.float32, "noisy_out")
+    b, h, w, c2 = moments_nhwc.shape
+    assert timesteps.numel() == b and noise_out.numel() == b * (c2 // 2) * h * w == noisy_out.numel()
+    _e = _ev()
+    _run("rwr_noisy_latents", lib().ddpo_rwr_noisy_latents(_p(moments_nhwc), _p(key_sample_dev), _p(key_noise_dev),
+                                                           _p(timesteps), _p(alphas_cumprod), float(scaling), b, c2 // 2,
+                                                           h, w, _p(noise_out), _p(noisy_out), _p(latents_out),
+                                                           _stream()), 0.0, _e)
+
+
+def rwr_mse_loss(eps_u, eps_c, noise, guidance, loss_out, ws, weights=None, per_sample=None, d_eps_u=None, d_eps_c=None):
+    """loss of ddpo/training/diffusion.py:77-90 and its gradient wrt both U-Net outputs; eps_* / noise are [B, n]."""
+    for t, nm in ((eps_u, "eps_u"), (eps_c, "eps_c"), (noise, "noise")):
+        _chk(t, torch.float32, nm)
+    b = noise.shape[0]
+    n = noise.numel() // b
+    if weights is not None:
+        _chk(weights, torch.float32, "weights")
+        assert weights.numel() == b
+    _e = _ev()
+    _run("rwr_mse_loss", lib().ddpo_rwr_mse_loss(_p(eps_u), _p(eps_c), _p(noise), _p(weights), float(guidance), b, n,
+                                                 _p(loss_out), _p(per_sample), _p(d_eps_u), _p(d_eps_c), _p(ws),
+                                                 _stream()), 0.0, _e)

@@ -235,6 +235,26 @@ int ddpo_dense_small_bwd(const float* x, const float* w, const float* bias, cons
 int ddpo_dilate2x_bf16(const float* x, void* y_bf16, int batch, int h, int w, int c, void* stream);
 int ddpo_copy2d(const float* src, int lds, float* dst, int ldd, int64_t rows, int cols, int accumulate, void* stream);
 
+/* ------------------------------------------------------------------ RWR ------------
+ * Reward-weighted regression step around the U-Net (ddpo/training/diffusion.py:6-102).
+ * ddpo_rwr_noisy_latents: latents = (mean + exp(0.5 clip(logvar,-30,20)) * normal(key_sample, NHWC shape)) * scaling
+ * (3P FlaxDiagonalGaussianDistribution.sample, :16-23), noise = normal(key_noise, NCHW shape) (:27),
+ * noisy = sqrt(a_t) latents + sqrt(1 - a_t) noise (3P add_noise_common, :36-41).
+ *   moments_nhwc [B, h, w, 2*channels] fp32 (mean | logvar); outputs NCHW [B, channels, h, w]; latents_out optional.
+ * ddpo_rwr_mse_loss: pred = e_u + g (e_c - e_u) (:77-79); per-sample mean squared error against `noise` (:83);
+ * loss = mean over the batch, or sum_b weights[b] * mse_b when weights != NULL (:84-90); d_eps_* = dloss/d eps
+ * (either may be NULL).  workspace: ddpo_rwr_workspace_floats(batch) floats, zero-initialised once. */
+/* host: jax.random.randint(key, (n,), minval, maxval) int32 -- the per-sample training timesteps (:27-32) */
+int ddpo_threefry_randint_host(const uint32_t key[2], int n, int32_t minval, int32_t maxval, int32_t* out);
+int64_t ddpo_rwr_workspace_floats(int batch);
+int ddpo_rwr_noisy_latents(const float* moments_nhwc, const uint32_t* key_sample_dev, const uint32_t* key_noise_dev,
+                           const int32_t* timesteps /*[B]*/, const float* alphas_cumprod, float scaling, int batch,
+                           int channels, int h, int w, float* noise_out, float* noisy_out, float* latents_out,
+                           void* stream);
+int ddpo_rwr_mse_loss(const float* eps_uncond, const float* eps_cond, const float* noise, const float* weights,
+                      float guidance_scale, int batch, int n, float* loss_out /*[1]*/, float* per_sample_out /*[B] or NULL*/,
+                      float* d_eps_uncond, float* d_eps_cond, float* workspace, void* stream);
+
 /* ---------------------------------------------------------------- optimizer --------
  * optax.chain(clip_by_global_norm, adamw(mu_dtype=bf16)) + AccumulatingTrainState.apply_gradients(do_update=True)
  * (pipeline/policy_gradient.py:130-150, ddpo/training/policy_gradient.py:32-43). */

@@ -99,3 +99,19 @@ def normal(key, shape):
     lo = np.nextafter(np.float32(-1.0), np.float32(0.0), dtype=np.float32)
     u = uniform(key, shape, lo, 1.0)
     return (np.float32(np.sqrt(2)) * erfinv_f32(u)).astype(np.float32)
+
+
+def randint(key, shape, minval, maxval):
+    """``jax.random.randint`` for int32 (jax==0.4.8 ``jax/_src/random.py:_randint``): two independent 32-bit draws
+    ``higher, lower`` from ``split(key)``; ``offset = ((higher % span) * (2**32 % span) + lower % span) % span`` in
+    uint32 arithmetic, ``2**32 % span`` formed as ``((2**16 % span) ** 2) % span``.  Call site: reference
+    ``ddpo/training/diffusion.py:29-34`` (timesteps).  Unpinned against a live JAX run (none available offline)."""
+    k1, k2 = split(key)
+    higher = random_bits(k1, shape)
+    lower = random_bits(k2, shape)
+    span = np.uint32(max(int(maxval) - int(minval), 1))
+    with np.errstate(over="ignore"):
+        mult = np.uint32(2 ** 16) % span
+        mult = np.uint32((mult * mult) % span)
+        off = ((higher % span) * mult + (lower % span)).astype(np.uint32) % span
+    return (np.int32(minval) + off.astype(np.int32)).astype(np.int32)
