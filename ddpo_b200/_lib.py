@@ -97,10 +97,14 @@ SIGNATURES = {
     "ddpo_dense_small_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "ddpo_dilate2x_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_copy2d": (i32, [vp, i32, vp, i32, i64, i32, i32, vp]),
+    "ddpo_vae_post_quant": (i32, [vp, vp, vp, f32, i32, i32, i32, i32, vp, vp]),
+    "ddpo_softmax_rows": (i32, [vp, i64, f32, vp, i64, i32, i32, vp]),
+    "ddpo_vae_conv_out": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_threefry_randint_host": (i32, [vp, i32, i32, i32, vp]),
     "ddpo_rwr_workspace_floats": (i64, [i32]),
     "ddpo_rwr_noisy_latents": (i32, [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp, vp, vp, vp]),
     "ddpo_rwr_mse_loss": (i32, [vp, vp, vp, vp, f32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "ddpo_gather_rows": (i32, [vp, vp, vp, i32, i64, vp]),
     "ddpo_optim_workspace_bytes": (i64, []),
     "ddpo_grad_sumsq": (i32, [vp, i64, vp, vp, vp]),
     "ddpo_clip_adamw": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, f32, i32, vp, vp]),

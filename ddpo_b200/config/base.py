@@ -30,6 +30,9 @@ base = {
         "weight_decay": 1e-4, "epsilon": 1e-8, "max_grad_norm": 1.0, "save_freq": 10, "optimizer": "adamw",
         "train_timestep_ratio": 1.0, "prompt_kwargs": {}, "per_prompt_stats_bufsize": 32,
         "per_prompt_stats_min_count": 16,
+        # extension (not in the reference): timesteps of one minibatch stacked into one U-Net pass; 1 = the
+        # reference's call sequence (ddpo_b200/pipeline/policy_gradient.py)
+        "train_macro": 10,
     },
 }
 

@@ -310,6 +310,18 @@ __global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __r
   }
 }
 
+// dst[r, :] = src[index[r], :]: the trajectory buffer's (sample, timestep) rows picked by the epoch's shuffles
+// (reference pipeline/policy_gradient.py:385-404,415-423 does this with host advanced indexing + H2D per step)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ index,
+                                   float* __restrict__ dst, int rows, int64_t row4) {
+  const int r = blockIdx.y;
+  const float4* s = reinterpret_cast<const float4*>(src) + index[r] * row4;
+  float4* d = reinterpret_cast<float4*>(dst) + static_cast<int64_t>(r) * row4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < row4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    d[i] = s[i];
+}
+
 static inline int grid_for(int64_t n, int threads) {
   int64_t g = (n + threads - 1) / threads;
   const int64_t cap = 148 * 32;
@@ -437,6 +449,18 @@ extern "C" int ddpo_dilate2x_bf16(const float* x, void* y_bf16, int batch, int h
   DDPO_REQUIRE(x && y_bf16 && c % 4 == 0, "dilate2x: bad arguments");
   dilate2x_bf16_kernel<<<grid_for(static_cast<int64_t>(batch) * 4 * h * w * (c / 4), 256), 256, 0,
                          static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y_bf16), batch, h, w, c / 4);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_gather_rows(const float* src, const int64_t* index_dev, float* dst, int rows, int64_t row_floats,
+                                void* stream) {
+  DDPO_REQUIRE(src && index_dev && dst && rows > 0 && rows <= 65535 && row_floats > 0 && row_floats % 4 == 0,
+               "gather_rows: bad arguments (rows=%d row_floats=%lld)", rows, (long long)row_floats);
+  const int64_t row4 = row_floats / 4;
+  int gx = static_cast<int>((row4 + 255) / 256);
+  if (gx > 64) gx = 64;
+  gather_rows_kernel<<<dim3(gx, rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, index_dev, dst, rows, row4);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }

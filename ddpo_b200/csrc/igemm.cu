@@ -96,13 +96,14 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             const int ms = m0 + sub * BM;
             if (p.is_conv) {
               const int b0 = ms / HW, h0 = (ms % HW) / p.W;
+              const int w0 = ms % p.W;  // non-zero only when a pixel row is wider than a tile (W > 128)
               const int tap = kit / kcs, ch = kit - tap * kcs;
               int dy = 0, dx = 0;
               if (p.taps == 9) {
                 dy = tap / 3;
                 dx = tap - dy * 3;
               }
-              const int cx = dx - p.pad;
+              const int cx = w0 * p.conv_stride + dx - p.pad;
               const int cy = h0 * p.conv_stride + dy - p.pad;
               if (ch < p.kc0)
                 tma_load_4d(sA + sub * A_TILE_BYTES, &p.tmA0, &full_bar[stage], ch * BK, cx, cy, b0);
@@ -241,8 +242,11 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
     // output grid W x H per sample (input grid is stride x larger)
     const int W = a->w, H = a->h, B = a->batch, s = a->conv_stride;
     DDPO_REQUIRE(s == 1 || s == 2, "ddpo_igemm: stride must be 1 or 2");
-    DDPO_REQUIRE(W > 0 && H > 0 && (W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128, "ddpo_igemm: W,H must be powers of two, W<=128 (W=%d H=%d)", W, H);
-    int bw = W, bh = (BM / W < H) ? BM / W : H;
+    DDPO_REQUIRE(W > 0 && H > 0 && (W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 1024,
+                 "ddpo_igemm: W,H must be powers of two, W<=1024 (W=%d H=%d)", W, H);
+    DDPO_REQUIRE(W <= BM || (s == 1 && a->mt_override == 0), "ddpo_igemm: rows wider than %d pixels need stride 1 (W=%d)", BM, W);
+    // a 128-row tile is bb samples x bh rows x bw pixels; rows wider than the tile are cut into W/128 tiles
+    int bw = W < BM ? W : BM, bh = (BM / bw < H) ? BM / bw : H;
     int bb = BM / (bw * bh);
     M_total = B * W * H;
     const int Wi = W * s, Hi = H * s;

@@ -84,10 +84,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
         const int tm = tile / tiles_n, tn = tile % tiles_n;
         const int m0 = tm * 2 * BM + static_cast<int>(rank) * BM;  // this CTA's 128 rows
         const int n0 = tn * BN + static_cast<int>(rank) * HB;       // this CTA's half of the weight tile
-        int b0 = 0, h0 = 0;
+        int b0 = 0, h0 = 0, w0 = 0;
         if (p.is_conv) {
           b0 = m0 / HW;
           h0 = (m0 % HW) / p.W;
+          w0 = m0 % p.W;  // non-zero only for rows wider than a tile (W > 128: the VAE decoder's 256 / 512 px levels)
         }
         for (int kit = 0; kit < kiters; ++kit) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -101,7 +102,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
               dy = tap / 3;
               dx = tap - dy * 3;
             }
-            const int cx = dx - p.pad;
+            const int cx = w0 * p.conv_stride + dx - p.pad;
             const int cy = h0 * p.conv_stride + dy - p.pad;
             if (ch < p.kc0)
               tma_load_4d_2sm(sA, &p.tmA0, &full_bar[stage], ch * BK, cx, cy, b0);

@@ -177,14 +177,16 @@ def groupnorm_workspace_floats(batch, hw, channels):
     return int(lib().ddpo_groupnorm_workspace_floats(batch, hw, channels))
 
 
-def _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, y_bf16, y_f32, raw_bf16, ws, ld0=0, ld1=0, skip_stats=False):
+def _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, y_bf16, y_f32, raw_bf16, ws, ld0=0, ld1=0, skip_stats=False,
+             eps=1e-5):
     return GroupNormArgs(_p(x0), _p(x1), int(c0), int(c1), int(ld0), int(ld1), int(batch), int(hw), _p(scale),
-                         _p(bias), 1e-5, int(silu), _p(y_bf16), _p(y_f32), _p(raw_bf16), _p(ws), int(skip_stats))
+                         _p(bias), float(eps), int(silu), _p(y_bf16), _p(y_f32), _p(raw_bf16), _p(ws), int(skip_stats))
 
 
 def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, y_bf16=None, y_f32=None,
-                  raw_bf16=None, skip_stats=False):
-    a = _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, y_bf16, y_f32, raw_bf16, ws, skip_stats=skip_stats)
+                  raw_bf16=None, skip_stats=False, eps=1e-5):
+    a = _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, y_bf16, y_f32, raw_bf16, ws, skip_stats=skip_stats,
+                 eps=eps)
     _e = _ev()
     per = 4 + (2 if y_bf16 is not None else 0) + (4 if y_f32 is not None else 0) + (2 if raw_bf16 is not None else 0)
     _run("groupnorm_fwd", lib().ddpo_groupnorm_fwd(C.byref(a), _stream()), float(batch) * hw * (c0 + c1) * per, _e)
@@ -394,6 +396,19 @@ def copy2d(src, lds, dst, ldd, rows, cols, accumulate=False):
                                      _stream()), 0.0, _e)
 
 
+def gather_rows(src, index, dst):
+    """dst[r] = src[index[r]] for fp32 [rows, row_floats] matrices; index int64 on the device."""
+    _chk(src, torch.float32, "src")
+    _chk(dst, torch.float32, "dst")
+    _chk(index, torch.int64, "index")
+    rows = index.numel()
+    row_floats = dst.numel() // rows
+    assert src.numel() % row_floats == 0 and dst.numel() == rows * row_floats
+    _e = _ev()
+    _run("gather_rows", lib().ddpo_gather_rows(_p(src), _p(index), _p(dst), rows, row_floats, _stream()),
+         float(rows) * row_floats * 8, _e)
+
+
 def optim_workspace(device):
     return torch.empty(int(lib().ddpo_optim_workspace_bytes()), dtype=torch.uint8, device=device)
 
@@ -445,3 +460,29 @@ def rwr_mse_loss(eps_u, eps_c, noise, guidance, loss_out, ws, weights=None, per_
     _run("rwr_mse_loss", lib().ddpo_rwr_mse_loss(_p(eps_u), _p(eps_c), _p(noise), _p(weights), float(guidance), b, n,
                                                  _p(loss_out), _p(per_sample), _p(d_eps_u), _p(d_eps_c), _p(ws),
                                                  _stream()), 0.0, _e)
+
+
+# --------------------------------------------------------------------- VAE -------
+def vae_post_quant(latents, w, bias, out, scaling=0.18215):
+    _chk(latents, torch.float32, "latents")
+    _chk(out, torch.float32, "out")
+    b, c, h, wd = latents.shape
+    _e = _ev()
+    _run("vae_post_quant", lib().ddpo_vae_post_quant(_p(latents), _p(w), _p(bias), float(scaling), b, c, h, wd, _p(out),
+                                                     _stream()), 0.0, _e)
+
+
+def softmax_rows(scores, probs_bf16, scale):
+    """probs[r] = softmax(scale * scores[r]); scores fp32 [rows, n], probs bf16 [rows, n] (row-contiguous)."""
+    _chk(scores, torch.float32, "scores")
+    _chk(probs_bf16, torch.bfloat16, "probs")
+    rows, n = scores.shape
+    _e = _ev()
+    _run("softmax_rows", lib().ddpo_softmax_rows(_p(scores), n, float(scale), _p(probs_bf16), n, rows, n, _stream()),
+         float(rows) * n * 6, _e)
+
+
+def vae_conv_out(x_nhwc, w, bias, batch, h, wd, cin, raw_nchw=None, img_nhwc=None):
+    _e = _ev()
+    _run("vae_conv_out", lib().ddpo_vae_conv_out(_p(x_nhwc), _p(w), _p(bias), _p(raw_nchw), _p(img_nhwc), batch, h, wd,
+                                                 cin, _stream()), 0.0, _e)

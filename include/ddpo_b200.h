@@ -234,6 +234,26 @@ int ddpo_dense_small_bwd(const float* x, const float* w, const float* bias, cons
                          void* stream);
 int ddpo_dilate2x_bf16(const float* x, void* y_bf16, int batch, int h, int w, int c, void* stream);
 int ddpo_copy2d(const float* src, int lds, float* dst, int ldd, int64_t rows, int cols, int accumulate, void* stream);
+/* dst[r, :] = src[index[r], :] (fp32 rows of row_floats, a multiple of 4; index is a DEVICE int64 array): the
+ * per-minibatch gather of (sample, timestep) rows out of the on-device trajectory buffer that replaces the
+ * reference's host-side shuffles + per-step H2D (pipeline/policy_gradient.py:385-404,415-423) */
+int ddpo_gather_rows(const float* src, const int64_t* index_dev, float* dst, int rows, int64_t row_floats, void* stream);
+
+/* ---------------------------------------------------------------- VAE decode --------
+ * vae_decode (pipeline/policy_gradient.py:174-182, ddpo/training/diffusion.py:105-112): latents / 0.18215 ->
+ * 3P diffusers FlaxAutoencoderKL.decode -> (x/2 + 0.5).clip(0,1), NHWC.  The decoder's 3x3 / 1x1 convolutions,
+ * GroupNorm(32, eps 1e-6)+swish and Dense layers run on ddpo_igemm / ddpo_groupnorm_fwd (pixel rows up to 1024 wide);
+ * these three entry points are the pieces that are not GEMM shaped. */
+/* out = post_quant_conv(latents / scaling): 1x1 conv on NCHW fp32, w_in_out [channels, channels] (HWIO 1x1) */
+int ddpo_vae_post_quant(const float* latents_nchw, const float* w_in_out, const float* bias, float scaling, int batch,
+                        int channels, int h, int w, float* out_nchw, void* stream);
+/* probs[r, :] = softmax(scale * scores[r, :]) (bf16): FlaxAttentionBlock's single-head attention weights */
+int ddpo_softmax_rows(const float* scores, int64_t ld_scores, float scale, void* probs_bf16, int64_t ld_probs, int rows,
+                      int n, void* stream);
+/* decoder conv_out (3x3, cin -> 3) on the normalised fp32 NHWC input; raw_nchw [B,3,H,W] (decoder .sample, optional)
+ * and img_nhwc [B,H,W,3] = (raw/2 + 0.5).clip(0,1) (optional) */
+int ddpo_vae_conv_out(const float* x_nhwc, const float* w_hwio, const float* bias, float* raw_nchw, float* img_nhwc,
+                      int batch, int h, int w, int cin, void* stream);
 
 /* ------------------------------------------------------------------ RWR ------------
  * Reward-weighted regression step around the U-Net (ddpo/training/diffusion.py:6-102).

@@ -1,0 +1,100 @@
+"""TEST INFRASTRUCTURE: a torch-CPU emulation of the handful of ``ddpo_b200.ops`` entry points the VAE decoder
+sequences, with the same argument conventions (bf16 operands, fp32 accumulation, [N, K] weights, NHWC).  It lets the
+CPU suite dry-run the HOST-side assembly of ``ddpo_b200/vae.py`` (buffer shapes, operand order, bias / residual
+plumbing, chunking) against the oracle without a GPU.  It is never imported by the package: the product path has no
+CPU fallback (``ops._p`` asserts CUDA tensors)."""
+import torch
+import torch.nn.functional as F
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+class CpuArena:
+    def __init__(self, device=None):
+        self.total_bytes = 0
+
+    def alloc(self, shape, dtype):
+        return torch.zeros(*shape, dtype=dtype)
+
+    def release(self, t):
+        pass
+
+
+def groupnorm_workspace_floats(batch, hw, channels):
+    return 8
+
+
+def prep_weight(src, dst, k, n, ldk=None, row_offset=0, col_offset=0, geglu_bn=0):
+    dst.copy_(src.reshape(k, n).t().to(BF16))
+
+
+def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, y_bf16=None, y_f32=None, raw_bf16=None,
+                  skip_stats=False, eps=1e-5):
+    assert x1 is None
+    x = x0.reshape(batch, hw, 32, c0 // 32).float()
+    mean = x.mean(dim=(1, 3), keepdim=True)
+    var = ((x * x).mean(dim=(1, 3), keepdim=True) - mean * mean).clamp(min=0)
+    y = ((x - mean) * torch.rsqrt(var + eps)).reshape(batch * hw, c0) * scale + bias
+    if silu:
+        y = y * torch.sigmoid(y)
+    if y_bf16 is not None:
+        y_bf16.copy_(y.to(BF16))
+    if y_f32 is not None:
+        y_f32.copy_(y)
+    if raw_bf16 is not None:
+        raw_bf16.copy_(x0.reshape(batch * hw, c0).to(BF16))
+
+
+def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None, m=None, taps=1, stride=1, bias=None,
+          rowvec=None, rows_per_sample=0, rowvec_ld=0, residual=None, ld_res=0, out_f32=None, out_bf16=None, ld_out=0,
+          geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0):
+    assert a1 is None and not geglu and rowvec is None and stride == 1
+    assert a0.dtype == BF16 and wt.dtype == BF16
+    c0 = int(c0 if c0 is not None else a0.shape[-1])
+    assert c0 % 64 == 0 and n % 32 == 0, (c0, n)
+    w = wt.reshape(n, taps * c0).float()
+    if conv is not None:
+        b, h, wd = conv
+        assert wd & (wd - 1) == 0 and h & (h - 1) == 0
+        x = a0.reshape(b, h, wd, c0).float().permute(0, 3, 1, 2)
+        ks = 3 if taps == 9 else 1
+        wk = w.reshape(n, ks, ks, c0).permute(0, 3, 1, 2)
+        y = F.conv2d(x, wk, None, padding=ks // 2).permute(0, 2, 3, 1).reshape(b * h * wd, n)
+    else:
+        assert taps == 1
+        y = a0.reshape(m, c0).float() @ w.t()
+    if bias is not None:
+        y = y + bias.reshape(1, n)
+    if residual is not None:
+        y = y + residual.reshape(y.shape)
+    if out_f32 is not None:
+        out_f32.reshape(y.shape).copy_(y)
+    if out_bf16 is not None:
+        out_bf16.reshape(y.shape).copy_(y.to(BF16))
+
+
+def conv_in(x_nchw, w, bias, y_nhwc, batch, cin, h, wd, cout):
+    assert cin <= 8 and cout % 4 == 0
+    y = F.conv2d(x_nchw, w.permute(3, 2, 0, 1), bias, padding=1).permute(0, 2, 3, 1)
+    y_nhwc.reshape(batch, h, wd, cout).copy_(y)
+
+
+def vae_post_quant(latents, w, bias, out, scaling=0.18215):
+    out.copy_(torch.einsum("bihw,io->bohw", latents / scaling, w.reshape(4, 4)) + bias[None, :, None, None])
+
+
+def upsample2x_bf16(x, y, batch, h, w, c):
+    v = x.reshape(batch, h, w, c).repeat_interleave(2, 1).repeat_interleave(2, 2)
+    y.reshape(batch, 2 * h, 2 * w, c).copy_(v.to(BF16))
+
+
+def softmax_rows(scores, probs_bf16, scale):
+    probs_bf16.copy_(torch.softmax(scores * scale, -1).to(BF16))
+
+
+def vae_conv_out(x_nhwc, w, bias, batch, h, wd, cin, raw_nchw=None, img_nhwc=None):
+    raw = F.conv2d(x_nhwc.reshape(batch, h, wd, cin).permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, padding=1)
+    if raw_nchw is not None:
+        raw_nchw.copy_(raw)
+    if img_nhwc is not None:
+        img_nhwc.copy_((raw / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1))
