@@ -36,17 +36,33 @@ base = {
     },
 }
 
+_SPARSE_SAMPLE = {"max_samples": 1024, "mask_mode": "percentile", "mask_param": 90, "identical_batch": True}
+_RWR_SAMPLE = {"max_samples": 10240, "mask_mode": "streaming_percentile", "mask_param": 0, "identical_batch": False}
+_SPARSE_TRAIN = {"train_cfg": True, "num_train_epochs": 50, "save_freq": 20, "dtype": "float32"}
+_RWR_TRAIN = {"train_cfg": True, "train_batch_size": 1, "num_train_epochs": 5, "save_freq": 20, "dtype": "float32",
+              "weighted_dataset": True, "temperature": 1 / 5.0}
+
+# dataset overrides with the reference's names and values (config/base.py:105-200, :300-340); logbase is local
+# (the reference prefixes its GCS bucket, config/user.py)
 compressed_animals = {
     "common": {"logbase": "logs/compressed-animals", "prompt_fn": "imagenet_animals", "filter_field": "jpeg"},
-    "pg": {},
-}
-aesthetic_animals = {
-    "common": {"logbase": "logs/aesthetic-animals", "prompt_fn": "common_animals", "filter_field": "aesthetic"},
-    "pg": {},
+    "sample": dict(_SPARSE_SAMPLE), "train": dict(_SPARSE_TRAIN, train_batch_size=4), "pg": {},
 }
 neg_compressed_animals = {
     "common": {"logbase": "logs/neg-compressed-animals", "prompt_fn": "imagenet_animals", "filter_field": "neg_jpeg"},
-    "pg": {},
+    "sample": dict(_SPARSE_SAMPLE), "train": dict(_SPARSE_TRAIN, train_batch_size=1), "pg": {},
+}
+compressed_animals_rwr = {
+    "common": {"logbase": "logs/rwr-compressed-animals", "prompt_fn": "imagenet_animals", "filter_field": "jpeg"},
+    "sample": dict(_RWR_SAMPLE), "train": dict(_RWR_TRAIN), "pg": {},
+}
+neg_compressed_animals_rwr = {
+    "common": {"logbase": "logs/rwr-neg-compressed-animals", "prompt_fn": "imagenet_animals", "filter_field": "neg_jpeg"},
+    "sample": dict(_RWR_SAMPLE), "train": dict(_RWR_TRAIN), "pg": {},
+}
+aesthetic_animals = {
+    "common": {"logbase": "logs/aesthetic-animals", "prompt_fn": "common_animals", "filter_field": "aesthetic"},
+    "sample": dict(_SPARSE_SAMPLE), "train": dict(_SPARSE_TRAIN, train_batch_size=4), "pg": {},
 }
 llava_alignment = {
     "common": {"logbase": "logs/llava-alignment", "prompt_fn": "nouns_activities", "filter_field": "llava_bertscore"},

@@ -97,3 +97,42 @@ def test_single_process_helpers_are_identity():
         D.shard_bounds(7, 0, 2)
     with pytest.raises(ValueError):
         D.grad_scale(0, 1)
+
+
+# ------------------------------------------------------------------ epoch driver: reward / advantage exchange ----
+def _driver_worker(rank, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        from ddpo_b200.pipeline import policy_gradient as PG
+        from ddpo_b200.utils.stat_tracking import PerPromptStatTracker
+        local_rewards = np.arange(4, dtype=np.float64)[:, None] * (rank + 1)        # jpeg-style [N, 1]
+        local_prompts = np.array([f"p{(i + rank) % 2}" for i in range(4)])
+        rewards = PG.allgather_array(local_rewards)                                  # process_allgather(tiled=True)
+        prompts = PG.allgather_array(local_prompts)
+        tracker = PerPromptStatTracker(32, 2)
+        adv = PG.compute_advantages(rewards, prompts, tracker)
+        mine = np.asarray(adv).reshape(WORLD, -1)[rank]                               # reference :349
+        glob = PG.compute_advantages(rewards, prompts, None).reshape(WORLD, -1)[rank]
+        np.savez(os.path.join(out_dir, f"drv{rank}.npz"), rewards=rewards, prompts=prompts, mine=mine, glob=glob)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_reward_allgather_and_advantage_slices(tmp_path):
+    """each worker sees the pod's rewards in rank order, normalises over ALL of them and keeps its own slice
+    (reference pipeline/policy_gradient.py:323-349)"""
+    port = _free_port()
+    mp.spawn(_driver_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    r = [np.load(tmp_path / f"drv{i}.npz") for i in range(WORLD)]
+    want_rewards = np.concatenate([np.arange(4)[:, None] * 1.0, np.arange(4)[:, None] * 2.0])
+    want_prompts = np.array(["p0", "p1", "p0", "p1", "p1", "p0", "p1", "p0"])
+    from ddpo_b200.utils.stat_tracking import PerPromptStatTracker
+    full = PerPromptStatTracker(32, 2).update(want_prompts, want_rewards)
+    z = (want_rewards - want_rewards.mean()) / want_rewards.std()
+    for i in range(WORLD):
+        np.testing.assert_array_equal(r[i]["rewards"], want_rewards)
+        assert list(r[i]["prompts"]) == list(want_prompts)
+        np.testing.assert_allclose(r[i]["mine"], np.asarray(full).reshape(WORLD, -1)[i])
+        np.testing.assert_allclose(r[i]["glob"], z.reshape(WORLD, -1)[i])
