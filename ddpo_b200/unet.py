@@ -74,6 +74,7 @@ class UNet:
         self.w: Dict[str, torch.Tensor] = {}       # bf16 forward GEMM operands
         self.aux: Dict[str, torch.Tensor] = {}     # permuted biases etc.
         self.ctx_kv: Optional[Dict[str, torch.Tensor]] = None
+        self._ctx_cache: Dict[tuple, dict] = {}     # context shape -> persistent bf16 context + K/V buffers
         self.ctx_batch = 0
         self._layers = self._enumerate_layers()
         self.wd: Dict[str, torch.Tensor] = {}      # bf16 backward (dgrad) GEMM operands, built on demand
@@ -161,18 +162,28 @@ class UNet:
 
     # ----------------------------------------------------------------- context ----
     def prepare_context(self, ctx: torch.Tensor):
-        """ctx fp32 [B, L, D]: computes every cross-attention K/V projection once."""
+        """ctx fp32 [B, L, D]: computes every cross-attention K/V projection once.
+
+        The bf16 context and the K/V buffers are allocated ONCE per context shape and reused: their addresses are baked
+        into captured CUDA graphs (the sampler captures one denoising step and calls this method eagerly before every
+        trajectory; the train steps capture this method itself), so a fresh allocation per call would leave a replayed
+        graph reading the previous call's freed buffers."""
         b, l, d = ctx.shape
-        ctx = ctx.to(self.device, F32).contiguous()
-        ctx_bf = torch.empty(b * l, d, dtype=BF16, device=self.device)
-        ops.cast_bf16(ctx, ctx_bf)
-        kv = {}
-        for key, w in self.w.items():
-            if key.endswith("attn2/kv"):
-                c2 = w.shape[0]
-                out = torch.empty(b * l, c2, dtype=BF16, device=self.device)
-                ops.igemm(a0=ctx_bf, wt=w, n=c2, c0=d, m=b * l, out_bf16=out)
-                kv[key] = out
+        cache = self._ctx_cache.get((b, l, d))
+        if cache is None:
+            cache = {"f32": torch.empty(b, l, d, dtype=F32, device=self.device),
+                     "bf": torch.empty(b * l, d, dtype=BF16, device=self.device),
+                     "kv": {key: torch.empty(b * l, w.shape[0], dtype=BF16, device=self.device)
+                            for key, w in self.w.items() if key.endswith("attn2/kv")}}
+            self._ctx_cache[(b, l, d)] = cache
+        if ctx.data_ptr() != cache["f32"].data_ptr():
+            cache["f32"].copy_(ctx)
+        ctx_bf = cache["bf"]
+        ops.cast_bf16(cache["f32"], ctx_bf)
+        kv = cache["kv"]
+        for key, out in kv.items():
+            w = self.w[key]
+            ops.igemm(a0=ctx_bf, wt=w, n=w.shape[0], c0=d, m=b * l, out_bf16=out)
         self.ctx_kv = kv
         self.ctx_batch = b
         self.ctx_len = l

@@ -120,3 +120,27 @@ def test_rwr_loop_sample_then_finetune(tmp_path, monkeypatch):
     assert res["steps"] == 8 and len(res["losses"]) == 2 and all(np.isfinite(res["losses"]))
     assert not torch.equal(models[1]["unet"], p0)
     assert utils.get_latest_epoch("logs/rwr-compressed-animals/models/1/unet") == 2
+
+
+def test_sampler_graph_replay_sees_each_calls_context():
+    """the captured denoising step must read the K/V of the CURRENT prompt batch on every later call"""
+    from ddpo_b200 import unet_spec
+    from ddpo_b200.diffusers_patch import DDIMScheduler, StableDiffusionPipeline
+    from ddpo_b200.unet import UNet
+    cfg = unet_spec.TINY
+    flat = unet_spec.init_flat_params(cfg, 0)
+    g = torch.Generator().manual_seed(7)
+    embs = [torch.randn(2, cfg.ctx_len, cfg.cross_attention_dim, generator=g).cuda() for _ in range(3)]
+    neg = torch.randn(1, cfg.ctx_len, cfg.cross_attention_dim, generator=g).expand(2, -1, -1).contiguous().cuda()
+    outs = {}
+    for use_graph in (False, True):
+        net = UNet(cfg, flat, "cuda")
+        sched = DDIMScheduler(1000, 0.00085, 0.012, "scaled_linear", None, False, 1, "epsilon")
+        pipe = StableDiffusionPipeline(net, sched, use_cuda_graph=use_graph)
+        st = sched.create_state()
+        outs[use_graph] = [pipe(e, neg, {"unet": net.params, "scheduler": st}, (1, 2), 3, 128, 128, 5.0, 1.0)[0].clone()
+                           for e in embs]
+    torch.cuda.synchronize()
+    for a, b in zip(outs[False], outs[True]):
+        assert torch.equal(a, b)
+    assert not torch.equal(outs[True][0], outs[True][1])
