@@ -318,6 +318,36 @@ def main():
     h2d = (emb_host.numel() + neg_host.numel()) * 4 / T_STEPS
     d2h = (fin.numel() + lps.numel()) * 4 / T_STEPS
 
+    # ---------------- VAE decode of the sample batch (the step between sampling and the reward, reference
+    # pipeline/policy_gradient.py:271-275): device time per batch and end to end (images copied to the host) ------------
+    vae_info = None
+    try:
+        from ddpo_b200.vae import SD_VAE, VAEDecoder
+        dec = VAEDecoder(SD_VAE, device=dev, seed=1, decode_batch=2)
+        lat8 = (S["x_cur"].view(B, 4, 64, 64) * 0.18215).contiguous()
+        lcv = ops.LAUNCH_COUNT
+        dec.decode(lat8)
+        torch.cuda.synchronize()
+        vae_launches = ops.LAUNCH_COUNT - lcv
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(2):
+            img = dec.decode(lat8)
+        v1.record()
+        torch.cuda.synchronize()
+        ms_decode = v0.elapsed_time(v1) / 2
+        tv = time.perf_counter()
+        img_host = dec.decode(lat8).cpu()
+        ms_decode_e2e = (time.perf_counter() - tv) * 1e3
+        ok = bool(torch.isfinite(img).all().item()) and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+        vae_info = {"ms_per_batch": ms_decode, "ms_per_batch_e2e": ms_decode_e2e, "images": B, "launches": vae_launches,
+                    "d2h_bytes": img_host.numel() * 4, "finite_in_unit_range": ok,
+                    "tflops": B * 1.24e12 / (ms_decode * 1e-3) / 1e12}
+        del dec, img, img_host
+        torch.cuda.empty_cache()
+    except Exception as ex:  # reported, never hidden: the headline then excludes the decode and says so
+        vae_info = {"error": repr(ex)[:300]}
+
     # ---------------- phase: ppo train steps (fwd+bwd of the 2x2 CFG batch) + one optimizer update ----------------
     ppo = None
     if args.phase in ("auto", "ppo"):
@@ -416,8 +446,11 @@ def main():
                 tbreak[k]["tflops"] = round(tagg[k][1] / (tagg[k][0] * 1e-3) / 1e12, 1)
         # one PPO sample = T sampling steps (batch 8) + T train steps (batch 2) + its share of the update
         # (a macro train step covers J timesteps of Bt samples)
-        s_per_sample = T_STEPS * (ms_per_step / B) + (T_STEPS / J) * (ms_train / Bt) + ms_update / Bt
-        s_per_sample_e2e = T_STEPS * (1e3 / (e2e_steps_per_s / world)) + (T_STEPS / J) * (ms_train_e2e / Bt) + ms_update / Bt
+        dec_ms = vae_info.get("ms_per_batch", 0.0) / B if vae_info else 0.0          # VAE decode share per sample
+        dec_ms_e2e = vae_info.get("ms_per_batch_e2e", 0.0) / B if vae_info else 0.0
+        s_per_sample = T_STEPS * (ms_per_step / B) + dec_ms + (T_STEPS / J) * (ms_train / Bt) + ms_update / Bt
+        s_per_sample_e2e = (T_STEPS * (1e3 / (e2e_steps_per_s / world)) + dec_ms_e2e + (T_STEPS / J) * (ms_train_e2e / Bt)
+                            + ms_update / Bt)
         ppo = {"ms_per_train_step": ms_train, "ms_per_update": ms_update, "train_launches": train_launches,
                "samples_per_s": world * 1e3 / s_per_sample, "samples_per_s_e2e": world * 1e3 / s_per_sample_e2e,
                "ms_train_step_e2e": ms_train_e2e, "first_pass_approx_kl": first_pass_kl,
@@ -433,7 +466,7 @@ def main():
         step_flops = 2 * B * UNET_GFLOP * 1e9
         if ppo is not None:
             head = {"metric": "ppo_samples_per_sec", "value": ppo["samples_per_s"],
-                    "unit": "PPO samples/s (50 sampling steps + 50 train steps + optimizer share per sample)"}
+                    "unit": "PPO samples/s (50 sampling steps + VAE decode + 50 train steps + optimizer share per sample)"}
         else:
             head = {"metric": "denoising_steps_per_sec", "value": steps_per_s,
                     "unit": "denoising steps/s (1 sample, both CFG branches)"}
@@ -456,6 +489,7 @@ def main():
                      "d2h_bytes_per_step": d2h, "what": "pipeline(...) 50-step call from pinned host embeddings to host final latents + log-probs"}),
             "gpu_launches": launches_per_step * args.steps + (ppo["train_launches"] * args.steps if ppo else 0),
             "ppo": ppo,
+            "vae_decode": vae_info,
             "roofline": {"bound": "tensor", "achieved": igemm_tflops, "peak": sus_tf, "unit": "TFLOP/s",
                          "frac": igemm_tflops / sus_tf, "traffic": _ncu_traffic(), "kernel": "igemm2_kernel (CTA-pair implicit GEMM; igemm_kernel below 1024 rows)",
                          "peak_source": f"{peak_src} bf16_tflops_sustained",

@@ -97,8 +97,12 @@ def test_ddpo_driver_macro_equals_reference_call_sequence(tmp_path, monkeypatch)
     (p1, i1), (p4, i4) = res
     assert i1["approx_kl"].shape == (4,) and i4["approx_kl"].shape == (1,)
     np.testing.assert_allclose(i4["loss"][0], i1["loss"].mean(), rtol=1e-5, atol=1e-7)
-    diff = (p1 - p4).abs().max().item()
-    assert diff < 2e-5, diff        # lr 1e-4: an Adam step is ~1e-4; summation-order noise only flips near-zero entries
+    # lr 1e-4: every parameter moves ~1e-4 (Adam's first step is lr * g / (|g| + eps)); a semantic difference between
+    # the two schedules would show up at that size everywhere.  Summation-order noise (1e-6 relative on g) only matters
+    # for the handful of entries with |g| ~ eps = 1e-8, whose sign may flip: bounded by 2 lr.
+    d = (p1 - p4).abs()
+    assert d.mean().item() < 1e-6 and d.max().item() <= 2.5e-4, (d.mean().item(), d.max().item())
+    assert (p1 - _models(seed=1)[1]["unet"]).abs().mean().item() > 2e-5   # and the step itself is much larger
 
 
 def test_rwr_loop_sample_then_finetune(tmp_path, monkeypatch):
