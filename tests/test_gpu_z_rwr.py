@@ -36,7 +36,8 @@ def test_noisy_latents_match_oracle(b, hw):
     ops.rwr_noisy_latents(mom.to(dev), keys[0], keys[1], torch.tensor(ts, dtype=torch.int32, device=dev),
                           torch.as_tensor(np.asarray(ac, np.float32)).to(dev), noise, noisy, latents_out=lat)
     torch.cuda.synchronize()
-    assert np.array_equal(noise.cpu().numpy(), noise_r)                      # threefry normal: bit exact
+    # same threefry bits; erfinv's log1pf differs from NumPy's by an ulp (same bound as test_threefry_normal_matches_oracle)
+    np.testing.assert_allclose(noise.cpu().numpy(), noise_r, rtol=0, atol=2e-6)
     np.testing.assert_allclose(lat.cpu().numpy(), lat_r, rtol=2e-6, atol=1e-6)     # expf vs np.exp: ~1 ulp
     np.testing.assert_allclose(noisy.cpu().numpy(), noisy_r, rtol=2e-6, atol=1e-6)
 
@@ -106,7 +107,7 @@ def test_rwr_train_step_matches_oracle(train_cfg, weighted, use_graph):
     ac = OS.create_state(OS.SD_CONFIG).alphas_cumprod
     noisy, noise, ts, _ = OD.make_inputs(batch["vae"].numpy(), sample_rng, ac)
     assert D.train_step.last["timesteps"] == list(ts)
-    assert np.array_equal(D.train_step.last["noise"].cpu().numpy(), noise)
+    np.testing.assert_allclose(D.train_step.last["noise"].cpu().numpy(), noise, rtol=0, atol=2e-6)
     fp = flat.clone().requires_grad_(True)
     onet = UNetOracle(cfg, unet_spec.views(fp, cfg))
     loss_r, per_r = OD.train_loss(onet, (noisy, noise, ts), batch["prompt_embeds"], batch["uncond_embeds"], train_cfg,
