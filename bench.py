@@ -457,6 +457,40 @@ def main():
                "train_tflops_per_gpu": 3 * 2 * Bt * J * UNET_GFLOP * 1e9 / (ms_train * 1e-3) / 1e12,
                "train_batch": Bt, "timesteps_per_train_pass": J, "unet_batch_per_train_pass": 2 * Bt * J, "kernels": tbreak}
 
+    # ---------------- e2e through the epoch driver (the call a user makes): pipeline/policy_gradient.main ------------
+    # prompts -> text stub -> 50-step sampling of 8 samples -> VAE decode -> images to the host -> JPEG reward on the
+    # driver's thread pool -> advantages -> shuffles -> on-device gathers -> 20 macro train passes + 4 optimizer updates.
+    # Epoch 0 warms up (graph capture); epoch 1 is timed by the driver's own wall clock (includes every H2D / D2H).
+    driver = None
+    if ppo is not None and vae_info is not None and "error" not in vae_info and not args.ncu:
+        try:
+            import contextlib
+            from ddpo_b200.pipeline import policy_gradient as PG
+            from ddpo_b200.utils.text_stub import StubTextEncoder, StubTokenizer
+            from ddpo_b200.vae import SD_VAE, VAEDecoder
+            pipe.vae = VAEDecoder(SD_VAE, device=dev, seed=1, decode_batch=2)
+            net.grads.zero_()  # the timing passes above accumulated gradients the driver's fresh train state must not see
+            pipe.tokenizer, pipe.text_encoder = StubTokenizer(), StubTextEncoder(1024)
+            argv = ["--dataset", "compressed_animals", "--sample_batch_size", str(B), "--num_sample_batches_per_epoch", "1",
+                    "--train_batch_size", str(TRAIN_BATCH), "--train_macro", str(TRAIN_MACRO), "--num_train_epochs", "2",
+                    "--save_freq", "1000000", "--savepath", f"bench_driver_{rank}", "--seed", "0"]
+            with contextlib.redirect_stdout(sys.stderr):
+                out = PG.main(argv, models=(pipe, {"unet": net.params, "scheduler": state, "text_encoder": {}}),
+                              max_epochs=2, save_last=False)
+            h = out["history"][1]
+            tsec = torch.tensor([h["sample_seconds"], h["train_seconds"]], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+            ssec, trsec = tsec.tolist()
+            kl = out["history"][0]["infos"][0]["approx_kl"]
+            driver = {"samples_per_s": world * B / (ssec + trsec), "sample_seconds": ssec, "train_seconds": trsec,
+                      "samples_per_epoch_per_gpu": B, "mean_reward": h["mean_reward"], "epoch0_first_pass_approx_kl": float(kl[0]),
+                      "optimizer_updates_per_epoch": B // TRAIN_BATCH,
+                      "h2d_bytes_per_epoch": B * 77 * 1024 * 4 + (B // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * TRAIN_MACRO * TRAIN_BATCH * 40,
+                      "d2h_bytes_per_epoch": B * 512 * 512 * 3 * 4 + B * T_STEPS * 8 + (B // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * 12}
+        except Exception as ex:  # reported, never hidden
+            driver = {"error": repr(ex)[:300]}
+
     if rank == 0:
         cpu = None
         if not args.no_cpu:
@@ -487,6 +521,7 @@ def main():
                     if ppo is not None else
                     {"value": e2e_steps_per_s, "unit": "denoising steps/s", "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h, "what": "pipeline(...) 50-step call from pinned host embeddings to host final latents + log-probs"}),
+            "e2e_driver": driver,
             "gpu_launches": launches_per_step * args.steps + (ppo["train_launches"] * args.steps if ppo else 0),
             "ppo": ppo,
             "vae_decode": vae_info,

@@ -178,9 +178,10 @@ def save_png(path, image):
 
 
 # ------------------------------------------------------------------------ main ----
-def main(argv=None, models=None, max_epochs=None):
-    """``models``: optional ``(pipeline, params)`` (tests / bench inject a small random-init model);
-    ``max_epochs`` caps ``num_train_epochs``.  Returns a dict of per-epoch statistics."""
+def main(argv=None, models=None, max_epochs=None, save_last=True):
+    """``models``: optional ``(pipeline, params)`` (tests / bench inject a random-init model); ``max_epochs`` caps
+    ``num_train_epochs``; ``save_last=False`` skips the unconditional checkpoint of the final epoch (bench: a
+    3.5 GB file).  Returns a dict of per-epoch statistics."""
     args = Parser().parse_args("pg", argv)
     if not hasattr(args, "train_macro"):
         args.train_macro = 10
@@ -342,7 +343,7 @@ def main(argv=None, models=None, max_epochs=None):
         torch.cuda.synchronize()
         t_train = time.time() - t_train0
 
-        if (epoch + 1) % args.save_freq == 0 or epoch == n_epochs - 1:                                     # :457-464
+        if (epoch + 1) % args.save_freq == 0 or (epoch == n_epochs - 1 and save_last):                     # :457-464
             utils.save_checkpoint_multiprocess(os.path.join(args.savepath, "checkpoints"),
                                                utils.params_tree(state.params, cfg), step=epoch, keep=1e6,
                                                overwrite=True)
