@@ -35,7 +35,8 @@ class GroupNormArgs(C.Structure):
 
 class AttentionArgs(C.Structure):
     _fields_ = [("q", vp), ("k", vp), ("v", vp), ("out", vp), ("lse", vp), ("batch", i32), ("heads", i32),
-                ("nq", i32), ("nk", i32), ("head_dim", i32), ("ldq", i32), ("ldk", i32), ("ldv", i32), ("ldo", i32)]
+                ("nq", i32), ("nk", i32), ("head_dim", i32), ("ldq", i32), ("ldk", i32), ("ldv", i32), ("ldo", i32),
+                ("causal", i32)]
 
 
 class WgradArgs(C.Structure):
@@ -97,6 +98,9 @@ SIGNATURES = {
     "ddpo_dense_small_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "ddpo_dilate2x_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_copy2d": (i32, [vp, i32, vp, i32, i64, i32, i32, vp]),
+    "ddpo_embed_tokens": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "ddpo_act_bf16": (i32, [vp, vp, i64, i32, vp]),
+    "ddpo_layernorm_f32": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),
     "ddpo_vae_post_quant": (i32, [vp, vp, vp, f32, i32, i32, i32, i32, vp, vp]),
     "ddpo_softmax_rows": (i32, [vp, i64, f32, vp, i64, i32, i32, vp]),
     "ddpo_vae_conv_out": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),

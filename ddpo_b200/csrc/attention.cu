@@ -31,6 +31,7 @@ struct AttnArgs {
   __nv_bfloat16* out;
   float* lse;  // [B, heads, Nq] or null
   int nq, nk, heads, ldo;
+  int causal;         // 1: query i attends keys j <= i (CLIP text encoder); 0: all keys
   float scale_log2e;  // d^-0.5 * log2(e)
   float scale;
 };
@@ -137,13 +138,15 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
     float m_run = -INFINITY, l_run = 0.f;
     const float c = p.scale_log2e;
     uint8_t* sP = smem + AT_SMEM_P;
+    // keys [0, k_lim) are visible to this thread's query row (causal: j <= i; key 0 is always visible)
+    const int k_lim = p.causal ? min(p.nk, q0 + r + 1) : p.nk;
     // pass 1 of a block: row max over the 128 scores in X[j & 1] (full blocks take the predicate-free path: the
     // softmax warps are instruction bound)
     auto row_max = [&](int j) {
       const int xb = j & 1;
       mbar_wait(&s_full[xb], (j >> 1) & 1);
       tc_fence_after();
-      const int valid = min(AT_BKV, p.nk - j * AT_BKV);
+      const int valid = min(AT_BKV, k_lim - j * AT_BKV);
       const bool full = valid == AT_BKV;
       float m_blk = -INFINITY;
 #pragma unroll 1
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
     for (int j = 0; j < nkb; ++j) {
       const int xb = j & 1;
       const int kbase = j * AT_BKV;
-      const int valid = min(AT_BKV, p.nk - kbase);
+      const int valid = min(AT_BKV, k_lim - kbase);
       const bool full = valid == AT_BKV;
       const float m_blk = m_next;
       const float m_new = fmaxf(m_run, m_blk);
@@ -284,6 +287,8 @@ extern "C" int ddpo_attention_fwd(const ddpo_attention_args* a, void* stream) {
   p.out = static_cast<__nv_bfloat16*>(a->out);
   p.lse = a->lse;
   p.nq = a->nq, p.nk = a->nk, p.heads = a->heads, p.ldo = a->ldo;
+  p.causal = a->causal != 0;
+  DDPO_REQUIRE(!p.causal || a->nq == a->nk, "attention_fwd: causal masking needs nq == nk");
   p.scale = 1.0f / sqrtf(static_cast<float>(AT_D));
   p.scale_log2e = p.scale * 1.4426950408889634f;
   static bool attr = false;

@@ -268,8 +268,8 @@ def dense_small(x, w, bias, y, batch, k, n, silu_in=False, silu_out=False):
 
 
 # --------------------------------------------------------------- attention -------
-def attention_fwd(q, k, v, out, batch, heads, nq, nk, ldq, ldk, ldv, ldo, lse=None):
-    a = AttentionArgs(_p(q), _p(k), _p(v), _p(out), _p(lse), batch, heads, nq, nk, 64, ldq, ldk, ldv, ldo)
+def attention_fwd(q, k, v, out, batch, heads, nq, nk, ldq, ldk, ldv, ldo, lse=None, causal=False):
+    a = AttentionArgs(_p(q), _p(k), _p(v), _p(out), _p(lse), batch, heads, nq, nk, 64, ldq, ldk, ldv, ldo, int(causal))
     _e = _ev()
     _run("attention_fwd", lib().ddpo_attention_fwd(C.byref(a), _stream()), 4.0 * batch * heads * nq * nk * 64, _e,
          f"B{batch} H{heads} nq{nq} nk{nk}")
@@ -486,3 +486,28 @@ def vae_conv_out(x_nhwc, w, bias, batch, h, wd, cin, raw_nchw=None, img_nhwc=Non
     _e = _ev()
     _run("vae_conv_out", lib().ddpo_vae_conv_out(_p(x_nhwc), _p(w), _p(bias), _p(raw_nchw), _p(img_nhwc), batch, h, wd,
                                                  cin, _stream()), 0.0, _e)
+
+
+# ------------------------------------------------------------ text encoder -------
+def embed_tokens(ids, token_embedding, position_embedding, out, seq_len):
+    _chk(ids, torch.int32, "ids")
+    _chk(out, torch.float32, "out")
+    rows, dim = out.shape
+    _e = _ev()
+    _run("embed_tokens", lib().ddpo_embed_tokens(_p(ids), _p(token_embedding), _p(position_embedding), _p(out), rows,
+                                                 int(seq_len), dim, token_embedding.shape[0], _stream()), 0.0, _e)
+
+
+def act_bf16(x, y_bf16, act):
+    """act: "gelu" (erf form) or "quick_gelu"."""
+    _chk(x, torch.float32, "x")
+    _chk(y_bf16, torch.bfloat16, "y")
+    _e = _ev()
+    _run("act_bf16", lib().ddpo_act_bf16(_p(x), _p(y_bf16), x.numel(), {"gelu": 0, "quick_gelu": 1}[act], _stream()),
+         float(x.numel()) * 6, _e)
+
+
+def layernorm_f32(x, scale, bias, y, m, c, eps=1e-5):
+    _e = _ev()
+    _run("layernorm_f32", lib().ddpo_layernorm_f32(_p(x), _p(scale), _p(bias), _p(y), int(m), int(c), float(eps),
+                                                   _stream()), float(m) * c * 8, _e)

@@ -180,7 +180,7 @@ def load_flax_model(loadpath, epoch="latest"):
 
 # --------------------------------------------------------------------- loaders ----
 def load_unet(loadpath, epoch="latest", pretrained_model="stabilityai/stable-diffusion-2-base", dtype="float32",
-              cache="cache", device="cuda", seed=0, with_vae=True):
+              cache="cache", device="cuda", seed=0, with_vae=True, text_encoder="clip"):
     """Reference :320-371: returns ``(pipeline, params)`` with ``params`` = ``{"unet", "vae", "text_encoder",
     "scheduler"}``.  Weights are random-init (see module docstring) unless ``loadpath`` names a saved ``unet_*.pkl``."""
     from ..diffusers_patch import DDIMScheduler, StableDiffusionPipeline
@@ -201,11 +201,17 @@ def load_unet(loadpath, epoch="latest", pretrained_model="stabilityai/stable-dif
     if with_vae:
         from ..vae import VAEDecoder, vae_config_for
         vae = VAEDecoder(vae_config_for(pretrained_model), device=device, seed=seed + 1)
-    pipeline = StableDiffusionPipeline(unet, scheduler, tokenizer=StubTokenizer(),
-                                       text_encoder=StubTextEncoder(cfg.cross_attention_dim), vae=vae,
+    if text_encoder == "clip":
+        # the CLIP text tower on the GPU (random-init, like every weight here); ids come from the stub tokenizer
+        # (no vocabulary files offline), folded into the tower's vocabulary range
+        from ..text_encoder import CLIPTextEncoder, text_config_for
+        tenc = CLIPTextEncoder(text_config_for(pretrained_model), device=device, seed=seed + 2)
+    else:
+        tenc = StubTextEncoder(cfg.cross_attention_dim)
+    pipeline = StableDiffusionPipeline(unet, scheduler, tokenizer=StubTokenizer(), text_encoder=tenc, vae=vae,
                                        vae_scale_factor=8)
-    params = {"unet": unet.params, "vae": None if vae is None else vae.params, "text_encoder": {},
-              "scheduler": scheduler.create_state()}
+    params = {"unet": unet.params, "vae": None if vae is None else vae.params,
+              "text_encoder": getattr(tenc, "params", {}), "scheduler": scheduler.create_state()}
     return pipeline, params
 
 

@@ -181,6 +181,7 @@ typedef struct {
   float* lse;     /* fp32 [batch, heads, nq] log-sum-exp of the scaled scores, or NULL */
   int batch, heads, nq, nk, head_dim;
   int ldq, ldk, ldv, ldo;
+  int causal;     /* 1: query i sees keys j <= i (3P transformers FlaxCLIPTextModel's causal mask); needs nq == nk */
 } ddpo_attention_args;
 int ddpo_attention_fwd(const ddpo_attention_args* a, void* stream);
 
@@ -254,6 +255,19 @@ int ddpo_softmax_rows(const float* scores, int64_t ld_scores, float scale, void*
  * and img_nhwc [B,H,W,3] = (raw/2 + 0.5).clip(0,1) (optional) */
 int ddpo_vae_conv_out(const float* x_nhwc, const float* w_hwio, const float* bias, float* raw_nchw, float* img_nhwc,
                       int batch, int h, int w, int cin, void* stream);
+
+/* -------------------------------------------------------------- text encoder --------
+ * CLIP text model the reference runs on the host CPU (pipeline/policy_gradient.py:185-187; inside the RWR step at
+ * ddpo/training/diffusion.py:45-51,62-68; 3P transformers==4.28.1 FlaxCLIPTextModel).  Linears run on ddpo_igemm,
+ * the causal self-attention on ddpo_attention_fwd (causal = 1), the pre-LayerNorms on ddpo_layernorm_fwd. */
+/* out[m, :] = token_embedding[ids[m], :] + position_embedding[m % seq_len, :]  (fp32) */
+int ddpo_embed_tokens(const int32_t* ids, const float* token_embedding, const float* position_embedding, float* out,
+                      int rows, int seq_len, int dim, int vocab, void* stream);
+/* y = act(x) as bf16; act 0 = gelu (erf form), 1 = quick_gelu (x * sigmoid(1.702 x)) */
+int ddpo_act_bf16(const float* x, void* y_bf16, int64_t n, int act, void* stream);
+/* LayerNorm with fp32 output (final_layer_norm: the conditioning tensor is fp32) */
+int ddpo_layernorm_f32(const float* x, const float* scale, const float* bias, float* y, int m, int c, float eps,
+                       void* stream);
 
 /* ------------------------------------------------------------------ RWR ------------
  * Reward-weighted regression step around the U-Net (ddpo/training/diffusion.py:6-102).

@@ -25,7 +25,7 @@ def groupnorm_workspace_floats(batch, hw, channels):
 
 
 def prep_weight(src, dst, k, n, ldk=None, row_offset=0, col_offset=0, geglu_bn=0):
-    dst.copy_(src.reshape(k, n).t().to(BF16))
+    dst[row_offset:row_offset + n].copy_(src.reshape(k, n).t().to(BF16))
 
 
 def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, y_bf16=None, y_f32=None, raw_bf16=None,
@@ -98,3 +98,42 @@ def vae_conv_out(x_nhwc, w, bias, batch, h, wd, cin, raw_nchw=None, img_nhwc=Non
         raw_nchw.copy_(raw)
     if img_nhwc is not None:
         img_nhwc.copy_((raw / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1))
+
+
+# ---- text encoder ----
+def embed_tokens(ids, token_embedding, position_embedding, out, seq_len):
+    rows = ids.numel()
+    pos = position_embedding[torch.arange(rows) % seq_len]
+    out.copy_(token_embedding[ids.long()] + pos)
+
+
+def layernorm_fwd(x, scale, bias, y_bf16, m, c, stats=None):
+    xf = x.reshape(m, c).float()
+    mean = xf.mean(-1, keepdim=True)
+    var = ((xf * xf).mean(-1, keepdim=True) - mean * mean).clamp(min=0)
+    y_bf16.reshape(m, c).copy_(((xf - mean) * torch.rsqrt(var + 1e-5) * scale + bias).to(BF16))
+
+
+def layernorm_f32(x, scale, bias, y, m, c, eps=1e-5):
+    xf = x.reshape(m, c).float()
+    mean = xf.mean(-1, keepdim=True)
+    var = ((xf * xf).mean(-1, keepdim=True) - mean * mean).clamp(min=0)
+    y.reshape(m, c).copy_((xf - mean) * torch.rsqrt(var + eps) * scale + bias)
+
+
+def act_bf16(x, y_bf16, act):
+    y = x * torch.sigmoid(1.702 * x) if act == "quick_gelu" else F.gelu(x)
+    y_bf16.copy_(y.to(BF16))
+
+
+def attention_fwd(q, k, v, out, batch, heads, nq, nk, ldq, ldk, ldv, ldo, lse=None, causal=False):
+    """q/k/v are column-offset VIEWS of a [rows, ld] bf16 matrix, head h at columns [h*64, h*64+64)."""
+    def heads_of(t, n):
+        return t[:, : heads * 64].reshape(batch, n, heads, 64).permute(0, 2, 1, 3).float()
+    qq, kk, vv = heads_of(q, nq), heads_of(k, nk), heads_of(v, nk)
+    s = qq @ kk.transpose(-1, -2) * (64 ** -0.5)
+    if causal:
+        s = s + torch.full((nq, nk), float("-inf")).triu(1)
+    p = torch.softmax(s, -1).to(BF16).float()           # the kernel rounds P to bf16 before P V
+    o = (p @ vv).permute(0, 2, 1, 3).reshape(batch * nq, heads * 64)
+    out[:, : heads * 64].copy_(o.to(BF16))

@@ -10,9 +10,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _models(seed=0):
+def _models(seed=0, text_encoder="stub"):
     from ddpo_b200 import utils
-    return utils.load_unet(None, pretrained_model="tiny", device="cuda", seed=seed)
+    return utils.load_unet(None, pretrained_model="tiny", device="cuda", seed=seed, text_encoder=text_encoder)
 
 
 def test_epoch_buffer_gather_equals_direct_indexing():
@@ -148,3 +148,21 @@ def test_sampler_graph_replay_sees_each_calls_context():
     for a, b in zip(outs[False], outs[True]):
         assert torch.equal(a, b)
     assert not torch.equal(outs[True][0], outs[True][1])
+
+
+def test_ddpo_driver_with_the_gpu_text_encoder(tmp_path, monkeypatch):
+    """same loop with prompts embedded by the CLIP text tower on the GPU (utils.load_unet default)"""
+    from ddpo_b200.pipeline import policy_gradient as PG
+    from ddpo_b200.text_encoder import CLIPTextEncoder
+    from ddpo_b200.training import policy_gradient as pg
+    monkeypatch.chdir(tmp_path)
+    pg._GRAPHS.clear()
+    models = _models(seed=4, text_encoder="clip")
+    assert isinstance(models[0].text_encoder, CLIPTextEncoder)
+    argv = ["--dataset", "compressed_animals", "--pretrained_model", "tiny", "--resolution", "128",
+            "--sample_batch_size", "2", "--num_sample_batches_per_epoch", "1", "--n_inference_steps", "3",
+            "--train_batch_size", "2", "--train_macro", "3", "--num_train_epochs", "1", "--save_freq", "100",
+            "--savepath", "clip", "--seed", "1"]
+    out = PG.main(argv, models=models, max_epochs=1, save_last=False)
+    info = out["history"][0]["infos"][0]
+    assert info["approx_kl"].shape == (1,) and info["approx_kl"][0] == 0.0 and np.isfinite(out["history"][0]["mean_reward"])
