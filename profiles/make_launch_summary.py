@@ -54,6 +54,10 @@ def parse(path):
 
 def main():
     out = {}
+    prefix, traffic = "r1_launches_summary", "r1_traffic"
+    if len(sys.argv) > 2 and sys.argv[1] == "--out":        # --out NAME: write NAME.md / NAME.json instead
+        prefix = traffic = sys.argv[2]
+        del sys.argv[1:3]
     md = ["# Round 1 -- ncu launch lists of one eager step (current build)\n",
           "Per-launch times under ncu are cold-cache and serialised: the SHARE column is what must agree with the CUDA-event",
           "breakdown `bench.py` prints (`kernels` / `ppo.kernels`).  DRAM bytes are `dram__bytes_read.sum + dram__bytes_write.sum`.\n"]
@@ -75,9 +79,9 @@ def main():
             md.append(f"| {name} | {n} | {ms:.3f} | {100 * ms / tot:.1f}% | {b / n / 1e6:.1f} | {b / ms / 1e6 if ms else 0:.0f} |")
             out[tag][name] = {"launches": n, "ms": round(ms, 4), "share": round(ms / tot, 4),
                               "dram_bytes_per_launch": round(b / n), "dram_gbs": round(b / ms / 1e6, 1) if ms else None}
-    with open(os.path.join(HERE, "r1_launches_summary.md"), "w") as f:
+    with open(os.path.join(HERE, prefix + ".md"), "w") as f:
         f.write("\n".join(md) + "\n")
-    with open(os.path.join(HERE, "r1_traffic.json"), "w") as f:
+    with open(os.path.join(HERE, traffic + ".json"), "w") as f:
         json.dump(out, f, indent=1)
     print("\n".join(md))
 
