@@ -460,7 +460,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 }
 
 static int gn_chunking(int hw, int* chunks, int* ppc) {
+  // 32 chunks per sample for the U-Net's grids (hw <= 4096); at most 512 pixels per chunk beyond that, so the VAE
+  // decoder's 128^2 .. 512^2 levels (2-image chunks) still launch enough CTAs to fill 148 SMs.  The chunking depends
+  // on hw only -> reduction order (and the result bits) are independent of the batch size.
   int p = hw / 32;
+  if (p > 512) p = 512;
   if (p < 8) p = 8;
   if (p > hw) p = hw;
   *ppc = p;

@@ -93,14 +93,20 @@ __global__ void __launch_bounds__(256) vae_conv_out_kernel(const float* __restri
   const int b = static_cast<int>(pix / HW);
   const int hw = static_cast<int>(pix % HW), h = hw / W, ww = hw % W;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  const int C4 = Cin >> 2;
   for (int tap = 0; tap < 9; ++tap) {
     const int yy = h + tap / 3 - 1, xx = ww + tap % 3 - 1;
     if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-    const float* xr = x + ((static_cast<size_t>(b) * H + yy) * W + xx) * Cin;
-    const float* wr = w + static_cast<size_t>(tap) * Cin * 3;
-    for (int c = lane; c < Cin; c += 32) {
-      const float v = xr[c];
-      a0 = fmaf(v, __ldg(wr + c * 3), a0), a1 = fmaf(v, __ldg(wr + c * 3 + 1), a1), a2 = fmaf(v, __ldg(wr + c * 3 + 2), a2);
+    const float4* xr = reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * H + yy) * W + xx) * Cin);
+    const float4* wr = reinterpret_cast<const float4*>(w + static_cast<size_t>(tap) * Cin * 3);
+    for (int c4 = lane; c4 < C4; c4 += 32) {  // a lane owns 4 channels: one 16-byte activation load, 3 weight loads
+      const float4 v = xr[c4];
+      const float4 w0 = __ldg(wr + c4 * 3), w1 = __ldg(wr + c4 * 3 + 1), w2 = __ldg(wr + c4 * 3 + 2);
+      // [c][o] for c = 0..3, o = 0..2 laid out as 12 consecutive floats
+      a0 = fmaf(v.x, w0.x, a0), a1 = fmaf(v.x, w0.y, a1), a2 = fmaf(v.x, w0.z, a2);
+      a0 = fmaf(v.y, w0.w, a0), a1 = fmaf(v.y, w1.x, a1), a2 = fmaf(v.y, w1.y, a2);
+      a0 = fmaf(v.z, w1.z, a0), a1 = fmaf(v.z, w1.w, a1), a2 = fmaf(v.z, w2.x, a2);
+      a0 = fmaf(v.w, w2.y, a0), a1 = fmaf(v.w, w2.z, a1), a2 = fmaf(v.w, w2.w, a2);
     }
   }
   a0 = warp_sum(a0), a1 = warp_sum(a1), a2 = warp_sum(a2);
@@ -147,8 +153,8 @@ extern "C" int ddpo_softmax_rows(const float* scores, int64_t ld_scores, float s
 
 extern "C" int ddpo_vae_conv_out(const float* x_nhwc, const float* w_hwio, const float* bias, float* raw_nchw,
                                  float* img_nhwc, int batch, int h, int w, int cin, void* stream) {
-  DDPO_REQUIRE(x_nhwc && w_hwio && bias && (raw_nchw || img_nhwc) && batch > 0 && h > 0 && w > 0 && cin > 0,
-               "vae_conv_out: bad arguments");
+  DDPO_REQUIRE(x_nhwc && w_hwio && bias && (raw_nchw || img_nhwc) && batch > 0 && h > 0 && w > 0 && cin > 0 && cin % 4 == 0,
+               "vae_conv_out: bad arguments (cin=%d must be a multiple of 4)", cin);
   const int64_t pix = static_cast<int64_t>(batch) * h * w;
   DDPO_REQUIRE((pix + 7) / 8 < (int64_t(1) << 31), "vae_conv_out: too many pixels");
   vae_conv_out_kernel<<<static_cast<unsigned>((pix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(

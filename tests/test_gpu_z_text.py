@@ -48,7 +48,8 @@ def test_text_kernels():
         y = torch.empty(33, 256, dtype=torch.bfloat16, device=DEV)
         ops.act_bf16(x, y, act)
         torch.cuda.synchronize()
-        assert (y.float() - fn(x)).abs().max().item() < 2e-2
+        ref = fn(x)
+        assert ((y.float() - ref).abs() <= 5e-3 * ref.abs() + 1e-4).all()      # bf16 output: half an ulp = 0.4 %
     sc, bi = torch.randn(256, generator=g).to(DEV), torch.randn(256, generator=g).to(DEV)
     y = torch.empty(33, 256, device=DEV)
     ops.layernorm_f32(x, sc, bi, y, 33, 256, eps=1e-5)
