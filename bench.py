@@ -136,20 +136,62 @@ def _dump_shapes(prof, tags, path):
             f.write(f"{v[0]:8.3f} ms {100 * v[0] / tot:5.1f}%  n={v[2]:3d}  {v[0] / v[2] * 1e3:8.1f} us/launch  {name:16s} {tag}  {tf}\n")
 
 
+def cpu_train_step_seconds():
+    """Times the CPU oracle's PPO train step (oracle/pipeline.py::train_loss, the restated
+    ddpo/training/policy_gradient.py:86-138: cond + uncond U-Net forward, CFG, score-mode log-prob, clipped loss, and
+    jax.grad's counterpart -- torch autograd through both U-Net applications) for ONE sample at ONE timestep."""
+    import torch
+    from ddpo_b200 import unet_spec
+    from oracle import pipeline as OP, scheduler as OS
+    from oracle.unet import UNetOracle
+    cfg = unet_spec.SD2_BASE
+    fp = unet_spec.init_flat_params(cfg, 0).requires_grad_(True)
+    net = UNetOracle(cfg, unet_spec.views(fp, cfg))
+    st = OS.set_timesteps(OS.SD_CONFIG, OS.create_state(OS.SD_CONFIG), T_STEPS)
+    g = torch.Generator().manual_seed(2)
+    batch = {"latents": torch.randn(1, 4, 64, 64, generator=g).numpy(), "next_latents": torch.randn(1, 4, 64, 64, generator=g).numpy(),
+             "ts": np.array([int(st.timesteps[3])], np.int32), "log_probs": np.array([-1.4], np.float32),
+             "advantages": np.array([1.0], np.float32), "prompt_embeds": torch.randn(1, 77, 1024, generator=g).numpy(),
+             "uncond_embeds": torch.randn(1, 77, 1024, generator=g).numpy()}
+    t0 = time.perf_counter()
+    loss, info, lp = OP.train_loss(net, OS.SD_CONFIG, st, batch, True, GUIDANCE, ETA, CLIP)
+    loss.backward()
+    dt = time.perf_counter() - t0
+    assert fp.grad is not None
+    return dt
+
+
+def cpu_ppo_samples_per_sec(n_denoise):
+    """The headline metric on the host cores from a BOUNDED sample: `n_denoise` timed denoising steps of one sample
+    (after one warm-up step) and one PPO train step of one sample, extrapolated linearly to a PPO sample =
+    50 denoising steps + 50 train steps (every step of the trajectory costs the same: the scan / loop bodies are
+    step-invariant).  Returns (samples/s, denoising steps/s, seconds per train step, threads)."""
+    per_step, cores = cpu_step_seconds(n_denoise)
+    t_train = cpu_train_step_seconds()
+    s_per_sample = T_STEPS * per_step + T_STEPS * t_train
+    return 1.0 / s_per_sample, 1.0 / per_step, t_train, cores
+
+
 def run_reference(args):
+    """Reference arm: the reference's own path cannot be installed here (jax / flax / diffusers are absent and there
+    is no network), so this times the oracle port of it on the host cores -- same metric, unit and
+    workload as the B200 arm, each quantity from a bounded sample (see cpu_ppo_samples_per_sec)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step, cores = cpu_step_seconds(max(1, args.steps))
-    v = 1.0 / per_step
+    n = max(1, min(int(args.steps), 3))
+    v, dps, t_train, cores = cpu_ppo_samples_per_sec(n)
+    sample = (f"{n} denoising step(s) of 1 sample (2 U-Net applications each) + 1 PPO train step of 1 sample (2 U-Net "
+              f"forward + backward), torch-CPU oracle port, extrapolated x50 each")
     print(json.dumps({
-        "impl": "reference", "metric": "denoising_steps_per_sec", "value": v, "unit": "denoising steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "impl": "reference", "metric": "ppo_samples_per_sec", "value": v,
+        "unit": "PPO samples/s (50 sampling steps + 50 train steps per sample)",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / dps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DDPO SD2-base 512px 50-step DDIM, CFG 5.0 (BASELINE configs[1]); CPU arm: 1 sample/step"},
-        "cpu_baseline": {"value": v, "unit": "denoising steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} denoising step(s) of 1 sample (2 U-Net applications), torch-CPU oracle"},
-        "e2e": {"value": v, "unit": "denoising steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "denoising_steps_per_sec": dps, "seconds_per_train_step": t_train,
+        "config": {"workload": "DDPO SD2-base 512px, 50-step DDIM, CFG 5.0, eta 1.0 (BASELINE configs[1]); CPU arm: 1 sample"},
+        "cpu_baseline": {"value": v, "unit": "PPO samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "PPO samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
@@ -494,9 +536,16 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu:
-            per_step, cores = cpu_step_seconds(args.cpu_steps)
-            cpu = {"value": 1.0 / per_step, "unit": "denoising steps/s", "cores": cores, "kind": "port",
-                   "sample": f"{args.cpu_steps} denoising steps of 1 sample (2 U-Net applications each), torch-CPU oracle"}
+            if ppo is not None:
+                v, dps, t_train, cores = cpu_ppo_samples_per_sec(args.cpu_steps)
+                cpu = {"value": v, "unit": "PPO samples/s", "cores": cores, "kind": "port",
+                       "denoising_steps_per_sec": dps, "seconds_per_train_step": t_train,
+                       "sample": f"{args.cpu_steps} denoising steps of 1 sample (2 U-Net applications each) + 1 PPO train "
+                                 f"step of 1 sample (2 U-Net forward + backward), torch-CPU oracle port, extrapolated x50 each"}
+            else:
+                per_step, cores = cpu_step_seconds(args.cpu_steps)
+                cpu = {"value": 1.0 / per_step, "unit": "denoising steps/s", "cores": cores, "kind": "port",
+                       "sample": f"{args.cpu_steps} denoising steps of 1 sample (2 U-Net applications each), torch-CPU oracle"}
         step_flops = 2 * B * UNET_GFLOP * 1e9
         if ppo is not None:
             head = {"metric": "ppo_samples_per_sec", "value": ppo["samples_per_s"],
