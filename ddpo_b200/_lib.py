@@ -83,6 +83,7 @@ SIGNATURES = {
     "ddpo_conv_out": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "ddpo_timestep_sincos": (i32, [vp, i32, vp, i32, i32, vp]),
     "ddpo_dense_small": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "ddpo_dense_small_grouped": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_attention_fwd": (i32, [C.POINTER(AttentionArgs), vp]),
     "ddpo_wgrad_workspace_floats": (i64, [C.POINTER(WgradArgs)]),
     "ddpo_wgrad": (i32, [C.POINTER(WgradArgs), vp]),

@@ -263,6 +263,74 @@ __global__ void __launch_bounds__(DS_WARPS * 32) dense_small_kernel(const float*
   }
 }
 
+// Grouped form of dense_small for layers that share the input x (the 22 time-embedding projections of the ResNet
+// blocks all read silu(temb)): ONE launch, CTA -> (layer, 32-column block) through a small table of offsets.  Per
+// output the arithmetic (K split over warps, fixed-order cross-warp sum) is exactly dense_small_kernel's, so the
+// results are bit-identical to the separate launches.
+struct DsGroup {
+  int64_t w_off, bias_off, y_off;  // in floats, relative to the params / output base pointers
+  int32_t n, cta0;                 // output width, first CTA of the group
+};
+template <int BMAX>
+__global__ void __launch_bounds__(DS_WARPS * 32) dense_small_grouped_kernel(const float* __restrict__ x,
+                                                                            const float* __restrict__ params,
+                                                                            float* __restrict__ ybase,
+                                                                            const DsGroup* __restrict__ groups, int n_groups,
+                                                                            int B, int B_total, int row0, int K) {
+  extern __shared__ float sm[];  // xs[B][K] then red[DS_WARPS][B][32]
+  float* xs = sm;
+  float* red = sm + static_cast<size_t>(B) * K;
+  int g = 0;
+  while (g + 1 < n_groups && static_cast<int>(blockIdx.x) >= groups[g + 1].cta0) ++g;
+  const DsGroup grp = groups[g];
+  const int N = grp.n;
+  const int cblock = static_cast<int>(blockIdx.x) - grp.cta0;
+  const float* w = params + grp.w_off;
+  const float* bias = params + grp.bias_off;
+  float* y = ybase + grp.y_off + static_cast<size_t>(row0) * N;   // layer output is [B_total, N]
+  (void)B_total;
+  for (int i = threadIdx.x; i < B * K; i += DS_WARPS * 32) xs[i] = x[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = cblock * 32 + lane;
+  float acc[BMAX];
+#pragma unroll
+  for (int b = 0; b < BMAX; ++b) acc[b] = 0.f;
+  const int kper = (K + DS_WARPS - 1) / DS_WARPS;
+  const int k0 = warp * kper, k1 = min(K, k0 + kper);
+  if (n < N) {
+    int k = k0;
+    for (; k + 7 < k1; k += 8) {
+      float wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = w[static_cast<size_t>(k + u) * N + n];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int b = 0; b < BMAX; ++b)
+          if (b < B) acc[b] = fmaf(xs[b * K + k + u], wv[u], acc[b]);
+    }
+    for (; k < k1; ++k) {
+      const float wv = w[static_cast<size_t>(k) * N + n];
+#pragma unroll
+      for (int b = 0; b < BMAX; ++b)
+        if (b < B) acc[b] = fmaf(xs[b * K + k], wv, acc[b]);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < BMAX; ++b)
+    if (b < B) red[(warp * B + b) * 32 + lane] = acc[b];
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * 32; i += DS_WARPS * 32) {
+    const int b = i >> 5, l = i & 31;
+    const int nn = cblock * 32 + l;
+    if (nn >= N) continue;
+    float r = bias[nn];
+    for (int wq = 0; wq < DS_WARPS; ++wq) r += red[(wq * B + b) * 32 + l];
+    y[static_cast<size_t>(b) * N + nn] = r;
+  }
+}
+
 static inline int grid_for(int64_t n, int threads) {
   int64_t g = (n + threads - 1) / threads;
   const int64_t cap = 148 * 32;
@@ -350,6 +418,36 @@ extern "C" int ddpo_timestep_sincos(const int32_t* t, int t_stride, float* out, 
   const int n = batch * dim / 2;
   timestep_sincos_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, t_stride, out, batch, dim);
   DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_dense_small_grouped(const float* x, const float* params_base, float* y_base, const void* groups_dev,
+                                        int n_groups, int total_ctas, int batch, int k, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPO_REQUIRE(x && params_base && y_base && groups_dev && n_groups > 0 && total_ctas > 0 && batch > 0 && k > 0,
+               "dense_small_grouped: bad arguments");
+  static bool attr = false;
+  if (!attr) {
+    DDPO_CUDA_OK(cudaFuncSetAttribute(dense_small_grouped_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DDPO_CUDA_OK(cudaFuncSetAttribute(dense_small_grouped_kernel<DS_MAXB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  int slab = (200 * 1024) / (4 * k + 4 * DS_WARPS * 32);  // same slab rule as ddpo_dense_small (batch invariance)
+  if (slab > DS_MAXB) slab = DS_MAXB;
+  DDPO_REQUIRE(slab >= 1, "dense_small_grouped: k=%d too large", k);
+  const DsGroup* groups = static_cast<const DsGroup*>(groups_dev);
+  for (int b0 = 0; b0 < batch; b0 += slab) {
+    const int bb = batch - b0 < slab ? batch - b0 : slab;
+    const size_t smem = (static_cast<size_t>(bb) * k + static_cast<size_t>(DS_WARPS) * bb * 32) * sizeof(float);
+    const float* xb = x + static_cast<size_t>(b0) * k;
+    if (bb <= 8)
+      dense_small_grouped_kernel<8><<<total_ctas, DS_WARPS * 32, smem, stream>>>(xb, params_base, y_base, groups, n_groups,
+                                                                               bb, batch, b0, k);
+    else
+      dense_small_grouped_kernel<DS_MAXB><<<total_ctas, DS_WARPS * 32, smem, stream>>>(xb, params_base, y_base, groups,
+                                                                                     n_groups, bb, batch, b0, k);
+    DDPO_LAUNCH_OK();
+  }
   return DDPO_OK;
 }
 

@@ -267,6 +267,23 @@ def dense_small(x, w, bias, y, batch, k, n, silu_in=False, silu_out=False):
     _run("dense_small", lib().ddpo_dense_small(_p(x), _p(w), _p(bias), _p(y), batch, k, n, int(silu_in), int(silu_out), _stream()), 0.0, _e)
 
 
+def dense_small_group_table(entries, device):
+    """entries: [(w_off, bias_off, y_off, n)] in floats -> (device uint8 table, total CTAs) for dense_small_grouped."""
+    import numpy as np
+    rec = np.zeros(len(entries), dtype=[("w", "<i8"), ("b", "<i8"), ("y", "<i8"), ("n", "<i4"), ("cta0", "<i4")])
+    cta = 0
+    for i, (w_off, b_off, y_off, n) in enumerate(entries):
+        rec[i] = (w_off, b_off, y_off, n, cta)
+        cta += (n + 31) // 32
+    return torch.from_numpy(rec.view(np.uint8).copy()).to(device), cta
+
+
+def dense_small_grouped(x, params_base, y_base, table, n_groups, total_ctas, batch, k):
+    _e = _ev()
+    _run("dense_small", lib().ddpo_dense_small_grouped(_p(x), _p(params_base), _p(y_base), _p(table), int(n_groups),
+                                                       int(total_ctas), int(batch), int(k), _stream()), 0.0, _e)
+
+
 # --------------------------------------------------------------- attention -------
 def attention_fwd(q, k, v, out, batch, heads, nq, nk, ldq, ldk, ldv, ldo, lse=None, causal=False):
     a = AttentionArgs(_p(q), _p(k), _p(v), _p(out), _p(lse), batch, heads, nq, nk, 64, ldq, ldk, ldv, ldo, int(causal))

@@ -17,6 +17,7 @@ Data flow design (B200-first):
   * buffers come from a deterministic free-list arena so a whole step can be captured in a
     CUDA graph.
 """
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -80,6 +81,13 @@ class UNet:
         self.wd: Dict[str, torch.Tensor] = {}      # bf16 backward (dgrad) GEMM operands, built on demand
         self.grads: Optional[torch.Tensor] = None  # flat fp32 gradient accumulator (same layout as params)
         self.train_mode = False
+        # EXPERIMENTAL (default off, not yet measured on the GPU): all ResNet time-embedding projections in ONE launch
+        # (ops.dense_small_grouped; bit-identical to the 22 separate dense_small launches, which cost ~36 us each at
+        # 10-40 CTAs).  Enable with DDPO_GROUPED_TEMB=1.
+        self.grouped_temb = os.environ.get("DDPO_GROUPED_TEMB", "0") == "1"
+        self._temb_names = [n[: -len("/time_emb_proj/kernel")] for n in self.table if n.endswith("/time_emb_proj/kernel")]
+        self._temb_tables: Dict[int, tuple] = {}
+        self._tproj_views: Optional[Dict[str, torch.Tensor]] = None
         self.refresh_weights()
 
     # ------------------------------------------------------------------ params ----
@@ -201,9 +209,12 @@ class UNet:
         raw = A.alloc((m, cin), BF16) if has_sc else None
         ops.groupnorm_fwd(x0, self.p(name + "/norm1/scale"), self.p(name + "/norm1/bias"), gws, b, hw, c0, x1=x1,
                           c1=c1, silu=True, y_bf16=a, raw_bf16=raw)
-        tproj = A.alloc((b, cout), F32)
-        ops.dense_small(temb_act, self.p(name + "/time_emb_proj/kernel"), self.p(name + "/time_emb_proj/bias"),
-                        tproj, b, temb_act.shape[1], cout)
+        if self._tproj_views is not None:
+            tproj = self._tproj_views[name]          # computed by the grouped launch at the start of forward()
+        else:
+            tproj = A.alloc((b, cout), F32)
+            ops.dense_small(temb_act, self.p(name + "/time_emb_proj/kernel"), self.p(name + "/time_emb_proj/bias"),
+                            tproj, b, temb_act.shape[1], cout)
         hbuf = A.alloc((m, cout), F32)
         ops.igemm(a0=a, wt=self.w[name + "/conv1"], n=cout, c0=cin, conv=(b, h, w), taps=9,
                   bias=self.p(name + "/conv1/bias"), rowvec=tproj, rows_per_sample=hw, rowvec_ld=cout, out_f32=hbuf)
@@ -317,11 +328,31 @@ class UNet:
         temb_act = A.alloc((b, te), F32)
         ops.dense_small(t1, self.p("time_embedding/linear_2/kernel"), self.p("time_embedding/linear_2/bias"), temb_act,
                         b, te, te, silu_out=True)
+        tproj_all = None
+        self._tproj_views = None
+        if self.grouped_temb:
+            tab = self._temb_tables.get(b)
+            if tab is None:   # first (eager, pre-capture) pass at this batch size: offsets only, no addresses
+                entries, views, y_off = [], [], 0
+                for name in self._temb_names:
+                    w_off, wshape = self.table[name + "/time_emb_proj/kernel"]
+                    b_off, _ = self.table[name + "/time_emb_proj/bias"]
+                    n = int(wshape[1])
+                    entries.append((w_off, b_off, y_off, n))
+                    views.append((name, y_off, n))
+                    y_off += b * n
+                dev_tab, ctas = ops.dense_small_group_table(entries, self.device)
+                tab = self._temb_tables[b] = (dev_tab, ctas, views, y_off)
+            dev_tab, ctas, views, total = tab
+            tproj_all = A.alloc((total,), F32)
+            ops.dense_small_grouped(temb_act, self.params, tproj_all, dev_tab, len(views), ctas, b, te)
+            self._tproj_views = {name: tproj_all[o:o + b * n].view(b, n) for name, o, n in views}
         x = A.alloc((b * H * W, boc[0]), F32)
         ops.conv_in(latents, self.p("conv_in/kernel"), self.p("conv_in/bias"), x, b, cin_lat, H, W, boc[0])
         tap("conv_in", x, (b, H, W, boc[0]))
         if tape is not None:
-            tape.append(("head", dict(latents=latents, sincos=sincos, t1=t1, temb_act=temb_act, b=b, H=H, W=W, x=x)))
+            tape.append(("head", dict(latents=latents, sincos=sincos, t1=t1, temb_act=temb_act, b=b, H=H, W=W, x=x,
+                                      tproj_all=tproj_all)))
             self._temb_act = temb_act
         skips = [(x, boc[0], H, W)]
         h, w, c_prev = H, W, boc[0]
@@ -414,7 +445,7 @@ class UNet:
             out = torch.empty(b, cfg.out_channels, h, w, dtype=F32, device=self.device)
         ops.conv_out(yf, self.p("conv_out/kernel"), self.p("conv_out/bias"), out, b, h, w, c0, cfg.out_channels)
         if tape is None:
-            for t in (gws, yf, x, sincos, t1, temb_act):
+            for t in (gws, yf, x, sincos, t1, temb_act, tproj_all):
                 A.release(t)
         else:
             tape.append(("tail", dict(x=x, gws=gws, yf=yf, b=b, h=h, w=w, c=c0)))
@@ -530,7 +561,7 @@ class UNet:
                                         None, b, c0, te, silu_out=True)
                     for t in (dpre, d_t1, d_temb):
                         A.release(t)
-                for t in (r["sincos"], r["t1"], r["temb_act"]):
+                for t in (r["sincos"], r["t1"], r["temb_act"], r.get("tproj_all")):
                     A.release(t)
         assert not grads, f"{len(grads)} stream gradients were never consumed"
 

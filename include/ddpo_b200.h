@@ -170,6 +170,13 @@ int ddpo_conv_out(const float* x_nhwc, const float* w_hwio, const float* bias, f
 int ddpo_timestep_sincos(const int32_t* t, int t_stride, float* out, int batch, int dim, void* stream);
 int ddpo_dense_small(const float* x, const float* w_in_out, const float* bias, float* y, int batch, int k, int n,
                      int silu_in, int silu_out, void* stream);
+/* Grouped ddpo_dense_small for layers sharing the input x [batch, k] (the ResNet blocks' time_emb_proj Dense layers,
+ * 3P FlaxResnetBlock2D): one launch; `groups_dev` is a DEVICE array of n_groups records
+ * { int64 w_off, bias_off, y_off (floats, relative to params_base / y_base); int32 n, cta0 } sorted by cta0
+ * (cta0 = running sum of ceil(n/32)); layer g's output is y_base + y_off[g], shape [batch, n].  Bit-identical to the
+ * separate ddpo_dense_small calls (no activation on either side). */
+int ddpo_dense_small_grouped(const float* x, const float* params_base, float* y_base, const void* groups_dev, int n_groups,
+                             int total_ctas, int batch, int k, void* stream);
 
 /* ---------------------------------------------------------------- attention --------
  * FlaxAttention core (3P diffusers attention_flax.py): softmax(Q K^T d^-0.5) V, head_dim 64. */
