@@ -47,11 +47,61 @@ def arange_fn(devices=None, jit=False):
 def _cached_score_stub(name, shape_2d):
     def factory(devices=None, jit=False):
         def _fn(images, prompts, metadata):
-            rng = np.random.default_rng(abs(hash((name,) + tuple(prompts))) % (2 ** 32))
+            import hashlib
+            digest = hashlib.sha1("\x1f".join([name] + [str(p) for p in prompts]).encode()).hexdigest()
+            rng = np.random.default_rng(int(digest, 16) % (2 ** 32))   # reproducible across processes and runs
             s = rng.standard_normal(len(images)).astype(np.float32)
             return (s[:, None] if shape_2d else s), {"stub": True}
         return _fn
     return factory
+
+
+LLAVA_URL_ENV = "DDPO_LLAVA_URL"   # e.g. http://127.0.0.1:8085 (the reference hard-codes this address, callbacks.py:470)
+
+
+def llava_bertscore_fn(devices=None, jit=False, url=None, batch_size=16, timeout=120):
+    """Reference ``callbacks.py:464-537``: the alignment reward is computed by a LLaVA + BERTScore server spoken to with
+    pickle-over-HTTP.  Wire format kept byte for byte: POST body = ``pickle.dumps({"images": [JPEG q=80 bytes],
+    "queries": [["Answer concisely: what is going on in this image?"]] * n, "answers": [[f"The image contains {p}"]]})``
+    in batches of 16; response = pickle of ``{"recall", "precision", "f1", "outputs"}``; the reward is the recall.
+    Without a server (``url`` / ``$DDPO_LLAVA_URL`` unset -- the offline default, BASELINE config 5 "reward server stubbed
+    to cached scores") the cached-score stub answers instead."""
+    import os
+    url = url or os.environ.get(LLAVA_URL_ENV)
+    if not url:
+        return _cached_score_stub("llava_bertscore", False)(devices, jit)
+    import pickle
+    from io import BytesIO
+
+    import requests
+    from PIL import Image
+    from requests.adapters import HTTPAdapter, Retry
+    sess = requests.Session()
+    sess.mount("http://", HTTPAdapter(max_retries=Retry(total=1000, backoff_factor=1, status_forcelist=[500],
+                                                        allowed_methods=False)))
+
+    def _fn(images, prompts, metadata):
+        del metadata
+        images = (np.asarray(images) * 255).astype(np.uint8)
+        n_batches = int(np.ceil(len(images) / batch_size))
+        all_scores, all_info = [], {"precision": [], "f1": [], "outputs": []}
+        for image_batch, prompt_batch in zip(np.array_split(images, n_batches), np.array_split(np.asarray(prompts), n_batches)):
+            jpeg_images = []
+            for image in image_batch:
+                buffer = BytesIO()
+                Image.fromarray(image).save(buffer, format="JPEG", quality=80)
+                jpeg_images.append(buffer.getvalue())
+            data = {"images": jpeg_images,
+                    "queries": [["Answer concisely: what is going on in this image?"]] * len(image_batch),
+                    "answers": [[f"The image contains {prompt}"] for prompt in prompt_batch]}
+            response = sess.post(url, data=pickle.dumps(data), timeout=timeout)
+            response_data = pickle.loads(response.content)
+            all_scores += np.array(response_data["recall"]).reshape(-1).tolist()
+            all_info["precision"] += np.array(response_data["precision"]).reshape(-1).tolist()
+            all_info["f1"] += np.array(response_data["f1"]).reshape(-1).tolist()
+            all_info["outputs"] += np.array(response_data["outputs"]).reshape(-1).tolist()
+        return np.array(all_scores), {k: np.array(v) for k, v in all_info.items()}
+    return _fn
 
 
 def evaluate_callbacks(fns, images, prompts, metadata):
@@ -66,5 +116,5 @@ callback_fns = {
     "neg_jpeg": neg_jpeg_fn,
     "arange": arange_fn,
     "aesthetic": _cached_score_stub("aesthetic", True),
-    "llava_bertscore": _cached_score_stub("llava_bertscore", False),
+    "llava_bertscore": llava_bertscore_fn,
 }
