@@ -102,6 +102,9 @@ SIGNATURES = {
     "ddpo_embed_tokens": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_act_bf16": (i32, [vp, vp, i64, i32, vp]),
     "ddpo_layernorm_f32": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),
+    "ddpo_patchify_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "ddpo_vit_tokens": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "ddpo_l2norm_rows": (i32, [vp, vp, i32, i32, vp]),
     "ddpo_vae_post_quant": (i32, [vp, vp, vp, f32, i32, i32, i32, i32, vp, vp]),
     "ddpo_softmax_rows": (i32, [vp, i64, f32, vp, i64, i32, i32, vp]),
     "ddpo_vae_conv_out": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libddpo_b200.so")
 SOURCES = ["abi.cu", "igemm.cu", "igemm2.cu", "wgrad.cu", "wgrad2.cu", "attention.cu", "attention_bwd.cu", "norm.cu", "elementwise.cu",
-           "backward_ew.cu", "ddim.cu", "rwr.cu", "vae.cu", "text.cu", "optim.cu"]
+           "backward_ew.cu", "ddim.cu", "rwr.cu", "vae.cu", "text.cu", "vision.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

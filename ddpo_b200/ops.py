@@ -528,3 +528,26 @@ def layernorm_f32(x, scale, bias, y, m, c, eps=1e-5):
     _e = _ev()
     _run("layernorm_f32", lib().ddpo_layernorm_f32(_p(x), _p(scale), _p(bias), _p(y), int(m), int(c), float(eps),
                                                    _stream()), float(m) * c * 8, _e)
+
+
+# ------------------------------------------------------------ image tower --------
+def patchify_bf16(img_nhwc, out_bf16, patch):
+    _chk(img_nhwc, torch.float32, "img")
+    _chk(out_bf16, torch.bfloat16, "out")
+    b, s, _, _ = img_nhwc.shape
+    _e = _ev()
+    _run("patchify_bf16", lib().ddpo_patchify_bf16(_p(img_nhwc), _p(out_bf16), b, s, int(patch), out_bf16.shape[1],
+                                                   _stream()), 0.0, _e)
+
+
+def vit_tokens(patches, class_embedding, position_embedding, out, batch, n_patches, dim):
+    _e = _ev()
+    _run("vit_tokens", lib().ddpo_vit_tokens(_p(patches), _p(class_embedding), _p(position_embedding), _p(out), int(batch),
+                                             int(n_patches), int(dim), _stream()), 0.0, _e)
+
+
+def l2norm_rows(x, y):
+    _chk(x, torch.float32, "x")
+    m, c = x.shape
+    _e = _ev()
+    _run("l2norm_rows", lib().ddpo_l2norm_rows(_p(x), _p(y), m, c, _stream()), 0.0, _e)

@@ -56,6 +56,26 @@ def _cached_score_stub(name, shape_2d):
     return factory
 
 
+AESTHETIC_GPU_ENV = "DDPO_AESTHETIC_GPU"
+
+
+def aesthetic_fn(devices=None, rng=0, cache="cache", jit=True):
+    """Reference ``callbacks.py:60-95``: CLIP ViT-L/14 image features -> L2 normalise -> LAION aesthetic head; returns
+    ``[N, 1]`` scores.  With ``$DDPO_AESTHETIC_GPU=1`` the model runs on the GPU kernels (``ddpo_b200/clip_vision.py``,
+    random-init tower -- no checkpoints offline -- and the LAION head from ``cache/`` when that file exists; this path is
+    EXPERIMENTAL, see the module docstring); otherwise the cached-score stub answers (BASELINE config 3 offline)."""
+    import os
+    if os.environ.get(AESTHETIC_GPU_ENV) != "1":
+        return _cached_score_stub("aesthetic", True)(devices, jit)
+    from ..clip_vision import AestheticScorer
+    scorer = AestheticScorer(seed=int(rng), cache=cache)
+
+    def _wrapper(images, prompts, metadata):
+        del prompts, metadata
+        return scorer(images), {}
+    return _wrapper
+
+
 LLAVA_URL_ENV = "DDPO_LLAVA_URL"   # e.g. http://127.0.0.1:8085 (the reference hard-codes this address, callbacks.py:470)
 
 
@@ -115,6 +135,6 @@ callback_fns = {
     "jpeg": jpeg_fn,
     "neg_jpeg": neg_jpeg_fn,
     "arange": arange_fn,
-    "aesthetic": _cached_score_stub("aesthetic", True),
+    "aesthetic": aesthetic_fn,
     "llava_bertscore": llava_bertscore_fn,
 }

@@ -276,6 +276,19 @@ int ddpo_act_bf16(const float* x, void* y_bf16, int64_t n, int act, void* stream
 int ddpo_layernorm_f32(const float* x, const float* scale, const float* bias, float* y, int m, int c, float eps,
                        void* stream);
 
+/* ------------------------------------------------------------ aesthetic reward ------
+ * CLIP ViT image tower + LAION aesthetic head (ddpo/training/callbacks.py:60-95, ddpo/models/laion.py:7-18; 3P transformers
+ * FlaxCLIPModel.get_image_features).  Transformer layers run on the text tower's building blocks (non-causal attention,
+ * quick_gelu); the small Dense layers of the head on ddpo_dense_small.  EXPERIMENTAL: written after the round's GPU
+ * budget was spent, validated on the CPU only (oracle pinned against transformers, host assembly dry run). */
+/* non-overlapping patches: out bf16 [batch*(size/patch)^2, ldk], column (ky*patch + kx)*3 + c, zero padded to ldk */
+int ddpo_patchify_bf16(const float* img_nhwc, void* out_bf16, int batch, int size, int patch, int ldk, void* stream);
+/* out[b, 0] = class_embedding + pos[0]; out[b, 1+p] = patches[b, p] + pos[1+p]   (fp32 [batch, n_patches+1, dim]) */
+int ddpo_vit_tokens(const float* patches, const float* class_embedding, const float* position_embedding, float* out,
+                    int batch, int n_patches, int dim, void* stream);
+/* y[r] = x[r] / ||x[r]||_2 */
+int ddpo_l2norm_rows(const float* x, float* y, int m, int c, void* stream);
+
 /* ------------------------------------------------------------------ RWR ------------
  * Reward-weighted regression step around the U-Net (ddpo/training/diffusion.py:6-102).
  * ddpo_rwr_noisy_latents: latents = (mean + exp(0.5 clip(logvar,-30,20)) * normal(key_sample, NHWC shape)) * scaling

@@ -25,7 +25,7 @@ def groupnorm_workspace_floats(batch, hw, channels):
 
 
 def prep_weight(src, dst, k, n, ldk=None, row_offset=0, col_offset=0, geglu_bn=0):
-    dst[row_offset:row_offset + n].copy_(src.reshape(k, n).t().to(BF16))
+    dst[row_offset:row_offset + n, :k].copy_(src.reshape(k, n).t().to(BF16))
 
 
 def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, y_bf16=None, y_f32=None, raw_bf16=None,
@@ -137,3 +137,30 @@ def attention_fwd(q, k, v, out, batch, heads, nq, nk, ldq, ldk, ldv, ldo, lse=No
     p = torch.softmax(s, -1).to(BF16).float()           # the kernel rounds P to bf16 before P V
     o = (p @ vv).permute(0, 2, 1, 3).reshape(batch * nq, heads * 64)
     out[:, : heads * 64].copy_(o.to(BF16))
+
+
+# ---- image tower ----
+def patchify_bf16(img_nhwc, out_bf16, patch):
+    b, s, _, _ = img_nhwc.shape
+    n = s // patch
+    pt = img_nhwc.reshape(b, n, patch, n, patch, 3).permute(0, 1, 3, 2, 4, 5).reshape(b * n * n, patch * patch * 3)
+    out_bf16.zero_()
+    out_bf16[:, : pt.shape[1]].copy_(pt.to(BF16))
+
+
+def vit_tokens(patches, class_embedding, position_embedding, out, batch, n_patches, dim):
+    tok = torch.cat([class_embedding.expand(batch, 1, dim), patches.reshape(batch, n_patches, dim)], 1) + position_embedding[None]
+    out.copy_(tok.reshape(batch * (n_patches + 1), dim))
+
+
+def l2norm_rows(x, y):
+    y.copy_(x / x.norm(dim=-1, keepdim=True))
+
+
+def gather_rows(src, index, dst):
+    dst.copy_(src.reshape(-1, dst.shape[-1])[index.long()].reshape(dst.shape))
+
+
+def dense_small(x, w, bias, y, batch, k, n, silu_in=False, silu_out=False):
+    assert not silu_in and not silu_out
+    y.copy_(x.reshape(batch, k) @ w.reshape(k, n) + bias)

@@ -66,3 +66,54 @@ def test_unet_with_grouped_temb_is_bit_identical(cfg_name, batch, monkeypatch):
         outs.append(net.grads.clone())
     torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+
+
+# ------------------------------------------------------------------ aesthetic reward model (clip_vision.py) ----
+def test_vision_kernels():
+    from ddpo_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(2, 56, 56, 3, generator=g).to(DEV)
+    out = torch.empty(2 * 16, 640, dtype=torch.bfloat16, device=DEV)
+    ops.patchify_bf16(img, out, 14)
+    ref = img.reshape(2, 4, 14, 4, 14, 3).permute(0, 1, 3, 2, 4, 5).reshape(32, 588)
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :588], ref.to(torch.bfloat16)) and float(out[:, 588:].abs().max()) == 0.0
+    pe, cls, pos = torch.randn(32, 128, generator=g).to(DEV), torch.randn(128, generator=g).to(DEV), torch.randn(17, 128, generator=g).to(DEV)
+    tok = torch.empty(2 * 17, 128, device=DEV)
+    ops.vit_tokens(pe, cls, pos, tok, 2, 16, 128)
+    want = torch.cat([cls.expand(2, 1, 128), pe.view(2, 16, 128)], 1) + pos[None]
+    torch.cuda.synchronize()
+    assert torch.equal(tok.view(2, 17, 128), want)
+    x = torch.randn(5, 768, generator=g).to(DEV)
+    y = torch.empty_like(x)
+    ops.l2norm_rows(x, y)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(y.cpu().numpy(), (x / x.norm(dim=-1, keepdim=True)).cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("b", [3, 8])
+def test_aesthetic_scorer_matches_oracle(b):
+    from ddpo_b200 import clip_vision as CV
+    from oracle import clip_vision as OCV
+    cfg = CV.VIT_TINY
+    flat = CV.init_flat_params(cfg, 0)
+    sc = CV.AestheticScorer(cfg, flat, DEV)
+    x = torch.randn(b, cfg.image_size, cfg.image_size, 3, generator=torch.Generator().manual_seed(2))
+    feats = sc.image_features(x)
+    scores = sc.score_features(feats)
+    torch.cuda.synchronize()
+    ref = OCV.image_features(CV.views(flat, cfg), cfg, x)
+    rel = ((feats.cpu() - ref).norm() / ref.norm()).item()
+    assert rel < 2e-2, rel
+    np.testing.assert_allclose(scores.cpu().numpy(), OCV.aesthetic_score(CV.views(flat, cfg), ref).numpy(), rtol=5e-2, atol=5e-3)
+    alone = sc.image_features(x[1:2])
+    torch.cuda.synchronize()
+    assert torch.equal(alone[0], feats[1])                       # batch invariant
+
+
+def test_aesthetic_scorer_full_size_runs():
+    from ddpo_b200 import clip_vision as CV
+    sc = CV.AestheticScorer(CV.VIT_L14, device=DEV, seed=0)
+    imgs = np.random.default_rng(0).random((8, 512, 512, 3)).astype(np.float32)
+    s = sc(imgs, chunk=8)
+    assert s.shape == (8, 1) and np.isfinite(s).all()
