@@ -539,7 +539,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:   # the CPU baseline is reported by the N = 1 run only
             if ppo is not None:
                 v, dps, t_train, cores = cpu_ppo_samples_per_sec(args.cpu_steps)
                 cpu = {"value": v, "unit": "PPO samples/s", "cores": cores, "kind": "port",
