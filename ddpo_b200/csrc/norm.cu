@@ -12,6 +12,8 @@
 // sums written by the stats kernel, summed in chunk order by the apply kernel.  The
 // chunking depends only on HW, never on the batch size -> batch-invariant results.
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "reduce.cuh"
 
 namespace ddpo {
@@ -32,6 +34,9 @@ struct GnArgs {
   __nv_bfloat16* y_bf16;   // [B, HW, C] or null
   float* y_f32;            // [B, HW, C] or null
   __nv_bfloat16* raw_bf16;  // [B, HW, C] un-normalised copy or null
+  int reverse;  // EXPERIMENTAL (DDPO_GN_REVERSE=1): the apply passes walk samples / chunks in descending order, so they start
+                // with what the preceding stats pass left in L2 (ascending order re-reads x from DRAM: L2 hit rate 1.3 %,
+                // profiles/r1_gn.md).  Pure scheduling: results are bit-identical.
 };
 
 __device__ __forceinline__ float2 gn_load2(const GnArgs& a, size_t pix, int c) {
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
   const int cols = C4 < GN_THREADS ? C4 : GN_THREADS;
   const int R = GN_THREADS / cols;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
-  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int b = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, chunk = a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const int p_begin = chunk * a.pix_per_chunk;
   const int p_end = min(a.hw, p_begin + a.pix_per_chunk);
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
   const int cols = C4 < GN_THREADS ? C4 : GN_THREADS;
   const int R = GN_THREADS / cols;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
-  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int b = f.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, chunk = f.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const int p_begin = chunk * f.pix_per_chunk;
   const int p_end = min(f.hw, p_begin + f.pix_per_chunk);
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS], s_m1[GN_GROUPS], s_m2[GN_GROUPS];
@@ -484,6 +489,8 @@ static int fill_gn(GnArgs& g, const ddpo_groupnorm_args* a) {
   g.scale = a->scale, g.bias = a->bias, g.partial = a->workspace, g.eps = a->eps, g.silu = a->silu;
   g.y_bf16 = static_cast<__nv_bfloat16*>(a->y_bf16), g.y_f32 = a->y_f32;
   g.raw_bf16 = static_cast<__nv_bfloat16*>(a->raw_bf16);
+  static const int reverse = [] { const char* e = getenv("DDPO_GN_REVERSE"); return e != nullptr && e[0] == '1' ? 1 : 0; }();
+  g.reverse = reverse;
   return DDPO_OK;
 }
 
