@@ -60,6 +60,51 @@ neg_compressed_animals_rwr = {
     "common": {"logbase": "logs/rwr-neg-compressed-animals", "prompt_fn": "imagenet_animals", "filter_field": "neg_jpeg"},
     "sample": dict(_RWR_SAMPLE), "train": dict(_RWR_TRAIN), "pg": {},
 }
+# the reference's own dataset names (config/base.py:200-385); prompt files resolve to this repo's ``assets/``
+_AESTHETIC_COMMON = {"prompt_fn": "from_file", "prompt_kwargs": {"loadpath": "assets/common_animals.txt"},
+                     "filter_field": "aesthetic"}
+a_animals = {
+    "common": dict(_AESTHETIC_COMMON, logbase="logs/aesthetic_simple_animals"),
+    "sample": dict(_SPARSE_SAMPLE), "train": dict(_SPARSE_TRAIN, train_batch_size=1),
+    "pg": {"train_batch_size": 1, "train_accumulation_steps": 2},
+}
+a_animals_rwr = {
+    "common": dict(_AESTHETIC_COMMON, logbase="logs/aesthetic_simple_animals_rwr_ppb"),
+    "sample": dict(_RWR_SAMPLE),
+    "train": dict(_RWR_TRAIN, train_batch_size=4, save_freq=10000000, per_prompt_weights=True), "pg": {},
+}
+a_dog_1 = {
+    "common": {"logbase": "logs/aesthetic_dogs_sweep/one", "prompt_fn": "manual", "prompt_kwargs": {"prompts": ["a dog"]},
+               "filter_field": "aesthetic"},
+    "pg": {"per_prompt_stats_bufsize": None, "per_prompt_stats_min_count": None, "train_batch_size": 1,
+           "train_accumulation_steps": 2},
+}
+a_dog_2 = {
+    "common": {"logbase": "logs/aesthetic_dogs_sweep/imagenet", "prompt_fn": "imagenet_dogs", "prompt_kwargs": {},
+               "filter_field": "aesthetic"},
+    "pg": {"train_batch_size": 1, "train_accumulation_steps": 2},
+}
+llava_bertscore = {
+    "common": {"logbase": "logs/llava-bertscore-2-simple-animals", "prompt_fn": "nouns_activities",
+               "prompt_kwargs": {"nouns_path": "assets/common_animals.txt", "activities_path": "assets/activities_v0.txt"},
+               "filter_field": "llava_bertscore"},
+    "pg": {},
+}
+llava_counting = {
+    "common": {"logbase": "logs/llava-counting-v0-8", "prompt_fn": "counting",
+               "prompt_kwargs": {"nouns_path": "assets/very_simple_animals.txt", "number_range": (2, 8)},
+               "filter_field": "llava_vqa"},
+    "pg": {},
+}
+compressed_animals_nocfg = {
+    "common": {"logbase": "logs/nocfg-compressed-animals", "prompt_fn": "imagenet_animals", "filter_field": "jpeg"},
+    "sample": dict(_SPARSE_SAMPLE), "train": dict(_SPARSE_TRAIN, train_cfg=False, train_batch_size=2), "pg": {},
+}
+neg_compressed_animals_nocfg = {
+    "common": {"logbase": "logs/nocfg-neg-compressed-animals", "prompt_fn": "imagenet_animals", "filter_field": "neg_jpeg"},
+    "sample": dict(_SPARSE_SAMPLE), "train": dict(_SPARSE_TRAIN, train_cfg=False, train_batch_size=2), "pg": {},
+}
+# this repo's earlier names, kept as aliases (BASELINE.json configs 3 and 5)
 aesthetic_animals = {
     "common": {"logbase": "logs/aesthetic-animals", "prompt_fn": "common_animals", "filter_field": "aesthetic"},
     "sample": dict(_SPARSE_SAMPLE), "train": dict(_SPARSE_TRAIN, train_batch_size=4), "pg": {},

@@ -137,4 +137,6 @@ callback_fns = {
     "arange": arange_fn,
     "aesthetic": aesthetic_fn,
     "llava_bertscore": llava_bertscore_fn,
+    "llava_vqa": _cached_score_stub("llava_vqa", False),     # callbacks.py:401-461 needs the LLaVA server; offline stub
+    "vqa": _cached_score_stub("vqa", True),
 }
