@@ -27,12 +27,14 @@ def test_dataset_config_parses_and_prompts_run(dataset):
             continue
         args = Parser().parse_args(experiment, ["--dataset", dataset])
         assert args.filter_field in training.callback_fns, args.filter_field
+        assert args.savepath.startswith(cfg["common"]["logbase"])
+        if experiment == "train":        # the fine-tuning driver reads prompts from the stored samples
+            continue
         random.seed(0)
         inf, trn, meta = training.make_prompts(args.prompt_fn, 3, getattr(args, "identical_batch", False),
                                                evaluate=False, **args.prompt_kwargs)
         assert len(inf) == len(trn) == len(meta) == 3 and all(isinstance(p, str) and p for p in inf)
         assert all(isinstance(t, (list, tuple)) and t for t in trn)
-        assert args.savepath.startswith(cfg["common"]["logbase"])
 
 
 def test_prompt_functions_follow_the_reference_shapes():
