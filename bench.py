@@ -504,7 +504,7 @@ def main():
                "train_batch": Bt, "timesteps_per_train_pass": J, "unet_batch_per_train_pass": 2 * Bt * J, "kernels": tbreak}
 
     # ---------------- e2e through the epoch driver (the call a user makes): pipeline/policy_gradient.main ------------
-    # prompts -> text stub -> 50-step sampling of 8 samples -> VAE decode -> images to the host -> JPEG reward on the
+    # prompts -> CLIP text tower (GPU) -> 50-step sampling of 8 samples -> VAE decode -> images to the host -> JPEG reward on the
     # driver's thread pool -> advantages -> shuffles -> on-device gathers -> 20 macro train passes + 4 optimizer updates.
     # Epoch 0 warms up (graph capture); epoch 1 is timed by the driver's own wall clock (includes every H2D / D2H).
     driver = None
@@ -512,11 +512,14 @@ def main():
         try:
             import contextlib
             from ddpo_b200.pipeline import policy_gradient as PG
-            from ddpo_b200.utils.text_stub import StubTextEncoder, StubTokenizer
+            from ddpo_b200.text_encoder import SD2_TEXT, CLIPTextEncoder
+            from ddpo_b200.utils.text_stub import StubTokenizer
             from ddpo_b200.vae import SD_VAE, VAEDecoder
             pipe.vae = VAEDecoder(SD_VAE, device=dev, seed=1, decode_batch=2)
             net.grads.zero_()  # the timing passes above accumulated gradients the driver's fresh train state must not see
-            pipe.tokenizer, pipe.text_encoder = StubTokenizer(), StubTextEncoder(1024)
+            # prompts are embedded by the CLIP text tower on the GPU (random-init SD2 tower; ids from the stub tokenizer:
+            # no vocabulary files offline)
+            pipe.tokenizer, pipe.text_encoder = StubTokenizer(), CLIPTextEncoder(SD2_TEXT, device=dev, seed=2)
             argv = ["--dataset", "compressed_animals", "--sample_batch_size", str(B), "--num_sample_batches_per_epoch", "1",
                     "--train_batch_size", str(TRAIN_BATCH), "--train_macro", str(TRAIN_MACRO), "--num_train_epochs", "2",
                     "--save_freq", "1000000", "--savepath", f"bench_driver_{rank}", "--seed", "0"]
@@ -532,7 +535,7 @@ def main():
             driver = {"samples_per_s": world * B / (ssec + trsec), "sample_seconds": ssec, "train_seconds": trsec,
                       "samples_per_epoch_per_gpu": B, "mean_reward": h["mean_reward"], "epoch0_first_pass_approx_kl": float(kl[0]),
                       "optimizer_updates_per_epoch": B // TRAIN_BATCH,
-                      "h2d_bytes_per_epoch": B * 77 * 1024 * 4 + (B // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * TRAIN_MACRO * TRAIN_BATCH * 40,
+                      "h2d_bytes_per_epoch": (B + 1) * 77 * 8 + (B // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * TRAIN_MACRO * TRAIN_BATCH * 40,
                       "d2h_bytes_per_epoch": B * 512 * 512 * 3 * 4 + B * T_STEPS * 8 + (B // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * 12}
         except Exception as ex:  # reported, never hidden
             driver = {"error": repr(ex)[:300]}
