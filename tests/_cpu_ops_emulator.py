@@ -164,3 +164,124 @@ def gather_rows(src, index, dst):
 def dense_small(x, w, bias, y, batch, k, n, silu_in=False, silu_out=False):
     assert not silu_in and not silu_out
     y.copy_(x.reshape(batch, k) @ w.reshape(k, n) + bias)
+
+
+# ---- U-Net forward (sampling path) ----
+import math  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+
+def _geglu_row(n_idx, N, bn):
+    half, hn = bn >> 1, N >> 1
+    j = n_idx if n_idx < hn else n_idx - hn
+    return (j // half) * bn + (0 if n_idx < hn else half) + (j % half)
+
+
+_prep_weight_plain = prep_weight
+
+
+def prep_weight(src, dst, k, n, ldk=None, row_offset=0, col_offset=0, geglu_bn=0):  # noqa: F811
+    if not geglu_bn:
+        return _prep_weight_plain(src, dst, k, n, ldk, row_offset, col_offset, 0)
+    rows = torch.tensor([_geglu_row(i, n, geglu_bn) for i in range(n)])
+    dst[rows + row_offset, col_offset:col_offset + k] = src.reshape(k, n).t().to(BF16)
+
+
+def permute_geglu_bias(src, dst, n, bn):
+    rows = torch.tensor([_geglu_row(i, n, bn) for i in range(n)])
+    dst[rows] = src
+
+
+def cast_bf16(x, y):
+    y.copy_(x.reshape(y.shape).to(BF16))
+
+
+def timestep_sincos(t, out, batch, dim):
+    half = dim // 2
+    f = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000.0) / half))
+    tt = t.float().reshape(-1)
+    tt = tt.expand(batch) if tt.numel() == 1 else tt
+    a = tt[:, None] * f[None]
+    out.copy_(torch.cat([torch.cos(a), torch.sin(a)], 1))
+
+
+_silu = lambda v: v * torch.sigmoid(v)
+
+
+def dense_small(x, w, bias, y, batch, k, n, silu_in=False, silu_out=False):  # noqa: F811
+    xv = x.reshape(batch, k)
+    r = (_silu(xv) if silu_in else xv) @ w.reshape(k, n) + (bias if bias is not None else 0)
+    y.copy_(_silu(r) if silu_out else r)
+
+
+def dense_small_group_table(entries, device):
+    rec, cta = [], 0
+    for (w_off, b_off, y_off, n) in entries:
+        rec.append((w_off, b_off, y_off, n, cta))
+        cta += (n + 31) // 32
+    return rec, cta
+
+
+def dense_small_grouped(x, params_base, y_base, table, n_groups, total_ctas, batch, k):
+    assert len(table) == n_groups and table[-1][4] + (table[-1][3] + 31) // 32 == total_ctas
+    for (w_off, b_off, y_off, n, _) in table:
+        w = params_base[w_off:w_off + k * n].reshape(k, n)
+        y_base[y_off:y_off + batch * n].reshape(batch, n).copy_(x.reshape(batch, k) @ w + params_base[b_off:b_off + n])
+
+
+_groupnorm_single = groupnorm_fwd
+
+
+def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, y_bf16=None, y_f32=None,  # noqa: F811
+                  raw_bf16=None, skip_stats=False, eps=1e-5):
+    if x1 is None:
+        return _groupnorm_single(x0, scale, bias, ws, batch, hw, c0, None, 0, silu, y_bf16, y_f32, raw_bf16, skip_stats, eps)
+    cat = torch.cat([x0.reshape(batch * hw, c0), x1.reshape(batch * hw, c1)], 1)
+    return _groupnorm_single(cat, scale, bias, ws, batch, hw, c0 + c1, None, 0, silu, y_bf16, y_f32, raw_bf16, skip_stats, eps)
+
+
+def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None, m=None, taps=1, stride=1, bias=None,  # noqa: F811
+          rowvec=None, rows_per_sample=0, rowvec_ld=0, residual=None, ld_res=0, out_f32=None, out_bf16=None, ld_out=0,
+          geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0):
+    assert a0.dtype == BF16 and wt.dtype == BF16 and (a1 is None or a1.dtype == BF16)
+    c0 = int(c0 if c0 is not None else a0.shape[-1])
+    cin = c0 + c1
+    assert c0 % 64 == 0 and c1 % 64 == 0 and n % 32 == 0, (c0, c1, n)
+    w = wt.reshape(n, taps * cin).float()
+    if conv is not None:
+        b, h, wd = conv
+        hi, wi = h * stride, wd * stride
+        x = a0.reshape(b, hi, wi, c0).float()
+        if a1 is not None:
+            x = torch.cat([x, a1.reshape(b, hi, wi, c1).float()], -1)
+        ks = 3 if taps == 9 else 1
+        wk = w.reshape(n, ks, ks, cin).permute(0, 3, 1, 2)
+        y = F.conv2d(x.permute(0, 3, 1, 2), wk, None, stride=stride, padding=ks // 2).permute(0, 2, 3, 1).reshape(b * h * wd, n)
+    else:
+        assert taps == 1 and a1 is None
+        y = a0.reshape(m, c0).float() @ w.t()
+    if bias is not None:
+        y = y + bias.reshape(1, n)
+    if rowvec is not None:
+        rv = rowvec.reshape(-1, rowvec_ld)[:, :n]
+        y = (y.reshape(rv.shape[0], rows_per_sample, n) + rv[:, None]).reshape(-1, n)
+    if geglu:
+        assert bn and residual is None
+        if aux_bf16 is not None:
+            aux_bf16.reshape(y.shape).copy_(y.to(BF16))
+        t = y.reshape(y.shape[0], n // bn, 2, bn // 2)
+        lin, gate = t[:, :, 0], t[:, :, 1]
+        act = lin * 0.5 * gate * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (gate + 0.044715 * gate ** 3)))
+        out_bf16.reshape(y.shape[0], n // 2).copy_(act.reshape(y.shape[0], n // 2).to(BF16))
+        return
+    if residual is not None:
+        y = y + residual.reshape(y.shape)
+    if out_f32 is not None:
+        out_f32.reshape(y.shape).copy_(out_f32.reshape(y.shape) + y if accumulate else y)
+    if out_bf16 is not None:
+        out_bf16.reshape(y.shape).copy_(y.to(BF16))
+
+
+def conv_out(x_nhwc, w, bias, y_nchw, batch, h, wd, cin, cout):
+    y_nchw.copy_(F.conv2d(x_nhwc.reshape(batch, h, wd, cin).permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, padding=1))

@@ -1,0 +1,67 @@
+"""The U-Net's HOST assembly (ddpo_b200/unet.py: kernel sequencing of the sampling forward, weight preparation incl. the
+GEGLU tile interleave, two-source norms / convolutions, cross-attention K/V cache, skip bookkeeping) dry-run on the
+torch-CPU emulation of the ops it calls (tests/_cpu_ops_emulator.py) against the oracle -- and the default-off grouped
+time-embedding path against the default one.  The CUDA kernels themselves are checked on the GPU box."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(__file__))
+
+
+def _net(monkeypatch, cfg, flat, grouped):
+    import _cpu_ops_emulator as E
+    from ddpo_b200 import unet as U
+    monkeypatch.setattr(U, "ops", E)
+    monkeypatch.setattr(U, "Arena", E.CpuArena)
+    monkeypatch.setenv("DDPO_GROUPED_TEMB", "1" if grouped else "0")
+    return U.UNet(cfg, flat, device="cpu")
+
+
+@pytest.mark.parametrize("batch,scalar_t", [(2, False), (3, True)])
+def test_unet_forward_host_assembly_matches_oracle(monkeypatch, batch, scalar_t):
+    from ddpo_b200 import unet_spec
+    from oracle.unet import UNetOracle
+    cfg = unet_spec.TINY
+    flat = unet_spec.init_flat_params(cfg, 0)
+    g = torch.Generator().manual_seed(1)
+    lat = torch.randn(batch, 4, cfg.sample_size, cfg.sample_size, generator=g)
+    ctx = torch.randn(batch, cfg.ctx_len, cfg.cross_attention_dim, generator=g)
+    ts = torch.tensor([981] if scalar_t else [981, 21, 441][:batch], dtype=torch.int32)
+    net = _net(monkeypatch, cfg, flat, grouped=False)
+    net.prepare_context(ctx)
+    eps = net.forward(lat, ts)
+    with torch.no_grad():
+        ref = UNetOracle(cfg, unet_spec.views(flat, cfg))(lat, ts.expand(batch).long() if scalar_t else ts.long(), ctx)
+    rel = ((eps - ref).norm() / ref.norm()).item()
+    assert eps.shape == ref.shape and rel < 2e-2, rel            # bf16 operands through ~60 layers (GPU: 1.0e-2)
+    # a second call with another context must not see the first one's K/V (persistent buffers are refilled)
+    ctx2 = torch.randn(batch, cfg.ctx_len, cfg.cross_attention_dim, generator=g)
+    net.prepare_context(ctx2)
+    eps2 = net.forward(lat, ts)
+    assert not torch.equal(eps2, eps)
+    net.prepare_context(ctx)
+    assert torch.equal(net.forward(lat, ts), eps)
+
+
+def test_grouped_time_embedding_path_equals_default(monkeypatch):
+    from ddpo_b200 import unet_spec
+    cfg = unet_spec.TINY
+    flat = unet_spec.init_flat_params(cfg, 0)
+    g = torch.Generator().manual_seed(2)
+    lat = torch.randn(2, 4, cfg.sample_size, cfg.sample_size, generator=g)
+    ctx = torch.randn(2, cfg.ctx_len, cfg.cross_attention_dim, generator=g)
+    ts = torch.tensor([500, 3], dtype=torch.int32)
+    outs = []
+    for grouped in (False, True):
+        net = _net(monkeypatch, cfg, flat, grouped)
+        assert net.grouped_temb == grouped and len(net._temb_names) == 22
+        net.prepare_context(ctx)
+        outs.append(net.forward(lat, ts))
+        if grouped:
+            tab = net._temb_tables[2]
+            assert tab[1] == sum((n + 31) // 32 for _, _, n in tab[2])       # CTA count of the grouped launch
+    np.testing.assert_allclose(outs[0].numpy(), outs[1].numpy(), rtol=1e-5, atol=1e-6)
