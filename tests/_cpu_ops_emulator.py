@@ -285,3 +285,172 @@ def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None,
 
 def conv_out(x_nhwc, w, bias, y_nchw, batch, h, wd, cin, cout):
     y_nchw.copy_(F.conv2d(x_nhwc.reshape(batch, h, wd, cin).permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, padding=1))
+
+
+# ---- U-Net backward (training path).  Gradient ops are emulated with torch autograd of the emulated forward op ----
+def prep_weight_dgrad(src, dst, taps, k, n):
+    s = src.reshape(taps, k, n)
+    dst.reshape(k, taps, n).copy_(s.flip(0).permute(1, 0, 2).to(BF16))
+
+
+def layernorm_bwd_workspace_floats(m, c):
+    return 8
+
+
+def copy2d(src, lds, dst, ldd, rows, cols, accumulate=False):
+    s = src.reshape(rows, -1)[:, :cols]
+    d = dst.reshape(rows, -1)
+    d[:, :cols] = d[:, :cols] + s if accumulate else s
+
+
+def colsum_cast(dy, m, n, y_bf16=None, out=None, rows_per_group=None, accumulate=True, ld=0):
+    v = dy.reshape(m, -1)[:, :n].float()
+    if y_bf16 is not None:
+        y_bf16.reshape(m, -1)[:, :n] = v.to(BF16)
+    if out is not None:
+        rpg = int(rows_per_group or m)
+        s = v.reshape(m // rpg, rpg, n).sum(1)
+        out.reshape(m // rpg, n).copy_(out.reshape(m // rpg, n) + s if accumulate else s)
+
+
+def colsum_bf16(x, m, n, out, accumulate=True, ld=0):
+    s = x.reshape(m, -1)[:, :n].float().sum(0, keepdim=True)
+    out.reshape(1, n).copy_(out.reshape(1, n) + s if accumulate else s)
+
+
+def _patches(x_nhwc, taps, stride):
+    """[B, Hi, Wi, C] -> [B*Ho*Wo, taps*C] in (tap, c) order (pad 1 for 3x3)"""
+    b, hi, wi, c = x_nhwc.shape
+    if taps == 1:
+        return x_nhwc.reshape(-1, c)
+    u = F.unfold(x_nhwc.permute(0, 3, 1, 2), 3, padding=1, stride=stride)         # [B, C*9, L], (c, ky, kx) order
+    u = u.reshape(b, c, 9, -1).permute(0, 3, 2, 1).reshape(-1, 9 * c)
+    return u
+
+
+def wgrad(*, dy, n, x0, dw, x1=None, c0=None, c1=0, ldy=0, ldx0=0, ldx1=0, conv=None, m=None, taps=1, stride=1, kernel=0):
+    c0 = int(c0 if c0 is not None else x0.shape[-1])
+    if conv is not None:
+        b, h, wd = conv
+        x = x0.reshape(b, h * stride, wd * stride, -1)[..., :c0].float()
+        if x1 is not None:
+            x = torch.cat([x, x1.reshape(b, h * stride, wd * stride, -1)[..., :c1].float()], -1)
+        rows = b * h * wd
+        pt = _patches(x, taps, stride)
+    else:
+        rows = m
+        pt = x0.reshape(m, -1)[:, :c0].float()
+    g = dy.reshape(rows, -1)[:, :n].float()
+    dw.reshape(pt.shape[1], n).add_(pt.t() @ g)
+
+
+def upsample2x_bwd(dy, dx, batch, h, w, c, accumulate=False):
+    s = dy.reshape(batch, h, 2, w, 2, c).sum(dim=(2, 4)).reshape(batch * h * w, c)
+    dx.reshape(batch * h * w, c).copy_(dx.reshape(batch * h * w, c) + s if accumulate else s)
+
+
+def dilate2x_bf16(x, y, batch, h, w, c):
+    out = torch.zeros(batch, 2 * h, 2 * w, c, dtype=BF16)
+    out[:, ::2, ::2] = x.reshape(batch, h, w, c).to(BF16)
+    y.reshape(out.shape).copy_(out)
+
+
+def _gn_forward(x, scale, bias, batch, hw, c, silu, eps=1e-5):
+    xg = x.reshape(batch, hw, 32, c // 32)
+    mean = xg.mean(dim=(1, 3), keepdim=True)
+    var = ((xg * xg).mean(dim=(1, 3), keepdim=True) - mean * mean).clamp(min=0)
+    y = ((xg - mean) * torch.rsqrt(var + eps)).reshape(batch * hw, c) * scale + bias
+    return y * torch.sigmoid(y) if silu else y
+
+
+def groupnorm_bwd(x0, scale, bias, ws, batch, hw, c0, dy, dx0, dscale, dbias, x1=None, c1=0, dx1=None, silu=True,
+                  accumulate=False, ldd0=0, ldd1=0):
+    m, c = batch * hw, c0 + c1
+    x = x0.reshape(m, -1)[:, :c0]
+    if x1 is not None:
+        x = torch.cat([x, x1.reshape(m, -1)[:, :c1]], 1)
+    x = x.detach().float().clone().requires_grad_(True)
+    sc, bi = scale.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
+    _gn_forward(x, sc, bi, batch, hw, c, silu).backward(dy.reshape(m, -1)[:, :c].float())
+    dscale.add_(sc.grad)
+    dbias.add_(bi.grad)
+    d0 = dx0.reshape(m, -1)
+    d0[:, :c0] = d0[:, :c0] + x.grad[:, :c0] if accumulate else x.grad[:, :c0]
+    if x1 is not None:
+        d1 = dx1.reshape(m, -1) if dx1.dim() != 2 else dx1
+        d1[:, :c1] = d1[:, :c1] + x.grad[:, c0:] if accumulate else x.grad[:, c0:]
+
+
+def layernorm_bwd(x, scale, stats, dy, dx, dscale, dbias, ws, m, c, accumulate=False):
+    xv = x.reshape(m, c).detach().float().clone().requires_grad_(True)
+    sc = scale.detach().clone().requires_grad_(True)
+    bi = torch.zeros(c, requires_grad=True)
+    mean = xv.mean(-1, keepdim=True)
+    var = ((xv * xv).mean(-1, keepdim=True) - mean * mean).clamp(min=0)
+    ((xv - mean) * torch.rsqrt(var + 1e-5) * sc + bi).backward(dy.reshape(m, c).float())
+    dscale.add_(sc.grad)
+    dbias.add_(bi.grad)
+    d = dx.reshape(m, c)
+    d.copy_(d + xv.grad if accumulate else xv.grad)
+
+
+def geglu_bwd(pre, dff, dpre, m, n, bn=256):
+    p = pre.reshape(m, n // bn, 2, bn // 2).float().detach().clone().requires_grad_(True)
+    lin, gate = p[:, :, 0], p[:, :, 1]
+    act = lin * 0.5 * gate * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (gate + 0.044715 * gate ** 3)))
+    act.reshape(m, n // 2).backward(dff.reshape(m, n // 2).float())
+    # the kernel reads the tile-interleaved pre-activation but writes the gradient in PLAIN order [lin(n/2) | gate(n/2)]
+    gl, gg = p.grad[:, :, 0].reshape(m, n // 2), p.grad[:, :, 1].reshape(m, n // 2)
+    dpre.reshape(m, n).copy_(torch.cat([gl, gg], 1).to(BF16))
+
+
+def attention_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, batch, heads, nq, nk, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv):
+    def heads_of(t, n):
+        return t[:, : heads * 64].reshape(batch, n, heads, 64).permute(0, 2, 1, 3).float().detach().clone().requires_grad_(True)
+    qq, kk, vv = heads_of(q, nq), heads_of(k, nk), heads_of(v, nk)
+    o = torch.softmax(qq @ kk.transpose(-1, -2) * (64 ** -0.5), -1) @ vv
+    g = dout[:, : heads * 64].reshape(batch, nq, heads, 64).permute(0, 2, 1, 3).float()
+    o.backward(g)
+    back = lambda t, n: t.permute(0, 2, 1, 3).reshape(batch * n, heads * 64).to(BF16)
+    dq[:, : heads * 64] = back(qq.grad, nq)
+    dk[:, : heads * 64] = back(kk.grad, nk)
+    dv[:, : heads * 64] = back(vv.grad, nk)
+
+
+def conv_out_bwd(x_nhwc, w, dy_nchw, dx_nhwc, dw, dbias, batch, h, wd, cin):
+    x = x_nhwc.reshape(batch, h, wd, cin).detach().float().clone().requires_grad_(True)
+    wk = w.detach().clone().requires_grad_(True)
+    bz = torch.zeros(w.shape[-1], requires_grad=True)
+    F.conv2d(x.permute(0, 3, 1, 2), wk.permute(3, 2, 0, 1), bz, padding=1).backward(dy_nchw.reshape(batch, -1, h, wd).float())
+    dx_nhwc.reshape(x.shape).copy_(x.grad)
+    dw.add_(wk.grad)
+    dbias.add_(bz.grad)
+
+
+def conv_in_wgrad(lat, dx_nhwc, dw, batch, cin, h, wd, cout):
+    wk = torch.zeros(3, 3, cin, cout, requires_grad=True)
+    F.conv2d(lat.float(), wk.permute(3, 2, 0, 1), None, padding=1).backward(
+        dx_nhwc.reshape(batch, h, wd, cout).permute(0, 3, 1, 2).float())
+    dw.add_(wk.grad)
+
+
+def dense_small_bwd(x, w, bias, dy, dpre_ws, dw, db, dx, batch, k, n, silu_in=False, silu_out=False, dx_accumulate=False):
+    xv = x.reshape(batch, k).detach().float().clone().requires_grad_(True)
+    wk = w.reshape(k, n).detach().clone().requires_grad_(True)
+    bz = (bias.detach().clone() if bias is not None else torch.zeros(n)).requires_grad_(True)
+    r = (_silu(xv) if silu_in else xv) @ wk + bz
+    (_silu(r) if silu_out else r).backward(dy.reshape(batch, n).float())
+    dw.reshape(k, n).add_(wk.grad)
+    db.add_(bz.grad)
+    if dx is not None:
+        dx.reshape(batch, k).copy_(dx.reshape(batch, k) + xv.grad if dx_accumulate else xv.grad)
+
+
+_igemm_fwd = igemm
+
+
+def igemm(*, a0, lda0=None, c0=None, m=None, conv=None, **kw):  # noqa: F811
+    """column-offset views of wider matrices as the linear A operand (lda0 = pitch of the parent)"""
+    if conv is None and a0.dim() == 2 and c0 is not None and a0.shape[1] != c0:
+        a0 = a0[:, :c0].contiguous()
+    return _igemm_fwd(a0=a0, lda0=lda0, c0=c0, m=m, conv=conv, **kw)
