@@ -454,3 +454,102 @@ def igemm(*, a0, lda0=None, c0=None, m=None, conv=None, **kw):  # noqa: F811
     if conv is None and a0.dim() == 2 and c0 is not None and a0.shape[1] != c0:
         a0 = a0[:, :c0].contiguous()
     return _igemm_fwd(a0=a0, lda0=lda0, c0=c0, m=m, conv=conv, **kw)
+
+
+# ---- scheduler / PPO / optimizer ops (sampler + train_step dry runs); host-only helpers come from the real module ----
+from ddpo_b200 import ops as _real_ops  # noqa: E402
+
+prng_key, threefry_split, threefry_randint, key_tensor = (_real_ops.prng_key, _real_ops.threefry_split,
+                                                          _real_ops.threefry_randint, _real_ops.key_tensor)
+
+
+def _key_np(key_dev):
+    return key_dev.reshape(-1)[:2].to(torch.int64).numpy().astype(np.int64).astype(np.uint64).astype(np.uint32)
+
+
+def threefry_normal(key_dev, out):
+    from oracle import threefry
+    k = np.array([int(v) & 0xFFFFFFFF for v in key_dev.reshape(-1)[:2].tolist()], np.uint32)
+    out.copy_(torch.from_numpy(threefry.normal(k, (out.numel(),))).reshape(out.shape))
+    return out
+
+
+def ddim_workspace(batch, device):
+    return torch.zeros(batch * 9)
+
+
+def optim_workspace(device):
+    return torch.zeros(8, dtype=torch.uint8)
+
+
+def _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta):
+    b = sample.shape[0]
+    t = timesteps.reshape(-1).long()
+    t = t.expand(b) if t.numel() == 1 else t
+    pt = t - step_ratio
+    a_t = alphas_cumprod[t]
+    a_prev = torch.where(pt >= 0, alphas_cumprod[pt.clamp(min=0)], torch.tensor(float(final_alpha)))
+    var = ((1 - a_prev) / (1 - a_t)) * (1 - a_t / a_prev)
+    sigma = float(eta) * torch.sqrt(var)
+    a_t, a_prev, sigma = a_t[:, None], a_prev[:, None], sigma[:, None]
+    eps = eps_u + float(guidance) * (eps_c - eps_u)
+    x0 = (sample - torch.sqrt(1 - a_t) * eps) / torch.sqrt(a_t)
+    mean = torch.sqrt(a_prev) * x0 + torch.sqrt(1 - a_prev - sigma ** 2) * eps
+    c_eps = torch.sqrt(1 - a_prev - sigma ** 2) - torch.sqrt(a_prev) * torch.sqrt(1 - a_t) / torch.sqrt(a_t)
+    return mean, sigma, sigma.clamp(min=1e-6), c_eps
+
+
+def _logp(prev, mean, sd):
+    return (-((prev - mean) ** 2) / (2 * sd ** 2) - torch.log(sd) - 0.9189385332046727).mean(1)
+
+
+def ddim_step_sample(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, key_dev,
+                     prev_out, logp_out, ws):
+    mean, sigma, sd, _ = _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta)
+    z = torch.empty_like(sample)
+    threefry_normal(key_dev, z)
+    prev_out.copy_(mean + sigma * z)
+    logp_out.copy_(_logp(prev_out, mean, sd))
+
+
+def ddim_logprob_fwd(eps_u, eps_c, sample, prev, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta,
+                     logp_out, ws):
+    mean, _, sd, _ = _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta)
+    logp_out.copy_(_logp(prev, mean, sd))
+
+
+def ddim_logprob_bwd(eps_u, eps_c, sample, prev, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, dlogp,
+                     d_eps_u, d_eps_c, ws):
+    mean, _, sd, c_eps = _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta)
+    k = (prev - mean) / sd ** 2 * c_eps * dlogp[:, None] / sample.shape[1]
+    d_eps_c.copy_(float(guidance) * k)
+    if d_eps_u is not None:
+        d_eps_u.copy_((1.0 - float(guidance)) * k)
+
+
+def ppo_loss(logp, old_logp, adv, clip_range, info_out, dlogp_out, micro_batch=None):
+    from oracle import ppo
+    n = logp.numel()
+    loss, info, dlp = ppo.ppo_loss(logp.numpy(), old_logp.numpy(), adv.numpy(), clip_range)
+    info_out.copy_(torch.tensor([float(info["approx_kl"]), float(info["clipfrac"]), float(info["loss"])]))
+    dlogp_out.copy_(torch.from_numpy(dlp) * n / int(micro_batch or n))
+
+
+def grad_sumsq(g, ws, out):
+    out.copy_((g.double() ** 2).sum().float().reshape(1))
+
+
+def clip_adamw(params, grad_acc, mu, nu, sumsq, grad_scale, max_norm, lr, b1, b2, eps, wd, step, norm_out=None):
+    norm = float(grad_scale) * float(sumsq.sqrt())
+    g = grad_acc * float(grad_scale)
+    if not norm < max_norm:
+        g = g / norm * max_norm
+    m = (1 - b1) * g + b1 * mu.float()
+    v = (1 - b2) * g * g + b2 * nu
+    upd = (m / (1 - b1 ** step)) / (torch.sqrt(v / (1 - b2 ** step)) + eps) + wd * params
+    params.add_(-lr * upd)
+    mu.copy_(m.to(BF16))
+    nu.copy_(v)
+    grad_acc.zero_()
+    if norm_out is not None:
+        norm_out.fill_(norm)
