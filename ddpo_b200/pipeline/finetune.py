@@ -30,7 +30,9 @@ def main(argv=None, models=None):
     set_seed(args.seed)                                                                   # :48
     if torch.cuda.is_available():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    device = torch.device("cuda", torch.cuda.current_device())
+    # no CUDA device: the kernels refuse CPU tensors (ops._p), so this only serves the CPU dry run of the host logic
+    # on the test suite's ops emulator (tests/test_drivers_host_cpu.py)
+    device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     args.modelpath = None if args.iteration == 0 else args.modelpath                      # :51
     if models is None:
         stable_models, stable_params = utils.load_finetuned_stable_diffusion(

@@ -189,7 +189,9 @@ def main(argv=None, models=None, max_epochs=None, save_last=True):
     worker_id, process_count, n_devices = distributed.rank(), distributed.world_size(), 1
     if torch.cuda.is_available():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    device = torch.device("cuda", torch.cuda.current_device())
+    # no CUDA device: the kernels refuse CPU tensors (ops._p), so this only serves the CPU dry run of the host logic
+    # on the test suite's ops emulator (tests/test_drivers_host_cpu.py)
+    device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
 
     rng = ops.prng_key(args.seed)                                                   # :51
     sizes = batch_sizes(args, n_devices, process_count)
@@ -340,7 +342,8 @@ def main(argv=None, models=None, max_epochs=None, save_last=True):
                 np.save(utils.fs.join_and_create(localpath, f"train_info/{worker_id}_{epoch}_{inner_epoch}.npy"),
                         all_infos)
             epoch_infos.append(all_infos)
-        torch.cuda.synchronize()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
         t_train = time.time() - t_train0
 
         if (epoch + 1) % args.save_freq == 0 or (epoch == n_epochs - 1 and save_last):                     # :457-464

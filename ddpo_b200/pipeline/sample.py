@@ -35,7 +35,9 @@ def main(argv=None, models=None):
         args.seed = int(os.environ.get("RANK", "0"))
     if torch.cuda.is_available():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    device = torch.device("cuda", torch.cuda.current_device())
+    # no CUDA device: the kernels refuse CPU tensors (ops._p), so this only serves the CPU dry run of the host logic
+    # on the test suite's ops emulator (tests/test_drivers_host_cpu.py)
+    device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     rng = ops.prng_key(args.seed)                                                        # :23
     n_devices, process_count = 1, distributed.world_size()
     batch_size = n_devices * args.n_samples_per_device

@@ -553,3 +553,41 @@ def clip_adamw(params, grad_acc, mu, nu, sumsq, grad_scale, max_norm, lr, b1, b2
     grad_acc.zero_()
     if norm_out is not None:
         norm_out.fill_(norm)
+
+
+# ---- RWR ops ----
+def rwr_workspace(batch, device):
+    return torch.zeros(batch * 10 + 1)
+
+
+def rwr_noisy_latents(moments_nhwc, key_sample_dev, key_noise_dev, timesteps, alphas_cumprod, noise_out, noisy_out,
+                      latents_out=None, scaling=0.18215):
+    from oracle import threefry
+    kk = lambda k: np.array([int(v) & 0xFFFFFFFF for v in k.reshape(-1)[:2].tolist()], np.uint32)
+    mom = moments_nhwc.float()
+    mean, logvar = mom.chunk(2, dim=-1)
+    std = torch.exp(0.5 * logvar.clamp(-30.0, 20.0))
+    z = torch.from_numpy(threefry.normal(kk(key_sample_dev), tuple(mean.shape)))
+    lat = ((mean + std * z) * scaling).permute(0, 3, 1, 2)
+    nz = torch.from_numpy(threefry.normal(kk(key_noise_dev), tuple(lat.shape)))
+    a = alphas_cumprod[timesteps.long()].reshape(-1, 1, 1, 1)
+    noise_out.copy_(nz)
+    noisy_out.copy_(torch.sqrt(a) * lat + torch.sqrt(1 - a) * nz)
+    if latents_out is not None:
+        latents_out.copy_(lat)
+
+
+def rwr_mse_loss(eps_u, eps_c, noise, guidance, loss_out, ws, weights=None, per_sample=None, d_eps_u=None, d_eps_c=None):
+    b, n = noise.shape
+    pred = eps_u + float(guidance) * (eps_c - eps_u)
+    d = pred - noise
+    per = (d * d).mean(1)
+    w = weights if weights is not None else torch.full((b,), 1.0 / b)
+    loss_out.copy_((per * w).sum().reshape(1))
+    if per_sample is not None:
+        per_sample.copy_(per)
+    de = 2.0 * d * w[:, None] / n
+    if d_eps_c is not None:
+        d_eps_c.copy_(float(guidance) * de)
+    if d_eps_u is not None:
+        d_eps_u.copy_((1.0 - float(guidance)) * de)
