@@ -136,3 +136,34 @@ def test_two_rank_reward_allgather_and_advantage_slices(tmp_path):
         assert list(r[i]["prompts"]) == list(want_prompts)
         np.testing.assert_allclose(r[i]["mine"], np.asarray(full).reshape(WORLD, -1)[i])
         np.testing.assert_allclose(r[i]["glob"], z.reshape(WORLD, -1)[i])
+
+
+# ------------------------------------------------------------------ the whole epoch driver on two ranks ----
+@pytest.mark.timeout(600)
+def test_two_rank_ddpo_driver_dry_run_keeps_replicas_in_sync(tmp_path):
+    """world_size-2 gloo run of pipeline/policy_gradient.main on the CPU ops emulator (tests/_driver_worker.py): every
+    rank samples its own trajectories (seed + rank, reference utils/parser.py:177), rewards are all-gathered so both
+    ranks normalise over the pod's 4 samples, the gradient is all-reduced once per optimizer update, and the two model
+    replicas end bit-identical"""
+    import subprocess
+    import sys
+    port = str(_free_port())
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_driver_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", port, str(tmp_path)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    logs = [p.communicate(timeout=560)[0].decode(errors="replace") for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(l[-1500:] for l in logs)
+    r = [np.load(tmp_path / f"driver_rank{i}.npz", allow_pickle=True) for i in range(2)]
+    assert int(r[0]["samples"]) == 4 and int(r[0]["step"]) == int(r[1]["step"]) == 2     # 1 minibatch / epoch / rank
+    np.testing.assert_array_equal(r[0]["params"], r[1]["params"])                        # replicas in sync
+    assert not np.array_equal(r[0]["rewards"], r[1]["rewards"])                          # different samples per rank
+    np.testing.assert_allclose(r[0]["mean_reward"], r[1]["mean_reward"])                 # same pod statistics
+    for i in range(2):
+        assert float(r[i]["kl0"][0]) == 0.0                                              # first pass: ratio == 1
+    # info is pmean-ed: both ranks report the same numbers
+    np.testing.assert_allclose(r[0]["loss0"], r[1]["loss0"], rtol=1e-6)
+    np.testing.assert_allclose(r[0]["kl1"], r[1]["kl1"], rtol=1e-6)
+    assert float(r[0]["kl1"][0]) == 0.0       # epoch 1 re-samples with the updated policy: its first pass is on-policy again
+    from ddpo_b200 import unet_spec
+    init = unet_spec.init_flat_params(unet_spec.TINY, 0).numpy()
+    assert np.abs(r[0]["params"] - init).max() > 1e-5                                    # the synchronised updates moved it
