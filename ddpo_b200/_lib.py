@@ -16,7 +16,8 @@ vp, i32, i64, f32, u32p, f32p = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_v
 class DdimCommon(C.Structure):
     _fields_ = [("eps_uncond", vp), ("eps_cond", vp), ("sample", vp), ("alphas_cumprod", vp), ("timesteps", vp),
                 ("timestep_stride", i32), ("final_alpha_cumprod", f32), ("step_ratio", i32),
-                ("guidance_scale", f32), ("eta", f32), ("batch", i32), ("n", i32), ("workspace", vp)]
+                ("guidance_scale", f32), ("eta", f32), ("batch", i32), ("n", i32), ("workspace", vp),
+                ("prediction_type", i32)]
 
 
 class IGemmArgs(C.Structure):

@@ -33,6 +33,31 @@ struct DdimCoef {
   float sqrt_at, sqrt_bt, sqrt_aprev, dir, sigma, sd;
 };
 
+// prev_sample_mean of scheduling_ddim_flax.py:303-338 for the three prediction types.  `m` is the (guidance-combined)
+// model output.  NB the reference's `sample` branch leaves model_output untouched, so the "direction" term is
+// dir * m there too (:307-308, :331-333) -- reproduced as written.
+template <int PRED>
+__device__ __forceinline__ float ddim_mean(const DdimCoef& k, float inv_sqrt_at, float x, float m) {
+  if (PRED == DDPO_PRED_EPSILON) {
+    const float x0 = (x - k.sqrt_bt * m) * inv_sqrt_at;
+    return k.sqrt_aprev * x0 + k.dir * m;
+  } else if (PRED == DDPO_PRED_SAMPLE) {
+    return k.sqrt_aprev * m + k.dir * m;
+  } else {
+    const float x0 = k.sqrt_at * x - k.sqrt_bt * m;
+    const float e = k.sqrt_at * m + k.sqrt_bt * x;
+    return k.sqrt_aprev * x0 + k.dir * e;
+  }
+}
+
+// d mean / d m
+template <int PRED>
+__device__ __forceinline__ float ddim_dmean(const DdimCoef& k, float inv_sqrt_at) {
+  if (PRED == DDPO_PRED_EPSILON) return k.dir - k.sqrt_aprev * k.sqrt_bt * inv_sqrt_at;
+  if (PRED == DDPO_PRED_SAMPLE) return k.sqrt_aprev + k.dir;
+  return k.dir * k.sqrt_at - k.sqrt_aprev * k.sqrt_bt;
+}
+
 __device__ __forceinline__ DdimCoef ddim_coef(const ddpo_ddim_common& c, int b) {
   const int t = c.timesteps[b * c.timestep_stride];
   const int pt = t - c.step_ratio;
@@ -54,7 +79,7 @@ __device__ __forceinline__ DdimCoef ddim_coef(const ddpo_ddim_common& c, int b) 
 constexpr int DDIM_THREADS = 256;
 
 // MODE 0: sample (draw noise, write prev_sample, log_prob); MODE 1: score (read prev_sample, log_prob)
-template <int MODE>
+template <int MODE, int PRED>
 __global__ void __launch_bounds__(DDIM_THREADS) ddim_step_kernel(const ddpo_ddim_common c, const uint32_t* __restrict__ key,
                                                                  float* __restrict__ prev_sample,
                                                                  float* __restrict__ log_prob) {
@@ -88,8 +113,7 @@ __global__ void __launch_bounds__(DDIM_THREADS) ddim_step_kernel(const ddpo_ddim
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float eps = e_u[j] + g * (e_c[j] - e_u[j]);
-      const float x0 = (xs[j] - k.sqrt_bt * eps) * inv_sqrt_at;
-      const float mean = k.sqrt_aprev * x0 + k.dir * eps;
+      const float mean = ddim_mean<PRED>(k, inv_sqrt_at, xs[j], eps);
       if (MODE == 0) {
         const uint32_t gi = static_cast<uint32_t>(base) + i + j;
         const float z = bits_to_normal(random_bits_at(k0, k1, gi, half, ntot));
@@ -126,6 +150,7 @@ __global__ void __launch_bounds__(DDIM_THREADS) ddim_step_kernel(const ddpo_ddim
   }
 }
 
+template <int PRED>
 __global__ void __launch_bounds__(DDIM_THREADS) ddim_logprob_bwd_kernel(const ddpo_ddim_common c,
                                                                         const float* __restrict__ prev_sample,
                                                                         const float* __restrict__ dlogp,
@@ -137,7 +162,7 @@ __global__ void __launch_bounds__(DDIM_THREADS) ddim_logprob_bwd_kernel(const dd
   const float g = c.guidance_scale;
   const float inv_sqrt_at = 1.0f / k.sqrt_at;
   // d mean / d eps
-  const float c_eps = k.dir - k.sqrt_aprev * k.sqrt_bt * inv_sqrt_at;
+  const float c_eps = ddim_dmean<PRED>(k, inv_sqrt_at);
   const float scale = dlogp[b] * c_eps / (k.sd * k.sd * static_cast<float>(n));
   for (int i = (blockIdx.x * DDIM_THREADS + threadIdx.x) * 4; i < n; i += gridDim.x * DDIM_THREADS * 4) {
     const float4 eu = *reinterpret_cast<const float4*>(c.eps_uncond + base + i);
@@ -150,8 +175,7 @@ __global__ void __launch_bounds__(DDIM_THREADS) ddim_logprob_bwd_kernel(const dd
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float eps = e_u[j] + g * (e_c[j] - e_u[j]);
-      const float x0 = (xs[j] - k.sqrt_bt * eps) * inv_sqrt_at;
-      const float mean = k.sqrt_aprev * x0 + k.dir * eps;
+      const float mean = ddim_mean<PRED>(k, inv_sqrt_at, xs[j], eps);
       const float de = (pv[j] - mean) * scale;
       dc[j] = g * de;
       du[j] = (1.0f - g) * de;
@@ -229,6 +253,9 @@ static int check_ddim(const ddpo_ddim_common* c) {
   DDPO_REQUIRE(c->batch > 0 && c->n > 0 && c->n % 4 == 0, "ddim: batch=%d n=%d (n must be a multiple of 4)", c->batch,
                c->n);
   DDPO_REQUIRE(c->timestep_stride == 0 || c->timestep_stride == 1, "ddim: timestep_stride must be 0 or 1");
+  DDPO_REQUIRE(c->prediction_type >= DDPO_PRED_EPSILON && c->prediction_type <= DDPO_PRED_V,
+               "ddim: prediction_type given as %d must be one of epsilon (0), sample (1) or v_prediction (2)",
+               c->prediction_type);
   return DDPO_OK;
 }
 
@@ -238,7 +265,13 @@ extern "C" int ddpo_ddim_step_sample(const ddpo_ddim_common* c, const uint32_t* 
   if (rc) return rc;
   DDPO_REQUIRE(key_dev && prev_sample && log_prob, "ddim_step_sample: null output/key");
   dim3 grid(DDPO_DDIM_CHUNKS, c->batch);
-  ddim_step_kernel<0><<<grid, DDIM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*c, key_dev, prev_sample, log_prob);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->prediction_type == DDPO_PRED_EPSILON)
+    ddim_step_kernel<0, DDPO_PRED_EPSILON><<<grid, DDIM_THREADS, 0, st>>>(*c, key_dev, prev_sample, log_prob);
+  else if (c->prediction_type == DDPO_PRED_SAMPLE)
+    ddim_step_kernel<0, DDPO_PRED_SAMPLE><<<grid, DDIM_THREADS, 0, st>>>(*c, key_dev, prev_sample, log_prob);
+  else
+    ddim_step_kernel<0, DDPO_PRED_V><<<grid, DDIM_THREADS, 0, st>>>(*c, key_dev, prev_sample, log_prob);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }
@@ -249,8 +282,14 @@ extern "C" int ddpo_ddim_logprob_fwd(const ddpo_ddim_common* c, const float* pre
   if (rc) return rc;
   DDPO_REQUIRE(prev_sample && log_prob, "ddim_logprob_fwd: null pointer");
   dim3 grid(DDPO_DDIM_CHUNKS, c->batch);
-  ddim_step_kernel<1><<<grid, DDIM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      *c, nullptr, const_cast<float*>(prev_sample), log_prob);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* pv = const_cast<float*>(prev_sample);
+  if (c->prediction_type == DDPO_PRED_EPSILON)
+    ddim_step_kernel<1, DDPO_PRED_EPSILON><<<grid, DDIM_THREADS, 0, st>>>(*c, nullptr, pv, log_prob);
+  else if (c->prediction_type == DDPO_PRED_SAMPLE)
+    ddim_step_kernel<1, DDPO_PRED_SAMPLE><<<grid, DDIM_THREADS, 0, st>>>(*c, nullptr, pv, log_prob);
+  else
+    ddim_step_kernel<1, DDPO_PRED_V><<<grid, DDIM_THREADS, 0, st>>>(*c, nullptr, pv, log_prob);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }
@@ -261,8 +300,13 @@ extern "C" int ddpo_ddim_logprob_bwd(const ddpo_ddim_common* c, const float* pre
   if (rc) return rc;
   DDPO_REQUIRE(prev_sample && dlogp && d_eps_cond, "ddim_logprob_bwd: null pointer");
   dim3 grid(DDPO_DDIM_CHUNKS, c->batch);
-  ddim_logprob_bwd_kernel<<<grid, DDIM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*c, prev_sample, dlogp,
-                                                                                      d_eps_uncond, d_eps_cond);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->prediction_type == DDPO_PRED_EPSILON)
+    ddim_logprob_bwd_kernel<DDPO_PRED_EPSILON><<<grid, DDIM_THREADS, 0, st>>>(*c, prev_sample, dlogp, d_eps_uncond, d_eps_cond);
+  else if (c->prediction_type == DDPO_PRED_SAMPLE)
+    ddim_logprob_bwd_kernel<DDPO_PRED_SAMPLE><<<grid, DDIM_THREADS, 0, st>>>(*c, prev_sample, dlogp, d_eps_uncond, d_eps_cond);
+  else
+    ddim_logprob_bwd_kernel<DDPO_PRED_V><<<grid, DDIM_THREADS, 0, st>>>(*c, prev_sample, dlogp, d_eps_uncond, d_eps_cond);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }

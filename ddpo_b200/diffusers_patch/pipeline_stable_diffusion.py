@@ -65,7 +65,7 @@ class StableDiffusionPipeline:
         # context order is [uncond ; cond] (reference :187, :226)
         ops.ddim_step_sample(eps[:b], eps[b:], S["x_cur"], state.common.alphas_cumprod, S["t_dev"],
                              state.final_alpha_cumprod, ratio, guidance_scale, eta, S["key_dev"], S["x_next"],
-                             S["logp"], S["ws"])
+                             S["logp"], S["ws"], pred=self.scheduler.config.prediction_type)
 
     # ----------------------------------------------------------------- _generate ----
     @torch.no_grad()
@@ -108,7 +108,7 @@ class StableDiffusionPipeline:
         logps = torch.empty(T, b, device=dev)
 
         S = self._step_buffers(b, h, w, dev)
-        sig = (float(guidance_scale), float(eta), T, id(state.common.alphas_cumprod))
+        sig = (float(guidance_scale), float(eta), T, id(state.common.alphas_cumprod), self.scheduler.config.prediction_type)
         S["x_cur"].copy_(traj[0])
         for s in range(T):
             S["t_dev"].copy_(ts_dev[s:s + 1])

@@ -91,9 +91,8 @@ class DDIMScheduler:
         if state.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating "
                              "the scheduler")
-        if self.config.prediction_type != "epsilon":
-            raise ValueError(f"prediction_type given as {self.config.prediction_type}: only `epsilon` is "
-                             "implemented by the CUDA path")
+        pred = self.config.prediction_type
+        ops.prediction_code(pred)  # ValueError for anything but epsilon / sample / v_prediction (reference :317-321)
         if prev_sample is not None and key is not None:
             raise ValueError("Cannot pass both key and prev_sample. Please make sure that either `key` or"
                              " `prev_sample` stays `None`.")
@@ -116,10 +115,11 @@ class DDIMScheduler:
             kd = key if torch.is_tensor(key) else ops.key_tensor([tuple(int(v) for v in key)], dev)
             prev = torch.empty_like(x)
             ops.ddim_step_sample(eps, eps, x, ac, ts, state.final_alpha_cumprod, ratio, 0.0, float(eta), kd, prev,
-                                 logp, ws)
+                                 logp, ws, pred=pred)
         else:
             prev = prev_sample.contiguous().float()
-            ops.ddim_logprob_fwd(eps, eps, x, prev, ac, ts, state.final_alpha_cumprod, ratio, 0.0, float(eta), logp, ws)
+            ops.ddim_logprob_fwd(eps, eps, x, prev, ac, ts, state.final_alpha_cumprod, ratio, 0.0, float(eta), logp, ws,
+                                 pred=pred)
         return prev, state, logp
 
     def __len__(self):

@@ -97,7 +97,19 @@ def ddim_workspace(batch, device):
     return torch.zeros(batch * DDIM_CHUNKS + batch, dtype=torch.float32, device=device)
 
 
-def _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, ws):
+PREDICTION_TYPES = {"epsilon": 0, "sample": 1, "v_prediction": 2}   # scheduling_ddim_flax.py:303-321
+
+
+def prediction_code(prediction_type):
+    """FlaxDDIMScheduler's config string -> the C ABI's DDPO_PRED_* code; same ValueError text as the reference (:317-321)."""
+    if prediction_type not in PREDICTION_TYPES:
+        raise ValueError(f"prediction_type given as {prediction_type} must be one of `epsilon`, `sample`, or"
+                         " `v_prediction`")
+    return PREDICTION_TYPES[prediction_type]
+
+
+def _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, ws,
+                 pred="epsilon"):
     b = sample.shape[0]
     n = sample.numel() // b
     for t, nm in ((eps_u, "eps_u"), (eps_c, "eps_c"), (sample, "sample"), (alphas_cumprod, "alphas_cumprod")):
@@ -106,27 +118,27 @@ def _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, s
     assert timesteps.numel() in (1, b)
     c = DdimCommon(_p(eps_u), _p(eps_c), _p(sample), _p(alphas_cumprod), _p(timesteps),
                    1 if timesteps.numel() == b and b > 1 else (0 if timesteps.numel() == 1 else 1),
-                   float(final_alpha), int(step_ratio), float(guidance), float(eta), b, n, _p(ws))
+                   float(final_alpha), int(step_ratio), float(guidance), float(eta), b, n, _p(ws), prediction_code(pred))
     return c
 
 
 def ddim_step_sample(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta,
-                     key_dev, prev_out, logp_out, ws):
-    c = _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, ws)
+                     key_dev, prev_out, logp_out, ws, pred="epsilon"):
+    c = _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, ws, pred)
     _e = _ev()
     _run("ddim_step_sample", lib().ddpo_ddim_step_sample(C.byref(c), _p(key_dev), _p(prev_out), _p(logp_out), _stream()), 0.0, _e)
 
 
 def ddim_logprob_fwd(eps_u, eps_c, sample, prev, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta,
-                     logp_out, ws):
-    c = _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, ws)
+                     logp_out, ws, pred="epsilon"):
+    c = _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, ws, pred)
     _e = _ev()
     _run("ddim_logprob_fwd", lib().ddpo_ddim_logprob_fwd(C.byref(c), _p(prev), _p(logp_out), _stream()), 0.0, _e)
 
 
 def ddim_logprob_bwd(eps_u, eps_c, sample, prev, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta,
-                     dlogp, d_eps_u, d_eps_c, ws):
-    c = _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, ws)
+                     dlogp, d_eps_u, d_eps_c, ws, pred="epsilon"):
+    c = _ddim_common(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, ws, pred)
     _e = _ev()
     _run("ddim_logprob_bwd", lib().ddpo_ddim_logprob_bwd(C.byref(c), _p(prev), _p(dlogp), _p(d_eps_u), _p(d_eps_c), _stream()), 0.0, _e)
 

@@ -44,8 +44,23 @@ def arange_fn(devices=None, jit=False):
     return _fn
 
 
+ALLOW_STUB_ENV = "DDPO_ALLOW_STUB_REWARDS"
+
+
 def _cached_score_stub(name, shape_2d):
+    """Stand-in for a reward MODEL that cannot exist offline (weights / server): N(0,1) scores keyed by the prompts,
+    INDEPENDENT OF THE IMAGES.  Optimising it optimises noise, so instantiating one is an error unless the caller opts in
+    with ``$DDPO_ALLOW_STUB_REWARDS=1`` (benchmarks and tests of the plumbing do)."""
     def factory(devices=None, jit=False):
+        import os
+        if os.environ.get(ALLOW_STUB_ENV) != "1":
+            raise RuntimeError(
+                f"reward '{name}' needs a model that is not available here (LLaVA server / CLIP weights); the only "
+                f"offline substitute is a cached-score stub that ignores the images.  Set {ALLOW_STUB_ENV}=1 to accept "
+                f"it explicitly, point $DDPO_LLAVA_URL at a server, or set $DDPO_AESTHETIC_GPU=1 for the GPU aesthetic tower.")
+        import warnings
+        warnings.warn(f"reward '{name}' is a cached-score STUB: scores do not depend on the images", RuntimeWarning)
+
         def _fn(images, prompts, metadata):
             import hashlib
             digest = hashlib.sha1("\x1f".join([name] + [str(p) for p in prompts]).encode()).hexdigest()

@@ -118,7 +118,7 @@ USE_CUDA_GRAPH = True
 
 
 def _run_body(unet: UNet, G: _StepGraph, b, train_cfg, sched_state, ratio, guidance_scale, eta, clip_range,
-              micro_batch=None):
+              micro_batch=None, pred="epsilon"):
     n = G.lat[0].numel()
     if train_cfg:
         G.lat_in[:b].copy_(G.lat)
@@ -140,14 +140,14 @@ def _run_body(unet: UNet, G: _StepGraph, b, train_cfg, sched_state, ratio, guida
     x, nx = G.lat.view(b, n), G.nxt.view(b, n)
     ac = sched_state.common.alphas_cumprod
     fa = sched_state.final_alpha_cumprod
-    ops.ddim_logprob_fwd(eu, ec, x, nx, ac, G.ts, fa, ratio, g, float(eta), G.logp, G.ws)
+    ops.ddim_logprob_fwd(eu, ec, x, nx, ac, G.ts, fa, ratio, g, float(eta), G.logp, G.ws, pred=pred)
     ops.ppo_loss(G.logp, G.old_logp, G.adv, float(clip_range), G.info, G.dlogp, micro_batch=micro_batch or b)
     if dc is None:
         scratch = unet.arena.alloc((b, n), torch.float32)
-        ops.ddim_logprob_bwd(eu, ec, x, nx, ac, G.ts, fa, ratio, g, float(eta), G.dlogp, du, scratch, G.ws)
+        ops.ddim_logprob_bwd(eu, ec, x, nx, ac, G.ts, fa, ratio, g, float(eta), G.dlogp, du, scratch, G.ws, pred=pred)
         unet.arena.release(scratch)
     else:
-        ops.ddim_logprob_bwd(eu, ec, x, nx, ac, G.ts, fa, ratio, g, float(eta), G.dlogp, du, dc, G.ws)
+        ops.ddim_logprob_bwd(eu, ec, x, nx, ac, G.ts, fa, ratio, g, float(eta), G.dlogp, du, dc, G.ws, pred=pred)
     unet.backward(tape, G.d_eps)
 
 
@@ -182,20 +182,21 @@ def train_step(state: AccumulatingTrainState, batch, noise_scheduler_state, nois
     ratio = noise_scheduler.config.num_train_timesteps // noise_scheduler_state.num_inference_steps
     mb = int(micro_batch_size or b)
     assert b % mb == 0
-    sig = (float(guidance_scale), float(eta), float(clip_range), ratio, id(noise_scheduler_state.common.alphas_cumprod), mb)
+    pred = noise_scheduler.config.prediction_type   # the reference branches on it inside scheduler.step (:303-321)
+    sig = (float(guidance_scale), float(eta), float(clip_range), ratio, id(noise_scheduler_state.common.alphas_cumprod), mb, pred)
     if not USE_CUDA_GRAPH:
-        _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range, mb)
+        _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range, mb, pred)
     else:
         if G.graph is None or G.sig != sig:
             # warm-up outside capture (arena, workspaces, kernel attributes); undo its gradient contribution
             saved = state.grad_acc.clone()
-            _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range, mb)
+            _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range, mb, pred)
             torch.cuda.synchronize()
             state.grad_acc.copy_(saved)
             del saved
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range, mb)
+                _run_body(unet, G, b, bool(train_cfg), noise_scheduler_state, ratio, guidance_scale, eta, clip_range, mb, pred)
             G.graph, G.sig = g, sig
         G.graph.replay()
     info_t = G.info.clone()

@@ -4,7 +4,7 @@
 The reference embeds prompts on the host CPU (``pipeline/policy_gradient.py:185-187``) and feeds the U-Net
 ``[B, 77, D]`` float32 hidden states; everything downstream depends only on that tensor.  ``StubTokenizer`` maps a
 prompt to deterministic ids (so that the tokenizer encode -> decode round trip the reference uses to canonicalise
-prompts, ``:329-335``, is the identity on normalised text) and ``StubTextEncoder`` maps ids to a deterministic
+prompts, ``:329-335``, is the identity on normalised text of up to 75 characters, in ANY process) and ``StubTextEncoder`` maps ids to a deterministic
 N(0,1) embedding seeded by the ids -- same prompt => same conditioning, different prompts => independent ones."""
 import hashlib
 
@@ -12,21 +12,16 @@ import numpy as np
 
 
 class StubTokenizer:
+    """Character-level, STATELESS and reversible: id = 1000 + code point.  Every process decodes every other process's
+    ids to the same string (the multi-rank driver all-gathers prompt ids and decodes them locally to key the per-prompt
+    reward statistics, reference ``pipeline/policy_gradient.py:329-335``), with no vocabulary to share."""
     model_max_length = 77
     bos, eos = 49406, 49407
+    _base, _span = 1000, 40000
 
-    def __init__(self):
-        self._vocab = {}
-        self._inv = {}
-
-    def _id(self, word):
-        if word not in self._vocab:
-            i = 1000 + int(hashlib.sha1(word.encode()).hexdigest(), 16) % 40000
-            while i in self._inv and self._inv[i] != word:
-                i += 1
-            self._vocab[word] = i
-            self._inv[i] = word
-        return self._vocab[word]
+    @staticmethod
+    def normalise(text):
+        return " ".join(str(text).lower().split())
 
     def __call__(self, prompts, padding="max_length", max_length=None, truncation=True, return_tensors="np"):
         if isinstance(prompts, str):
@@ -34,15 +29,15 @@ class StubTokenizer:
         L = max_length or self.model_max_length
         ids = np.full((len(prompts), L), self.eos, np.int64)
         for r, p in enumerate(prompts):
-            toks = [self.bos] + [self._id(w) for w in str(p).lower().split()][: L - 2] + [self.eos]
+            toks = [self.bos] + [self._base + min(ord(ch), self._span - 1) for ch in self.normalise(p)][: L - 2] + [self.eos]
             ids[r, : len(toks)] = toks
         return type("Encoding", (), {"input_ids": ids})()
 
     def batch_decode(self, ids, skip_special_tokens=True):
         out = []
         for row in np.asarray(ids):
-            words = [self._inv.get(int(i), "") for i in row if int(i) not in (self.bos, self.eos)]
-            out.append(" ".join(w for w in words if w))
+            out.append("".join(chr(int(i) - self._base) for i in row
+                               if self._base <= int(i) < self._base + self._span).strip())
         return out
 
 

@@ -1,14 +1,15 @@
-"""``utils.Timer`` (reference ``ddpo/utils/timer.py``): seconds since the last call."""
+"""``utils.Timer``: a lap timer with the reference's call convention (``ddpo/utils/timer.py``) -- ``timer()`` gives the
+seconds since the previous lap and starts a new one; ``timer(reset=False)`` only reads."""
 import time
 
 
 class Timer:
     def __init__(self):
-        self._start = time.time()
+        self.lap_start = time.perf_counter()
 
     def __call__(self, reset=True):
-        now = time.time()
-        diff = now - self._start
+        t = time.perf_counter()
+        elapsed = t - self.lap_start
         if reset:
-            self._start = now
-        return diff
+            self.lap_start = t
+        return elapsed

@@ -67,7 +67,11 @@ typedef struct {
   int batch;
   int n;                       /* C*H*W elements per sample */
   float* workspace;            /* >= batch*DDPO_DDIM_CHUNKS floats + batch uint32 counters, zero-initialised once */
+  int prediction_type;         /* scheduling_ddim_flax.py:303-321: DDPO_PRED_EPSILON / _SAMPLE / _V_PREDICTION */
 } ddpo_ddim_common;
+#define DDPO_PRED_EPSILON 0
+#define DDPO_PRED_SAMPLE 1
+#define DDPO_PRED_V 2
 #define DDPO_DDIM_CHUNKS 8
 
 /* sample mode (scheduling_ddim_flax.py:346-348): prev = mean + sigma * normal(key) ; log_prob */

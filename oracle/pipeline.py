@@ -59,7 +59,16 @@ def train_loss(unet: UNetOracle, sched_cfg, sched_state, batch, train_cfg, guida
     tt = lambda v: torch.as_tensor(v, dtype=dt).view(-1, 1, 1, 1)
     a_t, a_prev, sigma = tt(a_t), tt(a_prev), tt(sigma)
     x = lat.to(dt)
-    x0 = (x - torch.sqrt(1 - a_t) * eps) / torch.sqrt(a_t)
+    pred = getattr(sched_cfg, "prediction_type", "epsilon")               # scheduling_ddim_flax.py:303-321
+    if pred == "epsilon":
+        x0 = (x - torch.sqrt(1 - a_t) * eps) / torch.sqrt(a_t)
+    elif pred == "sample":
+        x0 = eps
+    elif pred == "v_prediction":
+        x0 = torch.sqrt(a_t) * x - torch.sqrt(1 - a_t) * eps
+        eps = torch.sqrt(a_t) * eps + torch.sqrt(1 - a_t) * x
+    else:
+        raise ValueError(f"prediction_type given as {pred} must be one of `epsilon`, `sample`, or `v_prediction`")
     mean = torch.sqrt(a_prev) * x0 + torch.sqrt(1 - a_prev - sigma ** 2) * eps
     sd = torch.clamp(sigma, min=1e-6)
     nxt = torch.as_tensor(batch["next_latents"]).to(dt)

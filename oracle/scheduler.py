@@ -88,13 +88,21 @@ def step(cfg, state, model_output, timestep, sample, key=None, prev_sample=None,
         raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps'")
     if prev_sample is not None and key is not None:
         raise ValueError("Cannot pass both key and prev_sample.")
-    assert cfg.prediction_type == "epsilon"
     x = np.asarray(sample, f32)
     eps = np.asarray(model_output, f32)
     a_t, a_prev, sigma = coefficients(cfg, state, timestep, eta)
     a_t, a_prev, sigma = (_bcast(v, x.ndim) for v in (a_t, a_prev, sigma))
     b_t = f32(1) - a_t
-    x0 = (x - np.sqrt(b_t) * eps) / np.sqrt(a_t)
+    if cfg.prediction_type == "epsilon":                                   # :303-306
+        x0 = (x - np.sqrt(b_t) * eps) / np.sqrt(a_t)
+    elif cfg.prediction_type == "sample":                                  # :307-308 (model_output stays as is)
+        x0 = eps
+    elif cfg.prediction_type == "v_prediction":                            # :309-316
+        x0 = np.sqrt(a_t) * x - np.sqrt(b_t) * eps
+        eps = np.sqrt(a_t) * eps + np.sqrt(b_t) * x
+    else:
+        raise ValueError(f"prediction_type given as {cfg.prediction_type} must be one of `epsilon`, `sample`, or"
+                         " `v_prediction`")
     direction = np.sqrt(f32(1) - a_prev - sigma ** 2) * eps
     mean = (np.sqrt(a_prev) * x0 + direction).astype(f32)
     if prev_sample is None:
@@ -117,8 +125,16 @@ def logprob_grad_eps(cfg, state, model_output, timestep, sample, prev_sample, et
     eps = np.asarray(model_output, np.float64)
     a_t, a_prev, sigma = coefficients(cfg, state, timestep, eta)
     a_t, a_prev, sigma = (_bcast(v, x.ndim).astype(np.float64) for v in (a_t, a_prev, sigma))
-    c_eps = np.sqrt(1 - a_prev - sigma ** 2) - np.sqrt(a_prev) * np.sqrt(1 - a_t) / np.sqrt(a_t)
-    mean = np.sqrt(a_prev) * (x - np.sqrt(1 - a_t) * eps) / np.sqrt(a_t) + np.sqrt(1 - a_prev - sigma ** 2) * eps
+    d = np.sqrt(1 - a_prev - sigma ** 2)
+    if cfg.prediction_type == "epsilon":
+        c_eps = d - np.sqrt(a_prev) * np.sqrt(1 - a_t) / np.sqrt(a_t)
+        mean = np.sqrt(a_prev) * (x - np.sqrt(1 - a_t) * eps) / np.sqrt(a_t) + d * eps
+    elif cfg.prediction_type == "sample":
+        c_eps = np.sqrt(a_prev) + d
+        mean = c_eps * eps
+    else:
+        c_eps = d * np.sqrt(a_t) - np.sqrt(a_prev) * np.sqrt(1 - a_t)
+        mean = np.sqrt(a_prev) * (np.sqrt(a_t) * x - np.sqrt(1 - a_t) * eps) + d * (np.sqrt(a_t) * eps + np.sqrt(1 - a_t) * x)
     sd = np.maximum(sigma, 1e-6)
     n = x[0].size
     g = (np.asarray(prev_sample, np.float64) - mean) / sd ** 2 * c_eps / n

@@ -482,7 +482,7 @@ def optim_workspace(device):
     return torch.zeros(8, dtype=torch.uint8)
 
 
-def _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta):
+def _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, pred="epsilon"):
     b = sample.shape[0]
     t = timesteps.reshape(-1).long()
     t = t.expand(b) if t.numel() == 1 else t
@@ -493,9 +493,18 @@ def _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, st
     sigma = float(eta) * torch.sqrt(var)
     a_t, a_prev, sigma = a_t[:, None], a_prev[:, None], sigma[:, None]
     eps = eps_u + float(guidance) * (eps_c - eps_u)
-    x0 = (sample - torch.sqrt(1 - a_t) * eps) / torch.sqrt(a_t)
-    mean = torch.sqrt(a_prev) * x0 + torch.sqrt(1 - a_prev - sigma ** 2) * eps
-    c_eps = torch.sqrt(1 - a_prev - sigma ** 2) - torch.sqrt(a_prev) * torch.sqrt(1 - a_t) / torch.sqrt(a_t)
+    d = torch.sqrt(1 - a_prev - sigma ** 2)
+    if pred == "epsilon":
+        x0 = (sample - torch.sqrt(1 - a_t) * eps) / torch.sqrt(a_t)
+        mean = torch.sqrt(a_prev) * x0 + d * eps
+        c_eps = d - torch.sqrt(a_prev) * torch.sqrt(1 - a_t) / torch.sqrt(a_t)
+    elif pred == "sample":
+        c_eps = torch.sqrt(a_prev) + d
+        mean = c_eps * eps
+    else:
+        x0 = torch.sqrt(a_t) * sample - torch.sqrt(1 - a_t) * eps
+        mean = torch.sqrt(a_prev) * x0 + d * (torch.sqrt(a_t) * eps + torch.sqrt(1 - a_t) * sample)
+        c_eps = d * torch.sqrt(a_t) - torch.sqrt(a_prev) * torch.sqrt(1 - a_t)
     return mean, sigma, sigma.clamp(min=1e-6), c_eps
 
 
@@ -504,8 +513,8 @@ def _logp(prev, mean, sd):
 
 
 def ddim_step_sample(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, key_dev,
-                     prev_out, logp_out, ws):
-    mean, sigma, sd, _ = _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta)
+                     prev_out, logp_out, ws, pred="epsilon"):
+    mean, sigma, sd, _ = _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, pred)
     z = torch.empty_like(sample)
     threefry_normal(key_dev, z)
     prev_out.copy_(mean + sigma * z)
@@ -513,14 +522,14 @@ def ddim_step_sample(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alph
 
 
 def ddim_logprob_fwd(eps_u, eps_c, sample, prev, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta,
-                     logp_out, ws):
-    mean, _, sd, _ = _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta)
+                     logp_out, ws, pred="epsilon"):
+    mean, _, sd, _ = _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, pred)
     logp_out.copy_(_logp(prev, mean, sd))
 
 
 def ddim_logprob_bwd(eps_u, eps_c, sample, prev, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, dlogp,
-                     d_eps_u, d_eps_c, ws):
-    mean, _, sd, c_eps = _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta)
+                     d_eps_u, d_eps_c, ws, pred="epsilon"):
+    mean, _, sd, c_eps = _ddim_terms(eps_u, eps_c, sample, alphas_cumprod, timesteps, final_alpha, step_ratio, guidance, eta, pred)
     k = (prev - mean) / sd ** 2 * c_eps * dlogp[:, None] / sample.shape[1]
     d_eps_c.copy_(float(guidance) * k)
     if d_eps_u is not None:

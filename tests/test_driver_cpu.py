@@ -120,6 +120,8 @@ def test_text_stubs_are_deterministic_and_round_trip():
     ids = tok(["a dog", "A  dog", "a zebra riding a bike", ""], padding="max_length", return_tensors="np").input_ids
     assert ids.shape == (4, 77) and np.array_equal(ids[0], ids[1]) and not np.array_equal(ids[0], ids[2])
     assert tok.batch_decode(ids, skip_special_tokens=True) == ["a dog", "a dog", "a zebra riding a bike", ""]
+    # decoding needs no state: a tokenizer that never saw these prompts (another rank) gives the same strings
+    assert StubTokenizer().batch_decode(ids) == ["a dog", "a dog", "a zebra riding a bike", ""]
     enc = StubTextEncoder(64)
     e = enc(ids)[0]
     assert e.shape == (4, 77, 64) and e.dtype == np.float32

@@ -107,6 +107,47 @@ def test_ddim_step_sample_and_score(batch, t_scalar):
     np.testing.assert_allclose(du.cpu().numpy(), (1 - g) * gref, rtol=2e-4, atol=1e-7)
 
 
+@pytest.mark.parametrize("pred", ["sample", "v_prediction"])
+def test_ddim_prediction_types(pred):
+    """The `sample` and `v_prediction` branches of FlaxDDIMScheduler.step (scheduling_ddim_flax.py:307-316): sample
+    mode, score mode and the backward against the oracle; sample-mode and score-mode log-probs bit identical."""
+    from dataclasses import replace
+    from ddpo_b200 import ops
+    from oracle.ppo import cfg_combine
+    S, st = _sched()
+    cfg = replace(S.SD_CONFIG, prediction_type=pred)
+    batch, n = 3, 4 * 16 * 16
+    rng = np.random.default_rng(3)
+    eu, ec, x = (rng.standard_normal((batch, n)).astype(np.float32) for _ in range(3))
+    ts = np.array([981, 21, 501], np.int32)
+    key, g, eta = (5, 11), 3.0, 1.0
+    ac = torch.tensor(st.alphas_cumprod, device=DEV)
+    ws = ops.ddim_workspace(batch, DEV)
+    prev, lp, lp2 = torch.empty(batch, n, device=DEV), torch.empty(batch, device=DEV), torch.empty(batch, device=DEV)
+    teu, tec, tx, tts = (torch.tensor(a, device=DEV) for a in (eu, ec, x, ts))
+    fa = float(st.final_alpha_cumprod)
+    ops.ddim_step_sample(teu, tec, tx, ac, tts, fa, 20, g, eta, ops.key_tensor([key], DEV), prev, lp, ws, pred=pred)
+    m = cfg_combine(eu, ec, g)
+    rprev, _, rlp = S.step(cfg, st, m, ts, x, key=np.array(key, np.uint32), eta=eta)
+    np.testing.assert_allclose(prev.cpu().numpy(), rprev, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(lp.cpu().numpy(), rlp, rtol=1e-5, atol=1e-5)
+    ops.ddim_logprob_fwd(teu, tec, tx, prev, ac, tts, fa, 20, g, eta, lp2, ws, pred=pred)
+    assert torch.equal(lp, lp2)
+    # score mode on an unrelated next sample
+    other = torch.tensor(rng.standard_normal((batch, n)).astype(np.float32), device=DEV)
+    ops.ddim_logprob_fwd(teu, tec, tx, other, ac, tts, fa, 20, g, eta, lp2, ws, pred=pred)
+    _, _, rlp2 = S.step(cfg, st, m, ts, x, prev_sample=other.cpu().numpy(), eta=eta)
+    np.testing.assert_allclose(lp2.cpu().numpy(), rlp2, rtol=2e-5)
+    dl = torch.tensor(rng.standard_normal(batch).astype(np.float32), device=DEV)
+    du, dc = torch.empty(batch, n, device=DEV), torch.empty(batch, n, device=DEV)
+    ops.ddim_logprob_bwd(teu, tec, tx, other, ac, tts, fa, 20, g, eta, dl, du, dc, ws, pred=pred)
+    gref = S.logprob_grad_eps(cfg, st, m, ts, x, other.cpu().numpy(), eta, dl.cpu().numpy())
+    np.testing.assert_allclose(dc.cpu().numpy(), g * gref, rtol=3e-4, atol=1e-6)
+    np.testing.assert_allclose(du.cpu().numpy(), (1 - g) * gref, rtol=3e-4, atol=1e-6)
+    with pytest.raises(ValueError):
+        ops.ddim_logprob_fwd(teu, tec, tx, other, ac, tts, fa, 20, g, eta, lp2, ws, pred="velocity")
+
+
 def test_ppo_loss_matches_oracle():
     from ddpo_b200 import ops
     from oracle import ppo

@@ -49,7 +49,13 @@ def test_llava_bertscore_wire_format_and_fallback(monkeypatch):
     assert info["f1"].shape == (18,) and info["outputs"][10] == "caption 1"
     # no server configured -> the cached-score stub (deterministic per prompt batch)
     monkeypatch.delenv(C.LLAVA_URL_ENV, raising=False)
-    stub = C.callback_fns["llava_bertscore"]()
+    monkeypatch.delenv(C.ALLOW_STUB_ENV, raising=False)
+    import pytest
+    with pytest.raises(RuntimeError):                              # a reward that ignores the images needs an explicit opt-in
+        C.callback_fns["llava_bertscore"]()
+    monkeypatch.setenv(C.ALLOW_STUB_ENV, "1")
+    with pytest.warns(RuntimeWarning):
+        stub = C.callback_fns["llava_bertscore"]()
     a, meta = stub(images, prompts, None)
     b, _ = stub(images, prompts, None)
     assert a.shape == (18,) and np.array_equal(a, b) and meta == {"stub": True}

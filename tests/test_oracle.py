@@ -141,3 +141,36 @@ def test_unet_oracle_golden_and_param_count():
     y64 = UNetOracle(cfg, unet_spec.views(flat, cfg), torch.float64)(torch.from_numpy(g["lat"]),
                                                                       torch.from_numpy(g["ts"]), torch.from_numpy(g["ctx"]))
     assert (y64.float() - y).abs().max().item() < 1e-4
+
+
+def test_scheduler_prediction_types_are_consistent():
+    """`v_prediction` (scheduling_ddim_flax.py:309-316) is the epsilon branch fed eps = sqrt(a) v + sqrt(1-a) x; the
+    analytic gradient of every branch agrees with finite differences; unknown types raise the reference's ValueError."""
+    from dataclasses import replace
+    import pytest
+    from oracle import scheduler as S
+    st = S.set_timesteps(S.SD_CONFIG, S.create_state(S.SD_CONFIG), 50)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((2, 4, 8, 8)).astype(np.float32)
+    v = rng.standard_normal((2, 4, 8, 8)).astype(np.float32)
+    nxt = rng.standard_normal((2, 4, 8, 8)).astype(np.float32)
+    ts = np.array([981, 301])
+    a = st.alphas_cumprod[ts].reshape(2, 1, 1, 1)
+    eps = np.sqrt(a) * v + np.sqrt(1 - a) * x
+    vcfg = replace(S.SD_CONFIG, prediction_type="v_prediction")
+    _, _, lp_v, mean_v = S.step(vcfg, st, v, ts, x, prev_sample=nxt, eta=1.0, return_mean=True)
+    _, _, lp_e, mean_e = S.step(S.SD_CONFIG, st, eps, ts, x, prev_sample=nxt, eta=1.0, return_mean=True)
+    np.testing.assert_allclose(mean_v, mean_e, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(lp_v, lp_e, rtol=1e-4)
+    for pred in ("epsilon", "sample", "v_prediction"):
+        cfg = replace(S.SD_CONFIG, prediction_type=pred)
+        dl = np.array([1.0, -2.0])
+        g = S.logprob_grad_eps(cfg, st, v, ts, x, nxt, 1.0, dl)
+        d = rng.standard_normal(v.shape)
+        h = 1e-3
+        f = lambda m: float((S.step(cfg, st, m.astype(np.float64), ts, x, prev_sample=nxt, eta=1.0)[2].astype(np.float64) * dl).sum())
+        # step() computes in fp32: central difference with a step large enough for fp32 round-off
+        num = (f(v + h * d) - f(v - h * d)) / (2 * h)
+        np.testing.assert_allclose((g * d).sum(), num, rtol=5e-2)
+    with pytest.raises(ValueError):
+        S.step(replace(S.SD_CONFIG, prediction_type="velocity"), st, v, ts, x, prev_sample=nxt, eta=1.0)
