@@ -34,6 +34,7 @@ TRAIN_BATCH = 2
 TRAIN_MACRO = 10  # timesteps of the same train batch evaluated in one U-Net pass (same parameters, see train_step doc)
 GUIDANCE, ETA, CLIP = 5.0, 1.0, 1e-4
 UNET_GFLOP = 804.3  # algorithmic GFLOP of one SD2-base U-Net application (SURVEY.md §8d / BASELINE.md §2)
+WORKLOAD = "DDPO SD2-base 512px, 50-step DDIM, CFG 5.0, eta 1.0, sample batch 8/GPU (BASELINE configs[1])"
 
 
 def _peaks():
@@ -79,44 +80,110 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------- CPU arm ----
-def cpu_step_seconds(n_steps, threads=None):
-    """Times the CPU oracle (restated reference path: oracle/unet.py + oracle/scheduler.py) on one
-    denoising step of ONE sample (2 U-Net applications, SD2-base, fp32) -- bounded sample."""
+UNIT = "PPO samples/s"   # ONE unit string for both arms (the driver divides the two values only if metric/unit agree)
+UNIT_DETAIL = ("a PPO sample = 50 denoising steps (both CFG branches) + VAE decode of the final latent + 50 PPO train "
+               "steps (cond + uncond U-Net forward and backward) + its share of the optimizer update")
+
+
+def parity_inputs():
+    """The one-sample workload both arms evaluate for the parity block: x_T from threefry key (0, 7), its step key, and
+    N(0,1) prompt / negative-prompt embeddings (seeded torch CPU generator -> identical bytes on both sides)."""
     import torch
+    from oracle import threefry
+    g = torch.Generator().manual_seed(1)
+    ctx = torch.randn(2, 77, 1024, generator=g)                       # [uncond ; cond]
+    x = threefry.normal(np.array((0, 7), np.uint32), (1, 4, 64, 64)).astype(np.float32)
+    return x, ctx, (0, 11)
+
+
+def _cpu_threads():
+    """torchrun exports OMP_NUM_THREADS=1: the CPU arm must still use every host core (rank 0 is the only rank that
+    runs it)."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    if torch.get_num_threads() != n:
+        torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def _oracle_net():
     from ddpo_b200 import unet_spec
-    from oracle import scheduler as OS, ppo as OPPO, threefry
     from oracle.unet import UNetOracle
-    if threads:
-        torch.set_num_threads(threads)
     cfg = unet_spec.SD2_BASE
     flat = unet_spec.init_flat_params(cfg, 0)
-    net = UNetOracle(cfg, unet_spec.views(flat, cfg))
+    return cfg, flat, UNetOracle(cfg, unet_spec.views(flat, cfg))
+
+
+def cpu_step_seconds(n_steps, net=None):
+    """Times the CPU oracle (restated reference path: oracle/unet.py + oracle/scheduler.py) on denoising steps of ONE
+    sample (2 U-Net applications each, SD2-base, fp32) -- bounded sample.  The first (untimed, warm-up) step runs on
+    `parity_inputs()` and its outputs are returned for the GPU-vs-oracle parity block."""
+    import torch
+    from oracle import scheduler as OS, ppo as OPPO
+    cores = _cpu_threads()
+    if net is None:
+        _, _, net = _oracle_net()
     st = OS.set_timesteps(OS.SD_CONFIG, OS.create_state(OS.SD_CONFIG), T_STEPS)
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(1, 4, 64, 64, generator=g)
-    ctx = torch.randn(2, 77, 1024, generator=g)
-    times = []
+    x0, ctx, key = parity_inputs()
+    x = torch.from_numpy(x0)
+    times, first = [], None
     for s in range(n_steps + 1):
         t0 = time.perf_counter()
         with torch.no_grad():
             e = net(torch.cat([x, x]), torch.full((2,), int(st.timesteps[s])), ctx).numpy()
         eps = OPPO.cfg_combine(e[:1], e[1:], GUIDANCE)
         xn, _, lp = OS.step(OS.SD_CONFIG, st, eps, int(st.timesteps[s]), x.numpy(),
-                            key=threefry.PRNGKey(s), eta=ETA)
+                            key=np.array(key if s == 0 else (1, s), np.uint32), eta=ETA)
+        if s == 0:
+            first = {"eps_u": e[:1].copy(), "eps_c": e[1:].copy(), "prev": xn.copy(), "logp": np.asarray(lp).copy()}
         x = torch.from_numpy(xn)
         if s > 0:  # first step = warm-up (allocator, thread pool)
             times.append(time.perf_counter() - t0)
-    return float(np.mean(times)), torch.get_num_threads()
+    return float(np.mean(times)), cores, first
+
+
+def cpu_unet_application_seconds(net, n_timed, n_warm):
+    """Reference-arm step: ONE U-Net application of one sample (alternating uncond / cond context)."""
+    import torch
+    x0, ctx, _ = parity_inputs()
+    x = torch.from_numpy(x0)
+    ts = []
+    for i in range(n_warm + n_timed):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            net(x, torch.full((1,), 981 - 20 * (i % 50)), ctx[i % 2:i % 2 + 1])
+        if i >= n_warm:
+            ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def cpu_vae_decode_seconds():
+    """One image through the oracle's Flax VAE decoder (oracle/vae.py; reference pipeline/policy_gradient.py:174-182)."""
+    import torch
+    from ddpo_b200 import vae as V
+    from oracle import vae as OV
+    vflat = V.init_flat_params(V.SD_VAE, 1)
+    z = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(5)) * 0.18215
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        OV.decode(V.views(vflat, V.SD_VAE), V.SD_VAE, z)
+    return time.perf_counter() - t0
 
 
 def _ncu_traffic():
     """Average DRAM bytes (read + write) per igemm launch of one denoising step, from the committed ncu capture of
     `bench.py --ncu sample` (profiles/r1_traffic.json, written by profiles/make_launch_summary.py); None if absent."""
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
-            return json.load(f)["sample"]["igemm"]["dram_bytes_per_launch"]
-    except Exception:
-        return None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f)["sample"]["igemm"]["dram_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
 
 
 def _dump_shapes(prof, tags, path):
@@ -144,6 +211,7 @@ def cpu_train_step_seconds():
     from ddpo_b200 import unet_spec
     from oracle import pipeline as OP, scheduler as OS
     from oracle.unet import UNetOracle
+    _cpu_threads()
     cfg = unet_spec.SD2_BASE
     # every parameter its own autograd leaf, as in the reference's pytree (slices of one flat leaf would make each
     # of the 686 SliceBackward nodes materialise a 3.5 GB zero tensor)
@@ -167,35 +235,48 @@ def cpu_train_step_seconds():
 
 def cpu_ppo_samples_per_sec(n_denoise):
     """The headline metric on the host cores from a BOUNDED sample: `n_denoise` timed denoising steps of one sample
-    (after one warm-up step) and one PPO train step of one sample, extrapolated linearly to a PPO sample =
-    50 denoising steps + 50 train steps (every step of the trajectory costs the same: the scan / loop bodies are
-    step-invariant).  Returns (samples/s, denoising steps/s, seconds per train step, threads)."""
-    per_step, cores = cpu_step_seconds(n_denoise)
+    (after one warm-up step), one VAE decode of one image and one PPO train step of one sample, extrapolated linearly to
+    a PPO sample = 50 denoising steps + decode + 50 train steps (every step of the trajectory costs the same: the scan /
+    loop bodies are step-invariant).  Returns a dict (value, pieces, threads, first-step outputs for the parity block)."""
+    per_step, cores, first = cpu_step_seconds(n_denoise)
+    t_vae = cpu_vae_decode_seconds()
     t_train = cpu_train_step_seconds()
-    s_per_sample = T_STEPS * per_step + T_STEPS * t_train
-    return 1.0 / s_per_sample, 1.0 / per_step, t_train, cores
+    s_per_sample = T_STEPS * per_step + t_vae + T_STEPS * t_train
+    return {"value": 1.0 / s_per_sample, "denoising_steps_per_sec": 1.0 / per_step, "seconds_per_train_step": t_train,
+            "seconds_per_vae_decode": t_vae, "cores": cores, "first": first}
 
 
 def run_reference(args):
     """Reference arm: the reference's own path cannot be installed here (jax / flax / diffusers are absent and there
     is no network), so this times the oracle port of it on the host cores -- same metric, unit and
-    workload as the B200 arm, each quantity from a bounded sample (see cpu_ppo_samples_per_sec)."""
+    workload as the B200 arm.  A timed "step" is ONE U-Net application of one sample (what `ms_per_step` and `steps`
+    describe, so steps x ms_per_step is time really spent in this run); one VAE decode and one PPO train step (forward +
+    autograd backward through both CFG branches) are timed once each; `value` extrapolates those pieces to a PPO sample
+    (`extrapolated: true`): 100 applications + decode + 50 train steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = max(1, min(int(args.steps), 3))
-    v, dps, t_train, cores = cpu_ppo_samples_per_sec(n)
-    sample = (f"{n} denoising step(s) of 1 sample (2 U-Net applications each) + 1 PPO train step of 1 sample (2 U-Net "
-              f"forward + backward), torch-CPU oracle port, extrapolated x50 each")
+    cores = _cpu_threads()
+    _, _, net = _oracle_net()
+    ts = cpu_unet_application_seconds(net, max(1, int(args.steps)), max(0, int(args.warmup)))
+    del net
+    t_app = float(np.mean(ts))
+    t_vae = cpu_vae_decode_seconds()
+    t_train = cpu_train_step_seconds()
+    s_per_sample = 2 * T_STEPS * t_app + t_vae + T_STEPS * t_train
+    v = 1.0 / s_per_sample
+    sample = (f"{len(ts)} timed U-Net applications of 1 sample (fp32, SD2-base) + 1 VAE decode of 1 image + 1 PPO train "
+              f"step of 1 sample (2 U-Net forward + backward), torch-CPU oracle port on {cores} threads; extrapolated to "
+              f"100 applications + decode + 50 train steps")
     print(json.dumps({
-        "impl": "reference", "metric": "ppo_samples_per_sec", "value": v,
-        "unit": "PPO samples/s (50 sampling steps + 50 train steps per sample)",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / dps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "denoising_steps_per_sec": dps, "seconds_per_train_step": t_train,
-        "config": {"workload": "DDPO SD2-base 512px, 50-step DDIM, CFG 5.0, eta 1.0 (BASELINE configs[1]); CPU arm: 1 sample"},
-        "cpu_baseline": {"value": v, "unit": "PPO samples/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "PPO samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "ppo_samples_per_sec", "value": v, "unit": UNIT, "unit_detail": UNIT_DETAIL,
+        "n_gpus": args.gpus, "steps": len(ts), "warmup": max(0, int(args.warmup)), "ms_per_step": 1e3 * t_app,
+        "step_is": "one U-Net application of one sample on the host cores", "extrapolated": True,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "denoising_steps_per_sec": 1.0 / (2 * t_app), "seconds_per_train_step": t_train, "seconds_per_vae_decode": t_vae,
+        "config": {"workload": WORKLOAD, "cpu_arm": "1 sample at a time"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
@@ -213,6 +294,9 @@ def main():
                     help="run under `ncu --profile-from-start off`: bracket ONE eager denoising step / train pass with "
                          "cudaProfilerStart/Stop, print nothing, exit (profiles/README.md has the command lines)")
     ap.add_argument("--shapes", action="store_true", help="also write per-shape kernel tables to gpurun_out/shapes_*.txt")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 8 samples per GPU per epoch (default); strong: 64 samples per epoch for the whole job "
+                         "(SURVEY 8d: sample batch 8 x 8/N batches per GPU), visible in the epoch-driver e2e number")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -235,20 +319,11 @@ def main():
     sus_tf, burst_tf, hbm_gbs, peak_src = _peaks()
 
     cfg = unet_spec.SD2_BASE
-    # random-init weights generated on the device (identical on every rank: same seed)
-    table, total = unet_spec.param_offsets(cfg)
-    g = torch.Generator(device=dev).manual_seed(0)
-    flat = torch.empty(total, device=dev)
-    for name, (off, shape) in table.items():
-        n = int(np.prod(shape))
-        leaf = name.rsplit("/", 1)[1]
-        if leaf == "kernel":
-            flat[off:off + n] = torch.randn(n, generator=g, device=dev) / np.sqrt(np.prod(shape[:-1]))
-        elif leaf == "scale":
-            flat[off:off + n] = 1.0 + 0.1 * torch.randn(n, generator=g, device=dev)
-        else:
-            flat[off:off + n] = 0.02 * torch.randn(n, generator=g, device=dev)
+    # random-init weights from the seeded CPU generator: identical on every rank AND identical to what the CPU oracle
+    # leg builds, so the parity block below compares like with like
+    flat = unet_spec.init_flat_params(cfg, 0)
     net = UNet(cfg, flat, dev)
+    del flat
     sched = DDIMScheduler(1000, 0.00085, 0.012, "scaled_linear", None, False, 1, "epsilon", device=dev)
     pipe = StableDiffusionPipeline(net, sched, vae_scale_factor=8)
     state = sched.create_state()
@@ -460,6 +535,25 @@ def main():
             dist.all_reduce(tu, op=dist.ReduceOp.MAX)
         ms_train = tt.item() / args.steps
         ms_update = max(0.0, tu.item() - ms_train)
+        # the data-path collective on its own: sum all-reduce of the flat fp32 gradient (what one optimizer update issues)
+        allreduce_ms = allreduce_busbw = None
+        if world > 1:
+            from ddpo_b200.training import distributed as D
+            gbuf = tstate.grad_acc
+            D.allreduce_sum_(gbuf)
+            torch.cuda.synchronize()
+            dist.barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(3):
+                D.allreduce_sum_(gbuf)
+            a1.record()
+            torch.cuda.synchronize()
+            ta = torch.tensor([a0.elapsed_time(a1) / 3], device=dev)
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+            allreduce_ms = ta.item()
+            allreduce_busbw = 2 * (world - 1) / world * gbuf.numel() * 4 / (allreduce_ms * 1e-3) / 1e9
+            gbuf.zero_()
         # e2e train step: host-resident batch in, loss out
         hb = make_batch(1, host=True)
         pg.train_step(tstate, hb, st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
@@ -498,6 +592,7 @@ def main():
         s_per_sample_e2e = (T_STEPS * (1e3 / (e2e_steps_per_s / world)) + dec_ms_e2e + (T_STEPS / J) * (ms_train_e2e / Bt)
                             + ms_update / Bt)
         ppo = {"ms_per_train_step": ms_train, "ms_per_update": ms_update, "train_launches": train_launches,
+               "allreduce_ms": allreduce_ms, "allreduce_busbw_gbs": allreduce_busbw,
                "samples_per_s": world * 1e3 / s_per_sample, "samples_per_s_e2e": world * 1e3 / s_per_sample_e2e,
                "ms_train_step_e2e": ms_train_e2e, "first_pass_approx_kl": first_pass_kl,
                "train_tflops_per_gpu": 3 * 2 * Bt * J * UNET_GFLOP * 1e9 / (ms_train * 1e-3) / 1e12,
@@ -520,7 +615,8 @@ def main():
             # prompts are embedded by the CLIP text tower on the GPU (random-init SD2 tower; ids from the stub tokenizer:
             # no vocabulary files offline)
             pipe.tokenizer, pipe.text_encoder = StubTokenizer(), CLIPTextEncoder(SD2_TEXT, device=dev, seed=2)
-            argv = ["--dataset", "compressed_animals", "--sample_batch_size", str(B), "--num_sample_batches_per_epoch", "1",
+            nsb = max(1, 8 // world) if args.scaling == "strong" else 1   # strong: 64 samples per epoch over the whole job
+            argv = ["--dataset", "compressed_animals", "--sample_batch_size", str(B), "--num_sample_batches_per_epoch", str(nsb),
                     "--train_batch_size", str(TRAIN_BATCH), "--train_macro", str(TRAIN_MACRO), "--num_train_epochs", "2",
                     "--save_freq", "1000000", "--savepath", f"bench_driver_{rank}", "--seed", "0"]
             with contextlib.redirect_stdout(sys.stderr):
@@ -532,46 +628,79 @@ def main():
                 dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
             ssec, trsec = tsec.tolist()
             kl = out["history"][0]["infos"][0]["approx_kl"]
-            driver = {"samples_per_s": world * B / (ssec + trsec), "sample_seconds": ssec, "train_seconds": trsec,
-                      "samples_per_epoch_per_gpu": B, "mean_reward": h["mean_reward"], "epoch0_first_pass_approx_kl": float(kl[0]),
-                      "optimizer_updates_per_epoch": B // TRAIN_BATCH,
-                      "h2d_bytes_per_epoch": (B + 1) * 77 * 8 + (B // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * TRAIN_MACRO * TRAIN_BATCH * 40,
-                      "d2h_bytes_per_epoch": B * 512 * 512 * 3 * 4 + B * T_STEPS * 8 + (B // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * 12}
+            NB = B * nsb                                                   # samples per epoch on this GPU
+            driver = {"samples_per_s": world * NB / (ssec + trsec), "sample_seconds": ssec, "train_seconds": trsec,
+                      "samples_per_epoch_per_gpu": NB, "samples_per_epoch": world * NB, "mean_reward": h["mean_reward"],
+                      "epoch0_first_pass_approx_kl": float(kl[0]),
+                      "optimizer_updates_per_epoch": NB // TRAIN_BATCH,
+                      "h2d_bytes_per_epoch": (NB + 1) * 77 * 8 + (NB // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * TRAIN_MACRO * TRAIN_BATCH * 40,
+                      "d2h_bytes_per_epoch": NB * 512 * 512 * 3 * 4 + NB * T_STEPS * 8 + (NB // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * 12}
         except Exception as ex:  # reported, never hidden
             driver = {"error": repr(ex)[:300]}
 
+    # ---------------- parity of THIS build at THIS config against the fp32 oracle (N = 1 only: it needs the CPU leg) ----
+    # one denoising step of one sample on `parity_inputs()`: eps of both CFG branches, the sampled x_{t-1} and its log-prob,
+    # and -- the number PPO's importance ratio depends on -- the score-mode log-prob of the ORACLE's x_{t-1} under the
+    # GPU's eps (reference pipeline_flax_stable_diffusion.py:204-241, training/policy_gradient.py:103-125)
+    parity_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        x0, pctx, pkey = parity_inputs()
+        xg = torch.from_numpy(x0).to(dev).view(1, -1)
+        net.prepare_context(pctx.to(dev))
+        eps_g = net.forward(torch.cat([xg, xg]).view(2, 4, 64, 64), ts_dev[0:1]).view(2, -1)
+        prev_g, lp_g = torch.empty_like(xg), torch.empty(1, device=dev)
+        ws1 = ops.ddim_workspace(1, dev)
+        ops.ddim_step_sample(eps_g[:1], eps_g[1:], xg, st.common.alphas_cumprod, ts_dev[0:1], st.final_alpha_cumprod, ratio,
+                             GUIDANCE, ETA, ops.key_tensor([pkey], dev), prev_g, lp_g, ws1)
+        torch.cuda.synchronize()
+        parity_gpu = dict(eps=eps_g.cpu().numpy(), prev=prev_g.cpu().numpy(), logp=lp_g.cpu().numpy(), xg=xg, eps_dev=eps_g,
+                          ws=ws1)
+
     if rank == 0:
-        cpu = None
+        cpu, parity = None, None
         if not args.no_cpu and world == 1:   # the CPU baseline is reported by the N = 1 run only
-            if ppo is not None:
-                v, dps, t_train, cores = cpu_ppo_samples_per_sec(args.cpu_steps)
-                cpu = {"value": v, "unit": "PPO samples/s", "cores": cores, "kind": "port",
-                       "denoising_steps_per_sec": dps, "seconds_per_train_step": t_train,
-                       "sample": f"{args.cpu_steps} denoising steps of 1 sample (2 U-Net applications each) + 1 PPO train "
-                                 f"step of 1 sample (2 U-Net forward + backward), torch-CPU oracle port, extrapolated x50 each"}
-            else:
-                per_step, cores = cpu_step_seconds(args.cpu_steps)
-                cpu = {"value": 1.0 / per_step, "unit": "denoising steps/s", "cores": cores, "kind": "port",
-                       "sample": f"{args.cpu_steps} denoising steps of 1 sample (2 U-Net applications each), torch-CPU oracle"}
+            c = cpu_ppo_samples_per_sec(args.cpu_steps)
+            cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port",
+                   "denoising_steps_per_sec": c["denoising_steps_per_sec"], "seconds_per_train_step": c["seconds_per_train_step"],
+                   "seconds_per_vae_decode": c["seconds_per_vae_decode"],
+                   "sample": f"{args.cpu_steps} denoising steps of 1 sample (2 U-Net applications each) + 1 VAE decode + 1 PPO "
+                             f"train step of 1 sample (2 U-Net forward + backward), torch-CPU oracle port, extrapolated to "
+                             f"50 steps + decode + 50 train steps"}
+            f, g_ = c["first"], parity_gpu
+            rel = lambda a, b: float(np.linalg.norm(a.ravel() - b.ravel()) / np.linalg.norm(b.ravel()))
+            lp_s = torch.empty(1, device=dev)
+            ops.ddim_logprob_fwd(g_["eps_dev"][:1], g_["eps_dev"][1:], g_["xg"], torch.from_numpy(f["prev"]).to(dev).view(1, -1),
+                                 st.common.alphas_cumprod, ts_dev[0:1], st.final_alpha_cumprod, ratio, GUIDANCE, ETA, lp_s, g_["ws"])
+            lp_score = float(lp_s.item())
+            parity = {"what": "one denoising step (t=981) of one sample, SD2-base, this build vs the fp32 CPU oracle on the same "
+                              "weights / inputs / threefry key",
+                      "eps_rel": rel(g_["eps"], np.concatenate([f["eps_u"], f["eps_c"]]).reshape(2, -1)),
+                      "latents_rel": rel(g_["prev"], f["prev"]),
+                      "logp_rel": float(abs(g_["logp"][0] / f["logp"].ravel()[0] - 1.0)),
+                      "logp_score_rel": float(abs(lp_score / f["logp"].ravel()[0] - 1.0)),
+                      "ratio_minus_1": float(abs(np.exp(lp_score - float(f["logp"].ravel()[0])) - 1.0)),
+                      "logp_oracle": float(f["logp"].ravel()[0]), "logp_gpu": float(g_["logp"][0]), "logp_gpu_score_mode": lp_score,
+                      "tolerance": "north-star: per-step log_prob within 1e-3 relative"}
         step_flops = 2 * B * UNET_GFLOP * 1e9
         if ppo is not None:
-            head = {"metric": "ppo_samples_per_sec", "value": ppo["samples_per_s"],
-                    "unit": "PPO samples/s (50 sampling steps + VAE decode + 50 train steps + optimizer share per sample)"}
+            head = {"metric": "ppo_samples_per_sec", "value": ppo["samples_per_s"], "unit": UNIT, "unit_detail": UNIT_DETAIL}
         else:
             head = {"metric": "denoising_steps_per_sec", "value": steps_per_s,
                     "unit": "denoising steps/s (1 sample, both CFG branches)"}
         line = {
             **head, "denoising_steps_per_sec": steps_per_s, "denoising_steps_per_sec_per_gpu": steps_per_s / world,
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (fp32 accumulate, fp32 residual stream/norms)",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16 (fp32 accumulate, fp32 residual stream/norms)",
             "data": "synthetic",
-            "config": {"workload": "DDPO SD2-base 512px, 50-step DDIM, CFG 5.0, eta 1.0, sample batch 8/GPU (BASELINE configs[1])",
+            "config": {"workload": WORKLOAD,
                        "per_step": "one denoising step of the 8-sample batch (U-Net batch 16)",
+                       "samples_per_epoch": "8 per GPU (weak scaling; BASELINE's batch 64 = 8 GPUs x 8; per-sample work is identical)"
+                                            if args.scaling == "weak" else "64 over the whole job (strong scaling)",
                        "l2": "per-step working set (1.7 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush",
                        "cuda_graph": True, "per_gpu_steps_per_s": steps_per_s / world,
                        "unet_tflops_per_gpu": step_flops / (ms_per_step * 1e-3) / 1e12},
             "clocks": sampler.summary(),
-            "e2e": ({"value": ppo["samples_per_s_e2e"], "unit": "PPO samples/s", "h2d_bytes_per_step": h2d + TRAIN_MACRO * TRAIN_BATCH * (2 * 65536 + 2 * 77 * 1024 * 4 + 12),
+            "e2e": ({"value": ppo["samples_per_s_e2e"], "unit": UNIT, "h2d_bytes_per_step": h2d + TRAIN_MACRO * TRAIN_BATCH * (2 * 65536 + 2 * 77 * 1024 * 4 + 12),
                      "d2h_bytes_per_step": d2h + 12, "denoising_steps_per_sec": e2e_steps_per_s,
                      "what": "pipeline(...) from pinned host embeddings to host latents/log-probs + train_step(...) from a pinned host batch to host loss"}
                     if ppo is not None else
@@ -579,6 +708,11 @@ def main():
                      "d2h_bytes_per_step": d2h, "what": "pipeline(...) 50-step call from pinned host embeddings to host final latents + log-probs"}),
             "e2e_driver": driver,
             "e2e_composed": None,
+            "parity": parity,
+            "ms_per_train_step": ppo["ms_per_train_step"] if ppo else None,
+            "ms_per_update": ppo["ms_per_update"] if ppo else None,
+            "allreduce_ms": ppo["allreduce_ms"] if ppo else None,
+            "allreduce_busbw_gbs": ppo["allreduce_busbw_gbs"] if ppo else None,
             "gpu_launches": launches_per_step * args.steps + (ppo["train_launches"] * args.steps if ppo else 0),
             "ppo": ppo,
             "vae_decode": vae_info,
@@ -593,14 +727,16 @@ def main():
             # the call a user makes is the epoch driver: its wall-clock samples/s is THE end-to-end number; the figure
             # composed from pipeline(...) + train_step(...) with host buffers is kept next to it
             line["e2e_composed"] = dict(line["e2e"])
-            steps_per_epoch = T_STEPS + (SAMPLE_BATCH // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO)
-            line["e2e"] = {"value": driver["samples_per_s"], "unit": "PPO samples/s",
+            nb_ = driver["samples_per_epoch_per_gpu"]
+            steps_per_epoch = (nb_ // SAMPLE_BATCH) * T_STEPS + (nb_ // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO)
+            line["e2e"] = {"value": driver["samples_per_s"], "unit": UNIT,
                            "h2d_bytes_per_step": driver["h2d_bytes_per_epoch"] / steps_per_epoch,
                            "d2h_bytes_per_step": driver["d2h_bytes_per_epoch"] / steps_per_epoch,
                            "what": "ddpo_b200.pipeline.policy_gradient.main (epoch 1 of 2, the driver's wall clock): prompts -> "
-                                   "text embedding -> 50-step sampling of 8 samples/GPU -> VAE decode -> images to the host -> "
-                                   "JPEG reward (thread pool) -> advantages -> shuffles -> on-device gathers -> 20 train passes "
-                                   "+ 4 optimizer updates; a step = one denoising step or one train pass"}
+                                   "text embedding -> 50-step sampling in batches of 8 samples/GPU -> VAE decode -> images to the host -> "
+                                   "JPEG reward (thread pool) -> advantages -> shuffles -> on-device gathers -> 5 train passes "
+                                   "+ 1 optimizer update per 2 samples; a step = one denoising step or one train pass",
+                           "samples_per_epoch_per_gpu": nb_}
         line["gpu_mem_peak_gb"] = round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)
         print(json.dumps(line))
     # orderly teardown: drop captured graphs and cached buffers before the process exits
