@@ -25,13 +25,14 @@ class IGemmArgs(C.Structure):
                 ("is_conv", i32), ("batch", i32), ("h", i32), ("w", i32), ("conv_stride", i32), ("taps", i32),
                 ("m", i32), ("n", i32), ("wt", vp), ("bias", vp), ("rowvec", vp), ("rows_per_sample", i32),
                 ("rowvec_ld", i32), ("residual", vp), ("ld_res", i32), ("out_f32", vp), ("out_bf16", vp),
-                ("ld_out", i32), ("geglu", i32), ("accumulate_out", i32), ("bn_override", i32), ("aux_bf16", vp), ("mt_override", i32), ("pair_override", i32), ("epi_override", i32)]
+                ("ld_out", i32), ("geglu", i32), ("accumulate_out", i32), ("bn_override", i32), ("aux_bf16", vp), ("mt_override", i32), ("pair_override", i32), ("epi_override", i32),
+                ("gn_stats", vp)]
 
 
 class GroupNormArgs(C.Structure):
     _fields_ = [("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32), ("ld0", i32), ("ld1", i32), ("batch", i32),
                 ("hw", i32), ("scale", vp), ("bias", vp), ("eps", f32), ("silu", i32), ("y_bf16", vp),
-                ("y_f32", vp), ("raw_bf16", vp), ("workspace", vp), ("stats_only_skip", i32)]
+                ("y_f32", vp), ("raw_bf16", vp), ("workspace", vp), ("stats_only_skip", i32), ("stats0", vp), ("stats1", vp)]
 
 
 class AttentionArgs(C.Structure):
@@ -80,7 +81,7 @@ SIGNATURES = {
     "ddpo_cast_bf16": (i32, [vp, vp, i64, vp]),
     "ddpo_upsample2x_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_upsample2x_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
-    "ddpo_conv_in": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "ddpo_conv_in": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "ddpo_conv_out": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "ddpo_timestep_sincos": (i32, [vp, i32, vp, i32, i32, vp]),
     "ddpo_dense_small": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),

@@ -293,6 +293,10 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
   p.ld_out = a->ld_out > 0 ? a->ld_out : (a->geglu ? a->n / 2 : a->n);
   p.geglu = a->geglu, p.accumulate_out = a->accumulate_out;
   p.aux_bf16 = static_cast<__nv_bfloat16*>(a->aux_bf16);
+  p.gn_stats = a->gn_stats;
+  if (a->gn_stats != nullptr)
+    DDPO_REQUIRE(a->out_f32 != nullptr && !a->geglu && !a->accumulate_out,
+                 "ddpo_igemm: gn_stats describes a plain fp32 output (no GEGLU, no accumulate)");
   if (use_pair) {
     p.MT = 1;
     // TMA epilogue where the epilogue, not the main loop, bounds the tile: short K (the 1x1 / linear layers).

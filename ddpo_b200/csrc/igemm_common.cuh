@@ -28,6 +28,9 @@ struct IGemmArgs {
   int ld_out;
   int geglu;
   int accumulate_out;     // out_f32 += result (used by backward passes that sum two branches)
+  float* gn_stats;        // [ceil(M/32), N, 2] or null: per 32-row slab, per column (sum, sum of squares) of the fp32 OUTPUT
+                          // values -- the GroupNorm that consumes out_f32 takes its statistics from these instead of
+                          // re-reading the tensor (norm.cu gn_finalize_kernel)
   __nv_bfloat16* aux_bf16;  // GEGLU only: pre-activation [M, N] (tile-interleaved, bias included) kept for backward
   // TMA epilogue (CTA-pair kernel): residual / previous output fetched and results written as 32 x 32 boxes through
   // per-warp shared-memory staging, so that every global access is a full 128-byte (fp32) / 64-byte (bf16) row
@@ -43,6 +46,36 @@ constexpr int EPI_RING = 3;                 // fp32 tiles per warp: input fetche
 constexpr int EPI_WARP_BYTES = EPI_RING * EPI_F32_TILE + 2 * EPI_BF16_TILE;
 constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;  // 128 KB
 constexpr int EPI_BAR_BYTES = 256;             // 8 warps x EPI_RING barriers
+
+// Column sums over the 32 rows a warp holds (lane = row, v[j] = column j): a transposing butterfly -- at step h every lane
+// hands the half of its values that belongs to its xor-h partner over and adds what it receives, so 31 shuffles (not
+// 32 x 5) leave lane j with the sum of column j.  The pairing order is fixed: the result depends on the 32 values only.
+__device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h];
+      const float keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
+}
+
+// slab statistics of one 32 x 32 chunk of output values f (rows outside the matrix must already be zero)
+__device__ __forceinline__ void gn_slab_stats(float* __restrict__ stats, int N_total, int m_slab, int n, int lane,
+                                              const float (&f)[32]) {
+  float t[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) t[j] = f[j];
+  const float s = colsum32(t, lane);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) t[j] = f[j] * f[j];
+  const float ss = colsum32(t, lane);
+  *reinterpret_cast<float2*>(stats + (static_cast<size_t>(m_slab >> 5) * N_total + n + lane) * 2) = make_float2(s, ss);
+}
 
 struct EpiWarp {
   uint8_t* buf;   // this warp's EPI_WARP_BYTES
@@ -193,6 +226,13 @@ __device__ __forceinline__ void igemm_epilogue_tma(const IGemmArgs& p, EpiWarp& 
         *reinterpret_cast<uint4*>(bb + lane * 64 + ((j ^ sw64) << 4)) = u;
       }
     }
+    if (p.gn_stats != nullptr) {
+      if (row >= p.M_total) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+      }
+      gn_slab_stats(p.gn_stats, p.N_total, m_slab, n, lane, f);
+    }
     fence_proxy_async_smem();
     __syncwarp();
     ++e.g;
@@ -212,6 +252,7 @@ __device__ __forceinline__ void igemm_epilogue_tma(const IGemmArgs& p, EpiWarp& 
 // `t_row` = TMEM address of (lane quarter, accumulator buffer / sub-tile); row = global output row of this thread.
 __device__ __forceinline__ void igemm_epilogue(const IGemmArgs& p, uint32_t t_row, int row, bool row_ok, int n0, int tn,
                                                int BN, int cgrp, int cstep) {
+  const int lane = threadIdx.x & 31;
   const float* rv = nullptr;
       if (p.rowvec != nullptr && row_ok) rv = p.rowvec + static_cast<size_t>(row / p.rows_per_sample) * p.rowvec_ld;
       if (!p.geglu) {
@@ -219,11 +260,11 @@ __device__ __forceinline__ void igemm_epilogue(const IGemmArgs& p, uint32_t t_ro
           uint32_t v[32];
           tmem_ld_32x32(t_row + c0, v);
           tmem_ld_wait();
-          if (row_ok) {
-            const int n = n0 + c0;
-            float f[32];
+          const int n = n0 + c0;
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) f[j] = row_ok ? __uint_as_float(v[j]) : 0.f;
+          if (row_ok) {
             if (p.bias != nullptr) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -272,6 +313,8 @@ __device__ __forceinline__ void igemm_epilogue(const IGemmArgs& p, uint32_t t_ro
               }
             }
           }
+          // statistics for the consuming GroupNorm (warp-uniform branch: all 32 lanes shuffle; rows outside M are zero)
+          if (p.gn_stats != nullptr && row - lane < p.M_total) gn_slab_stats(p.gn_stats, p.N_total, row - lane, n, lane, f);
         }
       } else {
         // GEGLU: the weight rows of this N tile are [BN/2 linear | BN/2 gate] for the same

@@ -8,9 +8,19 @@
 //
 // Layout: x fp32 NHWC [B, HW, C] (optionally the channel concat of two tensors: the
 // U-Net skip connection is never materialised), y bf16 (the next GEMM's A operand).
-// Statistics use a two-level fixed-order reduction: per (sample, pixel-chunk) partial
-// sums written by the stats kernel, summed in chunk order by the apply kernel.  The
-// chunking depends only on HW, never on the batch size -> batch-invariant results.
+//
+// Statistics.  The GEMM that PRODUCES x leaves per-(32-row slab, channel) sums and sums of squares of what it writes
+// (igemm_common.cuh gn_slab_stats); gn_finalize_slabs_kernel folds them, in a fixed order, into one (mean, rstd) pair per
+// (sample, group) -- so the forward pass reads x ONCE (algorithmic traffic: 4 B in + 2 B out per element) instead of
+// once for the statistics and once more for the normalisation.  Inputs without slab statistics (conv_in's output, the VAE
+// decoder, grids with fewer than 32 pixels) go through gn_stats_kernel (per (sample, pixel-chunk) partial sums) and
+// gn_finalize_chunks_kernel.  Either way the reduction order depends on (HW, C) only, never on the batch size ->
+// batch-invariant, bit-reproducible results.
+//
+// Apply.  gn_apply_tma_kernel streams x through a 4-stage shared-memory ring filled by 1-D bulk copies (one producer
+// thread keeps ~100 KB per CTA in flight whatever the occupancy), consumer threads own a fixed channel quad (scale, bias,
+// mean, rstd in registers) and write 8-byte bf16 pieces of consecutive channels; work is a flat list of (sample, pixel
+// range) stages split evenly over 2 CTAs per SM -> one wave, no tail.
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -34,9 +44,11 @@ struct GnArgs {
   __nv_bfloat16* y_bf16;   // [B, HW, C] or null
   float* y_f32;            // [B, HW, C] or null
   __nv_bfloat16* raw_bf16;  // [B, HW, C] un-normalised copy or null
-  int reverse;  // EXPERIMENTAL (DDPO_GN_REVERSE=1): the apply passes walk samples / chunks in descending order, so they start
-                // with what the preceding stats pass left in L2 (ascending order re-reads x from DRAM: L2 hit rate 1.3 %,
-                // profiles/r1_gn.md).  Pure scheduling: results are bit-identical.
+  int reverse;  // DDPO_GN_REVERSE=1 (fallback two-pass path only): the apply pass walks samples / chunks in descending order
+                // so that it starts with what the preceding stats pass left in L2.  Pure scheduling: bit-identical results.
+  const float* stats0;  // slab statistics of x0 / x1 ([B*HW/32, c, 2]) or null
+  const float* stats1;
+  float* mr;            // [B, 32, 2] (mean, rstd): written by the finalize kernels, read by every apply / backward kernel
 };
 
 __device__ __forceinline__ float2 gn_load2(const GnArgs& a, size_t pix, int c) {
@@ -105,6 +117,141 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const GnArgs a) {
   }
 }
 
+// (mean, rstd) of every (sample, group) from the producing GEMMs' slab statistics.  One warp per (sample, group): lane l
+// adds items l, l + 32, ... of the (slab, channel-of-group) list in ascending order, then a fixed shuffle tree.
+__global__ void __launch_bounds__(256) gn_finalize_slabs_kernel(const GnArgs a, int batch) {
+  const int C = a.c0 + a.c1, cpg = C / GN_GROUPS;
+  const int wid = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wid >= batch * GN_GROUPS) return;
+  const int b = wid / GN_GROUPS, g = wid % GN_GROUPS;
+  const int nslab = a.hw >> 5;
+  const int items = nslab * cpg;
+  float s = 0.f, ss = 0.f;
+  for (int i = lane; i < items; i += 32) {
+    const int slab = i / cpg, c = g * cpg + (i - slab * cpg);
+    const size_t row = static_cast<size_t>(b) * nslab + slab;
+    const float2 v = c < a.c0 ? *reinterpret_cast<const float2*>(a.stats0 + (row * a.c0 + c) * 2)
+                              : *reinterpret_cast<const float2*>(a.stats1 + (row * a.c1 + (c - a.c0)) * 2);
+    s += v.x, ss += v.y;
+  }
+  s = warp_sum(s), ss = warp_sum(ss);
+  if (lane == 0) {
+    const float inv_n = 1.0f / (static_cast<float>(a.hw) * cpg);
+    const float mean = s * inv_n;
+    const float var = fmaxf(0.f, ss * inv_n - mean * mean);
+    a.mr[wid * 2] = mean, a.mr[wid * 2 + 1] = rsqrtf(var + a.eps);
+  }
+}
+
+// same from gn_stats_kernel's chunk partials (inputs nobody left slab statistics for): thread per (sample, group)
+__global__ void gn_finalize_chunks_kernel(const GnArgs a, int batch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * GN_GROUPS) return;
+  const int b = i / GN_GROUPS, g = i % GN_GROUPS, cpg = (a.c0 + a.c1) / GN_GROUPS;
+  float s = 0.f, ss = 0.f;
+  for (int ch = 0; ch < a.chunks; ++ch) {
+    const float* o = a.partial + ((static_cast<size_t>(b) * a.chunks + ch) * GN_GROUPS + g) * 2;
+    s += o[0], ss += o[1];
+  }
+  const float inv_n = 1.0f / (static_cast<float>(a.hw) * cpg);
+  const float mean = s * inv_n;
+  const float var = fmaxf(0.f, ss * inv_n - mean * mean);
+  a.mr[i * 2] = mean, a.mr[i * 2 + 1] = rsqrtf(var + a.eps);
+}
+
+// ------------------------------------------------------------ streamed apply (forward) ----
+constexpr int GNA_STAGES = 4;
+constexpr int GNA_STAGE_BYTES = 24 * 1024;
+
+struct GnStream {
+  int c4[2];        // channel quads per source
+  int pix[2];       // pixels per stage per source (power of two dividing hw)
+  int ctas[2];      // CTAs working on each source (blockIdx.z = source)
+  int consumers;    // consumer threads (block = 32 + consumers)
+};
+
+__global__ void __launch_bounds__(544, 1) gn_apply_tma_kernel(const GnArgs a, const GnStream g, int batch) {
+  extern __shared__ __align__(128) uint8_t gna_smem[];
+  const int src = blockIdx.z;
+  if (static_cast<int>(blockIdx.x) >= (src == 0 ? g.ctas[0] : g.ctas[1])) return;
+  uint64_t* full = reinterpret_cast<uint64_t*>(gna_smem + GNA_STAGES * GNA_STAGE_BYTES);
+  uint64_t* empty = full + GNA_STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cwarps = (g.consumers + 31) >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GNA_STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], n_cwarps);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int C = a.c0 + a.c1, cpg = C / GN_GROUPS;
+  const int cs = src == 0 ? a.c0 : a.c1, coff = src == 0 ? 0 : a.c0;
+  const float* x = src == 0 ? a.x0 : a.x1;
+  const int P = src == 0 ? g.pix[0] : g.pix[1];
+  const int n_ctas = src == 0 ? g.ctas[0] : g.ctas[1];
+  const int spp = a.hw / P;                                // stages per sample
+  const long total = static_cast<long>(batch) * spp;      // flat stage list of this source
+  const long per = (total + n_ctas - 1) / n_ctas;
+  const long it0 = per * blockIdx.x, it1 = it0 + per < total ? it0 + per : total;
+  const uint32_t stage_bytes = static_cast<uint32_t>(P) * cs * 4;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (long it = it0; it < it1; ++it) {
+        const int k = static_cast<int>(it - it0), st = k % GNA_STAGES;
+        mbar_wait(&empty[st], ((k / GNA_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full[st], stage_bytes);
+        bulk_load_1d(gna_smem + st * GNA_STAGE_BYTES, x + static_cast<size_t>(it) * P * cs, stage_bytes, &full[st]);
+      }
+    }
+    return;
+  }
+  const int ct = threadIdx.x - 32;
+  const int C4 = src == 0 ? g.c4[0] : g.c4[1], R = g.consumers / C4;
+  const int cq = ct % C4, pr = ct / C4;
+  const bool active = ct < R * C4;
+  const int c = coff + cq * 4;
+  float scv[4], biv[4], mu[4], rs[4];
+  {
+    const float4 sc = *reinterpret_cast<const float4*>(a.scale + c), bi = *reinterpret_cast<const float4*>(a.bias + c);
+    scv[0] = sc.x, scv[1] = sc.y, scv[2] = sc.z, scv[3] = sc.w;
+    biv[0] = bi.x, biv[1] = bi.y, biv[2] = bi.z, biv[3] = bi.w;
+  }
+  int cur_b = -1;
+  for (long it = it0; it < it1; ++it) {
+    const int k = static_cast<int>(it - it0), st = k % GNA_STAGES;
+    const int b = static_cast<int>(it / spp);
+    const size_t pix0 = static_cast<size_t>(it) * P;      // global pixel index (b * hw + p)
+    if (b != cur_b) {
+      cur_b = b;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 m = *reinterpret_cast<const float2*>(a.mr + (b * GN_GROUPS + (c + j) / cpg) * 2);
+        mu[j] = m.x, rs[j] = m.y;
+      }
+    }
+    mbar_wait(&full[st], (k / GNA_STAGES) & 1);
+    if (active) {
+      const float4* sm4 = reinterpret_cast<const float4*>(gna_smem + st * GNA_STAGE_BYTES);
+      for (int pp = pr; pp < P; pp += R) {
+        const float4 v = sm4[pp * C4 + cq];
+        const float xv[4] = {v.x, v.y, v.z, v.w};
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          y[j] = (xv[j] - mu[j]) * rs[j] * scv[j] + biv[j];   // same operation order as gn_apply_kernel
+          if (a.silu) y[j] = silu_f(y[j]);
+        }
+        const size_t o = (pix0 + pp) * C + c;
+        if (a.y_bf16) *reinterpret_cast<uint2*>(a.y_bf16 + o) = make_uint2(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]));
+        if (a.y_f32) *reinterpret_cast<float4*>(a.y_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
+        if (a.raw_bf16)
+          *reinterpret_cast<uint2*>(a.raw_bf16 + o) = make_uint2(pack_bf16(xv[0], xv[1]), pack_bf16(xv[2], xv[3]));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+}
+
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
   const int C = a.c0 + a.c1, C4 = C >> 2, cpg = C / GN_GROUPS;
   const int cols = C4 < GN_THREADS ? C4 : GN_THREADS;
@@ -115,16 +262,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
   const int p_end = min(a.hw, p_begin + a.pix_per_chunk);
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
   if (threadIdx.x < GN_GROUPS) {
-    float s = 0.f, ss = 0.f;
-    for (int ch = 0; ch < a.chunks; ++ch) {
-      const float* o = a.partial + ((static_cast<size_t>(b) * a.chunks + ch) * GN_GROUPS + threadIdx.x) * 2;
-      s += o[0], ss += o[1];
-    }
-    const float inv_n = 1.0f / (static_cast<float>(a.hw) * cpg);
-    const float mean = s * inv_n;
-    const float var = fmaxf(0.f, ss * inv_n - mean * mean);
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
+    s_mean[threadIdx.x] = a.mr[(b * GN_GROUPS + threadIdx.x) * 2];
+    s_rstd[threadIdx.x] = a.mr[(b * GN_GROUPS + threadIdx.x) * 2 + 1];
   }
   __syncthreads();
   if (tr >= R) return;
@@ -198,15 +337,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const GnBwdArg
   extern __shared__ float sm[];  // [R][C][4] : a0, a1, dscale, dbias per channel
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
   if (threadIdx.x < GN_GROUPS) {
-    float s = 0.f, ss = 0.f;
-    for (int ch = 0; ch < f.chunks; ++ch) {
-      const float* o = f.partial + ((static_cast<size_t>(b) * f.chunks + ch) * GN_GROUPS + threadIdx.x) * 2;
-      s += o[0], ss += o[1];
-    }
-    const float inv_n = 1.0f / (static_cast<float>(f.hw) * cpg);
-    const float mean = s * inv_n;
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rsqrtf(fmaxf(0.f, ss * inv_n - mean * mean) + f.eps);
+    s_mean[threadIdx.x] = f.mr[(b * GN_GROUPS + threadIdx.x) * 2];
+    s_rstd[threadIdx.x] = f.mr[(b * GN_GROUPS + threadIdx.x) * 2 + 1];
   }
   __syncthreads();
   const size_t base = static_cast<size_t>(b) * f.hw;
@@ -280,16 +412,14 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
   const int p_end = min(f.hw, p_begin + f.pix_per_chunk);
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS], s_m1[GN_GROUPS], s_m2[GN_GROUPS];
   if (threadIdx.x < GN_GROUPS) {
-    float s = 0.f, ss = 0.f, p1 = 0.f, p2 = 0.f;
+    float p1 = 0.f, p2 = 0.f;
     for (int ch = 0; ch < f.chunks; ++ch) {
       const size_t o = ((static_cast<size_t>(b) * f.chunks + ch) * GN_GROUPS + threadIdx.x) * 2;
-      s += f.partial[o], ss += f.partial[o + 1];
       p1 += a.partial2[o], p2 += a.partial2[o + 1];
     }
     const float inv_n = 1.0f / (static_cast<float>(f.hw) * cpg);
-    const float mean = s * inv_n;
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rsqrtf(fmaxf(0.f, ss * inv_n - mean * mean) + f.eps);
+    s_mean[threadIdx.x] = f.mr[(b * GN_GROUPS + threadIdx.x) * 2];
+    s_rstd[threadIdx.x] = f.mr[(b * GN_GROUPS + threadIdx.x) * 2 + 1];
     s_m1[threadIdx.x] = p1 * inv_n;
     s_m2[threadIdx.x] = p2 * inv_n;
   }
@@ -346,33 +476,64 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
 // dscale/dbias: partial [rows, 2, C] summed over rows in fixed order into the gradients: reduce_rows_kernel (reduce.cuh)
 
 // ------------------------------------------------------------------ LayerNorm ----
-// one warp per row; x fp32 [M, C] -> y bf16 [M, C]
+// one warp per row, ROWS rows per warp in flight; the row lives in registers (NC = ceil(C / 128) float4 per lane), so x is
+// read once and ROWS * NC independent 16-byte loads per lane are outstanding before the first reduction.
+// x fp32 [M, C] -> y bf16 [M, C].  Summation order per row: lane-strided columns in ascending order, then the xor tree.
+template <int NC, int ROWS>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                             const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                             float* __restrict__ stats, int M, int C, float eps) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * ROWS;
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  const float* xr = x + static_cast<size_t>(row) * C;
-  float s = 0.f, ss = 0.f;
-  for (int c = lane * 4; c < C; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(xr + c);
-    s += (v.x + v.y) + (v.z + v.w);
-    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  if (row0 >= M) return;
+  float4 v[ROWS][NC];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const float* xr = x + static_cast<size_t>(row0 + r) * C;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int c = lane * 4 + 128 * i;
+      v[r][i] = (c < C && row0 + r < M) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
-  s = warp_sum(s), ss = warp_sum(ss);
-  const float mean = s / C;
-  const float rstd = rsqrtf(fmaxf(0.f, ss / C - mean * mean) + eps);
-  if (stats != nullptr && lane == 0) stats[row * 2] = mean, stats[row * 2 + 1] = rstd;
-  __nv_bfloat16* yr = y + static_cast<size_t>(row) * C;
-  for (int c = lane * 4; c < C; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(xr + c);
-    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
-    const float4 bi = __ldg(reinterpret_cast<const float4*>(bias + c));
-    uint2 o;
-    o.x = pack_bf16((v.x - mean) * rstd * sc.x + bi.x, (v.y - mean) * rstd * sc.y + bi.y);
-    o.y = pack_bf16((v.z - mean) * rstd * sc.z + bi.z, (v.w - mean) * rstd * sc.w + bi.w);
-    *reinterpret_cast<uint2*>(yr + c) = o;
+  float4 sc[NC], bi[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = lane * 4 + 128 * i;
+    if (c < C) {
+      sc[i] = __ldg(reinterpret_cast<const float4*>(scale + c));
+      bi[i] = __ldg(reinterpret_cast<const float4*>(bias + c));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int row = row0 + r;
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      if (lane * 4 + 128 * i < C) {
+        const float4 q = v[r][i];
+        s += (q.x + q.y) + (q.z + q.w);
+        ss += (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
+      }
+    }
+    s = warp_sum(s), ss = warp_sum(ss);
+    if (row >= M) continue;   // warp-uniform
+    const float mean = s / C;
+    const float rstd = rsqrtf(fmaxf(0.f, ss / C - mean * mean) + eps);
+    if (stats != nullptr && lane == 0) stats[row * 2] = mean, stats[row * 2 + 1] = rstd;
+    __nv_bfloat16* yr = y + static_cast<size_t>(row) * C;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int c = lane * 4 + 128 * i;
+      if (c < C) {
+        const float4 q = v[r][i];
+        uint2 o;
+        o.x = pack_bf16((q.x - mean) * rstd * sc[i].x + bi[i].x, (q.y - mean) * rstd * sc[i].y + bi[i].y);
+        o.y = pack_bf16((q.z - mean) * rstd * sc[i].z + bi[i].z, (q.w - mean) * rstd * sc[i].w + bi[i].w);
+        *reinterpret_cast<uint2*>(yr + c) = o;
+      }
+    }
   }
 }
 
@@ -486,7 +647,11 @@ static int fill_gn(GnArgs& g, const ddpo_groupnorm_args* a) {
   g.ld0 = a->ld0 > 0 ? a->ld0 : a->c0, g.ld1 = a->ld1 > 0 ? a->ld1 : a->c1;
   g.hw = a->hw;
   gn_chunking(a->hw, &g.chunks, &g.pix_per_chunk);
-  g.scale = a->scale, g.bias = a->bias, g.partial = a->workspace, g.eps = a->eps, g.silu = a->silu;
+  g.scale = a->scale, g.bias = a->bias, g.eps = a->eps, g.silu = a->silu;
+  // workspace: [mr: B*64][forward chunk partials: B*chunks*64][backward partials: B*chunks*64][dscale/dbias partials]
+  g.mr = a->workspace;
+  g.partial = a->workspace + static_cast<size_t>(a->batch) * GN_GROUPS * 2;
+  g.stats0 = a->stats0, g.stats1 = a->stats1;
   g.y_bf16 = static_cast<__nv_bfloat16*>(a->y_bf16), g.y_f32 = a->y_f32;
   g.raw_bf16 = static_cast<__nv_bfloat16*>(a->raw_bf16);
   static const int reverse = [] { const char* e = getenv("DDPO_GN_REVERSE"); return e != nullptr && e[0] == '1' ? 1 : 0; }();
@@ -507,8 +672,56 @@ using namespace ddpo;
 extern "C" int64_t ddpo_groupnorm_workspace_floats(int batch, int hw, int channels) {
   int chunks, ppc;
   gn_chunking(hw, &chunks, &ppc);
-  // fwd partials + bwd partials + dparam partials
-  return static_cast<int64_t>(batch) * chunks * GN_GROUPS * 2 * 2 + static_cast<int64_t>(batch) * chunks * 2 * channels;
+  // (mean, rstd) table + fwd partials + bwd partials + dparam partials
+  return static_cast<int64_t>(batch) * GN_GROUPS * 2 + static_cast<int64_t>(batch) * chunks * GN_GROUPS * 2 * 2 +
+         static_cast<int64_t>(batch) * chunks * 2 * channels;
+}
+
+// plan of the streamed apply pass; returns false when the shape does not fit it (the two-pass kernels then run)
+static bool gn_stream_plan(const GnArgs& g, const ddpo_groupnorm_args* a, GnStream* st) {
+  const char* off = getenv("DDPO_GN_NO_STREAM");   // read per call: the bit-identity test toggles it (costs ~100 ns)
+  if (off != nullptr && off[0] == '1') return false;
+  const int nsrc = a->c1 > 0 ? 2 : 1;
+  if (g.ld0 != a->c0 || (nsrc == 2 && g.ld1 != a->c1)) return false;          // sources must be dense (1-D bulk copies)
+  if ((reinterpret_cast<uintptr_t>(a->x0) & 15) || (nsrc == 2 && (reinterpret_cast<uintptr_t>(a->x1) & 15))) return false;
+  if (a->c0 % 4 != 0 || a->c1 % 4 != 0 || (a->hw & (a->hw - 1)) != 0) return false;
+  long bytes[2] = {0, 0};
+  for (int s = 0; s < nsrc; ++s) {
+    const int cs = s == 0 ? a->c0 : a->c1;
+    st->c4[s] = cs / 4;
+    if (st->c4[s] > 512) return false;
+    int pix = 1;
+    while (pix * 2 <= a->hw && static_cast<long>(pix) * 2 * cs * 4 <= GNA_STAGE_BYTES) pix *= 2;
+    if (static_cast<long>(pix) * cs * 4 > GNA_STAGE_BYTES) return false;
+    st->pix[s] = pix;
+    bytes[s] = static_cast<long>(a->batch) * a->hw * cs * 4;
+  }
+  if (nsrc == 1) st->c4[1] = st->c4[0], st->pix[1] = st->pix[0];
+  // consumer threads: the candidate with the fewest idle lanes (a thread owns one channel quad of its source)
+  int best_t = 0;
+  double best_idle = 2.0;
+  for (int t : {256, 320, 384, 448, 512}) {
+    double idle = 0.0;
+    bool ok = true;
+    for (int s = 0; s < nsrc; ++s) {
+      if (st->c4[s] > t) ok = false;
+      else idle += static_cast<double>(bytes[s]) / (bytes[0] + bytes[1]) * (t % st->c4[s]) / t;
+    }
+    if (ok && idle < best_idle - 1e-9) best_idle = idle, best_t = t;
+  }
+  if (best_t == 0) return false;
+  st->consumers = best_t;
+  // 2 CTAs per SM in ONE wave, split between the sources in proportion to their bytes; never more CTAs than stages
+  const int slots = 2 * num_sms();
+  for (int s = 0; s < nsrc; ++s) {
+    long n = nsrc == 1 ? slots : (slots * bytes[s] + (bytes[0] + bytes[1]) / 2) / (bytes[0] + bytes[1]);
+    const long stages = static_cast<long>(a->batch) * (a->hw / st->pix[s]);
+    if (n < 1) n = 1;
+    if (n > stages) n = stages;
+    st->ctas[s] = static_cast<int>(n);
+  }
+  if (nsrc == 1) st->ctas[1] = 0;
+  return true;
 }
 
 extern "C" int ddpo_groupnorm_fwd(const ddpo_groupnorm_args* a, void* stream_) {
@@ -521,11 +734,31 @@ extern "C" int ddpo_groupnorm_fwd(const ddpo_groupnorm_args* a, void* stream_) {
   DDPO_REQUIRE(smem <= 48 * 1024, "groupnorm: too many channels (%d)", a->c0 + a->c1);
   DDPO_REQUIRE(a->c0 % 4 == 0 && g.ld0 % 4 == 0 && g.ld1 % 4 == 0, "groupnorm: channel counts / pitches must be multiples of 4");
   if (!a->stats_only_skip) {
-    gn_stats_kernel<<<grid, GN_THREADS, smem, stream>>>(g);
+    const bool have_slabs = a->stats0 != nullptr && (a->c1 == 0 || a->stats1 != nullptr) && a->hw % 32 == 0;
+    const int n = a->batch * GN_GROUPS;
+    if (have_slabs) {
+      gn_finalize_slabs_kernel<<<(n + 7) / 8, 256, 0, stream>>>(g, a->batch);
+    } else {
+      gn_stats_kernel<<<grid, GN_THREADS, smem, stream>>>(g);
+      DDPO_LAUNCH_OK();
+      gn_finalize_chunks_kernel<<<(n + 127) / 128, 128, 0, stream>>>(g, a->batch);
+    }
     DDPO_LAUNCH_OK();
   }
   if (g.y_bf16 || g.y_f32 || g.raw_bf16) {
-    gn_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(g);
+    GnStream st;
+    if (gn_stream_plan(g, a, &st)) {
+      static bool attr = false;
+      const int dyn = GNA_STAGES * GNA_STAGE_BYTES + 128;
+      if (!attr) {
+        DDPO_CUDA_OK(cudaFuncSetAttribute(gn_apply_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        attr = true;
+      }
+      dim3 sg(st.ctas[0] > st.ctas[1] ? st.ctas[0] : st.ctas[1], 1, a->c1 > 0 ? 2 : 1);
+      gn_apply_tma_kernel<<<sg, 32 + st.consumers, dyn, stream>>>(g, st, a->batch);
+    } else {
+      gn_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(g);
+    }
     DDPO_LAUNCH_OK();
   }
   return DDPO_OK;
@@ -541,7 +774,7 @@ extern "C" int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const float* dy,
   DDPO_REQUIRE(dy && dx0 && dscale && dbias, "groupnorm_bwd: null pointer");
   b.dy = dy, b.dx0 = dx0, b.dx1 = dx1, b.ldd0 = ldd0 > 0 ? ldd0 : a->c0, b.ldd1 = ldd1 > 0 ? ldd1 : a->c1;
   b.accumulate = accumulate;
-  b.partial2 = a->workspace + static_cast<size_t>(a->batch) * b.f.chunks * GN_GROUPS * 2;
+  b.partial2 = b.f.partial + static_cast<size_t>(a->batch) * b.f.chunks * GN_GROUPS * 2;
   b.dparam_part = b.partial2 + static_cast<size_t>(a->batch) * b.f.chunks * GN_GROUPS * 2;
   dim3 grid(b.f.chunks, a->batch);
   const size_t smem = 2 * gn_stats_smem(C);
@@ -563,9 +796,17 @@ extern "C" int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const float* dy,
 
 extern "C" int ddpo_layernorm_fwd(const float* x, const float* scale, const float* bias, void* y_bf16, float* stats,
                                   int m, int c, float eps, void* stream) {
-  DDPO_REQUIRE(x && scale && bias && y_bf16 && m > 0 && c % 4 == 0, "layernorm_fwd: bad arguments (m=%d c=%d)", m, c);
-  layernorm_fwd_kernel<<<(m + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, scale, bias, static_cast<__nv_bfloat16*>(y_bf16), stats, m, c, eps);
+  DDPO_REQUIRE(x && scale && bias && y_bf16 && m > 0 && c % 4 == 0 && c <= 1280,
+               "layernorm_fwd: bad arguments (m=%d c=%d; c <= 1280)", m, c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
+  const int nc = (c + 127) / 128;
+  if (nc <= 3)
+    layernorm_fwd_kernel<3, 4><<<(m + 31) / 32, 256, 0, st>>>(x, scale, bias, y, stats, m, c, eps);
+  else if (nc <= 5)
+    layernorm_fwd_kernel<5, 2><<<(m + 15) / 16, 256, 0, st>>>(x, scale, bias, y, stats, m, c, eps);
+  else
+    layernorm_fwd_kernel<10, 1><<<(m + 7) / 8, 256, 0, st>>>(x, scale, bias, y, stats, m, c, eps);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }

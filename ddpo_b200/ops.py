@@ -15,7 +15,7 @@ DDIM_CHUNKS = 8
 # ---- instrumentation (bench.py): kernel-launch counter and optional CUDA-event profile ----
 LAUNCH_COUNT = 0           # kernels launched through this module since import
 PROFILE = None             # list of (name, work, event0, event1) while profiling, else None
-_KERNELS_PER_CALL = {"groupnorm_fwd": 2, "groupnorm_bwd": 3, "layernorm_bwd": 2}
+_KERNELS_PER_CALL = {"groupnorm_fwd": 2, "groupnorm_bwd": 3, "layernorm_bwd": 2}   # groupnorm_fwd: finalize + apply
 
 
 PROFILE_TAGS = []          # parallel to PROFILE: a shape tag per entry (bench.py --shapes)
@@ -152,7 +152,7 @@ def ppo_loss(logp, old_logp, adv, clip_range, info_out, dlogp_out, micro_batch=N
 # ------------------------------------------------------------------ GEMM --------
 def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None, m=None, taps=1, stride=1,
           bias=None, rowvec=None, rows_per_sample=0, rowvec_ld=0, residual=None, ld_res=0, out_f32=None,
-          out_bf16=None, ld_out=0, geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0):
+          out_bf16=None, ld_out=0, geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0, gn_stats=None):
     """conv=(batch, h_out, w_out) for convolutions, else linear with m rows."""
     a = IGemmArgs()
     a.a0, a.a1 = _p(a0), _p(a1)
@@ -176,6 +176,7 @@ def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None,
     a.mt_override = int(mt)
     a.pair_override = int(pair)
     a.epi_override = int(epi)
+    a.gn_stats = _p(gn_stats)
     rows = a.batch * a.h * a.w if a.is_conv else a.m
     _e = _ev()
     _run("igemm", lib().ddpo_igemm(C.byref(a), _stream()), 2.0 * rows * a.n * a.taps * (a.c0 + a.c1), _e,
@@ -190,15 +191,23 @@ def groupnorm_workspace_floats(batch, hw, channels):
 
 
 def _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, y_bf16, y_f32, raw_bf16, ws, ld0=0, ld1=0, skip_stats=False,
-             eps=1e-5):
+             eps=1e-5, stats0=None, stats1=None):
     return GroupNormArgs(_p(x0), _p(x1), int(c0), int(c1), int(ld0), int(ld1), int(batch), int(hw), _p(scale),
-                         _p(bias), float(eps), int(silu), _p(y_bf16), _p(y_f32), _p(raw_bf16), _p(ws), int(skip_stats))
+                         _p(bias), float(eps), int(silu), _p(y_bf16), _p(y_f32), _p(raw_bf16), _p(ws), int(skip_stats),
+                         _p(stats0), _p(stats1))
+
+
+def gn_stats_shape(rows, channels):
+    """Shape of the slab-statistics buffer an igemm with ``gn_stats=`` fills for its [rows, channels] fp32 output."""
+    return ((int(rows) + 31) // 32, int(channels), 2)
 
 
 def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, y_bf16=None, y_f32=None,
-                  raw_bf16=None, skip_stats=False, eps=1e-5):
+                  raw_bf16=None, skip_stats=False, eps=1e-5, stats0=None, stats1=None):
+    """``stats0`` / ``stats1``: slab statistics of x0 / x1 left by the igemm that produced them (``gn_stats=``); with both
+    (or ``stats0`` alone for one source) and hw % 32 == 0 the statistics pass over x is skipped."""
     a = _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, y_bf16, y_f32, raw_bf16, ws, skip_stats=skip_stats,
-                 eps=eps)
+                 eps=eps, stats0=stats0, stats1=stats1)
     _e = _ev()
     per = 4 + (2 if y_bf16 is not None else 0) + (4 if y_f32 is not None else 0) + (2 if raw_bf16 is not None else 0)
     _run("groupnorm_fwd", lib().ddpo_groupnorm_fwd(C.byref(a), _stream()), float(batch) * hw * (c0 + c1) * per, _e)
@@ -259,9 +268,10 @@ def upsample2x_bwd(dy, dx, batch, h, w, c, accumulate=False):
     _run("upsample2x_bwd", lib().ddpo_upsample2x_bwd(_p(dy), _p(dx), batch, h, w, c, int(accumulate), _stream()), 0.0, _e)
 
 
-def conv_in(x_nchw, w, bias, y_nhwc, batch, cin, h, wd, cout):
+def conv_in(x_nchw, w, bias, y_nhwc, batch, cin, h, wd, cout, gn_stats=None):
     _e = _ev()
-    _run("conv_in", lib().ddpo_conv_in(_p(x_nchw), _p(w), _p(bias), _p(y_nhwc), batch, cin, h, wd, cout, _stream()), 0.0, _e)
+    _run("conv_in", lib().ddpo_conv_in(_p(x_nchw), _p(w), _p(bias), _p(y_nhwc), batch, cin, h, wd, cout, _p(gn_stats),
+                                       _stream()), 0.0, _e)
 
 
 def conv_out(x_nhwc, w, bias, y_nchw, batch, h, wd, cin, cout):

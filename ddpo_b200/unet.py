@@ -30,6 +30,11 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 
+def _st(t):
+    """slab statistics the producing GEMM left for tensor ``t`` (None: the GroupNorm computes them itself)"""
+    return getattr(t, "_gn_stats", None) if t is not None else None
+
+
 class Arena:
     """Deterministic free-list allocator (persistent torch tensors, reused by byte size)."""
 
@@ -51,9 +56,21 @@ class Arena:
         t._ddpo_raw = raw
         return t
 
+    def alloc_with_gn_stats(self, shape, hw):
+        """fp32 [rows, channels] GEMM output plus, when a sample's pixels fill whole 32-row slabs, the slab-statistics
+        buffer the GEMM epilogue writes for the GroupNorm that will consume it (``ops.igemm(gn_stats=...)``).  The
+        statistics travel with the tensor (``t._gn_stats``) and are released with it."""
+        t = self.alloc(shape, F32)
+        t._gn_stats = self.alloc(ops.gn_stats_shape(shape[0], shape[1]), F32) if hw % 32 == 0 else None
+        return t
+
     def release(self, t):
         if t is None:
             return
+        st = getattr(t, "_gn_stats", None)
+        if st is not None:
+            t._gn_stats = None
+            self.release(st)
         raw = getattr(t, "_ddpo_raw", None)
         if raw is not None:
             self.free.setdefault(raw.numel(), []).append(raw)
@@ -208,29 +225,30 @@ class UNet:
         a = A.alloc((m, cin), BF16)
         raw = A.alloc((m, cin), BF16) if has_sc else None
         ops.groupnorm_fwd(x0, self.p(name + "/norm1/scale"), self.p(name + "/norm1/bias"), gws, b, hw, c0, x1=x1,
-                          c1=c1, silu=True, y_bf16=a, raw_bf16=raw)
+                          c1=c1, silu=True, y_bf16=a, raw_bf16=raw, stats0=_st(x0), stats1=_st(x1))
         if self._tproj_views is not None:
             tproj = self._tproj_views[name]          # computed by the grouped launch at the start of forward()
         else:
             tproj = A.alloc((b, cout), F32)
             ops.dense_small(temb_act, self.p(name + "/time_emb_proj/kernel"), self.p(name + "/time_emb_proj/bias"),
                             tproj, b, temb_act.shape[1], cout)
-        hbuf = A.alloc((m, cout), F32)
+        hbuf = A.alloc_with_gn_stats((m, cout), hw)
         ops.igemm(a0=a, wt=self.w[name + "/conv1"], n=cout, c0=cin, conv=(b, h, w), taps=9,
-                  bias=self.p(name + "/conv1/bias"), rowvec=tproj, rows_per_sample=hw, rowvec_ld=cout, out_f32=hbuf)
+                  bias=self.p(name + "/conv1/bias"), rowvec=tproj, rows_per_sample=hw, rowvec_ld=cout, out_f32=hbuf,
+                  gn_stats=_st(hbuf))
         gws2 = A.alloc((ops.groupnorm_workspace_floats(b, hw, cout),), F32)
         a2 = A.alloc((m, cout), BF16)
         ops.groupnorm_fwd(hbuf, self.p(name + "/norm2/scale"), self.p(name + "/norm2/bias"), gws2, b, hw, cout,
-                          silu=True, y_bf16=a2)
+                          silu=True, y_bf16=a2, stats0=_st(hbuf))
         if has_sc:
             sc = A.alloc((m, cout), F32)
             ops.igemm(a0=raw, wt=self.w[name + "/conv_shortcut"], n=cout, c0=cin, conv=(b, h, w), taps=1,
                       bias=self.p(name + "/conv_shortcut/bias"), out_f32=sc)
         else:
             sc = x0
-        out = A.alloc((m, cout), F32)
+        out = A.alloc_with_gn_stats((m, cout), hw)
         ops.igemm(a0=a2, wt=self.w[name + "/conv2"], n=cout, c0=cout, conv=(b, h, w), taps=9,
-                  bias=self.p(name + "/conv2/bias"), residual=sc, out_f32=out)
+                  bias=self.p(name + "/conv2/bias"), residual=sc, out_f32=out, gn_stats=_st(out))
         if tape is None:
             for t in (gws, a, raw, tproj, hbuf, gws2, a2, sc if has_sc else None):
                 A.release(t)
@@ -248,7 +266,7 @@ class UNet:
         gws = A.alloc((ops.groupnorm_workspace_floats(b, hw, c),), F32)
         g = A.alloc((m, c), BF16)
         ops.groupnorm_fwd(x, self.p(name + "/norm/scale"), self.p(name + "/norm/bias"), gws, b, hw, c, silu=False,
-                          y_bf16=g)
+                          y_bf16=g, stats0=_st(x))
         h0 = A.alloc((m, c), F32)
         ops.igemm(a0=g, wt=self.w[name + "/proj_in"], n=c, c0=c, m=m, bias=self.p(name + "/proj_in/bias"), out_f32=h0)
         # --- self attention
@@ -290,9 +308,9 @@ class UNet:
         h3b = A.alloc((m, c), BF16)
         ops.igemm(a0=ff, wt=self.w[bl + "/ff/net_2"], n=c, c0=4 * c, m=m, bias=self.p(bl + "/ff/net_2/bias"),
                   residual=h2, out_f32=h3, out_bf16=h3b)
-        out = A.alloc((m, c), F32)
+        out = A.alloc_with_gn_stats((m, c), hw)
         ops.igemm(a0=h3b, wt=self.w[name + "/proj_out"], n=c, c0=c, m=m, bias=self.p(name + "/proj_out/bias"),
-                  residual=x, out_f32=out)
+                  residual=x, out_f32=out, gn_stats=_st(out))
         if tape is None:
             for t in (gws, g, h0, ln1, st1, qkv, ao1, h1, ln2, st2, q2, ao2, h2, ln3, st3, ff, h3, h3b):
                 A.release(t)
@@ -347,8 +365,8 @@ class UNet:
             tproj_all = A.alloc((total,), F32)
             ops.dense_small_grouped(temb_act, self.params, tproj_all, dev_tab, len(views), ctas, b, te)
             self._tproj_views = {name: tproj_all[o:o + b * n].view(b, n) for name, o, n in views}
-        x = A.alloc((b * H * W, boc[0]), F32)
-        ops.conv_in(latents, self.p("conv_in/kernel"), self.p("conv_in/bias"), x, b, cin_lat, H, W, boc[0])
+        x = A.alloc_with_gn_stats((b * H * W, boc[0]), H * W)
+        ops.conv_in(latents, self.p("conv_in/kernel"), self.p("conv_in/bias"), x, b, cin_lat, H, W, boc[0], gn_stats=_st(x))
         tap("conv_in", x, (b, H, W, boc[0]))
         if tape is not None:
             tape.append(("head", dict(latents=latents, sincos=sincos, t1=t1, temb_act=temb_act, b=b, H=H, W=W, x=x,
@@ -374,9 +392,9 @@ class UNet:
                 name = f"down_blocks_{i}/downsamplers_0"
                 xb = A.alloc((b * h * w, c), BF16)
                 ops.cast_bf16(x, xb)
-                y = A.alloc((b * (h // 2) * (w // 2), c), F32)
+                y = A.alloc_with_gn_stats((b * (h // 2) * (w // 2), c), (h // 2) * (w // 2))
                 ops.igemm(a0=xb, wt=self.w[name + "/conv"], n=c, c0=c, conv=(b, h // 2, w // 2), taps=9, stride=2,
-                          bias=self.p(name + "/conv/bias"), out_f32=y)
+                          bias=self.p(name + "/conv/bias"), out_f32=y, gn_stats=_st(y))
                 if tape is None:
                     A.release(xb)
                 else:
@@ -425,9 +443,9 @@ class UNet:
                 name = f"up_blocks_{i}/upsamplers_0"
                 up = A.alloc((b * 4 * h * w, c), BF16)
                 ops.upsample2x_bf16(x, up, b, h, w, c)
-                y = A.alloc((b * 4 * h * w, c), F32)
+                y = A.alloc_with_gn_stats((b * 4 * h * w, c), 4 * h * w)
                 ops.igemm(a0=up, wt=self.w[name + "/conv"], n=c, c0=c, conv=(b, 2 * h, 2 * w), taps=9,
-                          bias=self.p(name + "/conv/bias"), out_f32=y)
+                          bias=self.p(name + "/conv/bias"), out_f32=y, gn_stats=_st(y))
                 if tape is None:
                     A.release(up)
                     A.release(x)
@@ -440,7 +458,7 @@ class UNet:
         gws = A.alloc((ops.groupnorm_workspace_floats(b, h * w, c0),), F32)
         yf = A.alloc((b * h * w, c0), F32)
         ops.groupnorm_fwd(x, self.p("conv_norm_out/scale"), self.p("conv_norm_out/bias"), gws, b, h * w, c0, silu=True,
-                          y_f32=yf)
+                          y_f32=yf, stats0=_st(x))
         if out is None:
             out = torch.empty(b, cfg.out_channels, h, w, dtype=F32, device=self.device)
         ops.conv_out(yf, self.p("conv_out/kernel"), self.p("conv_out/bias"), out, b, h, w, c0, cfg.out_channels)

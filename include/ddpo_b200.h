@@ -122,6 +122,9 @@ typedef struct {
   int mt_override;          /* 0 = auto; 1 / 2 = force 128- / 256-row CTA tiles */
   int pair_override;        /* 0 = auto; 1 = force the CTA-pair (cta_group::2) kernel; 2 = force the 1-CTA kernel */
   int epi_override;         /* 0 = auto; 1 = force the TMA-staged epilogue (pair kernel); 2 = force the register epilogue */
+  float* gn_stats;          /* optional, with out_f32: fp32 [ceil(M/32), n, 2] = per 32-row slab and output column the (sum, sum
+                               of squares) of the values written to out_f32.  The GroupNorm that consumes out_f32 takes its
+                               statistics from these (ddpo_groupnorm_args.stats0/1) instead of reading the tensor twice. */
 } ddpo_igemm_args;
 int ddpo_igemm(const ddpo_igemm_args* a, void* stream);
 
@@ -143,6 +146,10 @@ typedef struct {
   float* workspace;     /* ddpo_groupnorm_workspace_floats(); the first batch*chunks*64 floats (forward
                            statistics) must be kept until the backward call */
   int stats_only_skip;  /* 1: statistics already in workspace, only apply */
+  const float* stats0;  /* optional: slab statistics [batch*hw/32, c0, 2] of x0 written by the GEMM that produced it
+                           (ddpo_igemm_args.gn_stats); needs hw % 32 == 0.  With stats for every source the forward is ONE pass
+                           over x (no statistics pass). */
+  const float* stats1;  /* same for x1 [batch*hw/32, c1, 2] */
 } ddpo_groupnorm_args;
 int64_t ddpo_groupnorm_workspace_floats(int batch, int hw, int channels);
 int ddpo_groupnorm_fwd(const ddpo_groupnorm_args* a, void* stream);
@@ -165,9 +172,10 @@ int ddpo_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
 /* FlaxUpsample2D's jax.image.resize(nearest): out[i] = in[i/2] */
 int ddpo_upsample2x_bf16(const float* x, void* y_bf16, int batch, int h, int w, int c, void* stream);
 int ddpo_upsample2x_bwd(const float* dy, float* dx, int batch, int h, int w, int c, int accumulate, void* stream);
-/* conv_in: NCHW fp32 latents -> NHWC fp32; conv_out: NHWC fp32 -> NCHW fp32 (N = 4) */
+/* conv_in: NCHW fp32 latents -> NHWC fp32; conv_out: NHWC fp32 -> NCHW fp32 (N = 4).
+ * gn_stats: optional [ceil(batch*h*w/32), cout, 2] slab statistics of y for the consuming GroupNorm (see ddpo_igemm_args) */
 int ddpo_conv_in(const float* x_nchw, const float* w_hwio, const float* bias, float* y_nhwc, int batch, int cin,
-                 int h, int w, int cout, void* stream);
+                 int h, int w, int cout, float* gn_stats, void* stream);
 int ddpo_conv_out(const float* x_nhwc, const float* w_hwio, const float* bias, float* y_nchw, int batch, int h,
                   int w, int cin, int cout, void* stream);
 /* FlaxTimesteps(flip_sin_to_cos=True, freq_shift=0) and the M=batch Dense layers of the time embedding */

@@ -16,6 +16,12 @@ class CpuArena:
     def alloc(self, shape, dtype):
         return torch.zeros(*shape, dtype=dtype)
 
+    def alloc_with_gn_stats(self, shape, hw):
+        t = self.alloc(shape, torch.float32)
+        # NaN-filled: a GroupNorm that reads statistics nobody wrote fails loudly
+        t._gn_stats = torch.full(gn_stats_shape(shape[0], shape[1]), float("nan")) if hw % 32 == 0 else None
+        return t
+
     def release(self, t):
         pass
 
@@ -28,12 +34,33 @@ def prep_weight(src, dst, k, n, ldk=None, row_offset=0, col_offset=0, geglu_bn=0
     dst[row_offset:row_offset + n, :k].copy_(src.reshape(k, n).t().to(BF16))
 
 
+def gn_stats_shape(rows, channels):
+    return ((int(rows) + 31) // 32, int(channels), 2)
+
+
+def _fill_gn_stats(gn_stats, y):
+    """what the igemm epilogue leaves for the consuming GroupNorm: per 32-row slab and column (sum, sum of squares)"""
+    rows, n = y.shape
+    pad = (-rows) % 32
+    yp = torch.cat([y, y.new_zeros(pad, n)]) if pad else y
+    t = yp.reshape(-1, 32, n)
+    gn_stats.copy_(torch.stack([t.sum(1), (t * t).sum(1)], -1))
+
+
 def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, y_bf16=None, y_f32=None, raw_bf16=None,
-                  skip_stats=False, eps=1e-5):
+                  skip_stats=False, eps=1e-5, stats0=None, stats1=None):
     assert x1 is None
     x = x0.reshape(batch, hw, 32, c0 // 32).float()
-    mean = x.mean(dim=(1, 3), keepdim=True)
-    var = ((x * x).mean(dim=(1, 3), keepdim=True) - mean * mean).clamp(min=0)
+    if stats0 is not None and hw % 32 == 0:
+        # the product takes mean / variance from the producer's slab statistics: do the same, so that a wrong or stale
+        # statistics buffer handed over by the host code shows up in the CPU dry runs
+        st = stats0.reshape(batch, hw // 32, 32, c0 // 32, 2).sum(dim=(1, 3))
+        cnt = hw * (c0 // 32)
+        mean = (st[..., 0] / cnt).reshape(batch, 1, 32, 1)
+        var = ((st[..., 1] / cnt).reshape(batch, 1, 32, 1) - mean * mean).clamp(min=0)
+    else:
+        mean = x.mean(dim=(1, 3), keepdim=True)
+        var = ((x * x).mean(dim=(1, 3), keepdim=True) - mean * mean).clamp(min=0)
     y = ((x - mean) * torch.rsqrt(var + eps)).reshape(batch * hw, c0) * scale + bias
     if silu:
         y = y * torch.sigmoid(y)
@@ -47,7 +74,7 @@ def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, 
 
 def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None, m=None, taps=1, stride=1, bias=None,
           rowvec=None, rows_per_sample=0, rowvec_ld=0, residual=None, ld_res=0, out_f32=None, out_bf16=None, ld_out=0,
-          geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0):
+          geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0, gn_stats=None):
     assert a1 is None and not geglu and rowvec is None and stride == 1
     assert a0.dtype == BF16 and wt.dtype == BF16
     c0 = int(c0 if c0 is not None else a0.shape[-1])
@@ -71,12 +98,16 @@ def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None,
         out_f32.reshape(y.shape).copy_(y)
     if out_bf16 is not None:
         out_bf16.reshape(y.shape).copy_(y.to(BF16))
+    if gn_stats is not None:
+        _fill_gn_stats(gn_stats, y)
 
 
-def conv_in(x_nchw, w, bias, y_nhwc, batch, cin, h, wd, cout):
+def conv_in(x_nchw, w, bias, y_nhwc, batch, cin, h, wd, cout, gn_stats=None):
     assert cin <= 8 and cout % 4 == 0
     y = F.conv2d(x_nchw, w.permute(3, 2, 0, 1), bias, padding=1).permute(0, 2, 3, 1)
     y_nhwc.reshape(batch, h, wd, cout).copy_(y)
+    if gn_stats is not None:
+        _fill_gn_stats(gn_stats, y.reshape(batch * h * wd, cout))
 
 
 def vae_post_quant(latents, w, bias, out, scaling=0.18215):
@@ -234,16 +265,19 @@ _groupnorm_single = groupnorm_fwd
 
 
 def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, y_bf16=None, y_f32=None,  # noqa: F811
-                  raw_bf16=None, skip_stats=False, eps=1e-5):
+                  raw_bf16=None, skip_stats=False, eps=1e-5, stats0=None, stats1=None):
     if x1 is None:
-        return _groupnorm_single(x0, scale, bias, ws, batch, hw, c0, None, 0, silu, y_bf16, y_f32, raw_bf16, skip_stats, eps)
+        return _groupnorm_single(x0, scale, bias, ws, batch, hw, c0, None, 0, silu, y_bf16, y_f32, raw_bf16, skip_stats, eps,
+                                 stats0)
     cat = torch.cat([x0.reshape(batch * hw, c0), x1.reshape(batch * hw, c1)], 1)
-    return _groupnorm_single(cat, scale, bias, ws, batch, hw, c0 + c1, None, 0, silu, y_bf16, y_f32, raw_bf16, skip_stats, eps)
+    st = torch.cat([stats0, stats1], 1) if stats0 is not None and stats1 is not None else None
+    return _groupnorm_single(cat, scale, bias, ws, batch, hw, c0 + c1, None, 0, silu, y_bf16, y_f32, raw_bf16, skip_stats, eps,
+                             st)
 
 
 def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None, m=None, taps=1, stride=1, bias=None,  # noqa: F811
           rowvec=None, rows_per_sample=0, rowvec_ld=0, residual=None, ld_res=0, out_f32=None, out_bf16=None, ld_out=0,
-          geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0):
+          geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0, gn_stats=None):
     assert a0.dtype == BF16 and wt.dtype == BF16 and (a1 is None or a1.dtype == BF16)
     c0 = int(c0 if c0 is not None else a0.shape[-1])
     cin = c0 + c1
@@ -281,6 +315,9 @@ def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None,
         out_f32.reshape(y.shape).copy_(out_f32.reshape(y.shape) + y if accumulate else y)
     if out_bf16 is not None:
         out_bf16.reshape(y.shape).copy_(y.to(BF16))
+    if gn_stats is not None:
+        assert out_f32 is not None and not accumulate
+        _fill_gn_stats(gn_stats, y)
 
 
 def conv_out(x_nhwc, w, bias, y_nchw, batch, h, wd, cin, cout):

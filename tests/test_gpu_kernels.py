@@ -316,7 +316,92 @@ def test_groupnorm_fwd(b, hw, c0, c1, silu):
     assert torch.equal(raw, bf(x))
 
 
-@pytest.mark.parametrize("m,c", [(64, 64), (1000, 320), (4096, 1280)])
+def _slab_stats_ref(y):
+    rows, n = y.shape
+    pad = (-rows) % 32
+    yp = torch.cat([y, y.new_zeros(pad, n)]) if pad else y
+    t = yp.double().reshape(-1, 32, n)
+    return torch.stack([t.sum(1), (t * t).sum(1)], -1).float()
+
+
+@pytest.mark.parametrize("kind,b,h,c,n,epi,pair", [("conv", 2, 16, 128, 160, 0, 0), ("conv", 4, 32, 64, 320, 1, 1),
+                                                   ("conv", 4, 32, 64, 320, 2, 1), ("conv", 3, 8, 128, 128, 0, 0),
+                                                   ("lin", 1, 1000, 128, 256, 1, 1), ("lin", 1, 1000, 128, 256, 2, 1),
+                                                   ("lin", 1, 333, 64, 96, 0, 2), ("lin", 1, 4096, 320, 320, 0, 0)])
+def test_igemm_gn_slab_stats(kind, b, h, c, n, epi, pair):
+    """The epilogue's per-(32-row slab, column) sums of what it writes (bias + row vector + residual included)."""
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(31)
+    bias = torch.randn(n, generator=g).to(DEV)
+    if kind == "conv":
+        m = b * h * h
+        x = bf(torch.randn(b, h, h, c, generator=g)).to(DEV)
+        w = (torch.randn(9 * c, n, generator=g) / math.sqrt(9 * c)).to(DEV)
+        res = torch.randn(m, n, generator=g).to(DEV)
+        tvec = torch.randn(b, n, generator=g).to(DEV)
+        out = torch.zeros(m, n, device=DEV)
+        st = torch.full(ops.gn_stats_shape(m, n), float("nan"), device=DEV)
+        ops.igemm(a0=x, wt=_prep_w(w), n=n, c0=c, conv=(b, h, h), taps=9, bias=bias, rowvec=tvec, rows_per_sample=h * h,
+                  rowvec_ld=n, residual=res, out_f32=out, gn_stats=st, epi=epi, pair=pair)
+        ref_out = torch.zeros(m, n, device=DEV)
+        ops.igemm(a0=x, wt=_prep_w(w), n=n, c0=c, conv=(b, h, h), taps=9, bias=bias, rowvec=tvec, rows_per_sample=h * h,
+                  rowvec_ld=n, residual=res, out_f32=ref_out, epi=epi, pair=pair)
+    else:
+        m = h
+        x = bf(torch.randn(m, c, generator=g)).to(DEV)
+        w = (torch.randn(c, n, generator=g) / math.sqrt(c)).to(DEV)
+        res = torch.randn(m, n, generator=g).to(DEV)
+        out = torch.zeros(m, n, device=DEV)
+        st = torch.full(ops.gn_stats_shape(m, n), float("nan"), device=DEV)
+        ops.igemm(a0=x, wt=_prep_w(w), n=n, c0=c, m=m, bias=bias, residual=res, out_f32=out, gn_stats=st, epi=epi, pair=pair)
+        ref_out = torch.zeros(m, n, device=DEV)
+        ops.igemm(a0=x, wt=_prep_w(w), n=n, c0=c, m=m, bias=bias, residual=res, out_f32=ref_out, epi=epi, pair=pair)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref_out), "asking for statistics must not change the output"
+    ref = _slab_stats_ref(out)
+    assert torch.isfinite(st).all()
+    assert (st - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("b,hw,c0,c1,silu", [(2, 64, 64, 0, True), (2, 4096, 320, 0, True), (3, 1024, 1280, 640, True),
+                                             (2, 256, 1280, 1280, False), (16, 64, 1280, 1280, True), (2, 4096, 640, 320, True)])
+def test_groupnorm_fwd_from_slab_stats(b, hw, c0, c1, silu, monkeypatch):
+    """One-pass GroupNorm: statistics from the producer's slab sums (here written by torch), streamed apply; the result
+    agrees with the oracle and with the two-pass path; the streamed and the plain apply kernels are bit-identical."""
+    from ddpo_b200 import ops
+    from oracle.unet import group_norm, silu as silu_ref
+    g = torch.Generator(device="cpu").manual_seed(6)
+    c = c0 + c1
+    x0 = (torch.randn(b, hw, c0, generator=g) * 2 + 0.5).to(DEV)
+    x1 = (torch.randn(b, hw, c1, generator=g) - 1.0).to(DEV) if c1 else None
+    sc = (1 + 0.1 * torch.randn(c, generator=g)).to(DEV)
+    bi = (0.1 * torch.randn(c, generator=g)).to(DEV)
+    s0 = _slab_stats_ref(x0.view(b * hw, c0))
+    s1 = _slab_stats_ref(x1.view(b * hw, c1)) if c1 else None
+    outs = []
+    for mode in ("slabs", "two_pass", "slabs_plain_apply"):
+        monkeypatch.setenv("DDPO_GN_NO_STREAM", "1" if mode == "slabs_plain_apply" else "0")
+        ws = torch.full((ops.groupnorm_workspace_floats(b, hw, c),), float("nan"), device=DEV)
+        y = torch.zeros(b, hw, c, dtype=torch.bfloat16, device=DEV)
+        yf = torch.zeros(b, hw, c, device=DEV)
+        raw = torch.zeros(b, hw, c, dtype=torch.bfloat16, device=DEV)
+        kw = dict(stats0=s0, stats1=s1) if mode != "two_pass" else {}
+        ops.groupnorm_fwd(x0, sc, bi, ws, b, hw, c0, x1=x1, c1=c1, silu=silu, y_bf16=y, y_f32=yf, raw_bf16=raw, **kw)
+        torch.cuda.synchronize()
+        outs.append((y, yf, raw))
+    x = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
+    ref = group_norm(x.view(b, hw, 1, c), sc, bi).view(b, hw, c)
+    if silu:
+        ref = silu_ref(ref)
+    for y, yf, raw in outs:
+        assert (yf - ref).abs().max().item() < 2e-4
+        assert rel_err(y, ref) < 4e-3
+        assert torch.equal(raw, bf(x))
+    assert (outs[0][1] - outs[1][1]).abs().max().item() < 2e-5
+    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
+
+
+@pytest.mark.parametrize("m,c", [(64, 64), (1000, 320), (4096, 1280), (777, 640), (154, 1024), (65536, 320)])
 def test_layernorm_fwd(m, c):
     from ddpo_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(6)
@@ -324,9 +409,12 @@ def test_layernorm_fwd(m, c):
     sc = (1 + 0.1 * torch.randn(c, generator=g)).to(DEV)
     bi = (0.1 * torch.randn(c, generator=g)).to(DEV)
     y = torch.zeros(m, c, dtype=torch.bfloat16, device=DEV)
-    ops.layernorm_fwd(x, sc, bi, y, m, c)
+    st = torch.zeros(m, 2, device=DEV)
+    ops.layernorm_fwd(x, sc, bi, y, m, c, stats=st)
     ref = torch.nn.functional.layer_norm(x, (c,), sc, bi, 1e-5)
     assert rel_err(y, ref) < 4e-3
+    assert (st[:, 0] - x.mean(-1)).abs().max().item() < 1e-5
+    assert (st[:, 1] * x.std(-1, unbiased=False) - 1).abs().max().item() < 1e-3
 
 
 # --------------------------------------------------------------- small layers ----
@@ -338,9 +426,11 @@ def test_conv_in_out_dense_upsample():
     w = torch.randn(3, 3, 4, c, generator=g).to(DEV) / 6
     bias = torch.randn(c, generator=g).to(DEV)
     y = torch.zeros(b * h * h, c, device=DEV)
-    ops.conv_in(lat, w, bias, y, b, 4, h, h, c)
+    st = torch.full(ops.gn_stats_shape(b * h * h, c), float("nan"), device=DEV)
+    ops.conv_in(lat, w, bias, y, b, 4, h, h, c, gn_stats=st)
     ref = torch.nn.functional.conv2d(lat, w.permute(3, 2, 0, 1), bias, padding=1).permute(0, 2, 3, 1).reshape(b * h * h, c)
     assert (y - ref).abs().max().item() < 1e-4
+    assert (st - _slab_stats_ref(y)).abs().max().item() < 1e-4
     x = torch.randn(b, h, h, c, generator=g).to(DEV)
     w2 = torch.randn(3, 3, c, 4, generator=g).to(DEV) / 24
     b2 = torch.randn(4, generator=g).to(DEV)
