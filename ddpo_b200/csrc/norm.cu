@@ -316,6 +316,8 @@ struct GnBwdArgs {
   int ldd0, ldd1;
   int accumulate;
   float* dparam_part;  // [B, chunks, 2, C]  partial (dscale, dbias)
+  int b0;              // first sample of this launch: the two passes run over groups of samples small enough that the
+                       // second pass finds x and dy in L2 (126 MB) instead of fetching them from DRAM again
 };
 
 __device__ __forceinline__ float silu_grad_f(float z) {
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const GnBwdArg
   const int cols = C4 < GN_THREADS ? C4 : GN_THREADS;
   const int R = GN_THREADS / cols;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
-  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int b = a.b0 + blockIdx.y, chunk = blockIdx.x;
   const int p_begin = chunk * f.pix_per_chunk;
   const int p_end = min(f.hw, p_begin + f.pix_per_chunk);
   extern __shared__ float sm[];  // [R][C][4] : a0, a1, dscale, dbias per channel
@@ -407,7 +409,8 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
   const int cols = C4 < GN_THREADS ? C4 : GN_THREADS;
   const int R = GN_THREADS / cols;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
-  const int b = f.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, chunk = f.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  // descending order within the launch: the stats pass finished on the last samples / chunks, start with those
+  const int b = a.b0 + (gridDim.y - 1 - blockIdx.y), chunk = gridDim.x - 1 - blockIdx.x;
   const int p_begin = chunk * f.pix_per_chunk;
   const int p_end = min(f.hw, p_begin + f.pix_per_chunk);
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS], s_m1[GN_GROUPS], s_m2[GN_GROUPS];
@@ -785,10 +788,20 @@ extern "C" int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const float* dy,
   }
   DDPO_REQUIRE(smem <= 96 * 1024, "groupnorm_bwd: too many channels (%d)", C);
   DDPO_REQUIRE(b.ldd0 % 4 == 0 && b.ldd1 % 4 == 0, "groupnorm_bwd: gradient pitches must be multiples of 4");
-  gn_bwd_stats_kernel<<<grid, GN_THREADS, smem, stream>>>(b);
-  DDPO_LAUNCH_OK();
-  gn_bwd_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(b);
-  DDPO_LAUNCH_OK();
+  // sample groups of <= ~48 MB of (x, dy): pass 2 of a group re-reads what pass 1 just streamed through L2
+  const double bytes_per_sample = static_cast<double>(a->hw) * C * 8.0;
+  int group = static_cast<int>(48.0 * 1024 * 1024 / bytes_per_sample);
+  if (group < 1) group = 1;
+  if (group > a->batch) group = a->batch;
+  for (int b0 = 0; b0 < a->batch; b0 += group) {
+    const int nb = a->batch - b0 < group ? a->batch - b0 : group;
+    b.b0 = b0;
+    dim3 g2(b.f.chunks, nb);
+    gn_bwd_stats_kernel<<<g2, GN_THREADS, smem, stream>>>(b);
+    DDPO_LAUNCH_OK();
+    gn_bwd_apply_kernel<<<g2, GN_THREADS, 0, stream>>>(b);
+    DDPO_LAUNCH_OK();
+  }
   launch_reduce_rows(b.dparam_part, 1, a->batch * b.f.chunks, 2 * C, C, dscale, dbias, 1, stream);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
