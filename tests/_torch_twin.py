@@ -235,3 +235,45 @@ def load_flax_params(model, views):
     assert not missing, sorted(missing)[:5]
     model.load_state_dict(sd)
     return model
+
+
+# ------------------------------------------------------------------------------ VAE decoder twin ----
+def vae_decode_twin(params, cfg, latents, scaling=0.18215):
+    """The KL-VAE decoder the PyTorch way (NCHW; F.group_norm / F.conv2d / F.scaled_dot_product_attention /
+    F.interpolate) on Flax-layout parameters converted on the fly.  Returns (images NHWC in [0, 1], raw NCHW)."""
+    def conv(x, name, stride=1, pad=1):
+        w = params[name + "/kernel"].permute(3, 2, 0, 1)
+        return F.conv2d(x, w, params[name + "/bias"], stride=stride, padding=pad)
+
+    def gn(x, name):
+        return F.group_norm(x, 32, params[name + "/scale"], params[name + "/bias"], eps=1e-6)
+
+    def lin(x, name):
+        return F.linear(x, params[name + "/kernel"].t(), params[name + "/bias"])
+
+    def resnet(x, name):
+        h = conv(F.silu(gn(x, name + "/norm1")), name + "/conv1")
+        h = conv(F.silu(gn(h, name + "/norm2")), name + "/conv2")
+        if name + "/conv_shortcut/kernel" in params:
+            x = conv(x, name + "/conv_shortcut", pad=0)
+        return x + h
+
+    def attention(x, name):
+        b, c, h, w = x.shape
+        g = gn(x, name + "/group_norm").permute(0, 2, 3, 1).reshape(b, 1, h * w, c)       # one head of width c
+        o = F.scaled_dot_product_attention(lin(g, name + "/query"), lin(g, name + "/key"), lin(g, name + "/value"))
+        return x + lin(o, name + "/proj_attn").reshape(b, h, w, c).permute(0, 3, 1, 2)
+
+    x = conv(latents / scaling, "post_quant_conv", pad=0)
+    x = conv(x, "decoder/conv_in")
+    x = resnet(x, "decoder/mid_block/resnets_0")
+    x = attention(x, "decoder/mid_block/attentions_0")
+    x = resnet(x, "decoder/mid_block/resnets_1")
+    n_up = len(cfg.block_out_channels)
+    for i in range(n_up):
+        for l in range(cfg.layers_per_block + 1):
+            x = resnet(x, f"decoder/up_blocks_{i}/resnets_{l}")
+        if i < n_up - 1:
+            x = conv(F.interpolate(x, scale_factor=2.0, mode="nearest"), f"decoder/up_blocks_{i}/upsamplers_0/conv")
+    raw = conv(F.silu(gn(x, "decoder/conv_norm_out")), "decoder/conv_out")
+    return (raw / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1), raw

@@ -72,3 +72,20 @@ def test_oracle_primitives_equal_torch_library_ops():
     fr = torch.tensor([0.0, 1.0, 500.0, 999.0], dtype=torch.float64)[:, None] * torch.exp(-np.log(10000.0) * k / 160)[None]
     # the oracle (like Flax) forms t * freq in fp32: arguments up to ~1e3 carry ~6e-5 of absolute error
     assert (e[:, :160] - torch.cos(fr)).abs().max().item() < 2e-4 and (e[:, 160:] - torch.sin(fr)).abs().max().item() < 2e-4
+
+
+def test_oracle_vae_decoder_equals_pytorch_idiom_twin():
+    """oracle/vae.py (Flax decoder, NHWC, hand-written single-head attention with the (C)^-1/4 double scaling) against the
+    decoder written with torch library primitives on the same Flax-layout weights."""
+    from _torch_twin import vae_decode_twin
+    from ddpo_b200 import vae as V
+    from oracle import vae as OV
+    for cfg, seed in ((V.VAE_MICRO, 3), (V.VAE_MICRO, 4)):
+        flat = V.init_flat_params(cfg, seed).double()
+        views = V.views(flat, cfg)
+        z = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(seed), dtype=torch.float64) * 0.18215
+        img_o, raw_o = OV.decode(views, cfg, z, dtype=torch.float64)
+        img_t, raw_t = vae_decode_twin(views, cfg, z)
+        assert raw_o.shape == raw_t.shape and img_o.shape == img_t.shape
+        assert ((raw_o - raw_t).norm() / raw_t.norm()).item() < 1e-9
+        assert (img_o - img_t).abs().max().item() < 1e-9
