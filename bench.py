@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 T_STEPS = 50
 SAMPLE_BATCH = 8
 TRAIN_BATCH = 2
-TRAIN_MACRO = 10  # timesteps of the same train batch evaluated in one U-Net pass (same parameters, see train_step doc)
+TRAIN_MACRO = int(os.environ.get("DDPO_BENCH_MACRO", "10"))  # timesteps of the same train batch evaluated in one U-Net pass (same parameters, see train_step doc)
 GUIDANCE, ETA, CLIP = 5.0, 1.0, 1e-4
 UNET_GFLOP = 804.3  # algorithmic GFLOP of one SD2-base U-Net application (SURVEY.md §8d / BASELINE.md §2)
 WORKLOAD = "DDPO SD2-base 512px, 50-step DDIM, CFG 5.0, eta 1.0, sample batch 8/GPU (BASELINE configs[1])"
@@ -97,14 +97,22 @@ def parity_inputs():
 
 
 def _cpu_threads():
-    """torchrun exports OMP_NUM_THREADS=1: the CPU arm must still use every host core (rank 0 is the only rank that
-    runs it)."""
+    """Threads of the CPU arm = PHYSICAL cores this process may use.  torchrun exports OMP_NUM_THREADS=1 (rank 0 is the
+    only rank that runs the CPU arm and must still use the whole host), while one thread per hyper-thread (128 on the
+    64-core GPU box) makes oneDNN's autograd path collapse -- measured: the 34 s train step did not finish in 10 minutes."""
     import torch
-    n = os.cpu_count() or 1
+    n = None
     try:
-        n = len(os.sched_getaffinity(0))
+        import psutil
+        n = psutil.cpu_count(logical=False)
     except Exception:
         pass
+    avail = os.cpu_count() or 1
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    n = max(1, min(n or avail, avail))
     if torch.get_num_threads() != n:
         torch.set_num_threads(n)
     return torch.get_num_threads()

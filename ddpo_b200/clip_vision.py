@@ -4,10 +4,9 @@ patch embedding, class + position embeddings, pre-LayerNorm, 24 pre-LN transform
 post-LayerNorm of the CLS token, visual projection 1024 -> 768), L2 normalisation, and the LAION ``AestheticClassifier``
 (``ddpo/models/laion.py:7-18``: five Dense layers 768-1024-128-64-16-1 without activations; dropout is deterministic).
 
-EXPERIMENTAL: written after this round's GPU budget was spent.  The oracle (``oracle/clip_vision.py``) is pinned against the
-installed ``transformers`` ``CLIPVisionModelWithProjection`` and this module's host assembly is dry-run against it on the
-CPU ops emulator; the CUDA path itself (``csrc/vision.cu`` + the text tower's building blocks) has not run on a GPU yet
-(``tests/test_gpu_zz_experimental.py``, DDPO_EXPERIMENTAL=1).  Weights are random-init (no checkpoints offline); the
+The oracle (``oracle/clip_vision.py``) is pinned against the installed ``transformers`` ``CLIPVisionModelWithProjection``;
+the CUDA path (``csrc/vision.cu`` + the text tower's building blocks) agrees with it within 2e-2 relative on the B200
+(``tests/test_gpu_zz_grouped_temb_aesthetic.py``; full-size ViT-L/14 run included).  Weights are random-init (no checkpoints offline); the
 LAION head loads ``sac+logos+ava1-l14-linearMSE.pth`` from ``cache/`` when the file exists, as the reference does.
 """
 import os

@@ -44,8 +44,6 @@ struct GnArgs {
   __nv_bfloat16* y_bf16;   // [B, HW, C] or null
   float* y_f32;            // [B, HW, C] or null
   __nv_bfloat16* raw_bf16;  // [B, HW, C] un-normalised copy or null
-  int reverse;  // DDPO_GN_REVERSE=1 (fallback two-pass path only): the apply pass walks samples / chunks in descending order
-                // so that it starts with what the preceding stats pass left in L2.  Pure scheduling: bit-identical results.
   const float* stats0;  // slab statistics of x0 / x1 ([B*HW/32, c, 2]) or null
   const float* stats1;
   float* mr;            // [B, 32, 2] (mean, rstd): written by the finalize kernels, read by every apply / backward kernel
@@ -257,7 +255,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
   const int cols = C4 < GN_THREADS ? C4 : GN_THREADS;
   const int R = GN_THREADS / cols;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
-  const int b = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, chunk = a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int b = blockIdx.y, chunk = blockIdx.x;
   const int p_begin = chunk * a.pix_per_chunk;
   const int p_end = min(a.hw, p_begin + a.pix_per_chunk);
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
@@ -657,8 +655,6 @@ static int fill_gn(GnArgs& g, const ddpo_groupnorm_args* a) {
   g.stats0 = a->stats0, g.stats1 = a->stats1;
   g.y_bf16 = static_cast<__nv_bfloat16*>(a->y_bf16), g.y_f32 = a->y_f32;
   g.raw_bf16 = static_cast<__nv_bfloat16*>(a->raw_bf16);
-  static const int reverse = [] { const char* e = getenv("DDPO_GN_REVERSE"); return e != nullptr && e[0] == '1' ? 1 : 0; }();
-  g.reverse = reverse;
   return DDPO_OK;
 }
 

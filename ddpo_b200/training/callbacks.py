@@ -76,11 +76,14 @@ AESTHETIC_GPU_ENV = "DDPO_AESTHETIC_GPU"
 
 def aesthetic_fn(devices=None, rng=0, cache="cache", jit=True):
     """Reference ``callbacks.py:60-95``: CLIP ViT-L/14 image features -> L2 normalise -> LAION aesthetic head; returns
-    ``[N, 1]`` scores.  With ``$DDPO_AESTHETIC_GPU=1`` the model runs on the GPU kernels (``ddpo_b200/clip_vision.py``,
-    random-init tower -- no checkpoints offline -- and the LAION head from ``cache/`` when that file exists; this path is
-    EXPERIMENTAL, see the module docstring); otherwise the cached-score stub answers (BASELINE config 3 offline)."""
+    ``[N, 1]`` scores.  The model runs on the GPU kernels (``ddpo_b200/clip_vision.py``: CLIP ViT-L/14 image tower +
+    LAION head; weights are random-init unless a checkpoint is found -- none exists offline -- and the LAION head is read
+    from ``cache/`` when that file exists).  ``$DDPO_AESTHETIC_GPU=0`` (or no CUDA device) selects the cached-score stub,
+    which itself needs ``$DDPO_ALLOW_STUB_REWARDS=1``."""
     import os
-    if os.environ.get(AESTHETIC_GPU_ENV) != "1":
+    import torch
+    want_gpu = os.environ.get(AESTHETIC_GPU_ENV, "1") == "1" and torch.cuda.is_available()
+    if not want_gpu:
         return _cached_score_stub("aesthetic", True)(devices, jit)
     from ..clip_vision import AestheticScorer
     scorer = AestheticScorer(seed=int(rng), cache=cache)

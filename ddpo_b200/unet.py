@@ -98,10 +98,10 @@ class UNet:
         self.wd: Dict[str, torch.Tensor] = {}      # bf16 backward (dgrad) GEMM operands, built on demand
         self.grads: Optional[torch.Tensor] = None  # flat fp32 gradient accumulator (same layout as params)
         self.train_mode = False
-        # EXPERIMENTAL (default off, not yet measured on the GPU): all ResNet time-embedding projections in ONE launch
-        # (ops.dense_small_grouped; bit-identical to the 22 separate dense_small launches, which cost ~36 us each at
-        # 10-40 CTAs).  Enable with DDPO_GROUPED_TEMB=1.
-        self.grouped_temb = os.environ.get("DDPO_GROUPED_TEMB", "0") == "1"
+        # all ResNet time-embedding projections of a pass in ONE launch (ops.dense_small_grouped): bit-identical to the 22
+        # separate dense_small launches (tests/test_gpu_kernels.py), which cost ~36 us each at 10-40 CTAs -- measured
+        # 21.08 -> 20.62 ms per denoising step (profiles/README.md).  DDPO_GROUPED_TEMB=0 restores the separate launches.
+        self.grouped_temb = os.environ.get("DDPO_GROUPED_TEMB", "1") == "1"
         self._temb_names = [n[: -len("/time_emb_proj/kernel")] for n in self.table if n.endswith("/time_emb_proj/kernel")]
         self._temb_tables: Dict[int, tuple] = {}
         self._tproj_views: Optional[Dict[str, torch.Tensor]] = None

@@ -38,7 +38,9 @@ def sd2():
     from ddpo_b200.unet import UNet
     from oracle import ppo as OPPO, scheduler as OS, threefry
     from oracle.unet import UNetOracle
-    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    import psutil
+    # physical cores: one thread per hyper-thread makes oneDNN's backward path collapse on the 64-core / 128-thread box
+    torch.set_num_threads(max(1, min(psutil.cpu_count(logical=False) or 8, len(os.sched_getaffinity(0)))))
     cfg = unet_spec.SD2_BASE
     flat = unet_spec.init_flat_params(cfg, 0)
     onet = UNetOracle(cfg, unet_spec.views(flat, cfg))
@@ -112,6 +114,7 @@ def test_sd2_base_batch_invariance_of_eps(sd2):
     assert torch.equal(e6[0], e2[0]) and torch.equal(e6[3], e2[1])
 
 
+@pytest.mark.timeout(420)
 def test_sd2_base_ppo_train_step_matches_oracle(sd2):
     """loss, log-prob, ratio and the parameter gradient of one reference-sized train step (train_cfg, batch 1)."""
     from ddpo_b200 import unet_spec
