@@ -9,8 +9,8 @@ Parameter names / layouts are the Flax checkpoint's (``decoder/...``, ``post_qua
 only the decoder half is held (the RWR path consumes stored posterior moments, it never encodes).
 
 B200 design: the same building blocks as the U-Net -- bf16 implicit-GEMM convolutions with fp32 TMEM accumulators
-(tcgen05), fused bias / residual epilogues, two-kernel GroupNorm+swish producing the bf16 GEMM operand, fp32 residual
-stream.  Pixel rows at the 256 / 512 px levels are wider than a 128-row tile: the igemm TMA producer walks them as
+(tcgen05), fused bias / residual epilogues, one-pass GroupNorm+swish (statistics from the producing GEMM's epilogue) writing the bf16
+GEMM operand, fp32 residual stream.  Pixel rows at the 256 / 512 px levels are wider than a 128-row tile: the igemm TMA producer walks them as
 W/128 tiles per row.  The one attention layer has a single 512-wide head: scores are materialised per sample with two
 GEMMs around a row-softmax kernel (Q K^T -> softmax -> P V, V^T produced directly by a GEMM with swapped operands);
 at 0.4 % of a PPO sample's FLOPs a flash kernel for d = 512 is not worth its shared memory.  Images are decoded
@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .unet import Arena
+from .unet import Arena, _st
 
 BF16, F32 = torch.bfloat16, torch.float32
 GN_EPS = 1e-6          # 3P vae_flax.py: nn.GroupNorm(num_groups=32, epsilon=1e-6)
@@ -163,16 +163,16 @@ class VAEDecoder:
         a = A.alloc((m, cin), BF16)
         raw = A.alloc((m, cin), BF16) if has_sc else None
         ops.groupnorm_fwd(x, self.p(name + "/norm1/scale"), self.p(name + "/norm1/bias"), gws, b, hw, cin, silu=True,
-                          y_bf16=a, raw_bf16=raw, eps=GN_EPS)
-        hbuf = A.alloc((m, cout), F32)
+                          y_bf16=a, raw_bf16=raw, eps=GN_EPS, stats0=_st(x))
+        hbuf = A.alloc_with_gn_stats((m, cout), hw)   # the GEMM epilogue leaves the statistics norm2 needs
         ops.igemm(a0=a, wt=self.w[name + "/conv1"], n=cout, c0=cin, conv=(b, h, w), taps=9,
-                  bias=self.p(name + "/conv1/bias"), out_f32=hbuf)
+                  bias=self.p(name + "/conv1/bias"), out_f32=hbuf, gn_stats=_st(hbuf))
         A.release(a)
         A.release(gws)
         gws2 = A.alloc((ops.groupnorm_workspace_floats(b, hw, cout),), F32)
         a2 = A.alloc((m, cout), BF16)
         ops.groupnorm_fwd(hbuf, self.p(name + "/norm2/scale"), self.p(name + "/norm2/bias"), gws2, b, hw, cout,
-                          silu=True, y_bf16=a2, eps=GN_EPS)
+                          silu=True, y_bf16=a2, eps=GN_EPS, stats0=_st(hbuf))
         A.release(hbuf)
         if has_sc:
             sc = A.alloc((m, cout), F32)
@@ -181,9 +181,9 @@ class VAEDecoder:
             A.release(raw)
         else:
             sc = x
-        out = A.alloc((m, cout), F32)
+        out = A.alloc_with_gn_stats((m, cout), hw)
         ops.igemm(a0=a2, wt=self.w[name + "/conv2"], n=cout, c0=cout, conv=(b, h, w), taps=9,
-                  bias=self.p(name + "/conv2/bias"), residual=sc, out_f32=out)
+                  bias=self.p(name + "/conv2/bias"), residual=sc, out_f32=out, gn_stats=_st(out))
         A.release(a2)
         A.release(gws2)
         if has_sc:
@@ -197,7 +197,7 @@ class VAEDecoder:
         gws = A.alloc((ops.groupnorm_workspace_floats(b, hw, c),), F32)
         g = A.alloc((m, c), BF16)
         ops.groupnorm_fwd(x, self.p(name + "/group_norm/scale"), self.p(name + "/group_norm/bias"), gws, b, hw, c,
-                          silu=False, y_bf16=g, eps=GN_EPS)
+                          silu=False, y_bf16=g, eps=GN_EPS, stats0=_st(x))
         q = A.alloc((m, c), BF16)
         k = A.alloc((m, c), BF16)
         ops.igemm(a0=g, wt=self.w[name + "/query"], n=c, c0=c, m=m, bias=self.p(name + "/query/bias"), out_bf16=q)
@@ -214,9 +214,9 @@ class VAEDecoder:
             ops.igemm(a0=q[rows], wt=k[rows], n=hw, c0=c, m=hw, out_f32=scores)
             ops.softmax_rows(scores, probs, 1.0 / float(np.sqrt(c)))
             ops.igemm(a0=probs, wt=vt, n=c, c0=hw, m=hw, bias=self.p(name + "/value/bias"), out_bf16=ao[rows])
-        out = A.alloc((m, c), F32)
+        out = A.alloc_with_gn_stats((m, c), hw)
         ops.igemm(a0=ao, wt=self.w[name + "/proj_attn"], n=c, c0=c, m=m, bias=self.p(name + "/proj_attn/bias"),
-                  residual=x, out_f32=out)
+                  residual=x, out_f32=out, gn_stats=_st(out))
         for t in (gws, g, q, k, ao, vt, scores, probs):
             A.release(t)
         return out
@@ -230,8 +230,8 @@ class VAEDecoder:
         ops.vae_post_quant(latents, self.p("post_quant_conv/kernel"), self.p("post_quant_conv/bias"), z,
                            scaling=VAE_SCALING)
         c = rev[0]
-        x = A.alloc((b * h * w, c), F32)
-        ops.conv_in(z, self.p("decoder/conv_in/kernel"), self.p("decoder/conv_in/bias"), x, b, lc, h, w, c)
+        x = A.alloc_with_gn_stats((b * h * w, c), h * w)
+        ops.conv_in(z, self.p("decoder/conv_in/kernel"), self.p("decoder/conv_in/bias"), x, b, lc, h, w, c, gn_stats=_st(x))
         A.release(z)
         for name, kind in (("decoder/mid_block/resnets_0", "r"), ("decoder/mid_block/attentions_0", "a"),
                            ("decoder/mid_block/resnets_1", "r")):
@@ -250,16 +250,16 @@ class VAEDecoder:
                 ops.upsample2x_bf16(x, up, b, h, w, co)      # jax.image.resize(nearest): out[i] = in[i // 2]
                 A.release(x)
                 h, w = 2 * h, 2 * w
-                x = A.alloc((b * h * w, co), F32)
+                x = A.alloc_with_gn_stats((b * h * w, co), h * w)
                 ops.igemm(a0=up, wt=self.w[name + "/conv"], n=co, c0=co, conv=(b, h, w), taps=9,
-                          bias=self.p(name + "/conv/bias"), out_f32=x)
+                          bias=self.p(name + "/conv/bias"), out_f32=x, gn_stats=_st(x))
                 A.release(up)
             prev = co
         c0 = rev[-1]
         gws = A.alloc((ops.groupnorm_workspace_floats(b, h * w, c0),), F32)
         yf = A.alloc((b * h * w, c0), F32)
         ops.groupnorm_fwd(x, self.p("decoder/conv_norm_out/scale"), self.p("decoder/conv_norm_out/bias"), gws, b, h * w,
-                          c0, silu=True, y_f32=yf, eps=GN_EPS)
+                          c0, silu=True, y_f32=yf, eps=GN_EPS, stats0=_st(x))
         ops.vae_conv_out(yf, self.p("decoder/conv_out/kernel"), self.p("decoder/conv_out/bias"), b, h, w, c0,
                          raw_nchw=raw_out, img_nhwc=img_out)
         for t in (x, gws, yf):
