@@ -4,8 +4,9 @@ path's drivers call: ``load_unet`` (:320-371), ``load_finetuned_stable_diffusion
 ``pipeline/policy_gradient.py:457-464`` (3P ``flax.training.checkpoints.save_checkpoint_multiprocess`` ->
 ``checkpoints/checkpoint_<step>``, a msgpack of the nested parameter dict).
 
-No network and no checkpoint files exist in this build: ``load_unet`` creates RANDOM-INIT weights of the architecture
-the ``pretrained_model`` label names (the benchmark's stated synthetic setting), or restores a U-Net this package saved.
+There is no network in this build: ``load_unet`` ingests a LOCAL diffusers checkpoint directory when ``pretrained_model``
+resolves to one (``utils/pretrained.py``: Flax msgpack or PyTorch safetensors), creates RANDOM-INIT weights only on the
+explicit ``random:<architecture>`` opt-in (the benchmark's stated synthetic setting), and restores U-Nets this package saved.
 On-disk formats follow the reference: ``unet_<epoch>.pkl`` is a pickle of the nested ``{module: {...: ndarray}}`` dict
 (Flax names, ``kernel`` = ``[in, out]`` / HWIO), ``checkpoint_<step>`` is flax==0.6.9's ``msgpack_serialize`` layout
 (ndarray = ExtType 1 holding ``packb((shape, dtype.name, bytes))``) -- both loadable by the reference's own readers.
@@ -179,36 +180,70 @@ def load_flax_model(loadpath, epoch="latest"):
 
 
 # --------------------------------------------------------------------- loaders ----
+RANDOM_PREFIX = "random:"
+ALLOW_RANDOM_ENV = "DDPO_ALLOW_RANDOM_INIT"
+
+
 def load_unet(loadpath, epoch="latest", pretrained_model="stabilityai/stable-diffusion-2-base", dtype="float32",
               cache="cache", device="cuda", seed=0, with_vae=True, text_encoder="clip"):
     """Reference :320-371: returns ``(pipeline, params)`` with ``params`` = ``{"unet", "vae", "text_encoder",
-    "scheduler"}``.  Weights are random-init (see module docstring) unless ``loadpath`` names a saved ``unet_*.pkl``."""
+    "scheduler"}``.
+
+    Weights: ``pretrained_model`` is resolved to a LOCAL diffusers checkpoint directory (a path, ``<cache>/<id>`` or the
+    hub cache layout under ``cache`` -- there is no network to download from); its U-Net / VAE decoder / text encoder /
+    scheduler config / tokenizer are ingested by ``utils/pretrained.py`` (Flax msgpack or PyTorch safetensors / .bin).
+    Random initialisation is an explicit opt-in: ``pretrained_model="random:<architecture>"`` (e.g.
+    ``random:stabilityai/stable-diffusion-2-base``), the test-sized ``"tiny"`` / ``"small"``, or
+    ``$DDPO_ALLOW_RANDOM_INIT=1``; anything else without a checkpoint on disk raises.  ``loadpath`` then overlays a
+    saved ``unet_<epoch>.pkl`` as in the reference."""
     from ..diffusers_patch import DDIMScheduler, StableDiffusionPipeline
     from ..unet import UNet
+    from . import pretrained
     from .text_stub import StubTextEncoder, StubTokenizer
-    cfg = unet_config_for(pretrained_model)
-    print(f"[ utils/serialization ] Building {pretrained_model} ({unet_spec.num_params(cfg) / 1e6:.1f}M-parameter "
-          f"U-Net, random-init: no checkpoints offline) | dtype: {dtype}")
-    flat = unet_spec.init_flat_params(cfg, seed)
+    ckpt_dir = pretrained.resolve_dir(pretrained_model, cache)
+    sched_kw = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                    set_alpha_to_one=False, steps_offset=1, prediction_type="epsilon")
+    vae_flat = vae_cfg = text_flat = text_cfg = tokenizer = None
+    if ckpt_dir is not None:
+        print(f"[ utils/serialization ] Loading {pretrained_model} from {ckpt_dir} | dtype: {dtype}")
+        cfg, flat = pretrained.load_unet_weights(ckpt_dir)
+        sched_kw.update(pretrained.load_scheduler_config(ckpt_dir))
+        if with_vae and os.path.isdir(os.path.join(ckpt_dir, "vae")):
+            vae_cfg, vae_flat = pretrained.load_vae_decoder_weights(ckpt_dir)
+        if text_encoder == "clip" and os.path.isdir(os.path.join(ckpt_dir, "text_encoder")):
+            text_cfg, text_flat = pretrained.load_text_encoder_weights(ckpt_dir)
+        tokenizer = pretrained.load_tokenizer(ckpt_dir)
+        arch = pretrained_model
+    else:
+        explicit = str(pretrained_model).startswith(RANDOM_PREFIX)
+        arch = str(pretrained_model)[len(RANDOM_PREFIX):] if explicit else pretrained_model
+        if not (explicit or arch in ("tiny", "small") or os.environ.get(ALLOW_RANDOM_ENV) == "1"):
+            raise FileNotFoundError(
+                f"[ utils/serialization ] no local checkpoint for {pretrained_model!r} (looked for <dir>/unet/config.json at "
+                f"the path itself and under {cache!r}); there is no network to download it.  For random-init weights of "
+                f"that architecture say pretrained_model='{RANDOM_PREFIX}{pretrained_model}' or set {ALLOW_RANDOM_ENV}=1.")
+        cfg = unet_config_for(arch)
+        print(f"[ utils/serialization ] Building {arch} ({unet_spec.num_params(cfg) / 1e6:.1f}M-parameter U-Net) with "
+              f"RANDOM-INIT weights | dtype: {dtype}")
+        flat = unet_spec.init_flat_params(cfg, seed)
     if loadpath:
         tree = load_flax_model(os.path.join(filesystem.localize(loadpath), "unet"), epoch=epoch)
         flat = flat_from_tree(tree, cfg)
     unet = UNet(cfg, flat, device)
-    scheduler = DDIMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012,
-                              beta_schedule="scaled_linear", set_alpha_to_one=False, steps_offset=1,
-                              prediction_type="epsilon", device=device)
+    scheduler = DDIMScheduler(device=device, **sched_kw)
     vae = None
     if with_vae:
         from ..vae import VAEDecoder, vae_config_for
-        vae = VAEDecoder(vae_config_for(pretrained_model), device=device, seed=seed + 1)
+        vae = (VAEDecoder(vae_cfg, vae_flat, device=device) if vae_flat is not None
+               else VAEDecoder(vae_config_for(arch), device=device, seed=seed + 1))
     if text_encoder == "clip":
-        # the CLIP text tower on the GPU (random-init, like every weight here); ids come from the stub tokenizer
-        # (no vocabulary files offline), folded into the tower's vocabulary range
+        # the CLIP text tower on the GPU; without tokenizer files the stub tokenizer's ids are folded into its vocabulary
         from ..text_encoder import CLIPTextEncoder, text_config_for
-        tenc = CLIPTextEncoder(text_config_for(pretrained_model), device=device, seed=seed + 2)
+        tenc = (CLIPTextEncoder(text_cfg, text_flat, device=device) if text_flat is not None
+                else CLIPTextEncoder(text_config_for(arch), device=device, seed=seed + 2))
     else:
         tenc = StubTextEncoder(cfg.cross_attention_dim)
-    pipeline = StableDiffusionPipeline(unet, scheduler, tokenizer=StubTokenizer(), text_encoder=tenc, vae=vae,
+    pipeline = StableDiffusionPipeline(unet, scheduler, tokenizer=tokenizer or StubTokenizer(), text_encoder=tenc, vae=vae,
                                        vae_scale_factor=8)
     params = {"unet": unet.params, "vae": None if vae is None else vae.params,
               "text_encoder": getattr(tenc, "params", {}), "scheduler": scheduler.create_state()}

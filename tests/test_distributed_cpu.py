@@ -114,7 +114,16 @@ def _driver_worker(rank, port, out_dir):
         adv = PG.compute_advantages(rewards, prompts, tracker)
         mine = np.asarray(adv).reshape(WORLD, -1)[rank]                               # reference :349
         glob = PG.compute_advantages(rewards, prompts, None).reshape(WORLD, -1)[rank]
-        np.savez(os.path.join(out_dir, f"drv{rank}.npz"), rewards=rewards, prompts=prompts, mine=mine, glob=glob)
+        # the driver keys the per-prompt statistics by tokenizer-decoded prompt ids gathered from every rank
+        # (reference :329-335): a rank must decode prompts it never tokenized itself to the very same strings
+        from ddpo_b200.utils.text_stub import StubTokenizer
+        tok = StubTokenizer()
+        own = [f"a {w} riding a bike" for w in (("zebra", "llama", "zebra", "yak") if rank == 0 else ("otter", "zebra", "emu", "emu"))]
+        ids = PG.allgather_array(tok(own, padding="max_length", return_tensors="np").input_ids)
+        decoded = np.array(tok.batch_decode(ids, skip_special_tokens=True))
+        adv_tok = PerPromptStatTracker(32, 2).update(decoded, rewards)
+        np.savez(os.path.join(out_dir, f"drv{rank}.npz"), rewards=rewards, prompts=prompts, mine=mine, glob=glob,
+                 decoded=decoded, adv_tok=np.asarray(adv_tok))
     finally:
         dist.destroy_process_group()
 
@@ -136,6 +145,8 @@ def test_two_rank_reward_allgather_and_advantage_slices(tmp_path):
         assert list(r[i]["prompts"]) == list(want_prompts)
         np.testing.assert_allclose(r[i]["mine"], np.asarray(full).reshape(WORLD, -1)[i])
         np.testing.assert_allclose(r[i]["glob"], z.reshape(WORLD, -1)[i])
+        assert list(r[i]["decoded"]) == [f"a {w} riding a bike" for w in ("zebra", "llama", "zebra", "yak", "otter", "zebra", "emu", "emu")]
+    np.testing.assert_array_equal(r[0]["adv_tok"], r[1]["adv_tok"])     # same per-prompt grouping on every rank
 
 
 # ------------------------------------------------------------------ the whole epoch driver on two ranks ----
