@@ -86,6 +86,15 @@ __device__ __forceinline__ float rcpf_approx(float x) {
 // ~10 more instructions per element in the GroupNorm apply kernels, which are issue- as much as bandwidth-limited.
 __device__ __forceinline__ float sigmoid_f(float x) { return rcpf_approx(1.0f + exp2f_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+// SiLU on ONE MUFU op: x sigmoid(x) = z + z tanh(z), z = x / 2 (tanh.approx: max relative error 2^-11, an order below
+// bf16 resolution).  Used where the result is rounded to bf16 anyway (the GroupNorm -> GEMM-operand path, which is
+// MUFU-/issue-bound with the two-MUFU form); fp32 consumers keep silu_f.
+__device__ __forceinline__ float silu_bf16_f(float x) {
+  const float z = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(z));
+  return fmaf(z, t, z);
+}
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float k = 0.7978845608028654f;  // sqrt(2/pi)
   float u = k * (x + 0.044715f * x * x * x);

@@ -125,13 +125,15 @@ __global__ void upsample2x_bwd_kernel(const float* __restrict__ dy, float* __res
 // ------------------------------------------------------------------ conv_in ----
 // x fp32 NCHW [B,Cin,H,W] (Cin <= 8), w fp32 HWIO [3,3,Cin,Cout], y fp32 NHWC [B,H,W,Cout]
 constexpr int CI_PIX = 32;
-// gn_stats (optional): a CTA's 32 pixels are exactly one statistics slab; the outputs are staged in shared memory and
-// thread c adds the 32 rows of channel c in ascending order -> [slab, Cout, 2] as the igemm epilogues write it.
+// A thread owns ONE channel quad and walks the CTA's pixels p = grp, grp + R, ... (R = 256 / (Cout / 4) thread groups), so the
+// per-channel sums the consuming GroupNorm needs stay in registers: gn_stats (optional) = [slab, Cout, 2] (sum, sum of
+// squares) of this CTA's 32 pixels -- exactly one statistics slab, as the igemm epilogues write it -- combined over the
+// R groups in ascending order.
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y, int B, int Cin,
                                                       int H, int W, int Cout, float* __restrict__ gn_stats) {
   __shared__ float patch[CI_PIX][9 * 8];
-  extern __shared__ float ci_tile[];  // [CI_PIX][Cout] when gn_stats
+  __shared__ float part[2][1024];  // [sum | sumsq][grp * Cout + c], R * Cout <= 1024
   const int64_t pix0 = static_cast<int64_t>(blockIdx.x) * CI_PIX;
   const int HW = H * W;
   for (int i = threadIdx.x; i < CI_PIX * 9 * Cin; i += 256) {
@@ -149,33 +151,36 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   __syncthreads();
   const int K = 9 * Cin;
   const int C4 = Cout >> 2;
-  for (int i = threadIdx.x; i < CI_PIX * C4; i += 256) {
-    const int p = i / C4, c = (i % C4) * 4;
-    const int64_t pix = pix0 + p;
-    if (pix >= static_cast<int64_t>(B) * HW) {
-      if (gn_stats != nullptr) *reinterpret_cast<float4*>(ci_tile + p * Cout + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      continue;
+  const int R = 256 / C4 < CI_PIX ? 256 / C4 : CI_PIX;   // thread groups (C4 <= 256 checked on the host)
+  const int grp = threadIdx.x / C4, c = (threadIdx.x % C4) * 4;
+  if (grp < R) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = grp; p < CI_PIX; p += R) {
+      const int64_t pix = pix0 + p;
+      if (pix >= static_cast<int64_t>(B) * HW) break;
+      float4 acc = b4;
+      for (int k = 0; k < K; ++k) {
+        const float a = patch[p][k];
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(k) * Cout + c));
+        acc.x = fmaf(a, wv.x, acc.x), acc.y = fmaf(a, wv.y, acc.y), acc.z = fmaf(a, wv.z, acc.z),
+        acc.w = fmaf(a, wv.w, acc.w);
+      }
+      *reinterpret_cast<float4*>(y + pix * Cout + c) = acc;
+      s.x += acc.x, s.y += acc.y, s.z += acc.z, s.w += acc.w;
+      ss.x += acc.x * acc.x, ss.y += acc.y * acc.y, ss.z += acc.z * acc.z, ss.w += acc.w * acc.w;
     }
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias + c));
-    for (int k = 0; k < K; ++k) {
-      const float a = patch[p][k];
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(k) * Cout + c));
-      acc.x = fmaf(a, wv.x, acc.x), acc.y = fmaf(a, wv.y, acc.y), acc.z = fmaf(a, wv.z, acc.z),
-      acc.w = fmaf(a, wv.w, acc.w);
+    if (gn_stats != nullptr) {
+      *reinterpret_cast<float4*>(&part[0][grp * Cout + c]) = s;
+      *reinterpret_cast<float4*>(&part[1][grp * Cout + c]) = ss;
     }
-    *reinterpret_cast<float4*>(y + pix * Cout + c) = acc;
-    if (gn_stats != nullptr) *reinterpret_cast<float4*>(ci_tile + p * Cout + c) = acc;
   }
   if (gn_stats != nullptr) {
     __syncthreads();
-    for (int c = threadIdx.x; c < Cout; c += 256) {
+    for (int ch = threadIdx.x; ch < Cout; ch += 256) {
       float s = 0.f, ss = 0.f;
-#pragma unroll 8
-      for (int p = 0; p < CI_PIX; ++p) {
-        const float v = ci_tile[p * Cout + c];
-        s += v, ss += v * v;
-      }
-      *reinterpret_cast<float2*>(gn_stats + (static_cast<size_t>(blockIdx.x) * Cout + c) * 2) = make_float2(s, ss);
+      for (int g = 0; g < R; ++g) s += part[0][g * Cout + ch], ss += part[1][g * Cout + ch];
+      *reinterpret_cast<float2*>(gn_stats + (static_cast<size_t>(blockIdx.x) * Cout + ch) * 2) = make_float2(s, ss);
     }
   }
 }
@@ -416,9 +421,8 @@ extern "C" int ddpo_conv_in(const float* x_nchw, const float* w_hwio, const floa
                             int cin, int h, int w, int cout, float* gn_stats, void* stream) {
   DDPO_REQUIRE(x_nchw && w_hwio && bias && y_nhwc && cin > 0 && cin <= 8 && cout % 4 == 0, "conv_in: bad arguments");
   const int64_t pix = static_cast<int64_t>(batch) * h * w;
-  const size_t smem = gn_stats != nullptr ? static_cast<size_t>(CI_PIX) * cout * sizeof(float) : 0;
-  DDPO_REQUIRE(smem <= 44 * 1024, "conv_in: cout=%d too wide for the statistics tile", cout);
-  conv_in_kernel<<<static_cast<int>((pix + CI_PIX - 1) / CI_PIX), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  DDPO_REQUIRE(cout <= 1024, "conv_in: cout=%d (at most 1024 output channels)", cout);
+  conv_in_kernel<<<static_cast<int>((pix + CI_PIX - 1) / CI_PIX), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x_nchw, w_hwio, bias, y_nhwc, batch, cin, h, w, cout, gn_stats);
   DDPO_LAUNCH_OK();
   return DDPO_OK;

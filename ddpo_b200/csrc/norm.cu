@@ -115,29 +115,35 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const GnArgs a) {
   }
 }
 
-// (mean, rstd) of every (sample, group) from the producing GEMMs' slab statistics.  One warp per (sample, group): lane l
-// adds items l, l + 32, ... of the (slab, channel-of-group) list in ascending order, then a fixed shuffle tree.
-__global__ void __launch_bounds__(256) gn_finalize_slabs_kernel(const GnArgs a, int batch) {
+// (mean, rstd) of every (sample, group) from the producing GEMMs' slab statistics.  One 128-thread CTA per (sample, group):
+// thread t adds items t, t + 128, ... of the (slab, channel-of-group) list in ascending order (all loads independent and
+// in flight together: a warp-per-group loop of 40 dependent-latency iterations took longer than the apply pass), then a
+// fixed shuffle tree and the four warp sums in warp order.
+constexpr int GNF_THREADS = 128;
+__global__ void __launch_bounds__(GNF_THREADS) gn_finalize_slabs_kernel(const GnArgs a, int batch) {
   const int C = a.c0 + a.c1, cpg = C / GN_GROUPS;
-  const int wid = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (wid >= batch * GN_GROUPS) return;
-  const int b = wid / GN_GROUPS, g = wid % GN_GROUPS;
+  const int b = blockIdx.x / GN_GROUPS, g = blockIdx.x % GN_GROUPS;
   const int nslab = a.hw >> 5;
   const int items = nslab * cpg;
   float s = 0.f, ss = 0.f;
-  for (int i = lane; i < items; i += 32) {
+  for (int i = threadIdx.x; i < items; i += GNF_THREADS) {
     const int slab = i / cpg, c = g * cpg + (i - slab * cpg);
     const size_t row = static_cast<size_t>(b) * nslab + slab;
     const float2 v = c < a.c0 ? *reinterpret_cast<const float2*>(a.stats0 + (row * a.c0 + c) * 2)
                               : *reinterpret_cast<const float2*>(a.stats1 + (row * a.c1 + (c - a.c0)) * 2);
     s += v.x, ss += v.y;
   }
+  __shared__ float red[2][GNF_THREADS / 32];
   s = warp_sum(s), ss = warp_sum(ss);
-  if (lane == 0) {
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s, red[1][threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+    ss = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
     const float inv_n = 1.0f / (static_cast<float>(a.hw) * cpg);
     const float mean = s * inv_n;
     const float var = fmaxf(0.f, ss * inv_n - mean * mean);
-    a.mr[wid * 2] = mean, a.mr[wid * 2 + 1] = rsqrtf(var + a.eps);
+    a.mr[blockIdx.x * 2] = mean, a.mr[blockIdx.x * 2 + 1] = rsqrtf(var + a.eps);
   }
 }
 
@@ -155,6 +161,21 @@ __global__ void gn_finalize_chunks_kernel(const GnArgs a, int batch) {
   const float mean = s * inv_n;
   const float var = fmaxf(0.f, ss * inv_n - mean * mean);
   a.mr[i * 2] = mean, a.mr[i * 2 + 1] = rsqrtf(var + a.eps);
+}
+
+// Per-element arithmetic shared by the two apply kernels (bit-identical outputs whichever runs): the affine part as ONE
+// fused multiply-add y = x * A + B with A = rstd * scale, B = bias - mean * A (per thread and channel, computed once), SiLU
+// on one MUFU op when the only consumer is the bf16 GEMM operand.  The apply pass was issue- / MUFU-bound with the
+// three-instruction affine and the two-MUFU sigmoid (measured: 58 us for 126 MB, profiles/r2_norm.md).
+__device__ __forceinline__ void gn_coef(float mean, float rstd, float scale, float bias, float& A, float& B) {
+  A = rstd * scale;
+  B = fmaf(-mean, A, bias);
+}
+template <bool FAST>
+__device__ __forceinline__ float gn_act(float x, float A, float B, int silu) {
+  const float y = fmaf(x, A, B);
+  if (!silu) return y;
+  return FAST ? silu_bf16_f(y) : silu_f(y);
 }
 
 // ------------------------------------------------------------ streamed apply (forward) ----
@@ -207,12 +228,13 @@ __global__ void __launch_bounds__(544, 1) gn_apply_tma_kernel(const GnArgs a, co
   const int cq = ct % C4, pr = ct / C4;
   const bool active = ct < R * C4;
   const int c = coff + cq * 4;
-  float scv[4], biv[4], mu[4], rs[4];
+  float scv[4], biv[4], cA[4], cB[4];
   {
     const float4 sc = *reinterpret_cast<const float4*>(a.scale + c), bi = *reinterpret_cast<const float4*>(a.bias + c);
     scv[0] = sc.x, scv[1] = sc.y, scv[2] = sc.z, scv[3] = sc.w;
     biv[0] = bi.x, biv[1] = bi.y, biv[2] = bi.z, biv[3] = bi.w;
   }
+  const bool fast = a.y_f32 == nullptr;   // only the bf16 operand is written: one-MUFU SiLU
   int cur_b = -1;
   for (long it = it0; it < it1; ++it) {
     const int k = static_cast<int>(it - it0), st = k % GNA_STAGES;
@@ -223,7 +245,7 @@ __global__ void __launch_bounds__(544, 1) gn_apply_tma_kernel(const GnArgs a, co
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 m = *reinterpret_cast<const float2*>(a.mr + (b * GN_GROUPS + (c + j) / cpg) * 2);
-        mu[j] = m.x, rs[j] = m.y;
+        gn_coef(m.x, m.y, scv[j], biv[j], cA[j], cB[j]);
       }
     }
     mbar_wait(&full[st], (k / GNA_STAGES) & 1);
@@ -233,10 +255,12 @@ __global__ void __launch_bounds__(544, 1) gn_apply_tma_kernel(const GnArgs a, co
         const float4 v = sm4[pp * C4 + cq];
         const float xv[4] = {v.x, v.y, v.z, v.w};
         float y[4];
+        if (fast) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          y[j] = (xv[j] - mu[j]) * rs[j] * scv[j] + biv[j];   // same operation order as gn_apply_kernel
-          if (a.silu) y[j] = silu_f(y[j]);
+          for (int j = 0; j < 4; ++j) y[j] = gn_act<true>(xv[j], cA[j], cB[j], a.silu);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) y[j] = gn_act<false>(xv[j], cA[j], cB[j], a.silu);
         }
         const size_t o = (pix0 + pp) * C + c;
         if (a.y_bf16) *reinterpret_cast<uint2*>(a.y_bf16 + o) = make_uint2(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]));
@@ -271,20 +295,22 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
     const float4 sc = *reinterpret_cast<const float4*>(a.scale + c);
     const float4 bi = *reinterpret_cast<const float4*>(a.bias + c);
     const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, biv[4] = {bi.x, bi.y, bi.z, bi.w};
-    float mu[4], rs[4];
+    float cA[4], cB[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int g = (c + j) / cpg;
-      mu[j] = s_mean[g], rs[j] = s_rstd[g];
+      gn_coef(s_mean[g], s_rstd[g], scv[j], biv[j], cA[j], cB[j]);
     }
+    const bool fast = a.y_f32 == nullptr;
     auto emit = [&](size_t pix, const float4& v) {
       const float xv[4] = {v.x, v.y, v.z, v.w};
       float y[4];
+      if (fast) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // same operation order as before the vectorisation: ((x - mean) * rstd) * scale + bias
-        y[j] = (xv[j] - mu[j]) * rs[j] * scv[j] + biv[j];
-        if (a.silu) y[j] = silu_f(y[j]);
+        for (int j = 0; j < 4; ++j) y[j] = gn_act<true>(xv[j], cA[j], cB[j], a.silu);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = gn_act<false>(xv[j], cA[j], cB[j], a.silu);
       }
       if (a.y_bf16) *reinterpret_cast<uint2*>(a.y_bf16 + pix * C + c) = make_uint2(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]));
       if (a.y_f32) *reinterpret_cast<float4*>(a.y_f32 + pix * C + c) = make_float4(y[0], y[1], y[2], y[3]);
@@ -736,7 +762,7 @@ extern "C" int ddpo_groupnorm_fwd(const ddpo_groupnorm_args* a, void* stream_) {
     const bool have_slabs = a->stats0 != nullptr && (a->c1 == 0 || a->stats1 != nullptr) && a->hw % 32 == 0;
     const int n = a->batch * GN_GROUPS;
     if (have_slabs) {
-      gn_finalize_slabs_kernel<<<(n + 7) / 8, 256, 0, stream>>>(g, a->batch);
+      gn_finalize_slabs_kernel<<<n, GNF_THREADS, 0, stream>>>(g, a->batch);
     } else {
       gn_stats_kernel<<<grid, GN_THREADS, smem, stream>>>(g);
       DDPO_LAUNCH_OK();
@@ -784,11 +810,18 @@ extern "C" int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const float* dy,
   }
   DDPO_REQUIRE(smem <= 96 * 1024, "groupnorm_bwd: too many channels (%d)", C);
   DDPO_REQUIRE(b.ldd0 % 4 == 0 && b.ldd1 % 4 == 0, "groupnorm_bwd: gradient pitches must be multiples of 4");
-  // sample groups of <= ~48 MB of (x, dy): pass 2 of a group re-reads what pass 1 just streamed through L2
-  const double bytes_per_sample = static_cast<double>(a->hw) * C * 8.0;
-  int group = static_cast<int>(48.0 * 1024 * 1024 / bytes_per_sample);
-  if (group < 1) group = 1;
-  if (group > a->batch) group = a->batch;
+  // optional ($DDPO_GN_BWD_GROUP_MB > 0): the two passes run over groups of samples whose (x, dy) fit that many MB, so that
+  // pass 2 re-reads from L2 what pass 1 just streamed; a group must still fill the GPU (>= 256 CTAs)
+  const char* gmb = getenv("DDPO_GN_BWD_GROUP_MB");
+  const double group_mb = gmb != nullptr ? atof(gmb) : 0.0;
+  int group = a->batch;
+  if (group_mb > 0.0) {
+    const double bytes_per_sample = static_cast<double>(a->hw) * C * 8.0;
+    group = static_cast<int>(group_mb * 1024 * 1024 / bytes_per_sample);
+    const int min_group = (256 + b.f.chunks - 1) / b.f.chunks;
+    if (group < min_group) group = min_group;
+    if (group > a->batch) group = a->batch;
+  }
   for (int b0 = 0; b0 < a->batch; b0 += group) {
     const int nb = a->batch - b0 < group ? a->batch - b0 : group;
     b.b0 = b0;

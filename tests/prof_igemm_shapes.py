@@ -1,0 +1,58 @@
+"""ncu / timing target (not a test): the CTA-pair implicit-GEMM kernel on the four heaviest shapes of a sampling step
+(profiles/README.md) plus the 8x8 level that runs 20-40 tiles on 74 CTA pairs.
+    python tests/prof_igemm_shapes.py
+    ncu --set full --clock-control none --import-source on -k regex:igemm -c 6 -o gpurun_out/r2_igemm2_full \
+        python tests/prof_igemm_shapes.py --once
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ddpo_b200 import ops  # noqa: E402
+
+dev = "cuda"
+once = "--once" in sys.argv
+g = torch.Generator(device="cpu").manual_seed(0)
+
+
+def conv(b, h, c0, c1, n, stats=True):
+    x0 = torch.randn(b, h, h, c0, generator=g).to(dev).to(torch.bfloat16)
+    x1 = torch.randn(b, h, h, c1, generator=g).to(dev).to(torch.bfloat16) if c1 else None
+    w = (torch.randn(n, 9 * (c0 + c1), generator=g) / 50).to(dev).to(torch.bfloat16)
+    bias = torch.randn(n, generator=g).to(dev)
+    m = b * h * h
+    res = torch.randn(m, n, generator=g).to(dev)
+    out = torch.empty(m, n, device=dev)
+    st = torch.empty(ops.gn_stats_shape(m, n), device=dev) if stats else None
+    fn = lambda: ops.igemm(a0=x0, a1=x1, wt=w, n=n, c0=c0, c1=c1, conv=(b, h, h), taps=9, bias=bias, residual=res, out_f32=out,
+                           gn_stats=st)
+    for _ in range(0 if once else 3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 1 if once else 10
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / reps * 1e-3
+    fl = 2.0 * m * n * 9 * (c0 + c1)
+    print(f"conv3x3 B{b} {h}x{h} C{c0}+{c1} -> {n} (M{m} N{n} K{9 * (c0 + c1)}) stats={stats}: {t * 1e6:8.1f} us  "
+          f"{fl / t / 1e12:7.1f} TFLOP/s", flush=True)
+
+
+conv(16, 64, 320, 0, 320)        # M65536 N320 K2880   x7 per application
+conv(16, 32, 640, 0, 640)        # M16384 N640 K5760   x6
+conv(16, 16, 1280, 0, 1280)      # M4096  N1280 K11520 x7
+conv(16, 64, 320, 320, 320)      # M65536 N320 K5760 (skip concat)
+if not once:
+    conv(16, 64, 320, 0, 320, stats=False)
+    conv(16, 16, 1280, 0, 1280, stats=False)
+    conv(16, 8, 1280, 0, 1280)       # M1024: 8x8 level
+    conv(16, 8, 1280, 1280, 1280)    # K23040
+    conv(40, 64, 320, 0, 320)
+    conv(40, 8, 1280, 0, 1280)
+print("done")

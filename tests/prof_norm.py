@@ -53,10 +53,22 @@ def gn_fwd(b, hw, c0, c1, with_stats=True, tag=""):
     def run(i):
         x0, x1, s0, s1 = sets[i]
         ops.groupnorm_fwd(x0, sc, bi, ws, b, hw, c0, x1=x1, c1=c1, silu=True, y_bf16=y, stats0=s0, stats1=s1)
+
+    def run_stats_only(i):
+        x0, x1, s0, s1 = sets[i]
+        ops.groupnorm_fwd(x0, sc, bi, ws, b, hw, c0, x1=x1, c1=c1, silu=True, stats0=s0, stats1=s1)
+
+    def run_apply_only(i):
+        x0, x1, s0, s1 = sets[i]
+        ops.groupnorm_fwd(x0, sc, bi, ws, b, hw, c0, x1=x1, c1=c1, silu=True, y_bf16=y, skip_stats=True)
     t = timeit(run, 1 if once else 20)
     alg = b * hw * c * 6
-    print(f"gn_fwd{tag} B{b} hw{hw} C{c0}+{c1} stats={with_stats}: {t * 1e6:8.1f} us  {alg / t / 1e9:7.0f} GB/s algorithmic "
-          f"({alg / t / 1e9 / PEAK:.2f} of {PEAK:.0f})")
+    line = (f"gn_fwd{tag} B{b} hw{hw} C{c0}+{c1} stats={with_stats}: {t * 1e6:8.1f} us  {alg / t / 1e9:7.0f} GB/s algorithmic "
+            f"({alg / t / 1e9 / PEAK:.2f} of {PEAK:.0f})")
+    if not once:
+        ts, ta = timeit(run_stats_only, 20), timeit(run_apply_only, 20)
+        line += f" | statistics alone {ts * 1e6:6.1f} us, apply alone {ta * 1e6:6.1f} us ({alg / ta / 1e9:5.0f} GB/s)"
+    print(line, flush=True)
 
 
 def gn_bwd(b, hw, c):
@@ -104,6 +116,11 @@ def ln_bwd(m, c):
 
 gn_fwd(16, 4096, 320, 0)            # the dominant sampling shape (profiles/r1_gn.md)
 gn_fwd(16, 4096, 320, 0, with_stats=False, tag="[two-pass]")
+if not once:
+    os.environ["DDPO_GN_NO_STREAM"] = "1"
+    gn_fwd(16, 4096, 320, 0, tag="[plain apply]")
+    gn_fwd(40, 4096, 320, 0, tag="[plain apply]")
+    os.environ["DDPO_GN_NO_STREAM"] = "0"
 gn_fwd(16, 4096, 640, 320)          # up_blocks_3 concat
 gn_fwd(16, 1024, 640, 0)
 gn_fwd(16, 256, 1280, 1280)
@@ -112,8 +129,12 @@ ln_fwd(65536, 320)
 ln_fwd(16384, 640)
 ln_fwd(4096, 1280)
 if not once:
-    gn_bwd(40, 4096, 320)
-    gn_bwd(40, 1024, 640)
+    for mb in ("0", "64", "96"):
+        os.environ["DDPO_GN_BWD_GROUP_MB"] = mb
+        print(f"DDPO_GN_BWD_GROUP_MB={mb}")
+        gn_bwd(40, 4096, 320)
+        gn_bwd(40, 1024, 640)
+    os.environ["DDPO_GN_BWD_GROUP_MB"] = "0"
     ln_bwd(163840, 320)
     ln_bwd(40960, 640)
 print("done")
