@@ -148,9 +148,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
       tc_fence_after();
       const int valid = min(AT_BKV, k_lim - j * AT_BKV);
       const bool full = valid == AT_BKV;
-      // two independent chains of three-input maxima: 64 FMNMX3 with a dependent depth of 32 per block instead of
-      // 128 FMNMX in one 128-deep chain (the softmax warps have ~1 eligible warp per scheduler: latency shows)
-      float m_a = -INFINITY, m_b = -INFINITY;
+      float m_blk = -INFINITY;
 #pragma unroll 1
       for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
         uint32_t v[32];
@@ -158,17 +156,14 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
         tmem_ld_wait();
         if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            m_a = max3f(m_a, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-            m_b = max3f(m_b, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-          }
+          for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c0 + i < valid) m_a = fmaxf(m_a, __uint_as_float(v[i]));
+            if (c0 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
         }
       }
-      return fmaxf(m_a, m_b);
+      return m_blk;
     };
     // The row max of block j+1 is taken while the tensor core computes P_j V_j, so the wait for O_j is hidden
     // (it was 14 % of the stall samples when O_j was awaited right after P_j was published).
@@ -182,7 +177,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = ex2_mufu((m_run - m_new) * c);
       const float mc = m_new * c;
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};  // four interleaved partial row sums: dependent depth 32, not 128
+      float l_blk = 0.f;
       // pass 2: P = exp2(S*c - m*c) -> bf16 -> swizzled smem (K-major SW128, 2 sub-tiles of 64 keys)
 #pragma unroll 1
       for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
@@ -195,7 +190,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
           for (int i = 0; i < 32; ++i) {
             const float xe = __uint_as_float(v[i]) * c - mc;
             pr[i] = ex2_sel<DDPO_EXP_POLY_FWD>(i, xe);
-            l4[i & 3] += pr[i];
+            l_blk += pr[i];
           }
         } else {
 #pragma unroll
@@ -203,7 +198,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
             const float xe = __uint_as_float(v[i]) * c - mc;
             const float e = ex2_sel<DDPO_EXP_POLY_FWD>(i, xe);
             pr[i] = (c0 + i < valid) ? e : 0.f;
-            l4[i & 3] += pr[i];
+            l_blk += pr[i];
           }
         }
         uint8_t* tile = sP + (c0 >> 6) * AT_TILE + r * 128;
@@ -218,7 +213,6 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
           *reinterpret_cast<uint4*>(tile + ((chunk ^ (r & 7)) << 4)) = u;
         }
       }
-      const float l_blk = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       l_run = l_run * alpha + l_blk;
       m_run = m_new;
       // S consumed + P visible to the tensor core (generic -> async proxy)

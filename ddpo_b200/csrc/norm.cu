@@ -115,31 +115,42 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const GnArgs a) {
   }
 }
 
-// (mean, rstd) of every (sample, group) from the producing GEMMs' slab statistics.  One 128-thread CTA per (sample, group):
-// thread t adds items t, t + 128, ... of the (slab, channel-of-group) list in ascending order (all loads independent and
-// in flight together: a warp-per-group loop of 40 dependent-latency iterations took longer than the apply pass), then a
-// fixed shuffle tree and the four warp sums in warp order.
-constexpr int GNF_THREADS = 128;
+// (mean, rstd) of every (sample, group) from the producing GEMMs' slab statistics.  One 256-thread CTA per (sample, group):
+// thread t adds items t, t + 256, ... of the (slab, channel-of-group) list in ascending order, then a fixed shuffle tree and
+// the eight warp sums in warp order.
+constexpr int GNF_THREADS = 256;
 __global__ void __launch_bounds__(GNF_THREADS) gn_finalize_slabs_kernel(const GnArgs a, int batch) {
   const int C = a.c0 + a.c1, cpg = C / GN_GROUPS;
   const int b = blockIdx.x / GN_GROUPS, g = blockIdx.x % GN_GROUPS;
   const int nslab = a.hw >> 5;
   const int items = nslab * cpg;
   float s = 0.f, ss = 0.f;
-  for (int i = threadIdx.x; i < items; i += GNF_THREADS) {
-    const int slab = i / cpg, c = g * cpg + (i - slab * cpg);
-    const size_t row = static_cast<size_t>(b) * nslab + slab;
-    const float2 v = c < a.c0 ? *reinterpret_cast<const float2*>(a.stats0 + (row * a.c0 + c) * 2)
-                              : *reinterpret_cast<const float2*>(a.stats1 + (row * a.c1 + (c - a.c0)) * 2);
-    s += v.x, ss += v.y;
+  // eight independent loads per thread in flight (a plain accumulate loop serialises on the load latency: 10 us for the
+  // 5 MB of statistics of a 64x64x320 batch of 16), summed in ascending item order
+  for (int base = threadIdx.x; base < items; base += GNF_THREADS * 8) {
+    float2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + u * GNF_THREADS;
+      v[u] = make_float2(0.f, 0.f);
+      if (i < items) {
+        const int slab = i / cpg, c = g * cpg + (i - slab * cpg);
+        const size_t row = static_cast<size_t>(b) * nslab + slab;
+        v[u] = c < a.c0 ? *reinterpret_cast<const float2*>(a.stats0 + (row * a.c0 + c) * 2)
+                        : *reinterpret_cast<const float2*>(a.stats1 + (row * a.c1 + (c - a.c0)) * 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u].x, ss += v[u].y;
   }
   __shared__ float red[2][GNF_THREADS / 32];
   s = warp_sum(s), ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s, red[1][threadIdx.x >> 5] = ss;
   __syncthreads();
   if (threadIdx.x == 0) {
-    s = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
-    ss = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+    s = ss = 0.f;
+#pragma unroll
+    for (int w = 0; w < GNF_THREADS / 32; ++w) s += red[0][w], ss += red[1][w];
     const float inv_n = 1.0f / (static_cast<float>(a.hw) * cpg);
     const float mean = s * inv_n;
     const float var = fmaxf(0.f, ss * inv_n - mean * mean);
@@ -704,8 +715,12 @@ extern "C" int64_t ddpo_groupnorm_workspace_floats(int batch, int hw, int channe
 
 // plan of the streamed apply pass; returns false when the shape does not fit it (the two-pass kernels then run)
 static bool gn_stream_plan(const GnArgs& g, const ddpo_groupnorm_args* a, GnStream* st) {
-  const char* off = getenv("DDPO_GN_NO_STREAM");   // read per call: the bit-identity test toggles it (costs ~100 ns)
-  if (off != nullptr && off[0] == '1') return false;
+  // Opt-in ($DDPO_GN_STREAM=1; read per call: the bit-identity test toggles it).  Measured on B200 after the apply
+  // arithmetic was cut to one FMA + one MUFU per element (profiles/r2_norm.md): the plain kernel (960 threads / SM issuing
+  // their own 16-byte loads) moves 126 MB in 29.2 us and 315 MB in 62.1 us (5.07 TB/s = 0.77 of the copy peak); this
+  // TMA-staged one, with 20 consumer warps per SM, 34.8 / 72.2 us -- the pass is issue-bound before it is latency-bound.
+  const char* on = getenv("DDPO_GN_STREAM");
+  if (on == nullptr || on[0] != '1') return false;
   const int nsrc = a->c1 > 0 ? 2 : 1;
   if (g.ld0 != a->c0 || (nsrc == 2 && g.ld1 != a->c1)) return false;          // sources must be dense (1-D bulk copies)
   if ((reinterpret_cast<uintptr_t>(a->x0) & 15) || (nsrc == 2 && (reinterpret_cast<uintptr_t>(a->x1) & 15))) return false;

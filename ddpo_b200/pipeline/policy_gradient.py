@@ -165,6 +165,22 @@ class EpochBuffer:
                 "latents": lat, "next_latents": nxt, "log_probs": hd[0], "ts": ts}
 
 
+class _nvtx:
+    """NVTX range per phase of the epoch loop (sample / decode / reward wait / train / optimizer update) so that a timeline
+    capture of the driver reads like the reference's loop; a no-op without CUDA."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if torch.cuda.is_available():
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if torch.cuda.is_available():
+            torch.cuda.nvtx.range_pop()
+
+
 def vae_decode(pipeline, final_latents):
     """Reference :174-182 (``latents / 0.18215`` -> VAE decoder -> ``(x/2+.5).clip(0,1)`` NHWC float32)."""
     if pipeline.vae is None:
@@ -274,10 +290,12 @@ def main(argv=None, models=None, max_epochs=None, save_last=True):
             sample_prompt_embeds = text_encode(sample_prompt_ids).to(device)
             timer()
             sampling_params = {"unet": state.params, "scheduler": params["scheduler"]}
-            final_latents, latents, next_latents, log_probs, ts = pipeline(                                # :256-268
-                sample_prompt_embeds, sample_uncond, sampling_params, sample_seeds[0], T, jit=True,
-                height=args.resolution, width=args.resolution, guidance_scale=args.guidance_scale, eta=args.eta)
-            images = vae_decode(pipeline, final_latents)                                                   # :271
+            with _nvtx(f"ddpo/sample e{epoch} b{i}"):
+                final_latents, latents, next_latents, log_probs, ts = pipeline(                            # :256-268
+                    sample_prompt_embeds, sample_uncond, sampling_params, sample_seeds[0], T, jit=True,
+                    height=args.resolution, width=args.resolution, guidance_scale=args.guidance_scale, eta=args.eta)
+            with _nvtx("ddpo/vae_decode"):
+                images = vae_decode(pipeline, final_latents)                                               # :271
             images = images.detach().float().cpu().numpy()                                                 # :275
             callbacks = executor.submit(training.evaluate_callbacks, callback_fns, images, sample_prompts,
                                         prompt_metadata)                                                   # :277-283
@@ -331,9 +349,10 @@ def main(argv=None, models=None, max_epochs=None, save_last=True):
                 do_opt_update = step["do_opt_update"]
                 if do_opt_update:
                     print(f"opt update at {step['i']}, {step['j0'] + macro - 1}")
-                state, info = train_step(state, batch, noise_scheduler_state, pipeline.scheduler, args.train_cfg,
-                                         args.guidance_scale, args.eta, args.ppo_clip_range, do_opt_update,
-                                         micro_batch_size=args.train_batch_size)
+                with _nvtx("ddpo/train_step+update" if do_opt_update else "ddpo/train_step"):
+                    state, info = train_step(state, batch, noise_scheduler_state, pipeline.scheduler, args.train_cfg,
+                                             args.guidance_scale, args.eta, args.ppo_clip_range, do_opt_update,
+                                             micro_batch_size=args.train_batch_size)
                 all_infos.append(info)
             assert do_opt_update                                                                           # :446
             all_infos = {k: np.stack([float(i[k]) for i in all_infos]) for k in all_infos[0]}

@@ -117,10 +117,10 @@ def ln_bwd(m, c):
 gn_fwd(16, 4096, 320, 0)            # the dominant sampling shape (profiles/r1_gn.md)
 gn_fwd(16, 4096, 320, 0, with_stats=False, tag="[two-pass]")
 if not once:
-    os.environ["DDPO_GN_NO_STREAM"] = "1"
-    gn_fwd(16, 4096, 320, 0, tag="[plain apply]")
-    gn_fwd(40, 4096, 320, 0, tag="[plain apply]")
-    os.environ["DDPO_GN_NO_STREAM"] = "0"
+    os.environ["DDPO_GN_STREAM"] = "1"
+    gn_fwd(16, 4096, 320, 0, tag="[TMA-streamed apply]")
+    gn_fwd(40, 4096, 320, 0, tag="[TMA-streamed apply]")
+    os.environ["DDPO_GN_STREAM"] = "0"
 gn_fwd(16, 4096, 640, 320)          # up_blocks_3 concat
 gn_fwd(16, 1024, 640, 0)
 gn_fwd(16, 256, 1280, 1280)

@@ -380,7 +380,7 @@ def test_groupnorm_fwd_from_slab_stats(b, hw, c0, c1, silu, monkeypatch):
     s1 = _slab_stats_ref(x1.view(b * hw, c1)) if c1 else None
     outs = []
     for mode in ("slabs", "two_pass", "slabs_plain_apply"):
-        monkeypatch.setenv("DDPO_GN_NO_STREAM", "1" if mode == "slabs_plain_apply" else "0")
+        monkeypatch.setenv("DDPO_GN_STREAM", "0" if mode == "slabs_plain_apply" else "1")
         ws = torch.full((ops.groupnorm_workspace_floats(b, hw, c),), float("nan"), device=DEV)
         y = torch.zeros(b, hw, c, dtype=torch.bfloat16, device=DEV)
         yf = torch.zeros(b, hw, c, device=DEV)
