@@ -32,7 +32,8 @@ class IGemmArgs(C.Structure):
 class GroupNormArgs(C.Structure):
     _fields_ = [("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32), ("ld0", i32), ("ld1", i32), ("batch", i32),
                 ("hw", i32), ("scale", vp), ("bias", vp), ("eps", f32), ("silu", i32), ("y_bf16", vp),
-                ("y_f32", vp), ("raw_bf16", vp), ("workspace", vp), ("stats_only_skip", i32), ("stats0", vp), ("stats1", vp)]
+                ("y_f32", vp), ("raw_bf16", vp), ("workspace", vp), ("stats_only_skip", i32), ("stats0", vp), ("stats1", vp),
+                ("dy_bf16", i32)]
 
 
 class AttentionArgs(C.Structure):
@@ -74,9 +75,9 @@ SIGNATURES = {
     "ddpo_groupnorm_bwd": (i32, [C.POINTER(GroupNormArgs), vp, vp, vp, i32, i32, i32, vp, vp, vp]),
     "ddpo_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, f32, vp]),
     "ddpo_layernorm_bwd_workspace_floats": (i64, [i32, i32]),
-    "ddpo_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, vp]),
+    "ddpo_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp]),
     "ddpo_prep_weight": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
-    "ddpo_prep_weight_dgrad": (i32, [vp, vp, i32, i32, i32, vp]),
+    "ddpo_prep_weight_dgrad": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "ddpo_permute_geglu_bias": (i32, [vp, vp, i32, i32, vp]),
     "ddpo_cast_bf16": (i32, [vp, vp, i64, vp]),
     "ddpo_upsample2x_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp]),

@@ -42,13 +42,13 @@ __global__ void prep_transpose_kernel(const float* __restrict__ src, __nv_bfloat
 // backward-operand layout: dst bf16 [K_in, taps*N] = src[tap][k][n] with the tap index flipped
 // (dgrad of a 3x3 conv is a 3x3 conv with the kernel rotated by 180 degrees; for taps==1 it is a cast)
 __global__ void prep_dgrad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int taps, int K,
-                                  int N, int64_t total) {
+                                  int N, int64_t total, int ld_dst, int col_offset) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int n = i % N;
   const int64_t r = i / N;
   const int k = r % K, tap = r / K;
-  dst[(static_cast<size_t>(k) * taps + (taps - 1 - tap)) * N + n] = __float2bfloat16_rn(src[i]);
+  dst[static_cast<size_t>(k) * ld_dst + col_offset + (taps - 1 - tap) * N + n] = __float2bfloat16_rn(src[i]);
 }
 
 __global__ void permute_geglu_bias_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int bn) {
@@ -375,11 +375,15 @@ extern "C" int ddpo_prep_weight(const float* src, void* dst_bf16, int k, int n, 
   return DDPO_OK;
 }
 
-extern "C" int ddpo_prep_weight_dgrad(const float* src, void* dst_bf16, int taps, int k, int n, void* stream) {
+extern "C" int ddpo_prep_weight_dgrad(const float* src, void* dst_bf16, int taps, int k, int n, int ld_dst, int col_offset,
+                                      void* stream) {
   DDPO_REQUIRE(src && dst_bf16 && taps > 0 && k > 0 && n > 0, "prep_weight_dgrad: bad arguments");
+  if (ld_dst <= 0) ld_dst = taps * n;
+  DDPO_REQUIRE(col_offset >= 0 && col_offset + taps * n <= ld_dst, "prep_weight_dgrad: columns [%d, %d) exceed the row pitch %d",
+               col_offset, col_offset + taps * n, ld_dst);
   const int64_t total = static_cast<int64_t>(taps) * k * n;
   prep_dgrad_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst_bf16), taps, k, n, total);
+      src, static_cast<__nv_bfloat16*>(dst_bf16), taps, k, n, total, ld_dst, col_offset);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }

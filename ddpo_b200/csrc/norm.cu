@@ -344,7 +344,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnArgs a) {
 // and per-(sample, chunk) partial dscale / dbias (summed in fixed order by gn_param_grad_kernel).
 struct GnBwdArgs {
   GnArgs f;
-  const float* dy;     // [B, HW, C] gradient w.r.t. GN(+SiLU) output
+  const void* dy;      // [B, HW, C] gradient w.r.t. GN(+SiLU) output: fp32, or bf16 when dy_bf16
+  int dy_bf16;
   float* partial2;     // [B, chunks, 32, 2]: sum(dyh), sum(dyh * xhat)
   float* dx0;          // [B, HW, ld] gradient into x0 (+= if accumulate)
   float* dx1;
@@ -354,6 +355,15 @@ struct GnBwdArgs {
   int b0;              // first sample of this launch: the two passes run over groups of samples small enough that the
                        // second pass finds x and dy in L2 (126 MB) instead of fetching them from DRAM again
 };
+
+// four consecutive gradient values at element index `idx` (a multiple of 4)
+__device__ __forceinline__ float4 gn_load_dy4(const void* dy, int dy_bf16, size_t idx) {
+  if (dy_bf16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(dy) + idx);
+    return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  }
+  return *reinterpret_cast<const float4*>(static_cast<const float*>(dy) + idx);
+}
 
 __device__ __forceinline__ float silu_grad_f(float z) {
   const float s = sigmoid_f(z);
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const GnBwdArg
       for (int p = p_begin + tr; p < p_end; p += R) {
         const size_t pix = base + p;
         const float4 v = gn_load4(f, pix, c);
-        const float4 d4 = *reinterpret_cast<const float4*>(a.dy + pix * C + c);
+        const float4 d4 = gn_load_dy4(a.dy, a.dy_bf16, pix * C + c);
         const float xv[4] = {v.x, v.y, v.z, v.w};
         float d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
@@ -499,14 +509,14 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
     for (; p + R < p_end; p += 2 * R) {  // two pixels = up to six independent 16-byte loads in flight per thread
       const size_t q0 = base + p, q1 = base + p + R;
       const float4 v0 = gn_load4(f, q0, c), v1 = gn_load4(f, q1, c);
-      const float4 d0 = *reinterpret_cast<const float4*>(a.dy + q0 * C + c);
-      const float4 d1 = *reinterpret_cast<const float4*>(a.dy + q1 * C + c);
+      const float4 d0 = gn_load_dy4(a.dy, a.dy_bf16, q0 * C + c);
+      const float4 d1 = gn_load_dy4(a.dy, a.dy_bf16, q1 * C + c);
       const float4 o0 = load_old(q0), o1 = load_old(q1);
       emit(q0, v0, d0, o0), emit(q1, v1, d1, o1);
     }
     for (; p < p_end; p += R) {
       const size_t q0 = base + p;
-      emit(q0, gn_load4(f, q0, c), *reinterpret_cast<const float4*>(a.dy + q0 * C + c), load_old(q0));
+      emit(q0, gn_load4(f, q0, c), gn_load_dy4(a.dy, a.dy_bf16, q0 * C + c), load_old(q0));
     }
   }
 }
@@ -581,9 +591,9 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 constexpr int LN_BWD_ROWS = 64;  // rows per CTA (8 warps x 8 rows)
 template <int NC>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                                                            const float* __restrict__ stats, const float* __restrict__ dy,
+                                                            const float* __restrict__ stats, const void* __restrict__ dy,
                                                             float* __restrict__ dx, float* __restrict__ dparam_part,
-                                                            int M, int C, int accumulate) {
+                                                            int M, int C, int accumulate, int dy_bf16) {
   extern __shared__ float sm[];  // [8 warps][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float ds[NC][4], db[NC][4];
@@ -600,7 +610,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     if (row >= M) break;
     const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
     const float* xr = x + static_cast<size_t>(row) * C;
-    const float* dr = dy + static_cast<size_t>(row) * C;
+    const size_t dr = static_cast<size_t>(row) * C;   // element offset of this row in dy
     float* gr = dx + static_cast<size_t>(row) * C;
     float4 xv[NC], dv[NC], ov[NC];  // the old gradient (accumulate mode) is fetched with x and dy: 3 streams in flight
 #pragma unroll
@@ -609,7 +619,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       ov[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < C) {
         xv[i] = *reinterpret_cast<const float4*>(xr + c);
-        dv[i] = *reinterpret_cast<const float4*>(dr + c);
+        dv[i] = gn_load_dy4(dy, dy_bf16, dr + c);
         if (accumulate) ov[i] = *reinterpret_cast<const float4*>(gr + c);
       } else {
         xv[i] = make_float4(mean, mean, mean, mean);
@@ -804,7 +814,7 @@ extern "C" int ddpo_groupnorm_fwd(const ddpo_groupnorm_args* a, void* stream_) {
   return DDPO_OK;
 }
 
-extern "C" int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const float* dy, float* dx0, float* dx1, int ldd0,
+extern "C" int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const void* dy, float* dx0, float* dx1, int ldd0,
                                   int ldd1, int accumulate, float* dscale, float* dbias, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GnBwdArgs b;
@@ -812,7 +822,7 @@ extern "C" int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const float* dy,
   if (rc) return rc;
   const int C = a->c0 + a->c1;
   DDPO_REQUIRE(dy && dx0 && dscale && dbias, "groupnorm_bwd: null pointer");
-  b.dy = dy, b.dx0 = dx0, b.dx1 = dx1, b.ldd0 = ldd0 > 0 ? ldd0 : a->c0, b.ldd1 = ldd1 > 0 ? ldd1 : a->c1;
+  b.dy = dy, b.dy_bf16 = a->dy_bf16, b.dx0 = dx0, b.dx1 = dx1, b.ldd0 = ldd0 > 0 ? ldd0 : a->c0, b.ldd1 = ldd1 > 0 ? ldd1 : a->c1;
   b.accumulate = accumulate;
   b.partial2 = b.f.partial + static_cast<size_t>(a->batch) * b.f.chunks * GN_GROUPS * 2;
   b.dparam_part = b.partial2 + static_cast<size_t>(a->batch) * b.f.chunks * GN_GROUPS * 2;
@@ -872,8 +882,8 @@ extern "C" int64_t ddpo_layernorm_bwd_workspace_floats(int m, int c) {
   return static_cast<int64_t>((m + LN_BWD_ROWS - 1) / LN_BWD_ROWS) * 2 * c;
 }
 
-extern "C" int ddpo_layernorm_bwd(const float* x, const float* scale, const float* stats, const float* dy, float* dx,
-                                  int accumulate, float* dscale, float* dbias, float* workspace, int m, int c,
+extern "C" int ddpo_layernorm_bwd(const float* x, const float* scale, const float* stats, const void* dy, float* dx,
+                                  int accumulate, float* dscale, float* dbias, float* workspace, int m, int c, int dy_bf16,
                                   void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DDPO_REQUIRE(x && scale && stats && dy && dx && dscale && dbias && workspace && c % 4 == 0,
@@ -890,11 +900,11 @@ extern "C" int ddpo_layernorm_bwd(const float* x, const float* scale, const floa
   }
   const int nc = (c + 127) / 128;
   if (nc <= 3)
-    layernorm_bwd_kernel<3><<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate);
+    layernorm_bwd_kernel<3><<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate, dy_bf16);
   else if (nc <= 5)
-    layernorm_bwd_kernel<5><<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate);
+    layernorm_bwd_kernel<5><<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate, dy_bf16);
   else
-    layernorm_bwd_kernel<10><<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate);
+    layernorm_bwd_kernel<10><<<ctas, 256, smem, stream>>>(x, scale, stats, dy, dx, workspace, m, c, accumulate, dy_bf16);
   DDPO_LAUNCH_OK();
   launch_reduce_rows(workspace, 1, ctas, 2 * c, c, dscale, dbias, 1, stream);
   DDPO_LAUNCH_OK();

@@ -191,10 +191,10 @@ def groupnorm_workspace_floats(batch, hw, channels):
 
 
 def _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, y_bf16, y_f32, raw_bf16, ws, ld0=0, ld1=0, skip_stats=False,
-             eps=1e-5, stats0=None, stats1=None):
+             eps=1e-5, stats0=None, stats1=None, dy_bf16=False):
     return GroupNormArgs(_p(x0), _p(x1), int(c0), int(c1), int(ld0), int(ld1), int(batch), int(hw), _p(scale),
                          _p(bias), float(eps), int(silu), _p(y_bf16), _p(y_f32), _p(raw_bf16), _p(ws), int(skip_stats),
-                         _p(stats0), _p(stats1))
+                         _p(stats0), _p(stats1), int(dy_bf16))
 
 
 def gn_stats_shape(rows, channels):
@@ -215,7 +215,9 @@ def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, 
 
 def groupnorm_bwd(x0, scale, bias, ws, batch, hw, c0, dy, dx0, dscale, dbias, x1=None, c1=0, dx1=None, silu=True,
                   accumulate=False, ldd0=0, ldd1=0):
-    a = _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, None, None, None, ws)
+    """``dy`` fp32 or bf16 (the dtype selects the kernel's load path): the dgrad GEMM in front of a GroupNorm writes bf16."""
+    assert dy.dtype in (torch.float32, torch.bfloat16)
+    a = _gn_args(x0, x1, c0, c1, batch, hw, scale, bias, silu, None, None, None, ws, dy_bf16=dy.dtype == torch.bfloat16)
     _e = _ev()
     _run("groupnorm_bwd", lib().ddpo_groupnorm_bwd(C.byref(a), _p(dy), _p(dx0), _p(dx1), int(ldd0), int(ldd1), int(accumulate),
                                    _p(dscale), _p(dbias), _stream()), 0.0, _e)
@@ -231,9 +233,10 @@ def layernorm_bwd_workspace_floats(m, c):
 
 
 def layernorm_bwd(x, scale, stats, dy, dx, dscale, dbias, ws, m, c, accumulate=False):
+    assert dy.dtype in (torch.float32, torch.bfloat16)
     _e = _ev()
     _run("layernorm_bwd", lib().ddpo_layernorm_bwd(_p(x), _p(scale), _p(stats), _p(dy), _p(dx), int(accumulate), _p(dscale),
-                                   _p(dbias), _p(ws), int(m), int(c), _stream()), 0.0, _e)
+                                   _p(dbias), _p(ws), int(m), int(c), int(dy.dtype == torch.bfloat16), _stream()), 0.0, _e)
 
 
 # ------------------------------------------------------------ small layers -------
@@ -243,9 +246,10 @@ def prep_weight(src, dst, k, n, ldk=None, row_offset=0, col_offset=0, geglu_bn=0
                                  int(geglu_bn), _stream()), 0.0, _e)
 
 
-def prep_weight_dgrad(src, dst, taps, k, n):
+def prep_weight_dgrad(src, dst, taps, k, n, ld_dst=0, col_offset=0):
     _e = _ev()
-    _run("prep_weight_dgrad", lib().ddpo_prep_weight_dgrad(_p(src), _p(dst), int(taps), int(k), int(n), _stream()), 0.0, _e)
+    _run("prep_weight_dgrad", lib().ddpo_prep_weight_dgrad(_p(src), _p(dst), int(taps), int(k), int(n), int(ld_dst),
+                                                           int(col_offset), _stream()), 0.0, _e)
 
 
 def permute_geglu_bias(src, dst, n, bn):

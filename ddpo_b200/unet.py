@@ -176,6 +176,14 @@ class UNet:
             if leaf in ("to_k", "to_v") and "/attn2/" in base:
                 continue  # the text context receives no gradient
             cin, n = int(shape[-2]), int(shape[-1])
+            if leaf in ("to_q", "to_k", "to_v") and "/attn1/" in base:
+                # the input gradient of self-attention is ONE GEMM over K = 3C: d_ln = [dq | dk | dv] [Wq | Wk | Wv]^T
+                key = base.rsplit("/", 1)[0] + "/qkv"
+                if key not in self.wd:
+                    self.wd[key] = torch.empty(cin, 3 * n, dtype=BF16, device=self.device)
+                ops.prep_weight_dgrad(self.p(base + "/kernel"), self.wd[key], 1, cin, n, ld_dst=3 * n,
+                                      col_offset={"to_q": 0, "to_k": n, "to_v": 2 * n}[leaf])
+                continue
             taps = int(np.prod(shape[:-2])) if len(shape) == 4 else 1
             if base not in self.wd:
                 self.wd[base] = torch.empty(cin, taps * n, dtype=BF16, device=self.device)
@@ -595,8 +603,10 @@ class UNet:
         names = [name + "/conv2/bias"] + ([name + "/conv_shortcut/bias"] if r["has_sc"] else [])
         dyb = bias_grad_and_cast(dy, m, cout, names)
         ops.wgrad(dy=dyb, n=cout, x0=r["a2"], c0=cout, conv=(b, h, w), taps=9, dw=self.g(name + "/conv2/kernel"))
-        d_a2 = A.alloc((m, cout), F32)
-        ops.igemm(a0=dyb, wt=self.wd[name + "/conv2"], n=cout, c0=cout, conv=(b, h, w), taps=9, out_f32=d_a2)
+        # gradients that go straight from a dgrad GEMM into a norm's backward travel as bf16 (half the bytes on both sides;
+        # the forward value they belong to was itself a bf16 GEMM operand)
+        d_a2 = A.alloc((m, cout), BF16)
+        ops.igemm(a0=dyb, wt=self.wd[name + "/conv2"], n=cout, c0=cout, conv=(b, h, w), taps=9, out_bf16=d_a2)
         d_h = A.alloc((m, cout), F32)
         ops.groupnorm_bwd(r["hbuf"], self.p(name + "/norm2/scale"), self.p(name + "/norm2/bias"), r["gws2"], b, hw, cout,
                           d_a2, d_h, self.g(name + "/norm2/scale"), self.g(name + "/norm2/bias"), silu=True)
@@ -617,8 +627,8 @@ class UNet:
         A.release(dpre)
         A.release(d_tproj)
         ops.wgrad(dy=d_hb, n=cout, x0=r["a"], c0=cin, conv=(b, h, w), taps=9, dw=self.g(name + "/conv1/kernel"))
-        d_a = A.alloc((m, cin), F32)
-        ops.igemm(a0=d_hb, wt=self.wd[name + "/conv1"], n=cin, c0=cout, conv=(b, h, w), taps=9, out_f32=d_a)
+        d_a = A.alloc((m, cin), BF16)
+        ops.igemm(a0=d_hb, wt=self.wd[name + "/conv1"], n=cin, c0=cout, conv=(b, h, w), taps=9, out_bf16=d_a)
         A.release(d_hb)
         if r["has_sc"]:
             ops.wgrad(dy=dyb, n=cout, x0=r["raw"], c0=cin, conv=(b, h, w), taps=1,
@@ -682,8 +692,8 @@ class UNet:
         A.release(d_ff)
         ops.colsum_bf16(d_pre, m, 8 * c, self.g(bl + "/ff/net_0/proj/bias").view(1, 8 * c), accumulate=True)
         ops.wgrad(dy=d_pre, n=8 * c, x0=t["ln3"], c0=c, m=m, dw=self.g(bl + "/ff/net_0/proj/kernel"))
-        d_ln = A.alloc((m, c), F32)
-        ops.igemm(a0=d_pre, wt=self.wd[bl + "/ff/net_0/proj"], n=c, c0=8 * c, m=m, out_f32=d_ln)
+        d_ln = A.alloc((m, c), BF16)   # dgrad GEMM -> norm backward: bf16 (see _resnet_bwd)
+        ops.igemm(a0=d_pre, wt=self.wd[bl + "/ff/net_0/proj"], n=c, c0=8 * c, m=m, out_bf16=d_ln)
         A.release(d_pre)
         lws = A.alloc((ops.layernorm_bwd_workspace_floats(m, c),), F32)
         ops.layernorm_bwd(t["h2"], self.p(bl + "/norm3/scale"), t["st3"], d_ln, d_h, self.g(bl + "/norm3/scale"),
@@ -703,7 +713,7 @@ class UNet:
         ops.wgrad(dy=dq2, n=c, x0=t["ln2"], c0=c, m=m, dw=self.g(bl + "/attn2/to_q/kernel"))
         ops.wgrad(dy=dkv, ldy=2 * c, n=c, x0=self._ctx_bf, c0=dctx, m=b * L, dw=self.g(bl + "/attn2/to_k/kernel"))
         ops.wgrad(dy=dkv[:, c:], ldy=2 * c, n=c, x0=self._ctx_bf, c0=dctx, m=b * L, dw=self.g(bl + "/attn2/to_v/kernel"))
-        ops.igemm(a0=dq2, wt=self.wd[bl + "/attn2/to_q"], n=c, c0=c, m=m, out_f32=d_ln)
+        ops.igemm(a0=dq2, wt=self.wd[bl + "/attn2/to_q"], n=c, c0=c, m=m, out_bf16=d_ln)
         ops.layernorm_bwd(t["h1"], self.p(bl + "/norm2/scale"), t["st2"], d_ln, d_h, self.g(bl + "/norm2/scale"),
                           self.g(bl + "/norm2/bias"), lws, m, c, accumulate=True)
         A.release(dq2)
@@ -719,8 +729,7 @@ class UNet:
                           dqkv[:, 2 * c:], b, heads, hw, hw, 3 * c, 3 * c, 3 * c, c, c, 3 * c, 3 * c, 3 * c)
         for i, nm in enumerate(("to_q", "to_k", "to_v")):
             ops.wgrad(dy=dqkv[:, i * c:], ldy=3 * c, n=c, x0=t["ln1"], c0=c, m=m, dw=self.g(f"{bl}/attn1/{nm}/kernel"))
-            ops.igemm(a0=dqkv[:, i * c:], lda0=3 * c, c0=c, wt=self.wd[f"{bl}/attn1/{nm}"], n=c, m=m, out_f32=d_ln,
-                      accumulate=i > 0)
+        ops.igemm(a0=dqkv, c0=3 * c, wt=self.wd[bl + "/attn1/qkv"], n=c, m=m, out_bf16=d_ln)   # one GEMM over K = 3C
         ops.layernorm_bwd(t["h0"], self.p(bl + "/norm1/scale"), t["st1"], d_ln, d_h, self.g(bl + "/norm1/scale"),
                           self.g(bl + "/norm1/bias"), lws, m, c, accumulate=True)
         for z in (dqkv, d_ao, delta, lws):
@@ -728,7 +737,7 @@ class UNet:
         # h0 = proj_in(g)
         d0b = bias_grad_and_cast(d_h, m, c, [name + "/proj_in/bias"])
         ops.wgrad(dy=d0b, n=c, x0=t["g"], c0=c, m=m, dw=self.g(name + "/proj_in/kernel").view(c, c))
-        ops.igemm(a0=d0b, wt=self.wd[name + "/proj_in"], n=c, c0=c, m=m, out_f32=d_ln)
+        ops.igemm(a0=d0b, wt=self.wd[name + "/proj_in"], n=c, c0=c, m=m, out_bf16=d_ln)
         A.release(d0b)
         A.release(d_h)
         ops.groupnorm_bwd(t["x"], self.p(name + "/norm/scale"), self.p(name + "/norm/bias"), t["gws"], b, hw, c, d_ln,

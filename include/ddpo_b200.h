@@ -150,23 +150,28 @@ typedef struct {
                            (ddpo_igemm_args.gn_stats); needs hw % 32 == 0.  With stats for every source the forward is ONE pass
                            over x (no statistics pass). */
   const float* stats1;  /* same for x1 [batch*hw/32, c1, 2] */
+  int dy_bf16;          /* backward only: `dy` points to bf16 (the dgrad GEMM that produced it wrote its bf16 output) */
 } ddpo_groupnorm_args;
 int64_t ddpo_groupnorm_workspace_floats(int batch, int hw, int channels);
 int ddpo_groupnorm_fwd(const ddpo_groupnorm_args* a, void* stream);
 /* dx0/dx1 (+)= d/dx ; dscale/dbias += (parameter gradients always accumulate) */
-int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const float* dy, float* dx0, float* dx1, int ldd0, int ldd1,
+int ddpo_groupnorm_bwd(const ddpo_groupnorm_args* a, const void* dy, float* dx0, float* dx1, int ldd0, int ldd1,
                        int accumulate, float* dscale, float* dbias, void* stream);
 int ddpo_layernorm_fwd(const float* x, const float* scale, const float* bias, void* y_bf16, float* stats /*[m,2] or NULL*/,
                        int m, int c, float eps, void* stream);
 int64_t ddpo_layernorm_bwd_workspace_floats(int m, int c);
-int ddpo_layernorm_bwd(const float* x, const float* scale, const float* stats, const float* dy, float* dx,
-                       int accumulate, float* dscale, float* dbias, float* workspace, int m, int c, void* stream);
+/* dy: fp32, or bf16 when dy_bf16 != 0 (the output of the dgrad GEMM that feeds this norm) */
+int ddpo_layernorm_bwd(const float* x, const float* scale, const float* stats, const void* dy, float* dx,
+                       int accumulate, float* dscale, float* dbias, float* workspace, int m, int c, int dy_bf16,
+                       void* stream);
 
 /* --------------------------------------------------- layout / small layers ---------
  * weight re-layout: fp32 Flax params ([in,out] Dense, HWIO Conv == [(tap,cin), cout]) -> bf16 GEMM operands */
 int ddpo_prep_weight(const float* src, void* dst_bf16, int k, int n, int ldk, int row_offset, int col_offset,
                      int geglu_bn, void* stream);
-int ddpo_prep_weight_dgrad(const float* src, void* dst_bf16, int taps, int k, int n, void* stream);
+/* ld_dst (0 = taps*n): row pitch of dst; col_offset: first column written -- lets several weights share one K-concatenated
+ * dgrad operand (the q/k/v input gradients of self-attention are ONE GEMM over K = 3C) */
+int ddpo_prep_weight_dgrad(const float* src, void* dst_bf16, int taps, int k, int n, int ld_dst, int col_offset, void* stream);
 int ddpo_permute_geglu_bias(const float* src, float* dst, int n, int bn, void* stream);
 int ddpo_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
 /* FlaxUpsample2D's jax.image.resize(nearest): out[i] = in[i/2] */

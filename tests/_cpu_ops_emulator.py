@@ -325,9 +325,10 @@ def conv_out(x_nhwc, w, bias, y_nchw, batch, h, wd, cin, cout):
 
 
 # ---- U-Net backward (training path).  Gradient ops are emulated with torch autograd of the emulated forward op ----
-def prep_weight_dgrad(src, dst, taps, k, n):
+def prep_weight_dgrad(src, dst, taps, k, n, ld_dst=0, col_offset=0):
     s = src.reshape(taps, k, n)
-    dst.reshape(k, taps, n).copy_(s.flip(0).permute(1, 0, 2).to(BF16))
+    ld = ld_dst or taps * n
+    dst.reshape(k, ld)[:, col_offset:col_offset + taps * n].copy_(s.flip(0).permute(1, 0, 2).reshape(k, taps * n).to(BF16))
 
 
 def layernorm_bwd_workspace_floats(m, c):

@@ -55,8 +55,9 @@ def test_wgrad_conv(b, h, c0, c1, n, ks, stride, kernel):
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max err {err}"
 
 
+@pytest.mark.parametrize("dy_dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("b,hw,c0,c1,silu", [(2, 64, 64, 0, True), (2, 1024, 320, 0, True), (2, 256, 128, 64, False)])
-def test_groupnorm_bwd(b, hw, c0, c1, silu):
+def test_groupnorm_bwd(b, hw, c0, c1, silu, dy_dtype):
     from ddpo_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(2)
     c = c0 + c1
@@ -64,7 +65,8 @@ def test_groupnorm_bwd(b, hw, c0, c1, silu):
     x1 = torch.randn(b, hw, c1, generator=g).to(DEV) if c1 else None
     sc = (1 + 0.1 * torch.randn(c, generator=g)).to(DEV)
     bi = (0.1 * torch.randn(c, generator=g)).to(DEV)
-    dy = torch.randn(b, hw, c, generator=g).to(DEV)
+    dy_in = torch.randn(b, hw, c, generator=g).to(DEV).to(dy_dtype)   # bf16: what a dgrad GEMM hands to the norm's backward
+    dy = dy_in.float()
     ws = torch.zeros(ops.groupnorm_workspace_floats(b, hw, c), device=DEV)
     y = torch.zeros(b, hw, c, dtype=torch.bfloat16, device=DEV)
     ops.groupnorm_fwd(x0, sc, bi, ws, b, hw, c0, x1=x1, c1=c1, silu=silu, y_bf16=y)
@@ -72,7 +74,7 @@ def test_groupnorm_bwd(b, hw, c0, c1, silu):
     dx1 = torch.zeros(b, hw, c1, device=DEV) if c1 else None
     dsc = torch.zeros(c, device=DEV)
     dbi = torch.zeros(c, device=DEV)
-    ops.groupnorm_bwd(x0, sc, bi, ws, b, hw, c0, dy, dx0, dsc, dbi, x1=x1, c1=c1, dx1=dx1, silu=silu)
+    ops.groupnorm_bwd(x0, sc, bi, ws, b, hw, c0, dy_in, dx0, dsc, dbi, x1=x1, c1=c1, dx1=dx1, silu=silu)
     torch.cuda.synchronize()
     x = (x0 if x1 is None else torch.cat([x0, x1], -1)).clone().requires_grad_(True)
     scr, bir = sc.clone().requires_grad_(True), bi.clone().requires_grad_(True)
@@ -88,14 +90,16 @@ def test_groupnorm_bwd(b, hw, c0, c1, silu):
     assert (dbi - bir.grad).abs().max().item() < 2e-3 * bir.grad.abs().max().item()
 
 
+@pytest.mark.parametrize("dy_dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("m,c", [(64, 64), (1000, 320), (2048, 1280)])
-def test_layernorm_bwd(m, c):
+def test_layernorm_bwd(m, c, dy_dtype):
     from ddpo_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(3)
     x = (torch.randn(m, c, generator=g) * 3 + 1).to(DEV)
     sc = (1 + 0.1 * torch.randn(c, generator=g)).to(DEV)
     bi = (0.1 * torch.randn(c, generator=g)).to(DEV)
-    dy = torch.randn(m, c, generator=g).to(DEV)
+    dy_in = torch.randn(m, c, generator=g).to(DEV).to(dy_dtype)
+    dy = dy_in.float()
     y = torch.zeros(m, c, dtype=torch.bfloat16, device=DEV)
     st = torch.zeros(m, 2, device=DEV)
     ops.layernorm_fwd(x, sc, bi, y, m, c, stats=st)
@@ -103,7 +107,7 @@ def test_layernorm_bwd(m, c):
     dsc = torch.zeros(c, device=DEV)
     dbi = torch.zeros(c, device=DEV)
     ws = torch.zeros(ops.layernorm_bwd_workspace_floats(m, c), device=DEV)
-    ops.layernorm_bwd(x, sc, st, dy, dx, dsc, dbi, ws, m, c, accumulate=True)
+    ops.layernorm_bwd(x, sc, st, dy_in, dx, dsc, dbi, ws, m, c, accumulate=True)
     torch.cuda.synchronize()
     xr, scr, bir = x.clone().requires_grad_(True), sc.clone().requires_grad_(True), bi.clone().requires_grad_(True)
     torch.nn.functional.layer_norm(xr, (c,), scr, bir, 1e-5).backward(dy)
