@@ -94,7 +94,7 @@ SIGNATURES = {
     "ddpo_colsum_workspace_floats": (i64, [i32, i32, i32]),
     "ddpo_colsum_cast": (i32, [vp, i32, vp, vp, i32, i32, vp, i32, i32, vp]),
     "ddpo_colsum_bf16": (i32, [vp, i32, vp, i32, vp, i32, i32, vp]),
-    "ddpo_geglu_bwd": (i32, [vp, vp, vp, i64, i32, i32, vp]),
+    "ddpo_geglu_bwd": (i32, [vp, vp, vp, i64, i32, i32, i32, vp]),
     "ddpo_conv_out_bwd_workspace_floats": (i64, [i32]),
     "ddpo_conv_out_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_conv_in_wgrad_workspace_floats": (i64, [i32, i32]),

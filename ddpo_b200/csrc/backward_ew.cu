@@ -73,8 +73,10 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // ------------------------------------------------------------------- GEGLU ----
 // pre: bf16 [M, N] tile-interleaved ([bn/2 lin | bn/2 gate] per bn columns, bias included)
 // dff: fp32 [M, N/2] gradient w.r.t. lin*gelu(gate);  dpre: bf16 [M, N] in PLAIN order [lin(N/2) | gate(N/2)]
-__global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const float* __restrict__ dff,
-                                                        __nv_bfloat16* __restrict__ dpre, int64_t M, int N, int bn) {
+// dff: fp32, or bf16 when dff_bf16 (the bf16 output of the FF down-projection's dgrad GEMM)
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const void* __restrict__ dff,
+                                                        __nv_bfloat16* __restrict__ dpre, int64_t M, int N, int bn,
+                                                        int dff_bf16) {
   // 8 output channels per thread: 16-byte loads of lin / gate, 2 x 16 bytes of dff, two 16-byte stores
   const int half = bn >> 1, hn = N >> 1, groups = hn >> 3;
   const int64_t total = M * groups;
@@ -86,10 +88,17 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __r
     const __nv_bfloat16* pr = pre + r * N + tile * bn + pos;
     const uint4 lin8 = *reinterpret_cast<const uint4*>(pr);
     const uint4 gate8 = *reinterpret_cast<const uint4*>(pr + half);
-    const float4 d0 = *reinterpret_cast<const float4*>(dff + r * hn + j);
-    const float4 d1 = *reinterpret_cast<const float4*>(dff + r * hn + j + 4);
+    float dv[8];
+    if (dff_bf16) {
+      const uint4 d8 = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(dff) + r * hn + j);
+      dv[0] = bf16_lo(d8.x), dv[1] = bf16_hi(d8.x), dv[2] = bf16_lo(d8.y), dv[3] = bf16_hi(d8.y);
+      dv[4] = bf16_lo(d8.z), dv[5] = bf16_hi(d8.z), dv[6] = bf16_lo(d8.w), dv[7] = bf16_hi(d8.w);
+    } else {
+      const float4 d0 = *reinterpret_cast<const float4*>(static_cast<const float*>(dff) + r * hn + j);
+      const float4 d1 = *reinterpret_cast<const float4*>(static_cast<const float*>(dff) + r * hn + j + 4);
+      dv[0] = d0.x, dv[1] = d0.y, dv[2] = d0.z, dv[3] = d0.w, dv[4] = d1.x, dv[5] = d1.y, dv[6] = d1.z, dv[7] = d1.w;
+    }
     const uint32_t lw[4] = {lin8.x, lin8.y, lin8.z, lin8.w}, gw[4] = {gate8.x, gate8.y, gate8.z, gate8.w};
-    const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
     uint32_t ol[4], og[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -379,11 +388,11 @@ extern "C" int ddpo_colsum_bf16(const void* x_bf16, int ld, float* out, int accu
   return DDPO_OK;
 }
 
-extern "C" int ddpo_geglu_bwd(const void* pre_bf16, const float* dff, void* dpre_bf16, int64_t m, int n, int bn,
-                              void* stream) {
+extern "C" int ddpo_geglu_bwd(const void* pre_bf16, const void* dff, void* dpre_bf16, int64_t m, int n, int bn,
+                              int dff_bf16, void* stream) {
   DDPO_REQUIRE(pre_bf16 && dff && dpre_bf16 && n % bn == 0 && bn % 16 == 0, "geglu_bwd: bad arguments");
   geglu_bwd_kernel<<<grid_for(m * (n / 16), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(pre_bf16), dff, static_cast<__nv_bfloat16*>(dpre_bf16), m, n, bn);
+      static_cast<const __nv_bfloat16*>(pre_bf16), dff, static_cast<__nv_bfloat16*>(dpre_bf16), m, n, bn, dff_bf16);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }

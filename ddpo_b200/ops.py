@@ -395,8 +395,10 @@ def colsum_bf16(x, m, n, out, accumulate=True, ld=0):
 
 
 def geglu_bwd(pre, dff, dpre, m, n, bn=256):
+    assert dff.dtype in (torch.float32, torch.bfloat16)
     _e = _ev()
-    _run("geglu_bwd", lib().ddpo_geglu_bwd(_p(pre), _p(dff), _p(dpre), int(m), int(n), int(bn), _stream()), 0.0, _e)
+    _run("geglu_bwd", lib().ddpo_geglu_bwd(_p(pre), _p(dff), _p(dpre), int(m), int(n), int(bn),
+                                           int(dff.dtype == torch.bfloat16), _stream()), 0.0, _e)
 
 
 def conv_out_bwd(x_nhwc, w, dy_nchw, dx_nhwc, dw, dbias, batch, h, wd, cin):

@@ -684,8 +684,8 @@ class UNet:
         # h3 = ff2(ff) + h2
         d3b = bias_grad_and_cast(d_h, m, c, [bl + "/ff/net_2/bias"])
         ops.wgrad(dy=d3b, n=c, x0=t["ff"], c0=4 * c, m=m, dw=self.g(bl + "/ff/net_2/kernel"))
-        d_ff = A.alloc((m, 4 * c), F32)
-        ops.igemm(a0=d3b, wt=self.wd[bl + "/ff/net_2"], n=4 * c, c0=c, m=m, out_f32=d_ff)
+        d_ff = A.alloc((m, 4 * c), BF16)
+        ops.igemm(a0=d3b, wt=self.wd[bl + "/ff/net_2"], n=4 * c, c0=c, m=m, out_bf16=d_ff)
         A.release(d3b)
         d_pre = A.alloc((m, 8 * c), BF16)
         ops.geglu_bwd(t["ffpre"], d_ff, d_pre, m, 8 * c, 256)

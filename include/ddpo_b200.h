@@ -247,7 +247,9 @@ int64_t ddpo_colsum_workspace_floats(int m, int n, int rows_per_group);
 int ddpo_colsum_cast(const float* dy, int ld, void* y_bf16, float* out, int rows_per_group, int accumulate,
                      float* workspace, int m, int n, void* stream);
 int ddpo_colsum_bf16(const void* x_bf16, int ld, float* out, int accumulate, float* workspace, int m, int n, void* stream);
-int ddpo_geglu_bwd(const void* pre_bf16, const float* dff, void* dpre_bf16, int64_t m, int n, int bn, void* stream);
+/* dff: fp32 [m, n/2], or bf16 when dff_bf16 != 0 */
+int ddpo_geglu_bwd(const void* pre_bf16, const void* dff, void* dpre_bf16, int64_t m, int n, int bn, int dff_bf16,
+                   void* stream);
 int64_t ddpo_conv_out_bwd_workspace_floats(int cin);
 int ddpo_conv_out_bwd(const float* x_nhwc, const float* w_hwio, const float* dy_nchw, float* dx_nhwc, float* dw,
                       float* dbias, float* workspace, int batch, int h, int w, int cin, void* stream);

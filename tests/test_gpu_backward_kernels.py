@@ -211,3 +211,10 @@ def test_geglu_bwd(m, c):
     out = dpre.float().cpu()
     assert torch.allclose(out[:, :4 * c], lr.grad, rtol=1e-2, atol=1e-2)
     assert torch.allclose(out[:, 4 * c:], gr.grad, rtol=1e-2, atol=1e-2)
+    # bf16 upstream gradient (what the FF down-projection's dgrad GEMM writes): same result as fp32 of the rounded values
+    dpre2 = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
+    ops.geglu_bwd(pre.to(DEV), bf(dff).to(DEV), dpre2, m, n, 256)
+    dpre3 = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
+    ops.geglu_bwd(pre.to(DEV), bf(dff).float().to(DEV), dpre3, m, n, 256)
+    torch.cuda.synchronize()
+    assert torch.equal(dpre2, dpre3)
