@@ -13,6 +13,7 @@
 // per SM (256 TMEM columns, 113 KB shared each) so one CTA's softmax hides the other's MMAs.
 // Fixed reduction order; no atomics.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ddpo {
 
@@ -262,6 +263,222 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Cross-attention forward (Nk <= 128 keys: the 77 text tokens).  One 128-query tile is a single key block, so the general
+// kernel above spends its time on per-CTA fixed costs (TMEM allocation, barrier set-up, K/V fetch, pipeline fill and
+// drain for ONE block: 59 us for 84 MB of Q + O traffic at batch 16, 1.4 TB/s).  Here a CTA keeps K and V of its
+// (sample, head) resident and STREAMS query tiles through a 2-stage TMA ring; S_{i+1} = Q_{i+1} K^T is issued while the
+// softmax warps work on tile i, and only the columns that can hold keys are touched: S is a 128 x KB UMMA (KB = keys
+// rounded up to 16), the softmax walks ceil(KB / 32) chunks, P V runs KB / 16 k-steps.  No running max / rescale: one
+// block is the whole row.  Arithmetic per element and summation order are those of the general kernel (the dropped
+// columns / k-steps only ever contributed exact zeros) -> bit-identical outputs, same LSE.
+// The kernel is bound by HBM (77 FLOP per byte of Q + O: at most 0.31 of the bf16 tensor peak at the 6.58 TB/s copy rate).
+constexpr int AX_SMEM_K = 0, AX_SMEM_V = AT_TILE, AX_SMEM_Q = 2 * AT_TILE, AX_SMEM_P = 4 * AT_TILE, AX_SMEM_BAR = 6 * AT_TILE,
+              AX_SMEM_TOTAL = AX_SMEM_BAR + 256;
+
+__global__ void __launch_bounds__(AT_THREADS, 2) attention_cross_fwd_kernel(const __grid_constant__ AttnArgs p, int tiles_per_cta) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AX_SMEM_BAR);
+  uint64_t* kv_full = bars;              // 1
+  uint64_t* q_full = bars + 1;           // [2]
+  uint64_t* q_empty = bars + 3;          // [2]
+  uint64_t* s_full = bars + 5;           // [2]
+  uint64_t* o_full = bars + 7;           // [2]
+  uint64_t* x_free = bars + 9;           // [2]
+  uint64_t* p_full = bars + 11;          // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int n_qtiles = (p.nq + AT_BQ - 1) / AT_BQ;
+  const int t0 = blockIdx.x * tiles_per_cta;
+  const int nt = min(tiles_per_cta, n_qtiles - t0);   // >= 1 by construction of the grid
+  const int KB = (p.nk + 15) & ~15;                   // key columns the tensor core sees (multiple of 16, <= 128)
+  const int nchunk = (KB + 31) >> 5;                  // 32-column softmax chunks that can hold a key
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    prefetch_tmap(&p.tmQ);
+    prefetch_tmap(&p.tmK);
+    prefetch_tmap(&p.tmV);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&x_free[i], 4);
+    }
+    mbar_init(p_full, 4);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  // P columns >= 32 * nchunk are never written by the softmax warps but are read by no k-step either (k-steps cover KB
+  // <= 32 * nchunk columns); columns in [nk, 32 * nchunk) are written as zeros every tile.
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * AT_TILE);
+      tma_load_4d(smem + AX_SMEM_K, &p.tmK, kv_full, 0, head, 0, b);   // rows >= nk are zero-filled by TMA
+      tma_load_4d(smem + AX_SMEM_V, &p.tmV, kv_full, 0, head, 0, b);
+      for (int i = 0; i < nt; ++i) {
+        const int st = i & 1;
+        mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], AT_TILE);
+        tma_load_4d(smem + AX_SMEM_Q + st * AT_TILE, &p.tmQ, &q_full[st], 0, head, (t0 + i) * AT_BQ, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(AT_BQ, KB, 0, 0);     // S = Q K^T, N = KB key columns
+      const uint32_t idesc_o = umma_idesc_bf16(AT_BQ, AT_D, 0, 1);   // O = P V, B (V) MN-major
+      const uint32_t k_addr = smem_u32(smem + AX_SMEM_K), v_addr = smem_u32(smem + AX_SMEM_V);
+      const uint32_t p_addr = smem_u32(smem + AX_SMEM_P);
+      auto issue_s = [&](int i) {
+        const int st = i & 1, xb = i & 1;
+        mbar_wait(&x_free[xb], ((i >> 1) & 1) ^ 1);
+        mbar_wait(&q_full[st], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(smem + AX_SMEM_Q + st * AT_TILE);
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_bf16(tmem_base + xb * 128, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024),
+                    idesc_s, k != 0);
+        umma_commit(&s_full[xb]);
+        umma_commit(&q_empty[st]);   // the Q tile is free once these MMAs have read it
+      };
+      mbar_wait(kv_full, 0);
+      issue_s(0);
+      for (int i = 0; i < nt; ++i) {
+        if (i + 1 < nt) issue_s(i + 1);
+        const int xb = i & 1;
+        mbar_wait(p_full, i & 1);
+        tc_fence_after();
+        for (int k = 0; k < KB / 16; ++k) {
+          const uint32_t a = p_addr + (k >> 2) * AT_TILE + (k & 3) * 32;
+          const uint32_t bb = v_addr + k * 16 * 128;
+          umma_bf16(tmem_base + xb * 128, umma_desc(a, 16, 1024), umma_desc(bb, 8192, 1024), idesc_o, k != 0);
+        }
+        umma_commit(&o_full[xb]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float c = p.scale_log2e;
+    uint8_t* sP = smem + AX_SMEM_P;
+    const int nk = p.nk;
+    auto row_max = [&](int i) {
+      const int xb = i & 1;
+      mbar_wait(&s_full[xb], (i >> 1) & 1);
+      tc_fence_after();
+      float m_blk = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < nchunk * 32; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + xb * 128 + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 <= nk) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < nk) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
+        }
+      }
+      return m_blk;
+    };
+    float m_next = row_max(0);
+    for (int i = 0; i < nt; ++i) {
+      const int xb = i & 1;
+      const float m_row = m_next;
+      const float mc = m_row * c;
+      float l_row = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < nchunk * 32; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + xb * 128 + c0, v);
+        tmem_ld_wait();
+        float pr[32];
+        if (c0 + 32 <= nk) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            pr[j] = ex2_sel<DDPO_EXP_POLY_FWD>(j, __uint_as_float(v[j]) * c - mc);
+            l_row += pr[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e = ex2_sel<DDPO_EXP_POLY_FWD>(j, __uint_as_float(v[j]) * c - mc);
+            pr[j] = (c0 + j < nk) ? e : 0.f;
+            l_row += pr[j];
+          }
+        }
+        uint8_t* tile = sP + (c0 >> 6) * AT_TILE + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = ((c0 & 63) >> 3) + g;
+          uint4 u;
+          u.x = pack_bf16(pr[g * 8 + 0], pr[g * 8 + 1]);
+          u.y = pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]);
+          u.z = pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]);
+          u.w = pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(tile + ((chunk ^ (r & 7)) << 4)) = u;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (i + 1 < nt) m_next = row_max(i + 1);
+      mbar_wait(&o_full[xb], (i >> 1) & 1);
+      tc_fence_after();
+      const int row = (t0 + i) * AT_BQ + r;
+      // the general kernel's arithmetic: O_acc = 0 * alpha + O (alpha = exp2(-inf) = 0 on the first block), then * (1 / l)
+      const float inv = 1.0f / l_row;
+      __nv_bfloat16* o = p.out + (static_cast<size_t>(b) * p.nq + row) * p.ldo + head * AT_D;
+#pragma unroll
+      for (int c0 = 0; c0 < AT_D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + xb * 128 + c0, v);
+        tmem_ld_wait();
+        if (row < p.nq) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+            u.y = pack_bf16(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+            u.z = pack_bf16(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
+            u.w = pack_bf16(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
+            *reinterpret_cast<uint4*>(o + c0 + j) = u;
+          }
+        }
+      }
+      if (row < p.nq && p.lse != nullptr)
+        p.lse[(static_cast<size_t>(b) * p.heads + head) * p.nq + row] = m_row * p.scale + logf(l_row);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_free[xb]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 static int make_qkv_map(CUtensorMap* m, const void* base, int heads, int n, int batch, int ld) {
   uint64_t dims[4] = {(uint64_t)AT_D, (uint64_t)heads, (uint64_t)n, (uint64_t)batch};
   uint64_t strides[3] = {(uint64_t)AT_D * 2, (uint64_t)ld * 2, (uint64_t)ld * 2 * n};
@@ -296,7 +513,33 @@ extern "C" int ddpo_attention_fwd(const ddpo_attention_args* a, void* stream) {
     DDPO_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_TOTAL));
     attr = true;
   }
-  dim3 grid((a->nq + AT_BQ - 1) / AT_BQ, a->heads, a->batch);
+  const int n_qtiles = (a->nq + AT_BQ - 1) / AT_BQ;
+  const char* gen = getenv("DDPO_ATTN_GENERAL");   // developer switch: force the general kernel (bit-identity test, A/B timing)
+  if (a->nk <= AT_BKV && !p.causal && n_qtiles >= 2 && !(gen != nullptr && gen[0] == '1')) {
+    // cross-attention: K/V resident, query tiles streamed.  CTAs per (sample, head) so that the grid is ~2-4 CTAs per SM
+    static bool xattr = false;
+    if (!xattr) {
+      DDPO_CUDA_OK(cudaFuncSetAttribute(attention_cross_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AX_SMEM_TOTAL));
+      xattr = true;
+    }
+    // CTAs per (sample, head): minimise waves x (tiles per CTA + ~1.5 tiles of fixed cost) with 2 CTAs resident per SM
+    const int pairs = a->heads * a->batch, slots = 2 * num_sms();
+    int split = 1;
+    double best = 1e30;
+    for (int s = 1; s <= n_qtiles; ++s) {
+      const int tpc = (n_qtiles + s - 1) / s;
+      const int ctas = pairs * ((n_qtiles + tpc - 1) / tpc);
+      const double cost = static_cast<double>((ctas + slots - 1) / slots) * (tpc + 1.5);
+      if (cost < best - 1e-9) best = cost, split = s;
+    }
+    const int tiles_per_cta = (n_qtiles + split - 1) / split;
+    split = (n_qtiles + tiles_per_cta - 1) / tiles_per_cta;   // no empty CTAs
+    dim3 xgrid(split, a->heads, a->batch);
+    attention_cross_fwd_kernel<<<xgrid, AT_THREADS, AX_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(p, tiles_per_cta);
+    DDPO_LAUNCH_OK();
+    return DDPO_OK;
+  }
+  dim3 grid(n_qtiles, a->heads, a->batch);
   attention_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(p);
   DDPO_LAUNCH_OK();
   return DDPO_OK;

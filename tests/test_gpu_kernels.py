@@ -289,6 +289,31 @@ def test_attention_fwd(b, heads, nq, nk):
     assert (lse - torch.logsumexp(s, dim=-1)).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("b,heads,nq,nk", [(2, 2, 256, 77), (3, 5, 4096, 77), (2, 20, 256, 77), (1, 2, 1024, 128), (2, 1, 384, 16),
+                                           (2, 2, 300, 77)])
+def test_cross_attention_kernel_is_bit_identical_to_the_general_one(b, heads, nq, nk, monkeypatch):
+    """K/V-resident, query-streaming kernel (Nk <= 128) vs the general flash kernel: same bits, same LSE."""
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(41)
+    c = heads * 64
+    q = bf(torch.randn(b, nq, c, generator=g)).to(DEV)
+    kv = bf(torch.randn(b, nk, 2 * c, generator=g)).to(DEV)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DDPO_ATTN_GENERAL", flag)
+        out = torch.zeros(b, nq, c, dtype=torch.bfloat16, device=DEV)
+        lse = torch.zeros(b, heads, nq, device=DEV)
+        ops.attention_fwd(q, kv, kv[:, :, c:], out, b, heads, nq, nk, c, 2 * c, 2 * c, c, lse=lse)
+        torch.cuda.synchronize()
+        outs.append((out, lse))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    qh = q.float().view(b, nq, heads, 64).permute(0, 2, 1, 3)
+    kh = kv[:, :, :c].float().reshape(b, nk, heads, 64).permute(0, 2, 1, 3)
+    vh = kv[:, :, c:].float().reshape(b, nk, heads, 64).permute(0, 2, 1, 3)
+    ref = (torch.softmax((qh @ kh.transpose(-1, -2)) * 0.125, dim=-1) @ vh).permute(0, 2, 1, 3).reshape(b, nq, c)
+    assert rel_err(outs[1][0], ref) < 1e-2
+
+
 # ---------------------------------------------------------------------- norms ----
 @pytest.mark.parametrize("b,hw,c0,c1,silu", [(2, 64, 64, 0, True), (2, 4096, 320, 0, True), (3, 1024, 1280, 640, True),
                                              (2, 256, 1280, 1280, False), (1, 16, 128, 64, True)])
