@@ -58,7 +58,7 @@ def main():
     if len(sys.argv) > 2 and sys.argv[1] == "--out":        # --out NAME: write NAME.md / NAME.json instead
         prefix = traffic = sys.argv[2]
         del sys.argv[1:3]
-    md = ["# Round 1 -- ncu launch lists of one eager step (current build)\n",
+    md = [f"# {prefix}: ncu launch lists of one eager step (current build)\n",
           "Per-launch times under ncu are cold-cache and serialised: the SHARE column is what must agree with the CUDA-event",
           "breakdown `bench.py` prints (`kernels` / `ppo.kernels`).  DRAM bytes are `dram__bytes_read.sum + dram__bytes_write.sum`.\n"]
     for arg in sys.argv[1:]:
