@@ -501,6 +501,8 @@ def main():
     if args.phase in ("auto", "ppo"):
         from ddpo_b200.training import policy_gradient as pg
         Bt = TRAIN_BATCH
+        # pmean_info=False below: as the epoch driver does, the (3-float) info of a pass is not all-reduced after every pass
+        # but once per inner epoch -- the only per-pass collective of the reference loop that is not the gradient
         tstate = pg.AccumulatingTrainState(apply_fn=net)
         # a short real trajectory to train on (device resident)
         final, lat, nxt, lps, tss = pipe(emb[:Bt], neg[:Bt], {"unet": net.params, "scheduler": state}, seed_key, T_STEPS,
@@ -523,18 +525,18 @@ def main():
         batches = [make_batch((j * J) % T_STEPS) for j in range(5)]
         lc0 = ops.LAUNCH_COUNT
         pg.USE_CUDA_GRAPH = False
-        pg.train_step(tstate, batches[0], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
+        pg.train_step(tstate, batches[0], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt, pmean_info=False)
         torch.cuda.synchronize()
         train_launches = ops.LAUNCH_COUNT - lc0
         pg.USE_CUDA_GRAPH = True
         for i in range(max(3, args.warmup)):
-            _, info = pg.train_step(tstate, batches[i % len(batches)], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
+            _, info = pg.train_step(tstate, batches[i % len(batches)], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt, pmean_info=False)
         first_pass_kl = float(info["approx_kl"].item())
         if args.ncu == "train":
             pg.USE_CUDA_GRAPH = False
             torch.cuda.synchronize()
             torch.cuda.profiler.start()
-            pg.train_step(tstate, batches[1], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
+            pg.train_step(tstate, batches[1], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt, pmean_info=False)
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
             return
@@ -544,7 +546,7 @@ def main():
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record()
         for i in range(args.steps):
-            pg.train_step(tstate, batches[i % len(batches)], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
+            pg.train_step(tstate, batches[i % len(batches)], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt, pmean_info=False)
         t1e.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -553,7 +555,7 @@ def main():
         # one optimizer update: NCCL all-reduce of the flat gradient + global norm + clip/AdamW + bf16 weight refresh
         u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         u0.record()
-        pg.train_step(tstate, batches[0], st, sched, True, GUIDANCE, ETA, CLIP, True, micro_batch_size=Bt)
+        pg.train_step(tstate, batches[0], st, sched, True, GUIDANCE, ETA, CLIP, True, micro_batch_size=Bt, pmean_info=False)
         u1.record()
         torch.cuda.synchronize()
         tu = torch.tensor([u0.elapsed_time(u1)], device=dev)
@@ -583,17 +585,17 @@ def main():
             gbuf.zero_()
         # e2e train step: host-resident batch in, loss out
         hb = make_batch(1, host=True)
-        pg.train_step(tstate, hb, st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
+        pg.train_step(tstate, hb, st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt, pmean_info=False)
         torch.cuda.synchronize()
         te0 = time.perf_counter()
         for _ in range(3):
-            _, info = pg.train_step(tstate, hb, st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
+            _, info = pg.train_step(tstate, hb, st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt, pmean_info=False)
             _loss = float(info["loss"].item())
         ms_train_e2e = (time.perf_counter() - te0) / 3 * 1e3
         # profile one eager train step
         pg.USE_CUDA_GRAPH = False
         ops.PROFILE, ops.PROFILE_TAGS = [], []
-        pg.train_step(tstate, batches[1], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt)
+        pg.train_step(tstate, batches[1], st, sched, True, GUIDANCE, ETA, CLIP, False, micro_batch_size=Bt, pmean_info=False)
         torch.cuda.synchronize()
         tprof = ops.PROFILE
         ops.PROFILE = None

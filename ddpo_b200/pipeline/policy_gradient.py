@@ -112,9 +112,18 @@ def train_schedule(perm, perms, train_batch_size, num_train_ts, accumulation_ste
 def allgather_array(x):
     """``multihost_utils.process_allgather(x, tiled=True)``: concatenate over workers along axis 0."""
     x = np.asarray(x)
-    if distributed.world_size() == 1:
+    w = distributed.world_size()
+    if w == 1:
         return x
-    out = [None] * distributed.world_size()
+    if x.dtype.kind in "fiu":
+        # numeric arrays (rewards, prompt ids): one tensor all_gather -- every worker holds the same shape (the reference
+        # shards batches evenly) -- instead of pickling through all_gather_object
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.distributed.get_backend() == "nccl" else "cpu"
+        t = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+        out = [torch.empty_like(t) for _ in range(w)]
+        torch.distributed.all_gather(out, t)
+        return np.concatenate([o.cpu().numpy() for o in out])
+    out = [None] * w
     torch.distributed.all_gather_object(out, x)
     return np.concatenate(out)
 
@@ -352,10 +361,15 @@ def main(argv=None, models=None, max_epochs=None, save_last=True):
                 with _nvtx("ddpo/train_step+update" if do_opt_update else "ddpo/train_step"):
                     state, info = train_step(state, batch, noise_scheduler_state, pipeline.scheduler, args.train_cfg,
                                              args.guidance_scale, args.eta, args.ppo_clip_range, do_opt_update,
-                                             micro_batch_size=args.train_batch_size)
+                                             micro_batch_size=args.train_batch_size, pmean_info=False)
                 all_infos.append(info)
             assert do_opt_update                                                                           # :446
-            all_infos = {k: np.stack([float(i[k]) for i in all_infos]) for k in all_infos[0]}
+            # lax.pmean(info) (reference training/policy_gradient.py:142) for the whole inner epoch in one collective
+            keys = list(all_infos[0])
+            stacked = torch.stack([torch.stack([i[k] for k in keys]) for i in all_infos])                  # [steps, 3]
+            distributed.pmean_(stacked)
+            stacked = stacked.cpu().numpy()
+            all_infos = {k: stacked[:, j].astype(np.float64) for j, k in enumerate(keys)}
             print(f"mean info: { {k: float(np.mean(v)) for k, v in all_infos.items()} }")
             if worker_id == 0:
                 np.save(utils.fs.join_and_create(localpath, f"train_info/{worker_id}_{epoch}_{inner_epoch}.npy"),

@@ -152,12 +152,16 @@ def _run_body(unet: UNet, G: _StepGraph, b, train_cfg, sched_state, ratio, guida
 
 
 def train_step(state: AccumulatingTrainState, batch, noise_scheduler_state, noise_scheduler, train_cfg,
-               guidance_scale, eta, clip_range, do_opt_update, micro_batch_size=None):
+               guidance_scale, eta, clip_range, do_opt_update, micro_batch_size=None, pmean_info=True):
     """``micro_batch_size`` (extension, default = the batch size => exactly the reference call): the batch may
     stack several reference micro-batches -- e.g. the same ``train_batch_size`` samples at several of their
     timesteps, which the reference feeds through consecutive ``train_step`` calls at unchanged parameters
     (``pipeline/policy_gradient.py:410-441``) -- and is then processed as ONE large U-Net batch.  Gradients,
-    ``n_acc`` and the averaged ``info`` equal those of the consecutive calls (up to fp32 summation order)."""
+    ``n_acc`` and the averaged ``info`` equal those of the consecutive calls (up to fp32 summation order).
+
+    ``pmean_info`` (extension, default True = the reference's ``lax.pmean(info)`` every call, :142): with False the returned
+    ``info`` is this rank's; the epoch driver then averages the whole inner epoch's stack of infos over ranks in ONE
+    collective (the mean is linear: same numbers) instead of synchronising every rank after every pass."""
     assert isinstance(state, AccumulatingTrainState)
     unet = state.apply_fn
     lat = batch["latents"]
@@ -200,7 +204,8 @@ def train_step(state: AccumulatingTrainState, batch, noise_scheduler_state, nois
             G.graph, G.sig = g, sig
         G.graph.replay()
     info_t = G.info.clone()
-    distributed.pmean_(info_t)                                    # lax.pmean(info) (:142)
+    if pmean_info:
+        distributed.pmean_(info_t)                                # lax.pmean(info) (:142)
     state.apply_gradients(grads=None, do_update=do_opt_update, n_micro=b // mb)
     info = {"approx_kl": info_t[0], "clipfrac": info_t[1], "loss": info_t[2]}
     return state, info

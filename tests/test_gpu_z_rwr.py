@@ -127,6 +127,13 @@ def test_rwr_train_step_matches_oracle(train_cfg, weighted, use_graph):
     assert big.sum() > 10
     agree = np.sign(p_new - flat.numpy())[big] == np.sign(p_ref - flat.numpy())[big]
     assert agree.mean() > 0.95, agree.mean()
+    # the gradient itself, as a norm bound: Adam's first moment after one step is (1 - b1) x the clipped gradient
+    # (stored as bf16, 4e-3 relative) -> relative L2 and cosine against the oracle's clipped autograd gradient
+    g_gpu = state.opt_state["mu"].float().cpu().numpy() / (1.0 - 0.9)
+    g_clip = gref * min(1.0, 1.0 / float(gn_ref))
+    rel = np.linalg.norm(g_gpu - g_clip) / np.linalg.norm(g_clip)
+    cos = float(np.dot(g_gpu, g_clip) / (np.linalg.norm(g_gpu) * np.linalg.norm(g_clip)))
+    assert rel < 8e-2 and cos > 0.997, (rel, cos)
     assert state.step == 1 and state.n_acc == 0
 
 
