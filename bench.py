@@ -185,7 +185,7 @@ def cpu_vae_decode_seconds():
 def _ncu_traffic():
     """Average DRAM bytes (read + write) per igemm launch of one denoising step, from the committed ncu capture of
     `bench.py --ncu sample` (profiles/r1_traffic.json, written by profiles/make_launch_summary.py); None if absent."""
-    for name in ("r2_traffic.json", "r1_traffic.json"):
+    for name in ("r2_launches_summary.json",):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 return json.load(f)["sample"]["igemm"]["dram_bytes_per_launch"]

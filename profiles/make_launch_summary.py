@@ -54,7 +54,7 @@ def parse(path):
 
 def main():
     out = {}
-    prefix, traffic = "r1_launches_summary", "r1_traffic"
+    prefix, traffic = "r2_launches_summary", "r2_launches_summary"
     if len(sys.argv) > 2 and sys.argv[1] == "--out":        # --out NAME: write NAME.md / NAME.json instead
         prefix = traffic = sys.argv[2]
         del sys.argv[1:3]
