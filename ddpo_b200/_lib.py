@@ -26,7 +26,7 @@ class IGemmArgs(C.Structure):
                 ("m", i32), ("n", i32), ("wt", vp), ("bias", vp), ("rowvec", vp), ("rows_per_sample", i32),
                 ("rowvec_ld", i32), ("residual", vp), ("ld_res", i32), ("out_f32", vp), ("out_bf16", vp),
                 ("ld_out", i32), ("geglu", i32), ("accumulate_out", i32), ("bn_override", i32), ("aux_bf16", vp), ("mt_override", i32), ("pair_override", i32), ("epi_override", i32),
-                ("gn_stats", vp)]
+                ("conv_pad", i32), ("gn_stats", vp)]
 
 
 class GroupNormArgs(C.Structure):
@@ -82,6 +82,8 @@ SIGNATURES = {
     "ddpo_cast_bf16": (i32, [vp, vp, i64, vp]),
     "ddpo_upsample2x_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_upsample2x_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "ddpo_vae_image_to_nchw": (i32, [vp, vp, i32, i32, i32, vp]),
+    "ddpo_vae_encoder_head": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_conv_in": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "ddpo_conv_out": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "ddpo_timestep_sincos": (i32, [vp, i32, vp, i32, i32, vp]),

@@ -244,7 +244,8 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
     DDPO_REQUIRE(s == 1 || s == 2, "ddpo_igemm: stride must be 1 or 2");
     DDPO_REQUIRE(W > 0 && H > 0 && (W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 1024,
                  "ddpo_igemm: W,H must be powers of two, W<=1024 (W=%d H=%d)", W, H);
-    DDPO_REQUIRE(W <= BM || (s == 1 && a->mt_override == 0), "ddpo_igemm: rows wider than %d pixels need stride 1 (W=%d)", BM, W);
+    // rows wider than a tile are cut into W/128 tiles; with stride 2 the 128-pixel box spans 256 input elements (the TMA limit)
+    DDPO_REQUIRE(W <= BM || a->mt_override == 0, "ddpo_igemm: rows wider than %d pixels cannot use 256-row CTA tiles (W=%d)", BM, W);
     // a 128-row tile is bb samples x bh rows x bw pixels; rows wider than the tile are cut into W/128 tiles
     int bw = W < BM ? W : BM, bh = (BM / bw < H) ? BM / bw : H;
     int bb = BM / (bw * bh);
@@ -263,7 +264,7 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
       if (rc) return rc;
     }
     if (cin1 == 0) p.tmA1 = p.tmA0;
-    p.W = W, p.H = H, p.conv_stride = s, p.pad = a->taps == 9 ? 1 : 0;
+    p.W = W, p.H = H, p.conv_stride = s, p.pad = (a->taps == 9 && a->conv_pad == 0) ? 1 : 0;
   } else {
     DDPO_REQUIRE(a->taps == 1 && cin1 == 0, "ddpo_igemm: linear mode takes one source, one tap");
     M_total = a->m;

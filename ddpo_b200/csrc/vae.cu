@@ -125,9 +125,85 @@ __global__ void __launch_bounds__(256) vae_conv_out_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------ encoder pieces ----
+// images NHWC [B,H,W,3] in [0,1] -> NCHW (x - 0.5) / 0.5  (reference ddpo/training/callbacks.py:43-44)
+__global__ void __launch_bounds__(256) vae_image_to_nchw_kernel(const float* __restrict__ img, float* __restrict__ out,
+                                                                int64_t pixels, int64_t HW) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= pixels) return;
+  const int64_t b = i / HW, p = i % HW;
+  const float* s = img + i * 3;
+  float* o = out + b * 3 * HW + p;
+  o[0] = (s[0] - 0.5f) / 0.5f, o[HW] = (s[1] - 0.5f) / 0.5f, o[2 * HW] = (s[2] - 0.5f) / 0.5f;
+}
+
+// Encoder head in fp32: conv_out 3x3 (pad 1) Cin -> 8, quant_conv 1x1 8 -> 8, logvar clip.  One warp per pixel; a lane
+// owns 4 input channels per step (one 16-byte activation load, eight 16-byte weight loads = [4 c][8 o]).
+__global__ void __launch_bounds__(256) vae_encoder_head_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, const float* __restrict__ wq,
+                                                               const float* __restrict__ bq, float* __restrict__ moments,
+                                                               int B, int H, int W, int Cin) {
+  const int64_t pix = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  if (pix >= B * HW) return;
+  const int b = static_cast<int>(pix / HW);
+  const int hw = static_cast<int>(pix % HW), h = hw / W, ww = hw % W;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int C4 = Cin >> 2;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = h + tap / 3 - 1, xx = ww + tap % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const float4* xr = reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * H + yy) * W + xx) * Cin);
+    const float4* wr = reinterpret_cast<const float4*>(w + static_cast<size_t>(tap) * Cin * 8);
+    for (int c4 = lane; c4 < C4; c4 += 32) {
+      const float4 v = xr[c4];
+      const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 w0 = __ldg(wr + (c4 * 4 + c) * 2), w1 = __ldg(wr + (c4 * 4 + c) * 2 + 1);
+        acc[0] = fmaf(xv[c], w0.x, acc[0]), acc[1] = fmaf(xv[c], w0.y, acc[1]);
+        acc[2] = fmaf(xv[c], w0.z, acc[2]), acc[3] = fmaf(xv[c], w0.w, acc[3]);
+        acc[4] = fmaf(xv[c], w1.x, acc[4]), acc[5] = fmaf(xv[c], w1.y, acc[5]);
+        acc[6] = fmaf(xv[c], w1.z, acc[6]), acc[7] = fmaf(xv[c], w1.w, acc[7]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = warp_sum(acc[o]) + bias[o];
+  if (lane < 8) {
+    float m = bq[lane];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m = fmaf(acc[i], wq[i * 8 + lane], m);   // quant_conv kernel [in, out]
+    if (lane >= 4) m = fminf(fmaxf(m, -30.0f), 20.0f);                    // logvar half of the moments
+    moments[pix * 8 + lane] = m;
+  }
+}
+
 }  // namespace ddpo
 
 using namespace ddpo;
+
+extern "C" int ddpo_vae_image_to_nchw(const float* img_nhwc, float* out_nchw, int batch, int h, int w, void* stream) {
+  DDPO_REQUIRE(img_nhwc && out_nchw && batch > 0 && h > 0 && w > 0, "vae_image_to_nchw: bad arguments");
+  const int64_t px = static_cast<int64_t>(batch) * h * w;
+  vae_image_to_nchw_kernel<<<static_cast<unsigned>((px + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      img_nhwc, out_nchw, px, static_cast<int64_t>(h) * w);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
+extern "C" int ddpo_vae_encoder_head(const float* x_nhwc, const float* w_hwio, const float* bias, const float* wq_in_out,
+                                     const float* bq, float* moments_nhwc, int batch, int h, int w, int cin, void* stream) {
+  DDPO_REQUIRE(x_nhwc && w_hwio && bias && wq_in_out && bq && moments_nhwc && batch > 0 && h > 0 && w > 0 && cin > 0 &&
+                   cin % 4 == 0,
+               "vae_encoder_head: bad arguments (cin=%d must be a multiple of 4)", cin);
+  const int64_t pix = static_cast<int64_t>(batch) * h * w;
+  vae_encoder_head_kernel<<<static_cast<unsigned>((pix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nhwc, w_hwio, bias, wq_in_out, bq, moments_nhwc, batch, h, w, cin);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
 
 extern "C" int ddpo_vae_post_quant(const float* latents_nchw, const float* w_in_out, const float* bias, float scaling,
                                    int batch, int channels, int h, int w, float* out_nchw, void* stream) {

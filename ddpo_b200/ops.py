@@ -152,7 +152,8 @@ def ppo_loss(logp, old_logp, adv, clip_range, info_out, dlogp_out, micro_batch=N
 # ------------------------------------------------------------------ GEMM --------
 def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None, m=None, taps=1, stride=1,
           bias=None, rowvec=None, rows_per_sample=0, rowvec_ld=0, residual=None, ld_res=0, out_f32=None,
-          out_bf16=None, ld_out=0, geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0, gn_stats=None):
+          out_bf16=None, ld_out=0, geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0, gn_stats=None,
+          no_low_pad=False):
     """conv=(batch, h_out, w_out) for convolutions, else linear with m rows."""
     a = IGemmArgs()
     a.a0, a.a1 = _p(a0), _p(a1)
@@ -177,6 +178,7 @@ def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None,
     a.pair_override = int(pair)
     a.epi_override = int(epi)
     a.gn_stats = _p(gn_stats)
+    a.conv_pad = int(no_low_pad)
     rows = a.batch * a.h * a.w if a.is_conv else a.m
     _e = _ev()
     _run("igemm", lib().ddpo_igemm(C.byref(a), _stream()), 2.0 * rows * a.n * a.taps * (a.c0 + a.c1), _e,
@@ -525,6 +527,22 @@ def softmax_rows(scores, probs_bf16, scale):
     _e = _ev()
     _run("softmax_rows", lib().ddpo_softmax_rows(_p(scores), n, float(scale), _p(probs_bf16), n, rows, n, _stream()),
          float(rows) * n * 6, _e)
+
+
+def vae_image_to_nchw(img_nhwc, out_nchw):
+    _chk(img_nhwc, torch.float32, "images")
+    _chk(out_nchw, torch.float32, "out")
+    b, h, w, c = img_nhwc.shape
+    assert c == 3 and tuple(out_nchw.shape) == (b, 3, h, w)
+    _e = _ev()
+    _run("vae_image_to_nchw", lib().ddpo_vae_image_to_nchw(_p(img_nhwc), _p(out_nchw), b, h, w, _stream()), 0.0, _e)
+
+
+def vae_encoder_head(x_nhwc, w, bias, wq, bq, moments, batch, h, wd, cin):
+    _chk(moments, torch.float32, "moments")
+    _e = _ev()
+    _run("vae_encoder_head", lib().ddpo_vae_encoder_head(_p(x_nhwc), _p(w), _p(bias), _p(wq), _p(bq), _p(moments), batch, h,
+                                                         wd, cin, _stream()), 0.0, _e)
 
 
 def vae_conv_out(x_nhwc, w, bias, batch, h, wd, cin, raw_nchw=None, img_nhwc=None):

@@ -49,7 +49,11 @@ def main(argv=None, models=None):
                                  cache=args.cache, device=device)
     pipeline, params = models
     pipeline.safety_checker = None
-    callback_fns = {args.filter_field: training.callback_fns[args.filter_field]()}       # :47-48 ("vae": see docstring)
+    callback_fns = {args.filter_field: training.callback_fns[args.filter_field]()}       # :47-48
+    # the "vae" callback of the reference (:45-48): posterior moments of the DECODED image from the VAE encoder.  A pipeline
+    # without an encoder (models passed in by a caller) falls back to the latent's own moments, see latents_to_moments
+    vae_encoder = getattr(pipeline, "vae_encoder", None)
+    vae_callback = training.callback_fns["vae"](encoder=vae_encoder) if vae_encoder is not None else None
     training_diffusion.patch_scheduler(pipeline)                                         # :55
 
     writer = utils.ShardWriter(args.savepath, split_size=args.local_size)                # :59-67
@@ -89,7 +93,8 @@ def main(argv=None, models=None):
         avg(rewards.mean().item())
         mask = masker(rewards)                                                           # :139
         batch = {"inference_prompts": inference_prompts, "training_prompts": list(training_prompts), "images": images,
-                 "vae": latents_to_moments(final_latents), **{key: np.asarray(rew) for key, (rew, _) in infos.items()}}
+                 "vae": vae_callback(images)[0] if vae_callback is not None else latents_to_moments(final_latents),
+                 **{key: np.asarray(rew) for key, (rew, _) in infos.items()}}
         n_added = writer.add_batch(batch, mask=mask)
         n_steps += 1
         tot = torch.tensor([float(n_added)], dtype=torch.float64)

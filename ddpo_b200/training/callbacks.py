@@ -142,6 +142,22 @@ def llava_bertscore_fn(devices=None, jit=False, url=None, batch_size=16, timeout
     return _fn
 
 
+def vae_fn(devices=None, dtype="float32", jit=True, encoder=None, pretrained_model="tiny", seed=0, device="cuda"):
+    """Reference ``callbacks.py:37-57``: ``fn(images NHWC in [0, 1]) -> (concatenate([posterior mean, logvar], -1), {})``,
+    the ``"vae"`` field of the RWR shards.  ``encoder``: a ``ddpo_b200.vae.VAEEncoder`` (``utils.load_unet`` attaches the
+    checkpoint's, or a random-init one, as ``pipeline.vae_encoder``); without one an encoder of ``pretrained_model``'s
+    architecture is built with random-init weights."""
+    if encoder is None:
+        from ..vae import VAEEncoder, vae_config_for
+        encoder = VAEEncoder(vae_config_for(pretrained_model), device=device, seed=seed)
+
+    def _fn(images, prompts=None, metadata=None):
+        import torch
+        mom = encoder.encode(torch.as_tensor(np.asarray(images, np.float32)))
+        return mom.float().cpu().numpy(), {}
+    return _fn
+
+
 def evaluate_callbacks(fns, images, prompts, metadata):
     if type(prompts[0]) == list:
         prompts = [random.choice(p) for p in prompts]
@@ -157,4 +173,5 @@ callback_fns = {
     "llava_bertscore": llava_bertscore_fn,
     "llava_vqa": _cached_score_stub("llava_vqa", False),     # callbacks.py:401-461 needs the LLaVA server; offline stub
     "vqa": _cached_score_stub("vqa", True),
+    "vae": vae_fn,
 }

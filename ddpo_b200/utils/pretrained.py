@@ -149,7 +149,8 @@ def load_unet_weights(directory):
     return cfg, fill_flat(table, total, named, "unet")
 
 
-def load_vae_decoder_weights(directory):
+def load_vae_decoder_weights(directory, part="decoder"):
+    """-> (VAEConfig, flat fp32 parameters of the decoder (+ post_quant_conv) or, part="encoder", the encoder (+ quant_conv))"""
     from .. import vae as V
     folder = os.path.join(directory, "vae")
     with open(os.path.join(folder, "config.json")) as f:
@@ -157,7 +158,7 @@ def load_vae_decoder_weights(directory):
     cfg = V.VAEConfig(latent_channels=j.get("latent_channels", 4), out_channels=j.get("out_channels", 3),
                       block_out_channels=tuple(j["block_out_channels"]), layers_per_block=j.get("layers_per_block", 2),
                       sample_size=j.get("sample_size", 512) // 2 ** (len(j["block_out_channels"]) - 1))
-    table, total = V.param_offsets(cfg)
+    table, total = V.param_offsets(cfg, part=part)
     kind, w = _read_weights(folder, "diffusion_flax_model.msgpack",
                             ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.bin"))
     if kind == "flax":
@@ -172,7 +173,7 @@ def load_vae_decoder_weights(directory):
                 k = k.replace(f"attentions.0.{a}.", f"attentions.0.{b}.")
             w2[k] = v
         named = pt_state_to_flax_flat(w2, table)
-    return cfg, fill_flat(table, total, named, "vae decoder")
+    return cfg, fill_flat(table, total, named, f"vae {part}")
 
 
 def load_text_encoder_weights(directory):

@@ -203,13 +203,17 @@ def load_unet(loadpath, epoch="latest", pretrained_model="stabilityai/stable-dif
     ckpt_dir = pretrained.resolve_dir(pretrained_model, cache)
     sched_kw = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
                     set_alpha_to_one=False, steps_offset=1, prediction_type="epsilon")
-    vae_flat = vae_cfg = text_flat = text_cfg = tokenizer = None
+    vae_flat = vae_enc_flat = vae_cfg = text_flat = text_cfg = tokenizer = None
     if ckpt_dir is not None:
         print(f"[ utils/serialization ] Loading {pretrained_model} from {ckpt_dir} | dtype: {dtype}")
         cfg, flat = pretrained.load_unet_weights(ckpt_dir)
         sched_kw.update(pretrained.load_scheduler_config(ckpt_dir))
         if with_vae and os.path.isdir(os.path.join(ckpt_dir, "vae")):
             vae_cfg, vae_flat = pretrained.load_vae_decoder_weights(ckpt_dir)
+            try:
+                _, vae_enc_flat = pretrained.load_vae_decoder_weights(ckpt_dir, part="encoder")
+            except KeyError:      # a decoder-only checkpoint: the encoder stays random-init
+                vae_enc_flat = None
         if text_encoder == "clip" and os.path.isdir(os.path.join(ckpt_dir, "text_encoder")):
             text_cfg, text_flat = pretrained.load_text_encoder_weights(ckpt_dir)
         tokenizer = pretrained.load_tokenizer(ckpt_dir)
@@ -231,11 +235,14 @@ def load_unet(loadpath, epoch="latest", pretrained_model="stabilityai/stable-dif
         flat = flat_from_tree(tree, cfg)
     unet = UNet(cfg, flat, device)
     scheduler = DDIMScheduler(device=device, **sched_kw)
-    vae = None
+    vae = vae_encoder = None
     if with_vae:
-        from ..vae import VAEDecoder, vae_config_for
+        from ..vae import VAEDecoder, VAEEncoder, vae_config_for
         vae = (VAEDecoder(vae_cfg, vae_flat, device=device) if vae_flat is not None
                else VAEDecoder(vae_config_for(arch), device=device, seed=seed + 1))
+        if str(device) != "cpu":   # the RWR sampler's "vae" field; the CPU dry runs of the drivers never encode
+            vae_encoder = (VAEEncoder(vae_cfg, vae_enc_flat, device=device) if vae_enc_flat is not None
+                           else VAEEncoder(vae.cfg, device=device, seed=seed + 3))
     if text_encoder == "clip":
         # the CLIP text tower on the GPU; without tokenizer files the stub tokenizer's ids are folded into its vocabulary
         from ..text_encoder import CLIPTextEncoder, text_config_for
@@ -245,6 +252,7 @@ def load_unet(loadpath, epoch="latest", pretrained_model="stabilityai/stable-dif
         tenc = StubTextEncoder(cfg.cross_attention_dim)
     pipeline = StableDiffusionPipeline(unet, scheduler, tokenizer=tokenizer or StubTokenizer(), text_encoder=tenc, vae=vae,
                                        vae_scale_factor=8)
+    pipeline.vae_encoder = vae_encoder
     params = {"unet": unet.params, "vae": None if vae is None else vae.params,
               "text_encoder": getattr(tenc, "params", {}), "scheduler": scheduler.create_state()}
     return pipeline, params

@@ -84,22 +84,49 @@ def param_manifest(cfg: VAEConfig) -> List[Tuple[str, Tuple[int, ...]]]:
     return out
 
 
-def param_offsets(cfg: VAEConfig, align: int = 64):
+def encoder_param_manifest(cfg: VAEConfig) -> List[Tuple[str, Tuple[int, ...]]]:
+    """``encoder/...`` + ``quant_conv`` of the Flax checkpoint (3P ``FlaxEncoder``): conv_in, per level two ResNets (+ a
+    stride-2 ``downsamplers_0/conv`` on all but the last), mid block, conv_norm_out, conv_out -> 2 x latent channels."""
+    lc, boc = cfg.latent_channels, cfg.block_out_channels
+    out: List[Tuple[str, Tuple[int, ...]]] = [("encoder/conv_in/kernel", (3, 3, cfg.out_channels, boc[0])),
+                                              ("encoder/conv_in/bias", (boc[0],))]
+    prev = boc[0]
+    for i, co in enumerate(boc):
+        for l in range(cfg.layers_per_block):
+            _resnet(f"encoder/down_blocks_{i}/resnets_{l}", prev if l == 0 else co, co, out)
+        if i < len(boc) - 1:
+            out += [(f"encoder/down_blocks_{i}/downsamplers_0/conv/kernel", (3, 3, co, co)),
+                    (f"encoder/down_blocks_{i}/downsamplers_0/conv/bias", (co,))]
+        prev = co
+    c = boc[-1]
+    _resnet("encoder/mid_block/resnets_0", c, c, out)
+    a = "encoder/mid_block/attentions_0"
+    out += [(f"{a}/group_norm/scale", (c,)), (f"{a}/group_norm/bias", (c,))]
+    for leaf in ("query", "key", "value", "proj_attn"):
+        out += [(f"{a}/{leaf}/kernel", (c, c)), (f"{a}/{leaf}/bias", (c,))]
+    _resnet("encoder/mid_block/resnets_1", c, c, out)
+    out += [("encoder/conv_norm_out/scale", (c,)), ("encoder/conv_norm_out/bias", (c,)),
+            ("encoder/conv_out/kernel", (3, 3, c, 2 * lc)), ("encoder/conv_out/bias", (2 * lc,)),
+            ("quant_conv/kernel", (1, 1, 2 * lc, 2 * lc)), ("quant_conv/bias", (2 * lc,))]
+    return out
+
+
+def param_offsets(cfg: VAEConfig, align: int = 64, part: str = "decoder"):
     off, table = 0, {}
-    for name, shape in param_manifest(cfg):
+    for name, shape in (param_manifest(cfg) if part == "decoder" else encoder_param_manifest(cfg)):
         table[name] = (off, shape)
         off += (int(np.prod(shape)) + align - 1) // align * align
     return table, off
 
 
-def num_params(cfg: VAEConfig) -> int:
-    return sum(int(np.prod(s)) for _, s in param_manifest(cfg))
+def num_params(cfg: VAEConfig, part: str = "decoder") -> int:
+    return sum(int(np.prod(s)) for _, s in (param_manifest(cfg) if part == "decoder" else encoder_param_manifest(cfg)))
 
 
-def init_flat_params(cfg: VAEConfig, seed: int = 0) -> torch.Tensor:
-    """Random-init decoder weights (synthetic; no checkpoints offline): fan-in-scaled normal kernels, small biases,
-    norm scale 1 + N(0, .1); generated on the CPU so the oracle and the CUDA path see identical bytes."""
-    table, total = param_offsets(cfg)
+def init_flat_params(cfg: VAEConfig, seed: int = 0, part: str = "decoder") -> torch.Tensor:
+    """Random-init decoder (or encoder) weights (synthetic; no checkpoints offline): fan-in-scaled normal kernels, small
+    biases, norm scale 1 + N(0, .1); generated on the CPU so the oracle and the CUDA path see identical bytes."""
+    table, total = param_offsets(cfg, part=part)
     g = torch.Generator(device="cpu").manual_seed(seed)
     flat = torch.zeros(total, dtype=torch.float32)
     for name, (off, shape) in table.items():
@@ -115,21 +142,26 @@ def init_flat_params(cfg: VAEConfig, seed: int = 0) -> torch.Tensor:
     return flat
 
 
-def views(flat: torch.Tensor, cfg: VAEConfig) -> Dict[str, torch.Tensor]:
-    table, _ = param_offsets(cfg)
+def views(flat: torch.Tensor, cfg: VAEConfig, part: str = "decoder") -> Dict[str, torch.Tensor]:
+    table, _ = param_offsets(cfg, part=part)
     return {k: flat[o:o + int(np.prod(s))].view(*s) for k, (o, s) in table.items()}
 
 
-class VAEDecoder:
+class _VAEHalf:
+    """What the decoder and the encoder share: one flat fp32 parameter buffer in Flax layout, bf16 GEMM operands, an arena,
+    and the two building blocks (ResNet without time embedding, single-head attention block)."""
+    PART = "decoder"
+    CUDA_CORE_LAYERS = ()   # layers that are not tensor-core shaped (K = 4 / 27 / 36, N = 3 / 8): fp32 CUDA-core kernels
+
     def __init__(self, cfg: VAEConfig = SD_VAE, flat_params: torch.Tensor = None, device="cuda", seed: int = 0,
                  decode_batch: int = 2):
         assert all(c % 64 == 0 for c in cfg.block_out_channels), "channel counts must be multiples of 64"
         assert cfg.latent_channels == 4 and cfg.out_channels == 3
         self.cfg = cfg
         self.device = torch.device(device)
-        self.table, self.total = param_offsets(cfg)
+        self.table, self.total = param_offsets(cfg, part=self.PART)
         if flat_params is None:
-            flat_params = init_flat_params(cfg, seed)
+            flat_params = init_flat_params(cfg, seed, part=self.PART)
         assert flat_params.numel() == self.total
         self.params = flat_params.to(self.device, F32).contiguous()
         self.arena = Arena(self.device)
@@ -147,8 +179,8 @@ class VAEDecoder:
             if not name.endswith("/kernel"):
                 continue
             base = name[: -len("/kernel")]
-            if base in ("post_quant_conv", "decoder/conv_in", "decoder/conv_out"):
-                continue  # not tensor-core shaped (K = 4 / 36, N = 3): fp32 CUDA-core kernels
+            if base in self.CUDA_CORE_LAYERS:
+                continue
             k, n = int(np.prod(shape[:-1])), int(shape[-1])
             if base not in self.w:
                 self.w[base] = torch.empty(n, k, dtype=BF16, device=self.device)
@@ -221,6 +253,12 @@ class VAEDecoder:
             A.release(t)
         return out
 
+
+
+class VAEDecoder(_VAEHalf):
+    PART = "decoder"
+    CUDA_CORE_LAYERS = ("post_quant_conv", "decoder/conv_in", "decoder/conv_out")
+
     # ----------------------------------------------------------------- forward ----
     def _decode_chunk(self, latents, raw_out, img_out):
         cfg, A = self.cfg, self.arena
@@ -284,3 +322,70 @@ class VAEDecoder:
         return self.decode(latents, want_raw=False, want_images=True)
 
     __call__ = decode_to_images
+
+
+class VAEEncoder(_VAEHalf):
+    """VAE encoder on the same kernels -- what the reference's ``vae_fn`` computes for the RWR data path
+    (``ddpo/training/callbacks.py:37-57``: ``(images - 0.5) / 0.5`` -> 3P ``FlaxAutoencoderKL.encode`` ->
+    ``concatenate([latent_dist.mean, latent_dist.logvar], -1)``): conv_in, per level two ResNets and a stride-2 down-sample
+    whose Flax padding ((0,1),(0,1)) + VALID is the implicit GEMM's ``no_low_pad`` tap geometry (reads past the high edge
+    are TMA zero fill), mid block, GroupNorm + swish, then the fp32 head (conv_out to 8 channels, ``quant_conv`` 1x1, logvar
+    clip to [-30, 20]).  Parameter names / layouts are the Flax checkpoint's (``encoder/...``, ``quant_conv``)."""
+    PART = "encoder"
+    CUDA_CORE_LAYERS = ("encoder/conv_in", "encoder/conv_out", "quant_conv")
+
+    def _encode_chunk(self, images, moments_out):
+        cfg, A = self.cfg, self.arena
+        b, H, W, _ = images.shape
+        boc = cfg.block_out_channels
+        xin = A.alloc((b, 3, H, W), F32)
+        ops.vae_image_to_nchw(images, xin)
+        c, h, w = boc[0], H, W
+        x = A.alloc_with_gn_stats((b * h * w, c), h * w)
+        ops.conv_in(xin, self.p("encoder/conv_in/kernel"), self.p("encoder/conv_in/bias"), x, b, 3, h, w, c, gn_stats=_st(x))
+        A.release(xin)
+        prev = c
+        for i, co in enumerate(boc):
+            for l in range(cfg.layers_per_block):
+                y = self._resnet(f"encoder/down_blocks_{i}/resnets_{l}", x, prev if l == 0 else co, co, b, h, w)
+                A.release(x)
+                x = y
+            if i < len(boc) - 1:
+                name = f"encoder/down_blocks_{i}/downsamplers_0"
+                xb = A.alloc((b * h * w, co), BF16)
+                ops.cast_bf16(x, xb)
+                A.release(x)
+                h, w = h // 2, w // 2
+                x = A.alloc_with_gn_stats((b * h * w, co), h * w)
+                ops.igemm(a0=xb, wt=self.w[name + "/conv"], n=co, c0=co, conv=(b, h, w), taps=9, stride=2, no_low_pad=True,
+                          bias=self.p(name + "/conv/bias"), out_f32=x, gn_stats=_st(x))
+                A.release(xb)
+            prev = co
+        c = boc[-1]
+        for name, kind in (("encoder/mid_block/resnets_0", "r"), ("encoder/mid_block/attentions_0", "a"),
+                           ("encoder/mid_block/resnets_1", "r")):
+            y = self._resnet(name, x, c, c, b, h, w) if kind == "r" else self._attention(name, x, c, b, h, w)
+            A.release(x)
+            x = y
+        gws = A.alloc((ops.groupnorm_workspace_floats(b, h * w, c),), F32)
+        yf = A.alloc((b * h * w, c), F32)
+        ops.groupnorm_fwd(x, self.p("encoder/conv_norm_out/scale"), self.p("encoder/conv_norm_out/bias"), gws, b, h * w, c,
+                          silu=True, y_f32=yf, eps=GN_EPS, stats0=_st(x))
+        ops.vae_encoder_head(yf, self.p("encoder/conv_out/kernel"), self.p("encoder/conv_out/bias"),
+                             self.p("quant_conv/kernel"), self.p("quant_conv/bias"), moments_out, b, h, w, c)
+        for t in (x, gws, yf):
+            A.release(t)
+
+    @torch.no_grad()
+    def encode(self, images: torch.Tensor):
+        """images fp32 NHWC [B, H, W, 3] in [0, 1] -> posterior moments fp32 NHWC [B, H/8, W/8, 8] (mean | logvar)."""
+        images = torch.as_tensor(images).to(self.device, F32).contiguous()
+        B, H, W, _ = images.shape
+        down = 2 ** (len(self.cfg.block_out_channels) - 1)
+        out = torch.empty(B, H // down, W // down, 2 * self.cfg.latent_channels, device=self.device)
+        for s in range(0, B, self.decode_batch):
+            e = min(B, s + self.decode_batch)
+            self._encode_chunk(images[s:e], out[s:e])
+        return out
+
+    __call__ = encode

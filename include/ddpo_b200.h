@@ -122,6 +122,8 @@ typedef struct {
   int mt_override;          /* 0 = auto; 1 / 2 = force 128- / 256-row CTA tiles */
   int pair_override;        /* 0 = auto; 1 = force the CTA-pair (cta_group::2) kernel; 2 = force the 1-CTA kernel */
   int epi_override;         /* 0 = auto; 1 = force the TMA-staged epilogue (pair kernel); 2 = force the register epilogue */
+  int conv_pad;             /* 0 = the 3x3 default (symmetric pad 1); 1 = NO low-side padding: out[y,x] = sum in[s y + dy, s x + dx],
+                               reads past the high edge are zero -- the VAE encoder's down-sample (pad ((0,1),(0,1)) + VALID) */
   float* gn_stats;          /* optional, with out_f32: fp32 [ceil(M/32), n, 2] = per 32-row slab and output column the (sum, sum
                                of squares) of the values written to out_f32.  The GroupNorm that consumes out_f32 takes its
                                statistics from these (ddpo_groupnorm_args.stats0/1) instead of reading the tensor twice. */
@@ -279,6 +281,13 @@ int ddpo_softmax_rows(const float* scores, int64_t ld_scores, float scale, void*
                       int n, void* stream);
 /* decoder conv_out (3x3, cin -> 3) on the normalised fp32 NHWC input; raw_nchw [B,3,H,W] (decoder .sample, optional)
  * and img_nhwc [B,H,W,3] = (raw/2 + 0.5).clip(0,1) (optional) */
+/* VAE encoder pieces (reference ddpo/training/callbacks.py:37-57 `vae_fn`; 3P FlaxAutoencoderKL.encode):
+ * images NHWC in [0,1] -> NCHW (x - 0.5) / 0.5 */
+int ddpo_vae_image_to_nchw(const float* img_nhwc, float* out_nchw, int batch, int h, int w, void* stream);
+/* 3x3 conv (pad 1) to 8 channels in fp32 (encoder conv_out: precision-critical, N = 8 is not tensor-core shaped),
+ * then quant_conv (1x1, 8 -> 8) and the posterior's logvar clip to [-30, 20]: moments NHWC [batch, h, w, 8] = mean | logvar */
+int ddpo_vae_encoder_head(const float* x_nhwc, const float* w_hwio, const float* bias, const float* wq_in_out,
+                          const float* bq, float* moments_nhwc, int batch, int h, int w, int cin, void* stream);
 int ddpo_vae_conv_out(const float* x_nhwc, const float* w_hwio, const float* bias, float* raw_nchw, float* img_nhwc,
                       int batch, int h, int w, int cin, void* stream);
 

@@ -59,3 +59,34 @@ def decode(params, cfg, latents, dtype=torch.float32, taps=None):
     raw = _conv(x, p, "decoder/conv_out")                        # NHWC
     images = (raw / 2 + 0.5).clamp(0, 1)
     return images, raw.permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------ encoder ----
+def encode(params, cfg, images_nhwc, dtype=torch.float32):
+    """torch-CPU restatement of what the reference's ``vae_fn`` computes (``ddpo/training/callbacks.py:37-57``):
+    ``images`` NHWC in [0, 1] -> ``(x - 0.5) / 0.5`` -> 3P diffusers==0.12.1 ``FlaxAutoencoderKL.encode`` (``vae_flax.py``:
+    ``FlaxEncoder``: conv_in; per level two ResNets and -- on all but the last -- ``FlaxDownsample2D`` = pad ((0,1),(0,1)) on
+    the HIGH side only, then a VALID 3x3 stride-2 conv; mid block (ResNet, single-head attention, ResNet);
+    ``GroupNorm(32, eps 1e-6)`` -> swish -> conv_out to 2 x latent channels; then ``quant_conv`` 1x1) ->
+    ``FlaxDiagonalGaussianDistribution``: mean, logvar = split(moments), logvar clipped to [-30, 20].
+    Returns ``concatenate([mean, logvar], -1)`` NHWC ``[B, h/8, w/8, 8]``.  Parameter names follow the Flax checkpoint
+    (``encoder/...``, ``quant_conv``)."""
+    p = {k: v.to(dtype) for k, v in params.items()}
+    x = (torch.as_tensor(images_nhwc).to(dtype) - 0.5) / 0.5
+    x = _conv(x, p, "encoder/conv_in")
+    n = len(cfg.block_out_channels)
+    for i in range(n):
+        for l in range(cfg.layers_per_block):
+            x = _resnet(x, p, f"encoder/down_blocks_{i}/resnets_{l}")
+        if i < n - 1:
+            x = torch.nn.functional.pad(x, (0, 0, 0, 1, 0, 1))          # NHWC: pad W and H by one on the high side
+            x = _conv(x, p, f"encoder/down_blocks_{i}/downsamplers_0/conv", stride=2, pad=0)
+    x = _resnet(x, p, "encoder/mid_block/resnets_0")
+    x = _attention(x, p, "encoder/mid_block/attentions_0")
+    x = _resnet(x, p, "encoder/mid_block/resnets_1")
+    x = silu(group_norm(x, p["encoder/conv_norm_out/scale"], p["encoder/conv_norm_out/bias"], eps=GN_EPS))
+    x = _conv(x, p, "encoder/conv_out")
+    moments = _conv(x, p, "quant_conv", pad=0)
+    c = moments.shape[-1] // 2
+    mean, logvar = moments[..., :c], moments[..., c:].clamp(-30.0, 20.0)
+    return torch.cat([mean, logvar], dim=-1)

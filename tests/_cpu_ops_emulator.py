@@ -74,8 +74,8 @@ def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, 
 
 def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None, m=None, taps=1, stride=1, bias=None,
           rowvec=None, rows_per_sample=0, rowvec_ld=0, residual=None, ld_res=0, out_f32=None, out_bf16=None, ld_out=0,
-          geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0, gn_stats=None):
-    assert a1 is None and not geglu and rowvec is None and stride == 1
+          geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0, gn_stats=None, no_low_pad=False):
+    assert a1 is None and not geglu and rowvec is None
     assert a0.dtype == BF16 and wt.dtype == BF16
     c0 = int(c0 if c0 is not None else a0.shape[-1])
     assert c0 % 64 == 0 and n % 32 == 0, (c0, n)
@@ -83,10 +83,14 @@ def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None,
     if conv is not None:
         b, h, wd = conv
         assert wd & (wd - 1) == 0 and h & (h - 1) == 0
-        x = a0.reshape(b, h, wd, c0).float().permute(0, 3, 1, 2)
+        x = a0.reshape(b, h * stride, wd * stride, c0).float().permute(0, 3, 1, 2)
         ks = 3 if taps == 9 else 1
         wk = w.reshape(n, ks, ks, c0).permute(0, 3, 1, 2)
-        y = F.conv2d(x, wk, None, padding=ks // 2).permute(0, 2, 3, 1).reshape(b * h * wd, n)
+        if no_low_pad:      # pad on the high side only, then VALID (the VAE encoder's down-sample)
+            y = F.conv2d(F.pad(x, (0, 1, 0, 1)), wk, None, stride=stride)
+        else:
+            y = F.conv2d(x, wk, None, stride=stride, padding=ks // 2)
+        y = y.permute(0, 2, 3, 1).reshape(b * h * wd, n)
     else:
         assert taps == 1
         y = a0.reshape(m, c0).float() @ w.t()
@@ -121,6 +125,16 @@ def upsample2x_bf16(x, y, batch, h, w, c):
 
 def softmax_rows(scores, probs_bf16, scale):
     probs_bf16.copy_(torch.softmax(scores * scale, -1).to(BF16))
+
+
+def vae_image_to_nchw(img_nhwc, out_nchw):
+    out_nchw.copy_(((img_nhwc - 0.5) / 0.5).permute(0, 3, 1, 2))
+
+
+def vae_encoder_head(x_nhwc, w, bias, wq, bq, moments, batch, h, wd, cin):
+    hcv = F.conv2d(x_nhwc.reshape(batch, h, wd, cin).permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, padding=1)
+    m = torch.einsum("bihw,io->bhwo", hcv, wq.reshape(8, 8)) + bq
+    moments.copy_(torch.cat([m[..., :4], m[..., 4:].clamp(-30.0, 20.0)], -1))
 
 
 def vae_conv_out(x_nhwc, w, bias, batch, h, wd, cin, raw_nchw=None, img_nhwc=None):
@@ -277,7 +291,7 @@ def groupnorm_fwd(x0, scale, bias, ws, batch, hw, c0, x1=None, c1=0, silu=True, 
 
 def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None, m=None, taps=1, stride=1, bias=None,  # noqa: F811
           rowvec=None, rows_per_sample=0, rowvec_ld=0, residual=None, ld_res=0, out_f32=None, out_bf16=None, ld_out=0,
-          geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0, gn_stats=None):
+          geglu=False, accumulate=False, bn=0, aux_bf16=None, mt=0, pair=0, epi=0, gn_stats=None, no_low_pad=False):
     assert a0.dtype == BF16 and wt.dtype == BF16 and (a1 is None or a1.dtype == BF16)
     c0 = int(c0 if c0 is not None else a0.shape[-1])
     cin = c0 + c1
@@ -291,7 +305,11 @@ def igemm(*, a0, wt, n, a1=None, c0=None, c1=0, lda0=None, lda1=None, conv=None,
             x = torch.cat([x, a1.reshape(b, hi, wi, c1).float()], -1)
         ks = 3 if taps == 9 else 1
         wk = w.reshape(n, ks, ks, cin).permute(0, 3, 1, 2)
-        y = F.conv2d(x.permute(0, 3, 1, 2), wk, None, stride=stride, padding=ks // 2).permute(0, 2, 3, 1).reshape(b * h * wd, n)
+        if no_low_pad:      # pad on the high side only, then VALID (the VAE encoder's down-sample)
+            y = F.conv2d(F.pad(x.permute(0, 3, 1, 2), (0, 1, 0, 1)), wk, None, stride=stride)
+        else:
+            y = F.conv2d(x.permute(0, 3, 1, 2), wk, None, stride=stride, padding=ks // 2)
+        y = y.permute(0, 2, 3, 1).reshape(b * h * wd, n)
     else:
         assert taps == 1 and a1 is None
         y = a0.reshape(m, c0).float() @ w.t()

@@ -277,3 +277,44 @@ def vae_decode_twin(params, cfg, latents, scaling=0.18215):
             x = conv(F.interpolate(x, scale_factor=2.0, mode="nearest"), f"decoder/up_blocks_{i}/upsamplers_0/conv")
     raw = conv(F.silu(gn(x, "decoder/conv_norm_out")), "decoder/conv_out")
     return (raw / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1), raw
+
+
+def vae_encode_twin(params, cfg, images_nhwc):
+    """The KL-VAE encoder the PyTorch way (NCHW, F.* primitives; the PyTorch Downsample2D pads (0, 1, 0, 1) before its
+    padding-0 stride-2 conv) on Flax-layout parameters.  Returns moments NHWC [B, h/8, w/8, 8] (mean | clipped logvar)."""
+    def conv(x, name, stride=1, pad=1):
+        return F.conv2d(x, params[name + "/kernel"].permute(3, 2, 0, 1), params[name + "/bias"], stride=stride, padding=pad)
+
+    def gn(x, name):
+        return F.group_norm(x, 32, params[name + "/scale"], params[name + "/bias"], eps=1e-6)
+
+    def lin(x, name):
+        return F.linear(x, params[name + "/kernel"].t(), params[name + "/bias"])
+
+    def resnet(x, name):
+        h = conv(F.silu(gn(x, name + "/norm1")), name + "/conv1")
+        h = conv(F.silu(gn(h, name + "/norm2")), name + "/conv2")
+        if name + "/conv_shortcut/kernel" in params:
+            x = conv(x, name + "/conv_shortcut", pad=0)
+        return x + h
+
+    def attention(x, name):
+        b, c, h, w = x.shape
+        g = gn(x, name + "/group_norm").permute(0, 2, 3, 1).reshape(b, 1, h * w, c)
+        o = F.scaled_dot_product_attention(lin(g, name + "/query"), lin(g, name + "/key"), lin(g, name + "/value"))
+        return x + lin(o, name + "/proj_attn").reshape(b, h, w, c).permute(0, 3, 1, 2)
+
+    x = (images_nhwc.permute(0, 3, 1, 2) - 0.5) / 0.5
+    x = conv(x, "encoder/conv_in")
+    n = len(cfg.block_out_channels)
+    for i in range(n):
+        for l in range(cfg.layers_per_block):
+            x = resnet(x, f"encoder/down_blocks_{i}/resnets_{l}")
+        if i < n - 1:
+            x = conv(F.pad(x, (0, 1, 0, 1)), f"encoder/down_blocks_{i}/downsamplers_0/conv", stride=2, pad=0)
+    x = resnet(x, "encoder/mid_block/resnets_0")
+    x = attention(x, "encoder/mid_block/attentions_0")
+    x = resnet(x, "encoder/mid_block/resnets_1")
+    m = conv(conv(F.silu(gn(x, "encoder/conv_norm_out")), "encoder/conv_out"), "quant_conv", pad=0)
+    mean, logvar = m.chunk(2, dim=1)
+    return torch.cat([mean, logvar.clamp(-30.0, 20.0)], dim=1).permute(0, 2, 3, 1)

@@ -144,3 +144,80 @@ def test_vae_decode_full_size_properties():
     assert img.shape == (2, 512, 512, 3) and torch.isfinite(img).all()
     assert float(img.min()) >= 0.0 and float(img.max()) <= 1.0 and float(img.std()) > 1e-3
     assert torch.equal(img[0], img[1])
+
+
+# ------------------------------------------------------------------------------------------ VAE encoder ----
+@pytest.mark.parametrize("b,h,w,c,n", [(2, 8, 8, 64, 64), (1, 64, 64, 128, 128), (2, 128, 128, 64, 64), (1, 256, 256, 128, 128)])
+def test_igemm_stride2_without_low_padding(b, h, w, c, n):
+    """the VAE encoder's down-sample: Flax pad ((0,1),(0,1)) + VALID 3x3 stride 2 == out[y,x] = sum in[2y+dy, 2x+dx];
+    (h, w) is the OUTPUT grid; output rows up to 256 pixels wide (two 128-pixel tiles per row, 256-element TMA boxes)."""
+    from ddpo_b200 import ops
+    g = torch.Generator().manual_seed(30)
+    x = torch.randn(b, 2 * h, 2 * w, c, generator=g).to(torch.bfloat16).to(DEV)
+    wt = (torch.randn(3, 3, c, n, generator=g) / (3 * c ** 0.5)).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV)
+    wb = torch.empty(n, 9 * c, dtype=torch.bfloat16, device=DEV)
+    ops.prep_weight(wt.reshape(9 * c, n).contiguous(), wb, 9 * c, n)
+    out = torch.zeros(b * h * w, n, device=DEV)
+    ops.igemm(a0=x, wt=wb, n=n, c0=c, conv=(b, h, w), taps=9, stride=2, no_low_pad=True, bias=bias, out_f32=out)
+    torch.cuda.synchronize()
+    xin = torch.nn.functional.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = torch.nn.functional.conv2d(xin, wt.to(torch.bfloat16).float().permute(3, 2, 0, 1), bias, stride=2)
+    ref = ref.permute(0, 2, 3, 1).reshape(b * h * w, n)
+    assert (out - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_vae_encoder_kernels():
+    from ddpo_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    img = torch.rand(2, 24, 40, 3, generator=g).to(DEV)
+    out = torch.empty(2, 3, 24, 40, device=DEV)
+    ops.vae_image_to_nchw(img, out)
+    assert torch.equal(out, ((img - 0.5) / 0.5).permute(0, 3, 1, 2).contiguous())
+    b, h, w, c = 2, 16, 8, 128
+    x = torch.randn(b, h, w, c, generator=g).to(DEV)
+    wk = (torch.randn(3, 3, c, 8, generator=g) / 30).to(DEV)
+    bias = torch.randn(8, generator=g).to(DEV)
+    wq = torch.randn(1, 1, 8, 8, generator=g).to(DEV) * 20      # large: both logvar clip bounds are exercised
+    bq = torch.randn(8, generator=g).to(DEV)
+    mom = torch.empty(b, h, w, 8, device=DEV)
+    ops.vae_encoder_head(x, wk, bias, wq, bq, mom, b, h, w, c)
+    torch.cuda.synchronize()
+    hcv = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), wk.permute(3, 2, 0, 1), bias, padding=1)
+    m = torch.einsum("bihw,io->bhwo", hcv, wq.reshape(8, 8)) + bq
+    ref = torch.cat([m[..., :4], m[..., 4:].clamp(-30.0, 20.0)], -1)
+    assert (mom - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+    assert float(mom[..., 4:].max()) == 20.0 and float(mom[..., 4:].min()) == -30.0
+
+
+@pytest.mark.parametrize("cfg_name,b,px", [("VAE_MICRO", 3, 64), ("VAE_TINY", 2, 256)])
+def test_vae_encode_matches_oracle(cfg_name, b, px):
+    from ddpo_b200 import vae as V
+    from oracle import vae as OV
+    cfg = getattr(V, cfg_name)
+    flat = V.init_flat_params(cfg, 2, part="encoder")
+    enc = V.VAEEncoder(cfg, flat, device=DEV, decode_batch=2)
+    img = torch.rand(b, px, px, 3, generator=torch.Generator().manual_seed(9))
+    mom = enc.encode(img)
+    torch.cuda.synchronize()
+    ref = OV.encode(V.views(flat, cfg, part="encoder"), cfg, img)
+    assert tuple(mom.shape) == tuple(ref.shape) == (b, px // 8, px // 8, 8)
+    rel = ((mom.cpu() - ref).norm() / ref.norm()).item()
+    assert rel < 3e-2, rel
+    alone = enc.encode(img[1:2])
+    torch.cuda.synchronize()
+    assert torch.equal(alone[0], mom[1])        # batch invariant
+
+
+def test_vae_encode_full_size_and_callback():
+    """SD VAE encoder at 512 px (first down-sample writes rows 256 pixels wide) through the `vae` callback of the RWR path."""
+    from ddpo_b200 import vae as V
+    from ddpo_b200.training import callbacks as C
+    from oracle import vae as OV
+    enc = V.VAEEncoder(V.SD_VAE, device=DEV, seed=4, decode_batch=1)
+    img = np.random.default_rng(0).random((2, 512, 512, 3)).astype(np.float32)
+    mom, info = C.callback_fns["vae"](encoder=enc)(img)
+    assert mom.shape == (2, 64, 64, 8) and np.isfinite(mom).all() and mom[..., 4:].max() <= 20.0 and mom[..., 4:].min() >= -30.0
+    ref = OV.encode(V.views(enc.params.cpu(), V.SD_VAE, part="encoder"), V.SD_VAE, torch.from_numpy(img[:1])).numpy()
+    rel = np.linalg.norm(mom[:1] - ref) / np.linalg.norm(ref)
+    assert rel < 3e-2, rel

@@ -89,3 +89,23 @@ def test_oracle_vae_decoder_equals_pytorch_idiom_twin():
         assert raw_o.shape == raw_t.shape and img_o.shape == img_t.shape
         assert ((raw_o - raw_t).norm() / raw_t.norm()).item() < 1e-9
         assert (img_o - img_t).abs().max().item() < 1e-9
+
+
+def test_oracle_vae_encoder_equals_pytorch_idiom_twin_and_has_the_published_size():
+    from _torch_twin import vae_encode_twin
+    from ddpo_b200 import vae as V
+    from oracle import vae as OV
+    # SD VAE: 83 653 863 parameters = decoder 49 490 199 + post_quant_conv 20 + encoder 34 163 592 + quant_conv 72
+    assert V.num_params(V.SD_VAE, part="encoder") == 34_163_592 + 72
+    cfg = V.VAE_MICRO
+    flat = V.init_flat_params(cfg, 5, part="encoder").double()
+    views = V.views(flat, cfg, part="encoder")
+    img = torch.rand(2, 64, 64, 3, generator=torch.Generator().manual_seed(6), dtype=torch.float64)
+    m_o = OV.encode(views, cfg, img, dtype=torch.float64)
+    m_t = vae_encode_twin(views, cfg, img)
+    assert m_o.shape == m_t.shape == (2, 8, 8, 8)
+    assert ((m_o - m_t).norm() / m_t.norm()).item() < 1e-9
+    # logvar clipping: scale the last layer up so that both bounds are hit
+    views["quant_conv/kernel"].mul_(1e4)
+    m = OV.encode(views, cfg, img, dtype=torch.float64)
+    assert float(m[..., 4:].max()) == 20.0 and float(m[..., 4:].min()) == -30.0

@@ -80,3 +80,21 @@ def test_vae_host_assembly_dry_run_against_oracle(monkeypatch):
         rel = ((raw - raw_r).norm() / raw_r.norm()).item()
         assert rel < 3e-2, rel
         assert (img - img_r).abs().max().item() < 0.1
+
+
+def test_vae_encoder_host_assembly_dry_run_against_oracle(monkeypatch):
+    """ddpo_b200/vae.py::VAEEncoder's kernel sequencing on the CPU ops emulator against oracle/vae.py::encode: image
+    normalisation, conv_in, the one-sided stride-2 down-sampling, mid block, fp32 head (conv_out, quant_conv, logvar clip)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    import _cpu_ops_emulator as E
+    monkeypatch.setattr(V, "ops", E)
+    monkeypatch.setattr(V, "Arena", E.CpuArena)
+    cfg = V.VAE_MICRO
+    flat = V.init_flat_params(cfg, 1, part="encoder")
+    enc = V.VAEEncoder(cfg, flat, device="cpu", decode_batch=2)
+    img = torch.rand(3, 64, 64, 3, generator=torch.Generator().manual_seed(8))
+    mom = enc.encode(img)
+    ref = OV.encode(V.views(flat, cfg, part="encoder"), cfg, img)
+    assert mom.shape == ref.shape == (3, 8, 8, 8)
+    assert ((mom - ref).norm() / ref.norm()).item() < 3e-2
