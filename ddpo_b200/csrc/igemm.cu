@@ -187,27 +187,41 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
   }
 }
 
-// UMMA N of the CTA tile (multiple of 32, <= 256, divides N; GEGLU needs BN/2 % 32 == 0).  Tile shape is a pure
-// scheduling choice (the K order of every output element is fixed), so it is picked by a small cost model:
+// Width of the CTA(-pair) tile: BN = UMMA N (multiple of 32, <= 256, divides N; GEGLU needs BN/2 % 32 == 0), or -- CTA
+// pairs only -- 320 = two 160-column sub-tiles that share ONE fetch of the activation tile (igemm2.cu, NS = 2).  Tile
+// shape is a pure scheduling choice (the K order of every output element is fixed), so it is picked by a cost model:
 //   time ~ waves x (k-blocks x clks per k-block + fixed tile overhead)
-// with, per 64-deep k-block, the tensor pipe needing 2*BN clks (4096 MAC/clk/SM) and the shared-memory port
-// (128 B/clk, written once by TMA and read once by the MMA) needing 256 + BN clks in a CTA pair (128 A rows + BN/2
-// weight rows per CTA) or 256 + 2*BN clks for a single CTA.  Wide tiles win when there are many waves; narrower
-// tiles win when the widest tiling leaves most SMs idle in the last wave (e.g. 80 tiles on 74 CTA pairs).
-static int pick_bn(int N, int geglu, int M_total, int kiters, bool pair) {
+// with, per 64-deep k-block and per SM,
+//   * the tensor pipe: 2 * width clks (4096 MAC/clk/SM);
+//   * operand bytes out of L2: every tap and every column tile re-reads its operands, and the 148 SMs together get
+//     ~35 B/clk/SM out of L2 (measured: tests/microbench/l2_tma_bw.cu, and 32-35 B/clk/SM in every long-K igemm launch
+//     whatever its shape, profiles/r2_igemm.md).  16 KB of activations + 64 B x width of weights per CTA of a pair,
+//     128 B x width for a single CTA -> this, not the tensor pipe, bounds every shape: wider tiles = fewer bytes/FLOP;
+//   * the shared-memory port (128 B/clk: TMA writes + MMA reads; the activation tile is read once per sub-tile).
+// Narrower tiles win only when the widest tiling leaves most SMs idle in the last wave (e.g. 80 tiles on 74 pairs).
+static int pick_width(int N, int geglu, int M_total, int kiters, bool pair, bool allow_wide) {
   const int step = geglu ? 64 : 32;
   const int workers = pair ? num_sms() / 2 : num_sms();
   const int rows = pair ? 2 * BM : BM;
   const long tiles_m = (M_total + rows - 1) / rows;
   int best = 0;
   long best_cost = 0;
-  for (int bn = 256; bn >= step; bn -= step) {
-    if (N % bn != 0) continue;
-    const long tiles = tiles_m * (N / bn);
+  for (int w = (pair && allow_wide && !geglu) ? 320 : 256; w >= step; w -= step) {
+    if (w > 256 && w != 320) continue;
+    if (N % w != 0) continue;
+    const int ns = w > 256 ? 2 : 1;
+    const long tiles = tiles_m * (N / w);
     const long waves = (tiles + workers - 1) / workers;
-    const long mma = 2L * bn, port = pair ? 256L + bn : 256L + 2L * bn;
-    const long cost = waves * ((mma > port ? mma : port) * kiters + 1000);
-    if (best == 0 || cost < best_cost) best = bn, best_cost = cost;
+    const long mma = 2L * w;
+    const long bytes = 16384L + (pair ? 64L : 128L) * w;
+    const long l2 = bytes / 35;
+    const long port = 128L + 128L * ns + (pair ? 1L : 2L) * w;
+    long kb = mma > l2 ? mma : l2;
+    if (port > kb) kb = port;
+    // fixed cost per tile: pipeline hand-over; the wide tile cannot double-buffer its accumulators completely (3 slots of
+    // 160 TMEM columns): the drain of its first sub-tile is exposed
+    const long cost = waves * (kb * kiters + (ns == 2 ? 4000 : 1000));
+    if (best == 0 || cost < best_cost) best = w, best_cost = cost;
   }
   return best;
 }
@@ -229,8 +243,22 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
   const int m_rows = a->is_conv ? a->batch * a->w * a->h : a->m;
   // CTA pairs (cta_group::2, 256 x BN tiles) whenever the problem has enough rows; see igemm2.cu
   const bool use_pair = a->pair_override == 1 || (a->pair_override == 0 && a->mt_override == 0 && m_rows >= 1024);
+  // DDPO_IGEMM_WIDE=0 keeps every tile at one UMMA width (A/B switch for the 2 x 160 tiles)
+  static const bool allow_wide = []() {
+    const char* e = getenv("DDPO_IGEMM_WIDE");
+    return e == nullptr || e[0] != '0';
+  }();
   int BN = a->bn_override > 0 ? a->bn_override
-                              : pick_bn(a->n, a->geglu, m_rows, a->taps * (cin0 + cin1) / BK, use_pair);
+                              : pick_width(a->n, a->geglu, m_rows, a->taps * (cin0 + cin1) / BK, use_pair,
+                                           // short-K layers run the TMA-staged epilogue, whose buffers leave too few stages
+                                           allow_wide && a->epi_override != 1 &&
+                                               (a->epi_override == 2 || a->taps * (cin0 + cin1) / BK > 24));
+  int NS = 1;
+  if (BN > 256) {  // bn_override = 320 (or the cost model): two sub-tiles of 160 columns per CTA-pair tile
+    DDPO_REQUIRE(BN == 320 && use_pair && !a->geglu, "ddpo_igemm: 320-wide tiles need the CTA-pair kernel and no GEGLU");
+    DDPO_REQUIRE(a->n % 320 == 0, "ddpo_igemm: N=%d is not a multiple of 320", a->n);
+    NS = 2, BN = 160;
+  }
   DDPO_REQUIRE(BN > 0 && a->n % BN == 0 && BN % 32 == 0 && BN <= 256, "ddpo_igemm: no valid BN for N=%d", a->n);
   if (a->geglu) DDPO_REQUIRE(BN % 64 == 0 && a->out_bf16 != nullptr && a->bias != nullptr, "ddpo_igemm: bad GEGLU config");
 
@@ -285,7 +313,7 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
     int rc = make_tensor_map(&p.tmB, a->wt, 2, 2, dims, strides, box, es, 1);
     if (rc) return rc;
   }
-  p.M_total = M_total, p.N_total = a->n, p.BN = BN;
+  p.M_total = M_total, p.N_total = a->n, p.BN = BN, p.NS = NS;
   p.taps = a->taps, p.kc0 = cin0 / BK, p.kc1 = cin1 / BK, p.is_conv = a->is_conv;
   p.bias = a->bias, p.rowvec = a->rowvec, p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : 1;
   p.rowvec_ld = a->rowvec_ld;

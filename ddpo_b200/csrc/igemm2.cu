@@ -24,16 +24,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int BN = p.BN;
-  const int HB = BN >> 1;  // weight rows staged by each CTA
+  const int HB = BN >> 1;  // weight rows staged by each CTA (per sub-tile)
+  const int NS = p.NS;     // BN-wide sub-tiles per tile (1 or 2): NS = 2 fetches the activation tile ONCE for 2*BN columns
   const int stages = p.stages;
-  const int stage_bytes = A_TILE_BYTES + HB * BK * 2;
+  const int b_sub_bytes = HB * BK * 2;
+  const int stage_bytes = A_TILE_BYTES + NS * b_sub_bytes;
+  // accumulator ring in TMEM: sub-tile number jg (counted per CTA pair) lives in slot jg % nslot.  NS = 1: two slots of
+  // 256 columns (double buffering).  NS = 2: three slots of 160 columns -- the epilogue drains the first sub-tile of a
+  // tile first, which is exactly the slot the NEXT tile needs besides the free one.
+  const int nslot = NS == 2 ? 3 : 2;
+  const int slot_cols = NS == 2 ? 160 : 256;
   uint8_t* epi_base = smem;  // [EPI_BYTES] staging of the TMA epilogue (absent in register-epilogue mode)
   if (p.epi_tma) smem += EPI_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full = empty_bar + stages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_empty = tmem_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
   uint64_t* epi_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes + 256);  // [8 warps][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -41,7 +48,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   const int tiles_m = (p.M_total + 2 * BM - 1) / (2 * BM);
-  const int tiles_n = p.N_total / BN;
+  const int tiles_n = p.N_total / (NS * BN);
   const int num_tiles = tiles_m * tiles_n;
   const int kcs = p.kc0 + p.kc1;
   const int kiters = p.taps * kcs;
@@ -56,7 +63,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 16);
     }
@@ -83,7 +90,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int tm = tile / tiles_n, tn = tile % tiles_n;
         const int m0 = tm * 2 * BM + static_cast<int>(rank) * BM;  // this CTA's 128 rows
-        const int n0 = tn * BN + static_cast<int>(rank) * HB;       // this CTA's half of the weight tile
+        const int n0 = tn * NS * BN + static_cast<int>(rank) * HB;  // this CTA's half of (each sub-tile of) the weight tile
         int b0 = 0, h0 = 0, w0 = 0;
         if (p.is_conv) {
           b0 = m0 / HW;
@@ -111,7 +118,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
           } else {
             tma_load_2d_2sm(sA, &p.tmA0, &full_bar[stage], kit * BK, m0);
           }
-          tma_load_2d_2sm(sB, &p.tmB, &full_bar[stage], kit * BK, n0);
+          for (int j = 0; j < NS; ++j)
+            tma_load_2d_2sm(sB + j * b_sub_bytes, &p.tmB, &full_bar[stage], kit * BK, n0 + j * BN);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
@@ -127,10 +135,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
       uint32_t phase = 0;
       int it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        const int jg0 = it * NS, slot0 = jg0 % nslot, slot1 = (jg0 + 1) % nslot;
+        mbar_wait(&tmem_empty[slot0], ((jg0 / nslot) & 1) ^ 1);
+        if (NS == 2) mbar_wait(&tmem_empty[slot1], (((jg0 + 1) / nslot) & 1) ^ 1);
+        const uint32_t d_tmem0 = tmem_base + slot0 * slot_cols, d_tmem1 = tmem_base + slot1 * slot_cols;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 256;
         for (int kit = 0; kit < kiters; ++kit) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -138,8 +147,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
           const uint32_t b_base = a_base + A_TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16_2sm(d_tmem, umma_desc(a_base + k * 32, 16, 1024), umma_desc(b_base + k * 32, 16, 1024), idesc,
-                          (kit | k) != 0);
+            const uint64_t a_desc = umma_desc(a_base + k * 32, 16, 1024);
+            umma_bf16_2sm(d_tmem0, a_desc, umma_desc(b_base + k * 32, 16, 1024), idesc, (kit | k) != 0);
+            if (NS == 2)
+              umma_bf16_2sm(d_tmem1, a_desc, umma_desc(b_base + b_sub_bytes + k * 32, 16, 1024), idesc, (kit | k) != 0);
           }
           umma_commit_2sm(&empty_bar[stage], 0x3);
           if (++stage == stages) {
@@ -147,7 +158,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tmem_full[buf], 0x3);
+        umma_commit_2sm(&tmem_full[slot0], 0x3);
+        if (NS == 2) umma_commit_2sm(&tmem_full[slot1], 0x3);
       }
     }
   } else if (warp >= 4) {
@@ -164,34 +176,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
       EpiWarp e{epi_base + (warp - 4) * EPI_WARP_BYTES, epi_bar + (warp - 4) * EPI_RING, 0u, 0u};
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
         const int tm = tile / tiles_n, tn = tile % tiles_n;
-        const int m_slab = tm * 2 * BM + static_cast<int>(rank) * BM + q * 32, n0 = tn * BN;
-        const int buf = it & 1;
+        const int m_slab = tm * 2 * BM + static_cast<int>(rank) * BM + q * 32;
         const bool slab_ok = m_slab < p.M_total;  // warp-uniform; a slab entirely below the matrix has nothing to do
-        if (slab_ok && p.epi_in && lane == 0)
-          epi_request(p, e, e.g, (BN - cgrp * 32 + 63) / 64, e.g, n0 + cgrp * 32, 64, m_slab);
-        mbar_wait(&tmem_full[buf], (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
-        if (slab_ok) igemm_epilogue_tma(p, e, t_row, m_slab, lane, n0, BN, cgrp, 64);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&tmem_empty[buf], 0);
+        for (int j = 0; j < NS; ++j) {
+          const int jg = it * NS + j, sl = jg % nslot;
+          const int n0 = (tn * NS + j) * BN;
+          if (slab_ok && p.epi_in && lane == 0)
+            epi_request(p, e, e.g, (BN - cgrp * 32 + 63) / 64, e.g, n0 + cgrp * 32, 64, m_slab);
+          mbar_wait(&tmem_full[sl], (jg / nslot) & 1);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sl * slot_cols;
+          if (slab_ok) igemm_epilogue_tma(p, e, t_row, m_slab, lane, n0, BN, cgrp, 64);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty[sl], 0);
+        }
       }
       if (lane == 0) bulk_wait_all();
     } else
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int tm = tile / tiles_n, tn = tile % tiles_n;
-      const int m0 = tm * 2 * BM + static_cast<int>(rank) * BM, n0 = tn * BN;
-      const int buf = it & 1;
-      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
-      tc_fence_after();
+      const int m0 = tm * 2 * BM + static_cast<int>(rank) * BM;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M_total;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256;
-      igemm_epilogue(p, t_row, row, row_ok, n0, tn, BN, cgrp, 64);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tmem_empty[buf], 0);
+      for (int j = 0; j < NS; ++j) {
+        const int jg = it * NS + j, sl = jg % nslot;
+        mbar_wait(&tmem_full[sl], (jg / nslot) & 1);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sl * slot_cols;
+        igemm_epilogue(p, t_row, row, row_ok, (tn * NS + j) * BN, tn * NS + j, BN, cgrp, 64);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tmem_empty[sl], 0);
+      }
     }
   }
 
@@ -210,10 +227,11 @@ using namespace ddpo;
 
 // called by ddpo_igemm (igemm.cu) once the argument block is filled; tmB must have been encoded with box rows BN/2
 int ddpo_igemm2_launch(IGemmArgs& p, cudaStream_t stream) {
-  const int stage_bytes = A_TILE_BYTES + (p.BN / 2) * BK * 2;
+  const int stage_bytes = A_TILE_BYTES + p.NS * (p.BN / 2) * BK * 2;
   const int epi = p.epi_tma ? EPI_BYTES + EPI_BAR_BYTES : 0;
   int stages = (SMEM_BUDGET - epi) / stage_bytes;
   if (stages > 10) stages = 10;
+  DDPO_REQUIRE(stages >= 2, "ddpo_igemm: not enough shared memory for BN=%d NS=%d with the TMA epilogue", p.BN, p.NS);
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 256 + 1024 + epi;
   static bool attr_set = false;
@@ -221,7 +239,7 @@ int ddpo_igemm2_launch(IGemmArgs& p, cudaStream_t stream) {
     DDPO_CUDA_OK(cudaFuncSetAttribute(igemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int tiles = ((p.M_total + 2 * BM - 1) / (2 * BM)) * (p.N_total / p.BN);
+  const int tiles = ((p.M_total + 2 * BM - 1) / (2 * BM)) * (p.N_total / (p.NS * p.BN));
   int pairs = num_sms() / 2;
   if (pairs > tiles) pairs = tiles;
   igemm2_kernel<<<2 * pairs, IGEMM_THREADS, smem, stream>>>(p);

@@ -15,6 +15,7 @@ constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/
 struct IGemmArgs {
   CUtensorMap tmA0, tmA1, tmB;
   int M_total, N_total, BN, stages;
+  int NS;  // CTA-pair kernel: BN-wide sub-tiles per tile (1 or 2), see igemm2.cu
   int MT;  // 128-row sub-tiles per CTA tile (1 or 2).  MT = 2: BM = 256 sharing one B tile -> 33% less operand traffic
   int taps, kc0, kc1;
   int is_conv, W, H, conv_stride, pad;

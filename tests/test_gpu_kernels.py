@@ -315,6 +315,57 @@ def test_cross_attention_kernel_is_bit_identical_to_the_general_one(b, heads, nq
 
 
 # ---------------------------------------------------------------------- norms ----
+@pytest.mark.parametrize("kind,b,h,c0,c1,n,epi", [("conv", 20, 64, 320, 0, 320, 0),      # 320 tiles on 74 pairs: every TMEM slot rotation
+                                                  ("conv", 3, 32, 640, 320, 640, 0),     # two-source K, two column tiles
+                                                  ("conv", 2, 16, 128, 0, 1280, 0),      # 4 column tiles, 2 row tiles
+                                                  ("conv", 5, 8, 64, 0, 320, 0),         # 320 rows: ragged second half of the pair
+                                                  ("lin", 1, 1000, 2048, 0, 960, 0),     # ragged M, 3 column tiles, long K
+                                                  ("lin", 1, 70000, 256, 0, 320, 1)])    # TMA-staged epilogue, 274 tiles
+def test_igemm_wide_tiles_bit_identical(kind, b, h, c0, c1, n, epi):
+    """320-wide CTA-pair tiles (two 160-column sub-tiles sharing one activation fetch, three TMEM slots) are a scheduling
+    choice: outputs AND slab statistics are bit-identical to the 160-wide tiling."""
+    from ddpo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(77)
+    bias = torch.randn(n, generator=g).to(DEV)
+    c = c0 + c1
+    outs = []
+    if kind == "conv":
+        m = b * h * h
+        x0 = bf(torch.randn(b, h, h, c0, generator=g)).to(DEV)
+        x1 = bf(torch.randn(b, h, h, c1, generator=g)).to(DEV) if c1 else None
+        w = (torch.randn(9 * c, n, generator=g) / math.sqrt(9 * c)).to(DEV)
+        res = torch.randn(m, n, generator=g).to(DEV)
+        tvec = torch.randn(b, n, generator=g).to(DEV)
+        wb = _prep_w(w)
+        for bn in (160, 320):
+            out = torch.zeros(m, n, device=DEV)
+            ob = torch.zeros(m, n, device=DEV, dtype=torch.bfloat16)
+            st = torch.full(ops.gn_stats_shape(m, n), float("nan"), device=DEV)
+            ops.igemm(a0=x0, a1=x1, wt=wb, n=n, c0=c0, c1=c1, conv=(b, h, h), taps=9, bias=bias, rowvec=tvec,
+                      rows_per_sample=h * h, rowvec_ld=n, residual=res, out_f32=out, gn_stats=st, bn=bn, epi=2, pair=1)
+            ops.igemm(a0=x0, a1=x1, wt=wb, n=n, c0=c0, c1=c1, conv=(b, h, h), taps=9, bias=bias, out_bf16=ob, bn=bn, epi=2, pair=1)
+            outs.append((out, st, ob))
+    else:
+        m = h
+        x = bf(torch.randn(m, c, generator=g)).to(DEV)
+        w = (torch.randn(c, n, generator=g) / math.sqrt(c)).to(DEV)
+        res = torch.randn(m, n, generator=g).to(DEV)
+        wb = _prep_w(w)
+        for bn in (160, 320):
+            out = torch.zeros(m, n, device=DEV)
+            ob = torch.zeros(m, n, device=DEV, dtype=torch.bfloat16)
+            st = torch.full(ops.gn_stats_shape(m, n), float("nan"), device=DEV)
+            ops.igemm(a0=x, wt=wb, n=n, c0=c, m=m, bias=bias, residual=res, out_f32=out, out_bf16=ob, gn_stats=st, bn=bn,
+                      epi=1 if epi else 2, pair=1)
+            outs.append((out, st, ob))
+    torch.cuda.synchronize()
+    ref = (x.float() @ bf(w).float() + bias + res) if kind == "lin" else None
+    if ref is not None:
+        assert (outs[0][0] - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    for a, bb in zip(outs[0], outs[1]):
+        assert torch.isfinite(a.float()).all() and torch.equal(a, bb)
+
+
 @pytest.mark.parametrize("b,hw,c0,c1,silu", [(2, 64, 64, 0, True), (2, 4096, 320, 0, True), (3, 1024, 1280, 640, True),
                                              (2, 256, 1280, 1280, False), (1, 16, 128, 64, True)])
 def test_groupnorm_fwd(b, hw, c0, c1, silu):
