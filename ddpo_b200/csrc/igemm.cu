@@ -328,6 +328,12 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
                  "ddpo_igemm: gn_stats describes a plain fp32 output (no GEGLU, no accumulate)");
   if (use_pair) {
     p.MT = 1;
+    {
+      const char* e = getenv("DDPO_IGEMM_DEBUG");
+      p.dbg = e != nullptr ? atoi(e) : 0;
+      e = getenv("DDPO_IGEMM_PREFETCH");
+      p.res_prefetch = e == nullptr || e[0] != '0';
+    }
     // TMA epilogue where the epilogue, not the main loop, bounds the tile: short K (the 1x1 / linear layers).
     // Long-K convolutions hide the register epilogue behind the next tile's MMAs and keep every stage for operands.
     const int kiters = a->taps * (cin0 + cin1) / BK;

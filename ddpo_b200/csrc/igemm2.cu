@@ -19,21 +19,21 @@
 
 namespace ddpo {
 
+template <int NS>  // BN-wide sub-tiles per tile (1 or 2): NS = 2 fetches the activation tile ONCE for 2 * BN columns
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
     igemm2_kernel(const __grid_constant__ IGemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int BN = p.BN;
   const int HB = BN >> 1;  // weight rows staged by each CTA (per sub-tile)
-  const int NS = p.NS;     // BN-wide sub-tiles per tile (1 or 2): NS = 2 fetches the activation tile ONCE for 2*BN columns
   const int stages = p.stages;
   const int b_sub_bytes = HB * BK * 2;
   const int stage_bytes = A_TILE_BYTES + NS * b_sub_bytes;
   // accumulator ring in TMEM: sub-tile number jg (counted per CTA pair) lives in slot jg % nslot.  NS = 1: two slots of
   // 256 columns (double buffering).  NS = 2: three slots of 160 columns -- the epilogue drains the first sub-tile of a
   // tile first, which is exactly the slot the NEXT tile needs besides the free one.
-  const int nslot = NS == 2 ? 3 : 2;
-  const int slot_cols = NS == 2 ? 160 : 256;
+  constexpr int nslot = NS == 2 ? 3 : 2;
+  constexpr int slot_cols = NS == 2 ? 160 : 256;
   uint8_t* epi_base = smem;  // [EPI_BYTES] staging of the TMA epilogue (absent in register-epilogue mode)
   if (p.epi_tma) smem += EPI_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
@@ -81,45 +81,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The two single-role warps run their loops CONVERGED (all 32 lanes wait on the barriers and advance the counters) and
+  // elect one lane only for the issue instructions: loop state, coordinates and UMMA descriptors then live in uniform
+  // registers.  Inside an `if (lane == 0)` region the compiler keeps them in vector registers and wraps every UTMALDG /
+  // UTCHMMA in an R2UR + ELECT "waterfall": ~165 (producer) / ~120 (MMA) dependent instructions per 64-deep k-block,
+  // i.e. more clocks than the 2 * BN the tensor pipe needs for it -- the issue threads, not the tensor pipe, L2 or the
+  // shared-memory port, were what bounded the main loop (tests/prof_igemm_roles.py).
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int HW = p.W * p.H;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int tm = tile / tiles_n, tn = tile % tiles_n;
-        const int m0 = tm * 2 * BM + static_cast<int>(rank) * BM;  // this CTA's 128 rows
-        const int n0 = tn * NS * BN + static_cast<int>(rank) * HB;  // this CTA's half of (each sub-tile of) the weight tile
-        int b0 = 0, h0 = 0, w0 = 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    const int HW = p.W * p.H;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int tm = tile / tiles_n, tn = tile % tiles_n;
+      const int m0 = tm * 2 * BM + static_cast<int>(rank) * BM;    // this CTA's 128 rows
+      const int n0 = tn * NS * BN + static_cast<int>(rank) * HB;  // this CTA's half of (each sub-tile of) the weight tile
+      int b0 = 0, h0 = 0, w0 = 0;
+      if (p.is_conv) {
+        b0 = m0 / HW;
+        h0 = (m0 % HW) / p.W;
+        w0 = m0 % p.W;  // non-zero only for rows wider than a tile (W > 128: the VAE's 256 / 512 px levels)
+      }
+      int kit = 0;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        int cx = 0, cy = 0;
         if (p.is_conv) {
-          b0 = m0 / HW;
-          h0 = (m0 % HW) / p.W;
-          w0 = m0 % p.W;  // non-zero only for rows wider than a tile (W > 128: the VAE decoder's 256 / 512 px levels)
+          const int dy = p.taps == 9 ? tap / 3 : 0, dx = p.taps == 9 ? tap - dy * 3 : 0;
+          cx = w0 * p.conv_stride + dx - p.pad;
+          cy = h0 * p.conv_stride + dy - p.pad;
         }
-        for (int kit = 0; kit < kiters; ++kit) {
+        for (int ch = 0; ch < kcs; ++ch, ++kit) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * stage_bytes;
           uint8_t* sB = sA + A_TILE_BYTES;
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
-          if (p.is_conv) {
-            const int tap = kit / kcs, ch = kit - tap * kcs;
-            int dy = 0, dx = 0;
-            if (p.taps == 9) {
-              dy = tap / 3;
-              dx = tap - dy * 3;
+          if (elect_one()) {
+            if (p.dbg & 1) {
+              if (rank == 0) mbar_arrive(&full_bar[stage]);
+            } else {
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
+              if (p.is_conv) {
+                if (ch < p.kc0)
+                  tma_load_4d_2sm(sA, &p.tmA0, &full_bar[stage], ch * BK, cx, cy, b0);
+                else
+                  tma_load_4d_2sm(sA, &p.tmA1, &full_bar[stage], (ch - p.kc0) * BK, cx, cy, b0);
+              } else {
+                tma_load_2d_2sm(sA, &p.tmA0, &full_bar[stage], kit * BK, m0);
+              }
+#pragma unroll
+              for (int j = 0; j < NS; ++j)
+                tma_load_2d_2sm(sB + j * b_sub_bytes, &p.tmB, &full_bar[stage], kit * BK, n0 + j * BN);
             }
-            const int cx = w0 * p.conv_stride + dx - p.pad;
-            const int cy = h0 * p.conv_stride + dy - p.pad;
-            if (ch < p.kc0)
-              tma_load_4d_2sm(sA, &p.tmA0, &full_bar[stage], ch * BK, cx, cy, b0);
-            else
-              tma_load_4d_2sm(sA, &p.tmA1, &full_bar[stage], (ch - p.kc0) * BK, cx, cy, b0);
-          } else {
-            tma_load_2d_2sm(sA, &p.tmA0, &full_bar[stage], kit * BK, m0);
           }
-          for (int j = 0; j < NS; ++j)
-            tma_load_2d_2sm(sB + j * b_sub_bytes, &p.tmB, &full_bar[stage], kit * BK, n0 + j * BN);
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
@@ -129,7 +142,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       const uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -145,21 +158,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_base = a_base + A_TILE_BYTES;
+          if (elect_one()) {
+            if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t a_desc = umma_desc(a_base + k * 32, 16, 1024);
-            umma_bf16_2sm(d_tmem0, a_desc, umma_desc(b_base + k * 32, 16, 1024), idesc, (kit | k) != 0);
-            if (NS == 2)
-              umma_bf16_2sm(d_tmem1, a_desc, umma_desc(b_base + b_sub_bytes + k * 32, 16, 1024), idesc, (kit | k) != 0);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t a_desc = umma_desc(a_base + k * 32, 16, 1024);
+                umma_bf16_2sm(d_tmem0, a_desc, umma_desc(b_base + k * 32, 16, 1024), idesc, (kit | k) != 0);
+                if (NS == 2)
+                  umma_bf16_2sm(d_tmem1, a_desc, umma_desc(b_base + b_sub_bytes + k * 32, 16, 1024), idesc, (kit | k) != 0);
+              }
+            }
+            umma_commit_2sm(&empty_bar[stage], 0x3);
           }
-          umma_commit_2sm(&empty_bar[stage], 0x3);
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tmem_full[slot0], 0x3);
-        if (NS == 2) umma_commit_2sm(&tmem_full[slot1], 0x3);
+        if (elect_one()) {
+          umma_commit_2sm(&tmem_full[slot0], 0x3);
+          if (NS == 2) umma_commit_2sm(&tmem_full[slot1], 0x3);
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -181,12 +202,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
         for (int j = 0; j < NS; ++j) {
           const int jg = it * NS + j, sl = jg % nslot;
           const int n0 = (tn * NS + j) * BN;
-          if (slab_ok && p.epi_in && lane == 0)
+          if (slab_ok && p.epi_in && lane == 0 && !(p.dbg & 4))
             epi_request(p, e, e.g, (BN - cgrp * 32 + 63) / 64, e.g, n0 + cgrp * 32, 64, m_slab);
           mbar_wait(&tmem_full[sl], (jg / nslot) & 1);
           tc_fence_after();
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sl * slot_cols;
-          if (slab_ok) igemm_epilogue_tma(p, e, t_row, m_slab, lane, n0, BN, cgrp, 64);
+          if (slab_ok && !(p.dbg & 4)) igemm_epilogue_tma(p, e, t_row, m_slab, lane, n0, BN, cgrp, 64);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&tmem_empty[sl], 0);
@@ -199,12 +220,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
       const int m0 = tm * 2 * BM + static_cast<int>(rank) * BM;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M_total;
+      // while the main loop of this tile runs: the fp32 residual segments this thread will add (one 128-byte line per
+      // 32-column chunk) are pulled into L2, so the drain of the accumulators does not wait on DRAM
+      if (p.res_prefetch && p.residual != nullptr && row_ok) {
+        const float* r = p.residual + static_cast<size_t>(row) * p.ld_res + tn * NS * BN;
+        for (int j = 0; j < NS; ++j)
+          for (int c0 = cgrp * 32; c0 < BN; c0 += 64) prefetch_l2(r + j * BN + c0);
+      }
       for (int j = 0; j < NS; ++j) {
         const int jg = it * NS + j, sl = jg % nslot;
         mbar_wait(&tmem_full[sl], (jg / nslot) & 1);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sl * slot_cols;
-        igemm_epilogue(p, t_row, row, row_ok, (tn * NS + j) * BN, tn * NS + j, BN, cgrp, 64);
+        if (!(p.dbg & 4)) igemm_epilogue(p, t_row, row, row_ok, (tn * NS + j) * BN, tn * NS + j, BN, cgrp, 64);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&tmem_empty[sl], 0);
@@ -236,13 +264,17 @@ int ddpo_igemm2_launch(IGemmArgs& p, cudaStream_t stream) {
   const size_t smem = (size_t)stages * stage_bytes + 256 + 1024 + epi;
   static bool attr_set = false;
   if (!attr_set) {
-    DDPO_CUDA_OK(cudaFuncSetAttribute(igemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DDPO_CUDA_OK(cudaFuncSetAttribute(igemm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DDPO_CUDA_OK(cudaFuncSetAttribute(igemm2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int tiles = ((p.M_total + 2 * BM - 1) / (2 * BM)) * (p.N_total / (p.NS * p.BN));
   int pairs = num_sms() / 2;
   if (pairs > tiles) pairs = tiles;
-  igemm2_kernel<<<2 * pairs, IGEMM_THREADS, smem, stream>>>(p);
+  if (p.NS == 2)
+    igemm2_kernel<2><<<2 * pairs, IGEMM_THREADS, smem, stream>>>(p);
+  else
+    igemm2_kernel<1><<<2 * pairs, IGEMM_THREADS, smem, stream>>>(p);
   DDPO_LAUNCH_OK();
   return DDPO_OK;
 }

@@ -15,6 +15,9 @@ constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/
 struct IGemmArgs {
   CUtensorMap tmA0, tmA1, tmB;
   int M_total, N_total, BN, stages;
+  int dbg;  // profiling only (DDPO_IGEMM_DEBUG, CTA-pair kernel): bit 0 = no operand loads, bit 1 = no MMAs, bit 2 = no epilogue
+            // body -- results are garbage, the barrier protocol is unchanged: what each role costs on its own
+  int res_prefetch;  // CTA-pair register epilogue: prefetch the fp32 residual lines into L2 during the main loop
   int NS;  // CTA-pair kernel: BN-wide sub-tiles per tile (1 or 2), see igemm2.cu
   int MT;  // 128-row sub-tiles per CTA tile (1 or 2).  MT = 2: BM = 256 sharing one B tile -> 33% less operand traffic
   int taps, kc0, kc1;
