@@ -78,21 +78,27 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // warps 0 / 1 run their loops converged and elect one lane for the TMA / MMA issue only: addresses and descriptors stay
+  // in uniform registers (inside an `if (lane == 0)` region every UTMALDG / UTCHMMA is wrapped in an R2UR + ELECT loop)
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, AT_TILE);
       tma_load_4d(smem + AT_SMEM_Q, &p.tmQ, q_full, 0, head, q0, b);
-      for (int j = 0; j < nkb; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        uint8_t* sK = smem + AT_SMEM_KV + st * 2 * AT_TILE;
+    }
+    __syncwarp();
+    for (int j = 0; j < nkb; ++j) {
+      const int st = j & 1;
+      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+      uint8_t* sK = smem + AT_SMEM_KV + st * 2 * AT_TILE;
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[st], 2 * AT_TILE);
         tma_load_4d(sK, &p.tmK, &kv_full[st], 0, head, j * AT_BKV, b);
         tma_load_4d(sK + AT_TILE, &p.tmV, &kv_full[st], 0, head, j * AT_BKV, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc_s = umma_idesc_bf16(AT_BQ, AT_BKV, 0, 0);  // S = Q K^T: N = 128 keys
       const uint32_t idesc_o = umma_idesc_bf16(AT_BQ, AT_D, 0, 1);    // O = P V : N = 64, B (V) MN-major
       const uint32_t q_addr = smem_u32(smem + AT_SMEM_Q);
@@ -103,11 +109,14 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
         mbar_wait(&kv_full[st], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem + AT_SMEM_KV + st * 2 * AT_TILE);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tmem_base + xb * 128, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024),
-                    idesc_s, k != 0);
-        umma_commit(&s_full[xb]);
+          for (int k = 0; k < AT_D / 16; ++k)
+            umma_bf16(tmem_base + xb * 128, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024),
+                      idesc_s, k != 0);
+          umma_commit(&s_full[xb]);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -117,15 +126,18 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_fwd_kernel(const __gr
         mbar_wait(p_full, j & 1);
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem + AT_SMEM_KV + st * 2 * AT_TILE + AT_TILE);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_BKV / 16; ++k) {
-          // A = P: K-major, 64-key sub-tiles; B = V: MN-major, 16 keys = 16 rows of 128 B
-          const uint32_t a = p_addr + (k >> 2) * AT_TILE + (k & 3) * 32;
-          const uint32_t bb = v_addr + k * 16 * 128;
-          umma_bf16(tmem_base + xb * 128, umma_desc(a, 16, 1024), umma_desc(bb, 8192, 1024), idesc_o, k != 0);
+          for (int k = 0; k < AT_BKV / 16; ++k) {
+            // A = P: K-major, 64-key sub-tiles; B = V: MN-major, 16 keys = 16 rows of 128 B
+            const uint32_t a = p_addr + (k >> 2) * AT_TILE + (k & 3) * 32;
+            const uint32_t bb = v_addr + k * 16 * 128;
+            umma_bf16(tmem_base + xb * 128, umma_desc(a, 16, 1024), umma_desc(bb, 8192, 1024), idesc_o, k != 0);
+          }
+          umma_commit(&o_full[xb]);
+          umma_commit(&kv_empty[st]);
         }
-        umma_commit(&o_full[xb]);
-        umma_commit(&kv_empty[st]);
+        __syncwarp();
       }
     }
   } else {
@@ -323,20 +335,24 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_cross_fwd_kernel(cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp == 0) {   // converged loops, elected issue (see attention_fwd_kernel)
+    if (elect_one()) {
       mbar_expect_tx(kv_full, 2 * AT_TILE);
       tma_load_4d(smem + AX_SMEM_K, &p.tmK, kv_full, 0, head, 0, b);   // rows >= nk are zero-filled by TMA
       tma_load_4d(smem + AX_SMEM_V, &p.tmV, kv_full, 0, head, 0, b);
-      for (int i = 0; i < nt; ++i) {
-        const int st = i & 1;
-        mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int i = 0; i < nt; ++i) {
+      const int st = i & 1;
+      mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&q_full[st], AT_TILE);
         tma_load_4d(smem + AX_SMEM_Q + st * AT_TILE, &p.tmQ, &q_full[st], 0, head, (t0 + i) * AT_BQ, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc_s = umma_idesc_bf16(AT_BQ, KB, 0, 0);     // S = Q K^T, N = KB key columns
       const uint32_t idesc_o = umma_idesc_bf16(AT_BQ, AT_D, 0, 1);   // O = P V, B (V) MN-major
       const uint32_t k_addr = smem_u32(smem + AX_SMEM_K), v_addr = smem_u32(smem + AX_SMEM_V);
@@ -347,12 +363,15 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_cross_fwd_kernel(cons
         mbar_wait(&q_full[st], (i >> 1) & 1);
         tc_fence_after();
         const uint32_t q_addr = smem_u32(smem + AX_SMEM_Q + st * AT_TILE);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tmem_base + xb * 128, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024),
-                    idesc_s, k != 0);
-        umma_commit(&s_full[xb]);
-        umma_commit(&q_empty[st]);   // the Q tile is free once these MMAs have read it
+          for (int k = 0; k < AT_D / 16; ++k)
+            umma_bf16(tmem_base + xb * 128, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024),
+                      idesc_s, k != 0);
+          umma_commit(&s_full[xb]);
+          umma_commit(&q_empty[st]);   // the Q tile is free once these MMAs have read it
+        }
+        __syncwarp();
       };
       mbar_wait(kv_full, 0);
       issue_s(0);
@@ -361,12 +380,15 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_cross_fwd_kernel(cons
         const int xb = i & 1;
         mbar_wait(p_full, i & 1);
         tc_fence_after();
-        for (int k = 0; k < KB / 16; ++k) {
-          const uint32_t a = p_addr + (k >> 2) * AT_TILE + (k & 3) * 32;
-          const uint32_t bb = v_addr + k * 16 * 128;
-          umma_bf16(tmem_base + xb * 128, umma_desc(a, 16, 1024), umma_desc(bb, 8192, 1024), idesc_o, k != 0);
+        if (elect_one()) {
+          for (int k = 0; k < KB / 16; ++k) {
+            const uint32_t a = p_addr + (k >> 2) * AT_TILE + (k & 3) * 32;
+            const uint32_t bb = v_addr + k * 16 * 128;
+            umma_bf16(tmem_base + xb * 128, umma_desc(a, 16, 1024), umma_desc(bb, 8192, 1024), idesc_o, k != 0);
+          }
+          umma_commit(&o_full[xb]);
         }
-        umma_commit(&o_full[xb]);
+        __syncwarp();
       }
     }
   } else {

@@ -119,22 +119,28 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t T_S = tmem_base, T_DP = tmem_base + 128, T_DV = tmem_base + 256, T_DK = tmem_base + 320;
 
+  // warps 0 / 1: loops run converged, one elected lane issues TMA / MMA (operands stay in uniform registers; inside an
+  // `if (lane == 0)` region each of the 24 UMMAs per query block carried an R2UR + ELECT loop of ~20 instructions)
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(kv_full, 2 * AB_T);
       tma_load_4d(smem + KV_SMEM_K, &p.tmK, kv_full, 0, head, k0, b);
       tma_load_4d(smem + KV_SMEM_V, &p.tmV, kv_full, 0, head, k0, b);
-      for (int i = 0; i < nqb; ++i) {
-        const int st = i & 1;
-        mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
-        uint8_t* sQ = smem + KV_SMEM_RING + st * 2 * AB_T;
+    }
+    __syncwarp();
+    for (int i = 0; i < nqb; ++i) {
+      const int st = i & 1;
+      mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+      uint8_t* sQ = smem + KV_SMEM_RING + st * 2 * AB_T;
+      if (elect_one()) {
         mbar_expect_tx(&qdo_full[st], 2 * AB_T);
         tma_load_4d(sQ, &p.tmQ, &qdo_full[st], 0, head, i * 128, b);
         tma_load_4d(sQ + AB_T, &p.tmDO, &qdo_full[st], 0, head, i * 128, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);  // S = Q K^T, dP = dO V^T
       const uint32_t id_g = umma_idesc_bf16(128, 64, 1, 1);   // dV = P^T dO, dK = dS^T Q (both MN-major)
       const uint32_t k_addr = smem_u32(smem + KV_SMEM_K), v_addr = smem_u32(smem + KV_SMEM_V);
@@ -149,13 +155,16 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
         mbar_wait(&qdo_full[st], (i >> 1) & 1);
         mbar_wait(sdp_empty, (i & 1) ^ 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(T_S, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024), id_s, k != 0);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(T_S, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024), id_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(T_DP, umma_desc(do_addr + k * 32, 16, 1024), umma_desc(v_addr + k * 32, 16, 1024), id_s, k != 0);
-        umma_commit(sdp_full);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(T_DP, umma_desc(do_addr + k * 32, 16, 1024), umma_desc(v_addr + k * 32, 16, 1024), id_s, k != 0);
+          umma_commit(sdp_full);
+        }
+        __syncwarp();
       };
       issue_sdp(0);
       for (int i = 0; i < nqb; ++i) {
@@ -164,17 +173,21 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
         mbar_wait(pds_full, i & 1);
         if (i + 1 < nqb) issue_sdp(i + 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // K = 128 query rows, 16 per instruction
-          umma_bf16(T_DV, umma_desc(p_addr + k * 2048, AB_T, 1024), umma_desc(do_addr + k * 2048, AB_T, 1024), id_g,
-                    (i | k) != 0);
-          umma_bf16(T_DK, umma_desc(ds_addr + k * 2048, AB_T, 1024), umma_desc(q_addr + k * 2048, AB_T, 1024), id_g,
-                    (i | k) != 0);
+          for (int k = 0; k < 8; ++k) {  // K = 128 query rows, 16 per instruction
+            umma_bf16(T_DV, umma_desc(p_addr + k * 2048, AB_T, 1024), umma_desc(do_addr + k * 2048, AB_T, 1024), id_g,
+                      (i | k) != 0);
+            umma_bf16(T_DK, umma_desc(ds_addr + k * 2048, AB_T, 1024), umma_desc(q_addr + k * 2048, AB_T, 1024), id_g,
+                      (i | k) != 0);
+          }
+          umma_commit(&qdo_empty[st]);
+          umma_commit(pds_empty);
         }
-        umma_commit(&qdo_empty[st]);
-        umma_commit(pds_empty);
+        __syncwarp();
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
@@ -289,24 +302,28 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t T_S = tmem_base, T_DP = tmem_base + 64, T_DQ = tmem_base + 128;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp == 0) {   // converged loops, elected issue (see the dK/dV kernel)
+    if (elect_one()) {
       mbar_expect_tx(q_full, 2 * AB_T);
       tma_load_4d(smem + DQ_SMEM_Q, &p.tmQ, q_full, 0, head, q0, b);
       tma_load_4d(smem + DQ_SMEM_DO, &p.tmDO, q_full, 0, head, q0, b);
-      int st = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&kv_empty[st], ph ^ 1);
-        uint8_t* sK = smem + DQ_SMEM_RING + st * 2 * DQ_KVT;
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(&kv_empty[st], ph ^ 1);
+      uint8_t* sK = smem + DQ_SMEM_RING + st * 2 * DQ_KVT;
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[st], 2 * DQ_KVT);
         tma_load_4d(sK, &p.tmK64, &kv_full[st], 0, head, j * DQ_BKV, b);
         tma_load_4d(sK + DQ_KVT, &p.tmV64, &kv_full[st], 0, head, j * DQ_BKV, b);
-        if (++st == DQ_STAGES) st = 0, ph ^= 1;
       }
+      __syncwarp();
+      if (++st == DQ_STAGES) st = 0, ph ^= 1;
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t id_s = umma_idesc_bf16(128, DQ_BKV, 0, 0);
       const uint32_t id_q = umma_idesc_bf16(128, 64, 0, 1);  // dQ = dS K : A K-major, B (K) MN-major
       const uint32_t q_addr = smem_u32(smem + DQ_SMEM_Q), do_addr = smem_u32(smem + DQ_SMEM_DO);
@@ -319,13 +336,16 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
         mbar_wait(&kv_full[st], (j / DQ_STAGES) & 1);
         mbar_wait(sdp_empty, (j & 1) ^ 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(T_S, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024), id_s, k != 0);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(T_S, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024), id_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(T_DP, umma_desc(do_addr + k * 32, 16, 1024), umma_desc(v_addr + k * 32, 16, 1024), id_s, k != 0);
-        umma_commit(sdp_full);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(T_DP, umma_desc(do_addr + k * 32, 16, 1024), umma_desc(v_addr + k * 32, 16, 1024), id_s, k != 0);
+          umma_commit(sdp_full);
+        }
+        __syncwarp();
       };
       issue_sdp(0);
       for (int j = 0; j < nkb; ++j) {
@@ -334,14 +354,18 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
         mbar_wait(ds_full, j & 1);
         if (j + 1 < nkb) issue_sdp(j + 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DQ_BKV / 16; ++k)  // A = dS [128 q x 64 keys] K-major; B = K_j rows of 16 keys (MN-major)
-          umma_bf16(T_DQ, umma_desc(ds_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 2048, DQ_KVT, 1024), id_q,
-                    (j | k) != 0);
-        umma_commit(&kv_empty[st]);
-        umma_commit(ds_empty);
+          for (int k = 0; k < DQ_BKV / 16; ++k)  // A = dS [128 q x 64 keys] K-major; B = K_j rows of 16 keys (MN-major)
+            umma_bf16(T_DQ, umma_desc(ds_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 2048, DQ_KVT, 1024), id_q,
+                      (j | k) != 0);
+          umma_commit(&kv_empty[st]);
+          umma_commit(ds_empty);
+        }
+        __syncwarp();
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
   const int a_bytes = MT * A_TILE_BYTES;
   const int stage_bytes = a_bytes + b_tile_bytes;
   const int nbuf = MT == 2 ? 1 : 2;  // MT = 2 uses all 512 TMEM columns for one tile (no accumulator double buffering)
+  uint8_t* epi_base = smem;  // [EPI_STAGE_BYTES] of the coalescing register epilogue
+  if (p.epi_stage) smem += EPI_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full = empty_bar + stages;
@@ -78,42 +80,42 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // single-role warps: loops run converged, one elected lane issues (operands in uniform registers; see igemm2.cu)
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int HW = p.W * p.H;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile / tiles_n, tn = tile % tiles_n;
-        const int m0 = tm * TM, n0 = tn * BN;
-        for (int kit = 0; kit < kiters; ++kit) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const int HW = p.W * p.H;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / tiles_n, tn = tile % tiles_n;
+      const int m0 = tm * TM, n0 = tn * BN;
+      int kit = 0;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int dy = p.taps == 9 ? tap / 3 : 0, dx = p.taps == 9 ? tap - dy * 3 : 0;
+        for (int ch = 0; ch < kcs; ++ch, ++kit) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * stage_bytes;
           uint8_t* sB = sA + a_bytes;
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
-          for (int sub = 0; sub < MT; ++sub) {
-            const int ms = m0 + sub * BM;
-            if (p.is_conv) {
-              const int b0 = ms / HW, h0 = (ms % HW) / p.W;
-              const int w0 = ms % p.W;  // non-zero only when a pixel row is wider than a tile (W > 128)
-              const int tap = kit / kcs, ch = kit - tap * kcs;
-              int dy = 0, dx = 0;
-              if (p.taps == 9) {
-                dy = tap / 3;
-                dx = tap - dy * 3;
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], stage_bytes);
+            for (int sub = 0; sub < MT; ++sub) {
+              const int ms = m0 + sub * BM;
+              if (p.is_conv) {
+                const int b0 = ms / HW, h0 = (ms % HW) / p.W;
+                const int w0 = ms % p.W;  // non-zero only when a pixel row is wider than a tile (W > 128)
+                const int cx = w0 * p.conv_stride + dx - p.pad;
+                const int cy = h0 * p.conv_stride + dy - p.pad;
+                if (ch < p.kc0)
+                  tma_load_4d(sA + sub * A_TILE_BYTES, &p.tmA0, &full_bar[stage], ch * BK, cx, cy, b0);
+                else
+                  tma_load_4d(sA + sub * A_TILE_BYTES, &p.tmA1, &full_bar[stage], (ch - p.kc0) * BK, cx, cy, b0);
+              } else {
+                tma_load_2d(sA + sub * A_TILE_BYTES, &p.tmA0, &full_bar[stage], kit * BK, ms);
               }
-              const int cx = w0 * p.conv_stride + dx - p.pad;
-              const int cy = h0 * p.conv_stride + dy - p.pad;
-              if (ch < p.kc0)
-                tma_load_4d(sA + sub * A_TILE_BYTES, &p.tmA0, &full_bar[stage], ch * BK, cx, cy, b0);
-              else
-                tma_load_4d(sA + sub * A_TILE_BYTES, &p.tmA1, &full_bar[stage], (ch - p.kc0) * BK, cx, cy, b0);
-            } else {
-              tma_load_2d(sA + sub * A_TILE_BYTES, &p.tmA0, &full_bar[stage], kit * BK, ms);
             }
+            tma_load_2d(sB, &p.tmB, &full_bar[stage], kit * BK, n0);
           }
-          tma_load_2d(sB, &p.tmB, &full_bar[stage], kit * BK, n0);
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
@@ -123,21 +125,21 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it % nbuf;
-        mbar_wait(&tmem_empty[buf], ((it / nbuf) & 1) ^ 1);
+    const uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it % nbuf;
+      mbar_wait(&tmem_empty[buf], ((it / nbuf) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * 256;
+      for (int kit = 0; kit < kiters; ++kit) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 256;
-        for (int kit = 0; kit < kiters; ++kit) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_base = a_base + a_bytes;
+        const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
+        const uint32_t b_base = a_base + a_bytes;
+        if (elect_one()) {
           for (int sub = 0; sub < MT; ++sub) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
@@ -146,13 +148,15 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == stages) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tmem_full[buf]);
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(&tmem_full[buf]);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
@@ -172,7 +176,10 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M_total;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + sub * 256;
-      igemm_epilogue(p, t_row, row, row_ok, n0, tn, BN, cgrp, cstep);
+      if (p.epi_stage)
+        igemm_epilogue_staged(p, epi_base + (warp - 4) * EPI_STAGE_WARP_BYTES, t_row, m0 + q * 32, lane, n0, BN, cgrp, cstep);
+      else
+        igemm_epilogue(p, t_row, row, row_ok, n0, tn, BN, cgrp, cstep);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -326,6 +333,16 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
   if (a->gn_stats != nullptr)
     DDPO_REQUIRE(a->out_f32 != nullptr && !a->geglu && !a->accumulate_out,
                  "ddpo_igemm: gn_stats describes a plain fp32 output (no GEGLU, no accumulate)");
+  {
+    // DDPO_IGEMM_STAGED=0: register epilogue with one row per lane (A/B switch)
+    static const bool staged = []() {
+      const char* e = getenv("DDPO_IGEMM_STAGED");
+      return e == nullptr || e[0] != '0';
+    }();
+    p.epi_stage = staged && !a->geglu && p.ld_out % 8 == 0 && p.ld_res % 4 == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0;
+  }
   if (use_pair) {
     p.MT = 1;
     {
@@ -345,7 +362,7 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
                          (!a->geglu || (a->residual == nullptr && !a->accumulate_out && a->out_f32 == nullptr));
     const bool want_tma = a->epi_override == 1 || (a->epi_override == 0 && kiters <= 24);
     if (can_tma && want_tma) {
-      p.epi_tma = 1;
+      p.epi_tma = 1, p.epi_stage = 0;
       uint32_t box[2] = {32, 32}, es[2] = {1, 1};
       int rc;
       if (a->geglu) {
@@ -381,11 +398,11 @@ extern "C" int ddpo_igemm(const ddpo_igemm_args* a, void* stream_) {
   int MT = (a->mt_override > 0) ? a->mt_override : 1;
   p.MT = MT;
   const int stage_bytes = MT * A_TILE_BYTES + BN * BK * 2;
-  int stages = SMEM_BUDGET / stage_bytes;
+  int stages = (SMEM_BUDGET - (p.epi_stage ? EPI_STAGE_BYTES : 0)) / stage_bytes;
   if (stages > 8) stages = 8;
   DDPO_REQUIRE(stages >= 2, "ddpo_igemm: not enough shared memory for BN=%d MT=%d", BN, MT);
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 256 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 256 + 1024 + (p.epi_stage ? EPI_STAGE_BYTES : 0);
   static bool attr_set = false;
   if (!attr_set) {
     DDPO_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

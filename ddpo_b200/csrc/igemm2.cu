@@ -34,8 +34,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
   // tile first, which is exactly the slot the NEXT tile needs besides the free one.
   constexpr int nslot = NS == 2 ? 3 : 2;
   constexpr int slot_cols = NS == 2 ? 160 : 256;
-  uint8_t* epi_base = smem;  // [EPI_BYTES] staging of the TMA epilogue (absent in register-epilogue mode)
+  uint8_t* epi_base = smem;  // [EPI_BYTES] staging of the TMA epilogue / [EPI_STAGE_BYTES] of the coalescing register epilogue
   if (p.epi_tma) smem += EPI_BYTES;
+  else if (p.epi_stage) smem += EPI_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full = empty_bar + stages;
@@ -232,7 +233,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
         mbar_wait(&tmem_full[sl], (jg / nslot) & 1);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sl * slot_cols;
-        if (!(p.dbg & 4)) igemm_epilogue(p, t_row, row, row_ok, (tn * NS + j) * BN, tn * NS + j, BN, cgrp, 64);
+        if (!(p.dbg & 4)) {
+          if (p.epi_stage)
+            igemm_epilogue_staged(p, epi_base + (warp - 4) * EPI_STAGE_WARP_BYTES, t_row, m0 + q * 32, lane, (tn * NS + j) * BN, BN,
+                                  cgrp, 64);
+          else
+            igemm_epilogue(p, t_row, row, row_ok, (tn * NS + j) * BN, tn * NS + j, BN, cgrp, 64);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&tmem_empty[sl], 0);
@@ -256,7 +263,7 @@ using namespace ddpo;
 // called by ddpo_igemm (igemm.cu) once the argument block is filled; tmB must have been encoded with box rows BN/2
 int ddpo_igemm2_launch(IGemmArgs& p, cudaStream_t stream) {
   const int stage_bytes = A_TILE_BYTES + p.NS * (p.BN / 2) * BK * 2;
-  const int epi = p.epi_tma ? EPI_BYTES + EPI_BAR_BYTES : 0;
+  const int epi = p.epi_tma ? EPI_BYTES + EPI_BAR_BYTES : (p.epi_stage ? EPI_STAGE_BYTES : 0);
   int stages = (SMEM_BUDGET - epi) / stage_bytes;
   if (stages > 10) stages = 10;
   DDPO_REQUIRE(stages >= 2, "ddpo_igemm: not enough shared memory for BN=%d NS=%d with the TMA epilogue", p.BN, p.NS);

@@ -15,6 +15,8 @@ constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/
 struct IGemmArgs {
   CUtensorMap tmA0, tmA1, tmB;
   int M_total, N_total, BN, stages;
+  int epi_stage;  // register epilogue: 1 = global accesses go through a per-warp 4 KB shared-memory tile so that every
+                  // LDG / STG covers whole 128-byte row segments (igemm_epilogue_staged); 0 = one row per lane
   int dbg;  // profiling only (DDPO_IGEMM_DEBUG, CTA-pair kernel): bit 0 = no operand loads, bit 1 = no MMAs, bit 2 = no epilogue
             // body -- results are garbage, the barrier protocol is unchanged: what each role costs on its own
   int res_prefetch;  // CTA-pair register epilogue: prefetch the fp32 residual lines into L2 during the main loop
@@ -250,6 +252,133 @@ __device__ __forceinline__ void igemm_epilogue_tma(const IGemmArgs& p, EpiWarp& 
     __syncwarp();
   }
   e.req = e.g > e.req ? e.g : e.req;  // keeps lanes other than 0 (which never request) and the no-input mode consistent
+}
+
+constexpr int EPI_STAGE_WARP_BYTES = 32 * 32 * 4;           // one fp32 32 x 32 tile per epilogue warp
+constexpr int EPI_STAGE_BYTES = 8 * EPI_STAGE_WARP_BYTES;   // 32 KB
+
+// Register epilogue with coalesced global accesses.  tcgen05.ld hands every lane one ROW of the 32 x 32 chunk; a lane
+// that loads / stores its own row touches 16 bytes of 32 different 128-byte lines per instruction: 32 LSU wavefronts for
+// what fits in 4 -- 512 wavefronts per chunk with an fp32 residual and an fp32 output, ~10k LSU clocks per 128 x 160
+// sub-tile, and that drain is what the wide (2 x 160) tiles expose (tests/prof_igemm_roles.py: 82 us without the epilogue
+// body, 142 us with it).  Here rows change hands through a per-warp 4 KB tile (16-byte chunks XOR-swizzled by the row,
+// conflict-free for both access patterns): global instruction i of lane l covers chunk (l & 7) of row 4 i + (l >> 3), i.e.
+// four whole 128-byte row segments.  Arithmetic and its order are igemm_epilogue's: acc + bias + rowvec + residual
+// (+ old output) -> bit-identical results.  GEGLU layers keep the plain path (they run the TMA-staged epilogue anyway).
+__device__ __forceinline__ void igemm_epilogue_staged(const IGemmArgs& p, uint8_t* __restrict__ stg, uint32_t t_row,
+                                                      int m_slab, int lane, int n0, int BN, int cgrp, int cstep) {
+  if (m_slab >= p.M_total) return;  // warp-uniform: a slab entirely below the matrix has nothing to do
+  const int row = m_slab + lane;
+  const bool row_ok = row < p.M_total;
+  const float* rv = nullptr;
+  if (p.rowvec != nullptr && row_ok) rv = p.rowvec + static_cast<size_t>(row / p.rows_per_sample) * p.rowvec_ld;
+  const uint32_t swr = static_cast<uint32_t>(lane & 7);
+  const int crow = lane >> 3, cch = lane & 7;  // fp32 tiles: instruction i <-> row 4 i + crow, logical chunk cch
+  const int brow = lane >> 2, bch = lane & 3;  // bf16 tiles (64-byte rows): instruction i <-> row 8 i + brow, chunk bch
+  uint8_t* own = stg + lane * 128;
+  for (int c0 = cgrp * 32; c0 < BN; c0 += cstep) {
+    const int n = n0 + c0;
+    uint32_t v[32];
+    tmem_ld_32x32(t_row + c0, v);
+    // the residual's (coalesced) loads are in flight while the accumulator is fetched
+    float4 in[8];
+    if (p.residual != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = m_slab + 4 * i + crow;
+        in[i] = r < p.M_total ? *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(r) * p.ld_res + n + 4 * cch)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+      }
+    }
+    if (rv != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + n + j));
+        f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+      }
+    }
+    if (p.residual != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + crow;
+        *reinterpret_cast<float4*>(stg + rr * 128 + ((cch ^ (rr & 7)) << 4)) = in[i];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = *reinterpret_cast<const float4*>(own + ((j ^ swr) << 4));
+        f[4 * j] += b4.x, f[4 * j + 1] += b4.y, f[4 * j + 2] += b4.z, f[4 * j + 3] += b4.w;
+      }
+      __syncwarp();
+    }
+    if (p.out_f32 != nullptr && p.accumulate_out) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + crow, r = m_slab + rr;
+        const float4 o4 = r < p.M_total ? *reinterpret_cast<const float4*>(p.out_f32 + static_cast<size_t>(r) * p.ld_out + n + 4 * cch)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(stg + rr * 128 + ((cch ^ (rr & 7)) << 4)) = o4;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = *reinterpret_cast<const float4*>(own + ((j ^ swr) << 4));
+        f[4 * j] += b4.x, f[4 * j + 1] += b4.y, f[4 * j + 2] += b4.z, f[4 * j + 3] += b4.w;
+      }
+      __syncwarp();
+    }
+    if (p.out_f32 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(own + ((j ^ swr) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + crow, r = m_slab + rr;
+        const float4 o4 = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cch ^ (rr & 7)) << 4));
+        if (r < p.M_total) *reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(r) * p.ld_out + n + 4 * cch) = o4;
+      }
+      __syncwarp();
+    }
+    if (p.out_bf16 != nullptr) {
+      const uint32_t swb = static_cast<uint32_t>((lane >> 1) & 3);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16(f[8 * j], f[8 * j + 1]);
+        u.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+        u.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+        u.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+        *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ swb) << 4)) = u;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = 8 * i + brow, r = m_slab + rr;
+        const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((bch ^ ((rr >> 1) & 3)) << 4));
+        if (r < p.M_total) *reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(r) * p.ld_out + n + 8 * bch) = u;
+      }
+      __syncwarp();
+    }
+    if (p.gn_stats != nullptr) {
+      if (!row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+      }
+      gn_slab_stats(p.gn_stats, p.N_total, m_slab, n, lane, f);
+    }
+  }
 }
 
 // One epilogue warp: rows (row .. ) of TMEM lane quarter `q`, 32-column chunks c0 = cgrp*32, += cstep.

@@ -95,8 +95,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     blk = src ? mb - p.mt_per_tap0 : mb;
   };
 
+  // single-role warps run their loops converged and elect a lane for the issue instructions only (operands stay in
+  // uniform registers; see igemm2.cu)
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       const int HW = p.W * p.H;
@@ -113,25 +115,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * stage_bytes;
           uint8_t* sB = sA + WG_A_BYTES;
-          mbar_expect_tx(&full_bar[stage], WG_A_BYTES + (bn / 64) * WG_BOX_BYTES);
           const int row0 = pb * WG_BKP;
-          if (p.is_conv) {
-            const int b0 = row0 / HW, h0 = (row0 % HW) / p.W;
-            const int cx = dx - p.pad, cy = h0 * p.conv_stride + dy - p.pad;
-            tma_load_4d(sA, tmX, &full_bar[stage], blk * 128, cx, cy, b0);
-            tma_load_4d(sA + WG_BOX_BYTES, tmX, &full_bar[stage], blk * 128 + 64, cx, cy, b0);
-          } else {
-            tma_load_2d(sA, tmX, &full_bar[stage], blk * 128, row0);
-            tma_load_2d(sA + WG_BOX_BYTES, tmX, &full_bar[stage], blk * 128 + 64, row0);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], WG_A_BYTES + (bn / 64) * WG_BOX_BYTES);
+            if (p.is_conv) {
+              const int b0 = row0 / HW, h0 = (row0 % HW) / p.W;
+              const int cx = dx - p.pad, cy = h0 * p.conv_stride + dy - p.pad;
+              tma_load_4d(sA, tmX, &full_bar[stage], blk * 128, cx, cy, b0);
+              tma_load_4d(sA + WG_BOX_BYTES, tmX, &full_bar[stage], blk * 128 + 64, cx, cy, b0);
+            } else {
+              tma_load_2d(sA, tmX, &full_bar[stage], blk * 128, row0);
+              tma_load_2d(sA + WG_BOX_BYTES, tmX, &full_bar[stage], blk * 128 + 64, row0);
+            }
+            for (int j = 0; j < bn / 64; ++j)
+              tma_load_2d(sB + j * WG_BOX_BYTES, &p.tmDY, &full_bar[stage], nt * 256 + j * 64, row0);
           }
-          for (int j = 0; j < bn / 64; ++j)
-            tma_load_2d(sB + j * WG_BOX_BYTES, &p.tmDY, &full_bar[stage], nt * 256 + j * 64, row0);
+          __syncwarp();
           if (++stage == stages) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -151,16 +156,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_base = a_base + WG_A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < WG_BKP / 16; ++k) {
-            // 16 pixels = 16 rows of 128 B; LBO = stride between 64-channel groups, SBO = 8-row groups
-            umma_bf16(d_tmem, umma_desc(a_base + k * 2048, WG_BOX_BYTES, 1024),
-                      umma_desc(b_base + k * 2048, WG_BOX_BYTES, 1024), idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < WG_BKP / 16; ++k) {
+              // 16 pixels = 16 rows of 128 B; LBO = stride between 64-channel groups, SBO = 8-row groups
+              umma_bf16(d_tmem, umma_desc(a_base + k * 2048, WG_BOX_BYTES, 1024),
+                        umma_desc(b_base + k * 2048, WG_BOX_BYTES, 1024), idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == stages) stage = 0, phase ^= 1;
         }
-        umma_commit(&tmem_full[buf]);
+        if (elect_one()) umma_commit(&tmem_full[buf]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

@@ -96,7 +96,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // (loops run warp-converged, one elected lane issues: operands stay in uniform registers; see igemm2.cu)
+    {
       int stage = 0;
       uint32_t phase = 0;
       const int HW = p.W * p.H;
@@ -133,27 +134,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * WG2_STAGE;
           uint8_t* sB = sA + 2 * WG2_BOX;
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
           const int row0 = pb * WG2_BKP;
-          if (p.is_conv) {
-            const int b0 = row0 / HW, h0 = (row0 % HW) / p.W;
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
+            if (p.is_conv) {
+              const int b0 = row0 / HW, h0 = (row0 % HW) / p.W;
 #pragma unroll
-            for (int gi = 0; gi < 2; ++gi)
-              tma_load_4d_2sm(sA + gi * WG2_BOX, tmx[gi], &full_bar[stage], gch[gi], gdx[gi] - p.pad,
-                              h0 * p.conv_stride + gdy[gi] - p.pad, b0);
-          } else {
+              for (int gi = 0; gi < 2; ++gi)
+                tma_load_4d_2sm(sA + gi * WG2_BOX, tmx[gi], &full_bar[stage], gch[gi], gdx[gi] - p.pad,
+                                h0 * p.conv_stride + gdy[gi] - p.pad, b0);
+            } else {
 #pragma unroll
-            for (int gi = 0; gi < 2; ++gi) tma_load_2d_2sm(sA + gi * WG2_BOX, tmx[gi], &full_bar[stage], gch[gi], row0);
+              for (int gi = 0; gi < 2; ++gi) tma_load_2d_2sm(sA + gi * WG2_BOX, tmx[gi], &full_bar[stage], gch[gi], row0);
+            }
+            for (int j = 0; j < b_boxes; ++j)
+              tma_load_2d_2sm(sB + j * WG2_BOX, &p.tmDY, &full_bar[stage], nch + j * 64, row0);
           }
-          for (int j = 0; j < b_boxes; ++j)
-            tma_load_2d_2sm(sB + j * WG2_BOX, &p.tmDY, &full_bar[stage], nch + j * 64, row0);
+          __syncwarp();
           if (++stage == stages) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -173,16 +177,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1)
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * WG2_STAGE);
           const uint32_t b_base = a_base + 2 * WG2_BOX;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < WG2_BKP / 16; ++k) {
-            // 16 pixels = 16 rows of 128 B; LBO = stride between 64-channel boxes, SBO = 8-row groups
-            umma_bf16_2sm(d_tmem, umma_desc(a_base + k * 2048, WG2_BOX, 1024), umma_desc(b_base + k * 2048, WG2_BOX, 1024),
-                          idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < WG2_BKP / 16; ++k) {
+              // 16 pixels = 16 rows of 128 B; LBO = stride between 64-channel boxes, SBO = 8-row groups
+              umma_bf16_2sm(d_tmem, umma_desc(a_base + k * 2048, WG2_BOX, 1024), umma_desc(b_base + k * 2048, WG2_BOX, 1024),
+                            idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[stage], 0x3);
           }
-          umma_commit_2sm(&empty_bar[stage], 0x3);
+          __syncwarp();
           if (++stage == stages) stage = 0, phase ^= 1;
         }
-        umma_commit_2sm(&tmem_full[buf], 0x3);
+        if (elect_one()) umma_commit_2sm(&tmem_full[buf], 0x3);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
