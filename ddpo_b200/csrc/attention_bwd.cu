@@ -79,10 +79,80 @@ __device__ __forceinline__ void softmax_bwd_row(uint32_t t_s, uint32_t t_dp, uin
   }
 }
 
+// The same arithmetic split in two phases, so that the tensor core can compute dP of a block while the softmax warps
+// already turn its S into P (S is double-buffered in TMEM, dP is not: TMEM has 512 columns).
+// phase P: p[i] = exp2(S c - lse) for NCH chunks of 32 columns from col_begin (masked entries 0); optionally -> sP
+template <int NCH, bool WRITE_P>
+__device__ __forceinline__ void bwd_phase_p(uint32_t t_s, uint8_t* sP, int r, int valid_keys, bool row_ok, float lse_l2, float c,
+                                            int col_begin, bool full, float (&p)[NCH * 32]) {
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c0 = col_begin + ch * 32;
+    uint32_t s[32];
+    tmem_ld_32x32(t_s + c0, s);
+    tmem_ld_wait();
+    if (row_ok && full) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) p[ch * 32 + i] = ex2_sel<DDPO_EXP_POLY_BWD>(i, __uint_as_float(s[i]) * c - lse_l2);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool ok = row_ok && (c0 + i < valid_keys);
+        const float xe = __uint_as_float(s[i]) * c - lse_l2;
+        p[ch * 32 + i] = ok ? ex2_sel<DDPO_EXP_POLY_BWD>(i, xe) : 0.f;
+      }
+    }
+    if (WRITE_P) {
+      const int tile_off = (c0 >> 6) * AB_T + r * 128;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int chunk = ((c0 & 63) >> 3) + g;
+        uint4 u;
+        u.x = pack_bf16(p[ch * 32 + g * 8 + 0], p[ch * 32 + g * 8 + 1]), u.y = pack_bf16(p[ch * 32 + g * 8 + 2], p[ch * 32 + g * 8 + 3]);
+        u.z = pack_bf16(p[ch * 32 + g * 8 + 4], p[ch * 32 + g * 8 + 5]), u.w = pack_bf16(p[ch * 32 + g * 8 + 6], p[ch * 32 + g * 8 + 7]);
+        *reinterpret_cast<uint4*>(sP + tile_off + ((chunk ^ (r & 7)) << 4)) = u;
+      }
+    }
+  }
+}
+// phase dS: dS = p (dP scale - delta scale) -> sDS
+template <int NCH>
+__device__ __forceinline__ void bwd_phase_ds(uint32_t t_dp, uint8_t* sDS, int r, float delta_s, float scale, int col_begin,
+                                             const float (&p)[NCH * 32]) {
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c0 = col_begin + ch * 32;
+    uint32_t d[32];
+    tmem_ld_32x32(t_dp + c0, d);
+    tmem_ld_wait();
+    float ds[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) ds[i] = p[ch * 32 + i] * fmaf(__uint_as_float(d[i]), scale, -delta_s);
+    const int tile_off = (c0 >> 6) * AB_T + r * 128;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int chunk = ((c0 & 63) >> 3) + g;
+      uint4 w;
+      w.x = pack_bf16(ds[g * 8 + 0], ds[g * 8 + 1]), w.y = pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]);
+      w.z = pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]), w.w = pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]);
+      *reinterpret_cast<uint4*>(sDS + tile_off + ((chunk ^ (r & 7)) << 4)) = w;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ dK, dV ----
-// smem: K | V | 2 x (Q | dO) | P(2 tiles) | dS(2 tiles) | barriers
+// smem: K | V | 2 x (Q | dO) | 2 x (P(2 tiles) | dS(2 tiles)) | barriers
+//
+// Pipeline (per 128-key CTA, query blocks i = 0, 1, ...).  TMEM: S[2] (2 x 128 columns), dP (128), dV (64), dK (64) = 512.
+//   MMA lane:      S(0), dP(0), S(1); then per i: wait P/dS(i) -> dP(i+1), dV/dK(i), S(i+2)
+//   softmax warps: S(i) -> P(i) [registers + shared memory]; then dP(i) -> dS(i) [shared memory]
+// so the tensor core computes dP(i+1) / dV, dK(i) / S(i+2) while the softmax warps are already in the P phase of block
+// i+1 (S(i+1) has been ready for a whole block) and reaches them again before they need dP(i+1).  In round 1 S / dP and
+// P / dS were single-buffered and 28 % of the warp-stall samples sat in the two hand-over waits
+// (profiles/r2_attention.md).
 constexpr int KV_SMEM_K = 0, KV_SMEM_V = AB_T, KV_SMEM_RING = 2 * AB_T, KV_SMEM_P = 6 * AB_T, KV_SMEM_DS = 8 * AB_T,
-              KV_SMEM_BAR = 10 * AB_T, KV_SMEM_TOTAL = KV_SMEM_BAR + 256;
+              KV_PDS_STRIDE = 4 * AB_T,  // second (P | dS) buffer
+              KV_SMEM_BAR = 14 * AB_T, KV_SMEM_TOTAL = KV_SMEM_BAR + 256;
 
 __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const __grid_constant__ AttnBwdArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -90,12 +160,14 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
   uint64_t* kv_full = bars;          // 1
   uint64_t* qdo_full = bars + 1;     // [2]
   uint64_t* qdo_empty = bars + 3;    // [2]
-  uint64_t* sdp_full = bars + 5;     // 1
-  uint64_t* sdp_empty = bars + 6;    // 1 (count 4)
-  uint64_t* pds_full = bars + 7;     // 1 (count 4)
-  uint64_t* pds_empty = bars + 8;    // 1
-  uint64_t* acc_full = bars + 9;     // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* s_full = bars + 5;       // [2]
+  uint64_t* s_empty = bars + 7;      // [2] (count 8)
+  uint64_t* dp_full = bars + 9;      // 1
+  uint64_t* dp_empty = bars + 10;    // 1 (count 8)
+  uint64_t* pds_full = bars + 11;    // [2] (count 8)
+  uint64_t* pds_empty = bars + 13;   // [2]
+  uint64_t* acc_full = bars + 15;    // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
   const int nqb = (p.nq + 127) / 128;
@@ -104,8 +176,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     prefetch_tmap(&p.tmQ), prefetch_tmap(&p.tmK), prefetch_tmap(&p.tmV), prefetch_tmap(&p.tmDO);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&qdo_full[i], 1), mbar_init(&qdo_empty[i], 1);
-    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 8), mbar_init(pds_full, 8), mbar_init(pds_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1), mbar_init(&qdo_empty[i], 1);
+      mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 8);
+      mbar_init(&pds_full[i], 8), mbar_init(&pds_empty[i], 1);
+    }
+    mbar_init(dp_full, 1), mbar_init(dp_empty, 8);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -117,7 +193,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t T_S = tmem_base, T_DP = tmem_base + 128, T_DV = tmem_base + 256, T_DK = tmem_base + 320;
+  const uint32_t T_S = tmem_base /* [2] x 128 */, T_DP = tmem_base + 256, T_DV = tmem_base + 384, T_DK = tmem_base + 448;
 
   // warps 0 / 1: loops run converged, one elected lane issues TMA / MMA (operands stay in uniform registers; inside an
   // `if (lane == 0)` region each of the 24 UMMAs per query block carried an R2UR + ELECT loop of ~20 instructions)
@@ -140,81 +216,103 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
       __syncwarp();
     }
   } else if (warp == 1) {
-    {
-      const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);  // S = Q K^T, dP = dO V^T
-      const uint32_t id_g = umma_idesc_bf16(128, 64, 1, 1);   // dV = P^T dO, dK = dS^T Q (both MN-major)
-      const uint32_t k_addr = smem_u32(smem + KV_SMEM_K), v_addr = smem_u32(smem + KV_SMEM_V);
-      const uint32_t p_addr = smem_u32(smem + KV_SMEM_P), ds_addr = smem_u32(smem + KV_SMEM_DS);
-      mbar_wait(kv_full, 0);
-      // Software-pipelined issue order: S/dP of query block i+1 go to the tensor pipe BEFORE dV/dK of block i.  The
-      // softmax warps wait only for S/dP; queueing them behind the two gradient GEMMs of the previous block (the
-      // tensor pipe executes in order) left those warps idle for ~30 % of their time (profiles/r1_attention.md).
-      auto issue_sdp = [&](int i) {
-        const int st = i & 1;
-        const uint32_t q_addr = smem_u32(smem + KV_SMEM_RING + st * 2 * AB_T), do_addr = q_addr + AB_T;
-        mbar_wait(&qdo_full[st], (i >> 1) & 1);
-        mbar_wait(sdp_empty, (i & 1) ^ 1);
-        tc_fence_after();
-        if (elect_one()) {
+    const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);  // S = Q K^T, dP = dO V^T
+    const uint32_t id_g = umma_idesc_bf16(128, 64, 1, 1);   // dV = P^T dO, dK = dS^T Q (both MN-major)
+    const uint32_t k_addr = smem_u32(smem + KV_SMEM_K), v_addr = smem_u32(smem + KV_SMEM_V);
+    mbar_wait(kv_full, 0);
+    // the Q / dO stage of block i holds Q(i) for S(i) and dK(i), dO(i) for dP(i) and dV(i): with S running two blocks
+    // ahead of dV / dK the two-stage ring would deadlock, so S(i+2) is issued right AFTER dV / dK(i) released stage i & 1
+    auto issue_s = [&](int i) {
+      const int st = i & 1;
+      const uint32_t q_addr = smem_u32(smem + KV_SMEM_RING + st * 2 * AB_T);
+      mbar_wait(&qdo_full[st], (i >> 1) & 1);
+      mbar_wait(&s_empty[st], ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(T_S, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024), id_s, k != 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(T_DP, umma_desc(do_addr + k * 32, 16, 1024), umma_desc(v_addr + k * 32, 16, 1024), id_s, k != 0);
-          umma_commit(sdp_full);
-        }
-        __syncwarp();
-      };
-      issue_sdp(0);
-      for (int i = 0; i < nqb; ++i) {
-        const int st = i & 1;
-        const uint32_t q_addr = smem_u32(smem + KV_SMEM_RING + st * 2 * AB_T), do_addr = q_addr + AB_T;
-        mbar_wait(pds_full, i & 1);
-        if (i + 1 < nqb) issue_sdp(i + 1);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {  // K = 128 query rows, 16 per instruction
-            umma_bf16(T_DV, umma_desc(p_addr + k * 2048, AB_T, 1024), umma_desc(do_addr + k * 2048, AB_T, 1024), id_g,
-                      (i | k) != 0);
-            umma_bf16(T_DK, umma_desc(ds_addr + k * 2048, AB_T, 1024), umma_desc(q_addr + k * 2048, AB_T, 1024), id_g,
-                      (i | k) != 0);
-          }
-          umma_commit(&qdo_empty[st]);
-          umma_commit(pds_empty);
-        }
-        __syncwarp();
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(T_S + st * 128, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024), id_s, k != 0);
+        umma_commit(&s_full[st]);
       }
-      if (elect_one()) umma_commit(acc_full);
       __syncwarp();
+    };
+    auto issue_dp = [&](int i) {
+      const int st = i & 1;
+      const uint32_t do_addr = smem_u32(smem + KV_SMEM_RING + st * 2 * AB_T) + AB_T;
+      mbar_wait(&qdo_full[st], (i >> 1) & 1);
+      mbar_wait(dp_empty, (i & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(T_DP, umma_desc(do_addr + k * 32, 16, 1024), umma_desc(v_addr + k * 32, 16, 1024), id_s, k != 0);
+        umma_commit(dp_full);
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    issue_dp(0);
+    if (nqb > 1) issue_s(1);
+    for (int i = 0; i < nqb; ++i) {
+      const int st = i & 1;
+      const uint32_t q_addr = smem_u32(smem + KV_SMEM_RING + st * 2 * AB_T), do_addr = q_addr + AB_T;
+      const uint32_t p_addr = smem_u32(smem + KV_SMEM_P + st * KV_PDS_STRIDE), ds_addr = smem_u32(smem + KV_SMEM_DS + st * KV_PDS_STRIDE);
+      mbar_wait(&pds_full[st], (i >> 1) & 1);   // softmax warps are done with block i (and with dP(i))
+      if (i + 1 < nqb) issue_dp(i + 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // K = 128 query rows, 16 per instruction
+          umma_bf16(T_DV, umma_desc(p_addr + k * 2048, AB_T, 1024), umma_desc(do_addr + k * 2048, AB_T, 1024), id_g,
+                    (i | k) != 0);
+          umma_bf16(T_DK, umma_desc(ds_addr + k * 2048, AB_T, 1024), umma_desc(q_addr + k * 2048, AB_T, 1024), id_g,
+                    (i | k) != 0);
+        }
+        umma_commit(&qdo_empty[st]);
+        umma_commit(&pds_empty[st]);
+      }
+      __syncwarp();
+      if (i + 2 < nqb) issue_s(i + 2);
     }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;  // which 64 key columns of the 128-key block this warp handles
     const int r = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int valid_keys = min(128, p.nk - k0);
+    const size_t stat0 = (static_cast<size_t>(b) * p.heads + head) * p.nq;
+    // lse / delta of the NEXT query block are fetched a block ahead (the load sat right in front of its first use:
+    // 10 % of the stall samples)
+    float lse_n = 0.f, delta_n = 0.f;
+    if (r < p.nq) lse_n = p.lse[stat0 + r], delta_n = p.delta[stat0 + r];
     for (int i = 0; i < nqb; ++i) {
+      const int st = i & 1;
       const int row = i * 128 + r;
       const bool row_ok = row < p.nq;
-      float lse_l2 = 0.f, delta = 0.f;
-      if (row_ok) {
-        const size_t o = (static_cast<size_t>(b) * p.heads + head) * p.nq + row;
-        lse_l2 = p.lse[o] * 1.4426950408889634f;
-        delta = p.delta[o];
-      }
-      mbar_wait(sdp_full, i & 1);
-      mbar_wait(pds_empty, (i & 1) ^ 1);
+      const float lse_l2 = lse_n * 1.4426950408889634f, delta = delta_n;
+      if (row + 128 < p.nq) lse_n = p.lse[stat0 + row + 128], delta_n = p.delta[stat0 + row + 128];
+      uint8_t* sP = smem + KV_SMEM_P + st * KV_PDS_STRIDE;
+      uint8_t* sDS = smem + KV_SMEM_DS + st * KV_PDS_STRIDE;
+      float pr[64];
+      mbar_wait(&s_full[st], (i >> 1) & 1);
+      mbar_wait(&pds_empty[st], ((i >> 1) & 1) ^ 1);   // dV / dK of block i - 2 have read this (P | dS) buffer
       tc_fence_after();
-      softmax_bwd_row<true>(T_S + lane_off, T_DP + lane_off, smem + KV_SMEM_P, smem + KV_SMEM_DS, r, valid_keys, row_ok,
-                            lse_l2, delta, p.scale_log2e, p.scale, chalf * 64, valid_keys == 128);
+      bwd_phase_p<2, true>(T_S + st * 128 + lane_off, sP, r, valid_keys, row_ok, lse_l2, p.scale_log2e, chalf * 64,
+                           valid_keys == 128, pr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      mbar_wait(dp_full, i & 1);
+      tc_fence_after();
+      bwd_phase_ds<2>(T_DP + lane_off, sDS, r, delta * p.scale, p.scale, chalf * 64, pr);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(sdp_empty);
-        mbar_arrive(pds_full);
+        mbar_arrive(dp_empty);
+        mbar_arrive(&pds_full[st]);
       }
     }
     // epilogue: thread r <-> key row k0 + r
@@ -255,9 +353,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
 }
 
 // ---------------------------------------------------------------------- dQ ----
-// 64-key blocks, 192 TMEM columns and 97 KB of shared memory per CTA -> TWO CTAs per SM, so that one CTA's
-// softmax/dS phase overlaps the other's MMAs (a single CTA alternates strictly between the two).
-// smem: Q | dO | 3 x (K | V) [64 keys each] | dS (1 tile) | barriers
+// 64-key blocks, 256 TMEM columns and 113 KB of shared memory per CTA -> TWO CTAs per SM.
+// Same pipeline as the dK/dV kernel: S[2] (2 x 64 columns), dP (64), dQ (64) in TMEM, dS double-buffered in shared memory:
+//   MMA lane:      S(0), dP(0), S(1); then per key block j: wait dS(j) -> dP(j+1), dQ(j), S(j+2)
+//   softmax warps: S(j) -> P(j) [registers]; dP(j) -> dS(j) [shared memory]
+// smem: Q | dO | 3 x (K | V) [64 keys each] | 2 x dS | barriers
 constexpr int DQ_BKV = 64;
 constexpr int DQ_KVT = DQ_BKV * 64 * 2;  // 8 KB
 constexpr int DQ_STAGES = 3;
@@ -265,7 +365,7 @@ constexpr int DQ_THREADS = 320;          // warp0 TMA + TMEM alloc, warp1 MMA, w
                                          // 4 TMEM lane quarters x 2 halves of 32 key columns -> with 2 CTAs/SM four
                                          // latency-bound softmax warps per scheduler instead of two
 constexpr int DQ_SMEM_Q = 0, DQ_SMEM_DO = AB_T, DQ_SMEM_RING = 2 * AB_T, DQ_SMEM_DS = DQ_SMEM_RING + DQ_STAGES * 2 * DQ_KVT,
-              DQ_SMEM_BAR = DQ_SMEM_DS + AB_T, DQ_SMEM_TOTAL = DQ_SMEM_BAR + 256;
+              DQ_SMEM_BAR = DQ_SMEM_DS + 2 * AB_T, DQ_SMEM_TOTAL = DQ_SMEM_BAR + 256;
 
 __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const __grid_constant__ AttnBwdArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -273,12 +373,14 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;    // [3]
   uint64_t* kv_empty = bars + 4;   // [3]
-  uint64_t* sdp_full = bars + 7;
-  uint64_t* sdp_empty = bars + 8;  // count 8
-  uint64_t* ds_full = bars + 9;    // count 8
-  uint64_t* ds_empty = bars + 10;
-  uint64_t* acc_full = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_full = bars + 7;     // [2]
+  uint64_t* s_empty = bars + 9;    // [2] count 8
+  uint64_t* dp_full = bars + 11;
+  uint64_t* dp_empty = bars + 12;  // count 8
+  uint64_t* ds_full = bars + 13;   // [2] count 8
+  uint64_t* ds_empty = bars + 15;  // [2]
+  uint64_t* acc_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
   const int nkb = (p.nk + DQ_BKV - 1) / DQ_BKV;
@@ -288,7 +390,11 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
     prefetch_tmap(&p.tmQ), prefetch_tmap(&p.tmK64), prefetch_tmap(&p.tmV64), prefetch_tmap(&p.tmDO);
     mbar_init(q_full, 1);
     for (int i = 0; i < DQ_STAGES; ++i) mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
-    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 8), mbar_init(ds_full, 8), mbar_init(ds_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 8);
+      mbar_init(&ds_full[i], 8), mbar_init(&ds_empty[i], 1);
+    }
+    mbar_init(dp_full, 1), mbar_init(dp_empty, 8);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -300,7 +406,7 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t T_S = tmem_base, T_DP = tmem_base + 64, T_DQ = tmem_base + 128;
+  const uint32_t T_S = tmem_base /* [2] x 64 */, T_DP = tmem_base + 128, T_DQ = tmem_base + 192;
 
   if (warp == 0) {   // converged loops, elected issue (see the dK/dV kernel)
     if (elect_one()) {
@@ -323,50 +429,62 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
       if (++st == DQ_STAGES) st = 0, ph ^= 1;
     }
   } else if (warp == 1) {
-    {
-      const uint32_t id_s = umma_idesc_bf16(128, DQ_BKV, 0, 0);
-      const uint32_t id_q = umma_idesc_bf16(128, 64, 0, 1);  // dQ = dS K : A K-major, B (K) MN-major
-      const uint32_t q_addr = smem_u32(smem + DQ_SMEM_Q), do_addr = smem_u32(smem + DQ_SMEM_DO);
-      const uint32_t ds_addr = smem_u32(smem + DQ_SMEM_DS);
-      mbar_wait(q_full, 0);
-      // same issue order as the dK/dV kernel: S/dP of key block j+1 before dQ of block j
-      auto issue_sdp = [&](int j) {
-        const int st = j % DQ_STAGES;
-        const uint32_t k_addr = smem_u32(smem + DQ_SMEM_RING + st * 2 * DQ_KVT), v_addr = k_addr + DQ_KVT;
-        mbar_wait(&kv_full[st], (j / DQ_STAGES) & 1);
-        mbar_wait(sdp_empty, (j & 1) ^ 1);
-        tc_fence_after();
-        if (elect_one()) {
+    const uint32_t id_s = umma_idesc_bf16(128, DQ_BKV, 0, 0);
+    const uint32_t id_q = umma_idesc_bf16(128, 64, 0, 1);  // dQ = dS K : A K-major, B (K) MN-major
+    const uint32_t q_addr = smem_u32(smem + DQ_SMEM_Q), do_addr = smem_u32(smem + DQ_SMEM_DO);
+    mbar_wait(q_full, 0);
+    // stage j % 3 holds K(j) for S(j) and dQ(j), V(j) for dP(j); S runs two blocks ahead of dQ: three stages suffice
+    auto issue_s = [&](int j) {
+      const int st = j % DQ_STAGES, sb = j & 1;
+      const uint32_t k_addr = smem_u32(smem + DQ_SMEM_RING + st * 2 * DQ_KVT);
+      mbar_wait(&kv_full[st], (j / DQ_STAGES) & 1);
+      mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(T_S, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024), id_s, k != 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(T_DP, umma_desc(do_addr + k * 32, 16, 1024), umma_desc(v_addr + k * 32, 16, 1024), id_s, k != 0);
-          umma_commit(sdp_full);
-        }
-        __syncwarp();
-      };
-      issue_sdp(0);
-      for (int j = 0; j < nkb; ++j) {
-        const int st = j % DQ_STAGES;
-        const uint32_t k_addr = smem_u32(smem + DQ_SMEM_RING + st * 2 * DQ_KVT);
-        mbar_wait(ds_full, j & 1);
-        if (j + 1 < nkb) issue_sdp(j + 1);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < DQ_BKV / 16; ++k)  // A = dS [128 q x 64 keys] K-major; B = K_j rows of 16 keys (MN-major)
-            umma_bf16(T_DQ, umma_desc(ds_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 2048, DQ_KVT, 1024), id_q,
-                      (j | k) != 0);
-          umma_commit(&kv_empty[st]);
-          umma_commit(ds_empty);
-        }
-        __syncwarp();
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(T_S + sb * 64, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024), id_s, k != 0);
+        umma_commit(&s_full[sb]);
       }
-      if (elect_one()) umma_commit(acc_full);
       __syncwarp();
+    };
+    auto issue_dp = [&](int j) {
+      const int st = j % DQ_STAGES;
+      const uint32_t v_addr = smem_u32(smem + DQ_SMEM_RING + st * 2 * DQ_KVT) + DQ_KVT;
+      mbar_wait(&kv_full[st], (j / DQ_STAGES) & 1);
+      mbar_wait(dp_empty, (j & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(T_DP, umma_desc(do_addr + k * 32, 16, 1024), umma_desc(v_addr + k * 32, 16, 1024), id_s, k != 0);
+        umma_commit(dp_full);
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    issue_dp(0);
+    if (nkb > 1) issue_s(1);
+    for (int j = 0; j < nkb; ++j) {
+      const int st = j % DQ_STAGES, sb = j & 1;
+      const uint32_t k_addr = smem_u32(smem + DQ_SMEM_RING + st * 2 * DQ_KVT);
+      const uint32_t ds_addr = smem_u32(smem + DQ_SMEM_DS + sb * AB_T);
+      mbar_wait(&ds_full[sb], (j >> 1) & 1);
+      if (j + 1 < nkb) issue_dp(j + 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < DQ_BKV / 16; ++k)  // A = dS [128 q x 64 keys] K-major; B = K_j rows of 16 keys (MN-major)
+          umma_bf16(T_DQ, umma_desc(ds_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 2048, DQ_KVT, 1024), id_q,
+                    (j | k) != 0);
+        umma_commit(&kv_empty[st]);
+        umma_commit(&ds_empty[sb]);
+      }
+      __syncwarp();
+      if (j + 2 < nkb) issue_s(j + 2);
     }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;  // which 32 of the 64 key columns (and of the 64 dQ columns in the epilogue)
@@ -380,19 +498,28 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
       lse_l2 = p.lse[o] * 1.4426950408889634f;
       delta = p.delta[o];
     }
+    const float delta_s = delta * p.scale;
     for (int j = 0; j < nkb; ++j) {
+      const int sb = j & 1;
       const int valid_keys = min(DQ_BKV, p.nk - j * DQ_BKV);
-      mbar_wait(sdp_full, j & 1);
-      mbar_wait(ds_empty, (j & 1) ^ 1);
+      float pr[32];
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
-      softmax_bwd_row<false, 32>(T_S + lane_off, T_DP + lane_off, nullptr, smem + DQ_SMEM_DS, r, valid_keys, row_ok,
-                                 lse_l2, delta, p.scale_log2e, p.scale, chalf * 32, valid_keys == DQ_BKV);
+      bwd_phase_p<1, false>(T_S + sb * 64 + lane_off, nullptr, r, valid_keys, row_ok, lse_l2, p.scale_log2e, chalf * 32,
+                            valid_keys == DQ_BKV, pr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+      mbar_wait(dp_full, j & 1);
+      mbar_wait(&ds_empty[sb], ((j >> 1) & 1) ^ 1);   // dQ of block j - 2 has read this dS buffer
+      tc_fence_after();
+      bwd_phase_ds<1>(T_DP + lane_off, smem + DQ_SMEM_DS + sb * AB_T, r, delta_s, p.scale, chalf * 32, pr);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(sdp_empty);
-        mbar_arrive(ds_full);
+        mbar_arrive(dp_empty);
+        mbar_arrive(&ds_full[sb]);
       }
     }
     mbar_wait(acc_full, 0);

@@ -53,7 +53,7 @@ def run(B, H, Nq, Nk, bwd):
     print(line, flush=True)
 
 
-run(16, 5, 4096, 4096, False)     # self-attention, sampling batch
+run(16, 5, 4096, 4096, "--bwd" in sys.argv)     # self-attention, sampling batch (--bwd: both backward kernels too)
 run(16, 5, 4096, 77, False)       # cross-attention, sampling batch
 if not once:
     run(16, 10, 1024, 1024, False)
