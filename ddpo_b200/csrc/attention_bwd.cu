@@ -81,10 +81,10 @@ __device__ __forceinline__ void softmax_bwd_row(uint32_t t_s, uint32_t t_dp, uin
 
 // The same arithmetic split in two phases, so that the tensor core can compute dP of a block while the softmax warps
 // already turn its S into P (S is double-buffered in TMEM, dP is not: TMEM has 512 columns).
-// phase P: p[i] = exp2(S c - lse) for NCH chunks of 32 columns from col_begin (masked entries 0); optionally -> sP
-template <int NCH, bool WRITE_P>
-__device__ __forceinline__ void bwd_phase_p(uint32_t t_s, uint8_t* sP, int r, int valid_keys, bool row_ok, float lse_l2, float c,
-                                            int col_begin, bool full, float (&p)[NCH * 32]) {
+// phase P: p[i] = exp2(S c - lse) for NCH chunks of 32 columns from col_begin (masked entries 0), kept in registers
+template <int NCH>
+__device__ __forceinline__ void bwd_phase_p(uint32_t t_s, int valid_keys, bool row_ok, float lse_l2, float c, int col_begin, bool full,
+                                            float (&p)[NCH * 32]) {
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     const int c0 = col_begin + ch * 32;
@@ -102,70 +102,70 @@ __device__ __forceinline__ void bwd_phase_p(uint32_t t_s, uint8_t* sP, int r, in
         p[ch * 32 + i] = ok ? ex2_sel<DDPO_EXP_POLY_BWD>(i, xe) : 0.f;
       }
     }
-    if (WRITE_P) {
-      const int tile_off = (c0 >> 6) * AB_T + r * 128;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int chunk = ((c0 & 63) >> 3) + g;
-        uint4 u;
-        u.x = pack_bf16(p[ch * 32 + g * 8 + 0], p[ch * 32 + g * 8 + 1]), u.y = pack_bf16(p[ch * 32 + g * 8 + 2], p[ch * 32 + g * 8 + 3]);
-        u.z = pack_bf16(p[ch * 32 + g * 8 + 4], p[ch * 32 + g * 8 + 5]), u.w = pack_bf16(p[ch * 32 + g * 8 + 6], p[ch * 32 + g * 8 + 7]);
-        *reinterpret_cast<uint4*>(sP + tile_off + ((chunk ^ (r & 7)) << 4)) = u;
-      }
-    }
   }
 }
-// phase dS: dS = p (dP scale - delta scale) -> sDS
+// phase dS: ds = p (dP scale - delta scale), in place (p := ds unless KEEP_P, where ds goes to a second array)
 template <int NCH>
-__device__ __forceinline__ void bwd_phase_ds(uint32_t t_dp, uint8_t* sDS, int r, float delta_s, float scale, int col_begin,
-                                             const float (&p)[NCH * 32]) {
+__device__ __forceinline__ void bwd_phase_ds(uint32_t t_dp, float delta_s, float scale, int col_begin, const float (&p)[NCH * 32],
+                                             float (&ds)[NCH * 32]) {
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    uint32_t d[32];
+    tmem_ld_32x32(t_dp + col_begin + ch * 32, d);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) ds[ch * 32 + i] = p[ch * 32 + i] * fmaf(__uint_as_float(d[i]), scale, -delta_s);
+  }
+}
+// bf16 store of NCH chunks of row r into [128 rows][64 keys] SW128 tiles
+template <int NCH>
+__device__ __forceinline__ void bwd_store_tile(uint8_t* sT, int r, int col_begin, const float (&v)[NCH * 32]) {
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     const int c0 = col_begin + ch * 32;
-    uint32_t d[32];
-    tmem_ld_32x32(t_dp + c0, d);
-    tmem_ld_wait();
-    float ds[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) ds[i] = p[ch * 32 + i] * fmaf(__uint_as_float(d[i]), scale, -delta_s);
     const int tile_off = (c0 >> 6) * AB_T + r * 128;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int chunk = ((c0 & 63) >> 3) + g;
       uint4 w;
-      w.x = pack_bf16(ds[g * 8 + 0], ds[g * 8 + 1]), w.y = pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]);
-      w.z = pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]), w.w = pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]);
-      *reinterpret_cast<uint4*>(sDS + tile_off + ((chunk ^ (r & 7)) << 4)) = w;
+      w.x = pack_bf16(v[ch * 32 + g * 8 + 0], v[ch * 32 + g * 8 + 1]), w.y = pack_bf16(v[ch * 32 + g * 8 + 2], v[ch * 32 + g * 8 + 3]);
+      w.z = pack_bf16(v[ch * 32 + g * 8 + 4], v[ch * 32 + g * 8 + 5]), w.w = pack_bf16(v[ch * 32 + g * 8 + 6], v[ch * 32 + g * 8 + 7]);
+      *reinterpret_cast<uint4*>(sT + tile_off + ((chunk ^ (r & 7)) << 4)) = w;
     }
   }
 }
 
 // ------------------------------------------------------------------ dK, dV ----
-// smem: K | V | 2 x (Q | dO) | 2 x (P(2 tiles) | dS(2 tiles)) | barriers
+// smem: K | V | 3 x (Q | dO) | P(2 tiles) | dS(2 tiles) | barriers
 //
 // Pipeline (per 128-key CTA, query blocks i = 0, 1, ...).  TMEM: S[2] (2 x 128 columns), dP (128), dV (64), dK (64) = 512.
-//   MMA lane:      S(0), dP(0), S(1); then per i: wait P/dS(i) -> dP(i+1), dV/dK(i), S(i+2)
-//   softmax warps: S(i) -> P(i) [registers + shared memory]; then dP(i) -> dS(i) [shared memory]
-// so the tensor core computes dP(i+1) / dV, dK(i) / S(i+2) while the softmax warps are already in the P phase of block
-// i+1 (S(i+1) has been ready for a whole block) and reaches them again before they need dP(i+1).  In round 1 S / dP and
-// P / dS were single-buffered and 28 % of the warp-stall samples sat in the two hand-over waits
+//   MMA lane:      S(0), dP(0), S(1); then per i: S(i+2) [as soon as the P phase of block i has read S(i)],
+//                  wait P/dS(i) -> dP(i+1), dV/dK(i)
+//   softmax warps: S(i) -> P(i) [registers]; dP(i) -> dS(i) [registers]; wait until dV/dK(i-1) have read the (P | dS) tiles;
+//                  store both
+// so the tensor core computes S(i+2) / dP(i+1) / dV, dK(i) while the softmax warps are already in the P phase of block
+// i+1 (S(i+1) has been ready for a whole block) and reaches them again before they need dP(i+1); the one (P | dS) buffer is
+// free long before the stores at the END of a block (512 MMA clocks after the previous block's hand-over), and the
+// shared memory a second buffer would take holds a third Q / dO stage instead (stage i % 3 serves S(i), dP(i), dV/dK(i):
+// with two stages the load of block i+2 could not start before dV/dK(i) had finished).  In round 1 S / dP were
+// single-buffered, the stage ring was two deep, and 28 % of the warp-stall samples sat in the two hand-over waits
 // (profiles/r2_attention.md).
-constexpr int KV_SMEM_K = 0, KV_SMEM_V = AB_T, KV_SMEM_RING = 2 * AB_T, KV_SMEM_P = 6 * AB_T, KV_SMEM_DS = 8 * AB_T,
-              KV_PDS_STRIDE = 4 * AB_T,  // second (P | dS) buffer
-              KV_SMEM_BAR = 14 * AB_T, KV_SMEM_TOTAL = KV_SMEM_BAR + 256;
+constexpr int KV_STAGES = 3;
+constexpr int KV_SMEM_K = 0, KV_SMEM_V = AB_T, KV_SMEM_RING = 2 * AB_T, KV_SMEM_P = KV_SMEM_RING + KV_STAGES * 2 * AB_T,
+              KV_SMEM_DS = KV_SMEM_P + 2 * AB_T, KV_SMEM_BAR = KV_SMEM_DS + 2 * AB_T, KV_SMEM_TOTAL = KV_SMEM_BAR + 256;
 
 __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const __grid_constant__ AttnBwdArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + KV_SMEM_BAR);
   uint64_t* kv_full = bars;          // 1
-  uint64_t* qdo_full = bars + 1;     // [2]
-  uint64_t* qdo_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;       // [2]
-  uint64_t* s_empty = bars + 7;      // [2] (count 8)
-  uint64_t* dp_full = bars + 9;      // 1
-  uint64_t* dp_empty = bars + 10;    // 1 (count 8)
-  uint64_t* pds_full = bars + 11;    // [2] (count 8)
-  uint64_t* pds_empty = bars + 13;   // [2]
+  uint64_t* qdo_full = bars + 1;     // [3]
+  uint64_t* qdo_empty = bars + 4;    // [3]
+  uint64_t* s_full = bars + 7;       // [2]
+  uint64_t* s_empty = bars + 9;      // [2] (count 8)
+  uint64_t* dp_full = bars + 11;     // 1
+  uint64_t* dp_empty = bars + 12;    // 1 (count 8)
+  uint64_t* pds_full = bars + 13;    // 1 (count 8)
+  uint64_t* pds_empty = bars + 14;   // 1
   uint64_t* acc_full = bars + 15;    // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -176,12 +176,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     prefetch_tmap(&p.tmQ), prefetch_tmap(&p.tmK), prefetch_tmap(&p.tmV), prefetch_tmap(&p.tmDO);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&qdo_full[i], 1), mbar_init(&qdo_empty[i], 1);
-      mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 8);
-      mbar_init(&pds_full[i], 8), mbar_init(&pds_empty[i], 1);
-    }
+    for (int i = 0; i < KV_STAGES; ++i) mbar_init(&qdo_full[i], 1), mbar_init(&qdo_empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 8);
     mbar_init(dp_full, 1), mbar_init(dp_empty, 8);
+    mbar_init(pds_full, 8), mbar_init(pds_empty, 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -204,9 +202,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
       tma_load_4d(smem + KV_SMEM_V, &p.tmV, kv_full, 0, head, k0, b);
     }
     __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
     for (int i = 0; i < nqb; ++i) {
-      const int st = i & 1;
-      mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+      mbar_wait(&qdo_empty[st], ph ^ 1);
       uint8_t* sQ = smem + KV_SMEM_RING + st * 2 * AB_T;
       if (elect_one()) {
         mbar_expect_tx(&qdo_full[st], 2 * AB_T);
@@ -214,32 +213,32 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
         tma_load_4d(sQ + AB_T, &p.tmDO, &qdo_full[st], 0, head, i * 128, b);
       }
       __syncwarp();
+      if (++st == KV_STAGES) st = 0, ph ^= 1;
     }
   } else if (warp == 1) {
     const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);  // S = Q K^T, dP = dO V^T
     const uint32_t id_g = umma_idesc_bf16(128, 64, 1, 1);   // dV = P^T dO, dK = dS^T Q (both MN-major)
     const uint32_t k_addr = smem_u32(smem + KV_SMEM_K), v_addr = smem_u32(smem + KV_SMEM_V);
+    const uint32_t p_addr = smem_u32(smem + KV_SMEM_P), ds_addr = smem_u32(smem + KV_SMEM_DS);
     mbar_wait(kv_full, 0);
-    // the Q / dO stage of block i holds Q(i) for S(i) and dK(i), dO(i) for dP(i) and dV(i): with S running two blocks
-    // ahead of dV / dK the two-stage ring would deadlock, so S(i+2) is issued right AFTER dV / dK(i) released stage i & 1
     auto issue_s = [&](int i) {
-      const int st = i & 1;
+      const int st = i % KV_STAGES, sb = i & 1;
       const uint32_t q_addr = smem_u32(smem + KV_SMEM_RING + st * 2 * AB_T);
-      mbar_wait(&qdo_full[st], (i >> 1) & 1);
-      mbar_wait(&s_empty[st], ((i >> 1) & 1) ^ 1);
+      mbar_wait(&qdo_full[st], (i / KV_STAGES) & 1);
+      mbar_wait(&s_empty[sb], ((i >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(T_S + st * 128, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024), id_s, k != 0);
-        umma_commit(&s_full[st]);
+          umma_bf16(T_S + sb * 128, umma_desc(q_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 32, 16, 1024), id_s, k != 0);
+        umma_commit(&s_full[sb]);
       }
       __syncwarp();
     };
     auto issue_dp = [&](int i) {
-      const int st = i & 1;
+      const int st = i % KV_STAGES;
       const uint32_t do_addr = smem_u32(smem + KV_SMEM_RING + st * 2 * AB_T) + AB_T;
-      mbar_wait(&qdo_full[st], (i >> 1) & 1);
+      mbar_wait(&qdo_full[st], (i / KV_STAGES) & 1);
       mbar_wait(dp_empty, (i & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
@@ -254,10 +253,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
     issue_dp(0);
     if (nqb > 1) issue_s(1);
     for (int i = 0; i < nqb; ++i) {
-      const int st = i & 1;
+      const int st = i % KV_STAGES;
       const uint32_t q_addr = smem_u32(smem + KV_SMEM_RING + st * 2 * AB_T), do_addr = q_addr + AB_T;
-      const uint32_t p_addr = smem_u32(smem + KV_SMEM_P + st * KV_PDS_STRIDE), ds_addr = smem_u32(smem + KV_SMEM_DS + st * KV_PDS_STRIDE);
-      mbar_wait(&pds_full[st], (i >> 1) & 1);   // softmax warps are done with block i (and with dP(i))
+      if (i + 2 < nqb) issue_s(i + 2);   // waits for the P phase of block i (S buffer i & 1), not for the whole block
+      mbar_wait(pds_full, i & 1);        // softmax warps are done with block i (and with dP(i))
       if (i + 1 < nqb) issue_dp(i + 1);
       tc_fence_after();
       if (elect_one()) {
@@ -269,10 +268,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
                     (i | k) != 0);
         }
         umma_commit(&qdo_empty[st]);
-        umma_commit(&pds_empty[st]);
+        umma_commit(pds_empty);
       }
       __syncwarp();
-      if (i + 2 < nqb) issue_s(i + 2);
     }
     if (elect_one()) umma_commit(acc_full);
     __syncwarp();
@@ -288,32 +286,30 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
     float lse_n = 0.f, delta_n = 0.f;
     if (r < p.nq) lse_n = p.lse[stat0 + r], delta_n = p.delta[stat0 + r];
     for (int i = 0; i < nqb; ++i) {
-      const int st = i & 1;
+      const int sb = i & 1;
       const int row = i * 128 + r;
       const bool row_ok = row < p.nq;
       const float lse_l2 = lse_n * 1.4426950408889634f, delta = delta_n;
       if (row + 128 < p.nq) lse_n = p.lse[stat0 + row + 128], delta_n = p.delta[stat0 + row + 128];
-      uint8_t* sP = smem + KV_SMEM_P + st * KV_PDS_STRIDE;
-      uint8_t* sDS = smem + KV_SMEM_DS + st * KV_PDS_STRIDE;
-      float pr[64];
-      mbar_wait(&s_full[st], (i >> 1) & 1);
-      mbar_wait(&pds_empty[st], ((i >> 1) & 1) ^ 1);   // dV / dK of block i - 2 have read this (P | dS) buffer
+      float pr[64], ds[64];
+      mbar_wait(&s_full[sb], (i >> 1) & 1);
       tc_fence_after();
-      bwd_phase_p<2, true>(T_S + st * 128 + lane_off, sP, r, valid_keys, row_ok, lse_l2, p.scale_log2e, chalf * 64,
-                           valid_keys == 128, pr);
+      bwd_phase_p<2>(T_S + sb * 128 + lane_off, valid_keys, row_ok, lse_l2, p.scale_log2e, chalf * 64, valid_keys == 128, pr);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
       mbar_wait(dp_full, i & 1);
       tc_fence_after();
-      bwd_phase_ds<2>(T_DP + lane_off, sDS, r, delta * p.scale, p.scale, chalf * 64, pr);
+      bwd_phase_ds<2>(T_DP + lane_off, delta * p.scale, p.scale, chalf * 64, pr, ds);
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dp_empty);
+      mbar_wait(pds_empty, (i & 1) ^ 1);   // dV / dK of block i - 1 have read the (P | dS) tiles
+      bwd_store_tile<2>(smem + KV_SMEM_P, r, chalf * 64, pr);
+      bwd_store_tile<2>(smem + KV_SMEM_DS, r, chalf * 64, ds);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(dp_empty);
-        mbar_arrive(&pds_full[st]);
-      }
+      if (lane == 0) mbar_arrive(pds_full);
     }
     // epilogue: thread r <-> key row k0 + r
     mbar_wait(acc_full, 0);
@@ -354,31 +350,31 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_dkdv_kernel(const
 
 // ---------------------------------------------------------------------- dQ ----
 // 64-key blocks, 256 TMEM columns and 113 KB of shared memory per CTA -> TWO CTAs per SM.
-// Same pipeline as the dK/dV kernel: S[2] (2 x 64 columns), dP (64), dQ (64) in TMEM, dS double-buffered in shared memory:
-//   MMA lane:      S(0), dP(0), S(1); then per key block j: wait dS(j) -> dP(j+1), dQ(j), S(j+2)
-//   softmax warps: S(j) -> P(j) [registers]; dP(j) -> dS(j) [shared memory]
-// smem: Q | dO | 3 x (K | V) [64 keys each] | 2 x dS | barriers
+// Same pipeline as the dK/dV kernel: S[2] (2 x 64 columns), dP (64), dQ (64) in TMEM, one dS tile, four K / V stages:
+//   MMA lane:      S(0), dP(0), S(1); then per key block j: S(j+2), wait dS(j) -> dP(j+1), dQ(j)
+//   softmax warps: S(j) -> P(j) [registers]; dP(j) -> dS(j) [registers]; wait until dQ(j-1) has read the dS tile; store
+// smem: Q | dO | 4 x (K | V) [64 keys each] | dS | barriers
 constexpr int DQ_BKV = 64;
 constexpr int DQ_KVT = DQ_BKV * 64 * 2;  // 8 KB
-constexpr int DQ_STAGES = 3;
+constexpr int DQ_STAGES = 4;
 constexpr int DQ_THREADS = 320;          // warp0 TMA + TMEM alloc, warp1 MMA, warps 2..9 softmax/epilogue:
                                          // 4 TMEM lane quarters x 2 halves of 32 key columns -> with 2 CTAs/SM four
                                          // latency-bound softmax warps per scheduler instead of two
 constexpr int DQ_SMEM_Q = 0, DQ_SMEM_DO = AB_T, DQ_SMEM_RING = 2 * AB_T, DQ_SMEM_DS = DQ_SMEM_RING + DQ_STAGES * 2 * DQ_KVT,
-              DQ_SMEM_BAR = DQ_SMEM_DS + 2 * AB_T, DQ_SMEM_TOTAL = DQ_SMEM_BAR + 256;
+              DQ_SMEM_BAR = DQ_SMEM_DS + AB_T, DQ_SMEM_TOTAL = DQ_SMEM_BAR + 256;
 
 __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const __grid_constant__ AttnBwdArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_SMEM_BAR);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;    // [3]
-  uint64_t* kv_empty = bars + 4;   // [3]
-  uint64_t* s_full = bars + 7;     // [2]
-  uint64_t* s_empty = bars + 9;    // [2] count 8
-  uint64_t* dp_full = bars + 11;
-  uint64_t* dp_empty = bars + 12;  // count 8
-  uint64_t* ds_full = bars + 13;   // [2] count 8
-  uint64_t* ds_empty = bars + 15;  // [2]
+  uint64_t* kv_full = bars + 1;    // [4]
+  uint64_t* kv_empty = bars + 5;   // [4]
+  uint64_t* s_full = bars + 9;     // [2]
+  uint64_t* s_empty = bars + 11;   // [2] count 8
+  uint64_t* dp_full = bars + 13;
+  uint64_t* dp_empty = bars + 14;  // count 8
+  uint64_t* ds_full = bars + 15;   // count 8
+  uint64_t* ds_empty = bars + 16;
   uint64_t* acc_full = bars + 17;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -390,10 +386,8 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
     prefetch_tmap(&p.tmQ), prefetch_tmap(&p.tmK64), prefetch_tmap(&p.tmV64), prefetch_tmap(&p.tmDO);
     mbar_init(q_full, 1);
     for (int i = 0; i < DQ_STAGES; ++i) mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 8);
-      mbar_init(&ds_full[i], 8), mbar_init(&ds_empty[i], 1);
-    }
+    for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 8);
+    mbar_init(ds_full, 8), mbar_init(ds_empty, 1);
     mbar_init(dp_full, 1), mbar_init(dp_empty, 8);
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -433,7 +427,8 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
     const uint32_t id_q = umma_idesc_bf16(128, 64, 0, 1);  // dQ = dS K : A K-major, B (K) MN-major
     const uint32_t q_addr = smem_u32(smem + DQ_SMEM_Q), do_addr = smem_u32(smem + DQ_SMEM_DO);
     mbar_wait(q_full, 0);
-    // stage j % 3 holds K(j) for S(j) and dQ(j), V(j) for dP(j); S runs two blocks ahead of dQ: three stages suffice
+    // stage j % 4 holds K(j) for S(j) and dQ(j), V(j) for dP(j); S runs two blocks ahead of dQ, the fourth stage is the
+    // load in flight
     auto issue_s = [&](int j) {
       const int st = j % DQ_STAGES, sb = j & 1;
       const uint32_t k_addr = smem_u32(smem + DQ_SMEM_RING + st * 2 * DQ_KVT);
@@ -465,11 +460,12 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
     issue_s(0);
     issue_dp(0);
     if (nkb > 1) issue_s(1);
+    const uint32_t ds_addr = smem_u32(smem + DQ_SMEM_DS);
     for (int j = 0; j < nkb; ++j) {
-      const int st = j % DQ_STAGES, sb = j & 1;
+      const int st = j % DQ_STAGES;
       const uint32_t k_addr = smem_u32(smem + DQ_SMEM_RING + st * 2 * DQ_KVT);
-      const uint32_t ds_addr = smem_u32(smem + DQ_SMEM_DS + sb * AB_T);
-      mbar_wait(&ds_full[sb], (j >> 1) & 1);
+      if (j + 2 < nkb) issue_s(j + 2);   // waits for the P phase of block j only
+      mbar_wait(ds_full, j & 1);
       if (j + 1 < nkb) issue_dp(j + 1);
       tc_fence_after();
       if (elect_one()) {
@@ -478,10 +474,9 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
           umma_bf16(T_DQ, umma_desc(ds_addr + k * 32, 16, 1024), umma_desc(k_addr + k * 2048, DQ_KVT, 1024), id_q,
                     (j | k) != 0);
         umma_commit(&kv_empty[st]);
-        umma_commit(&ds_empty[sb]);
+        umma_commit(ds_empty);
       }
       __syncwarp();
-      if (j + 2 < nkb) issue_s(j + 2);
     }
     if (elect_one()) umma_commit(acc_full);
     __syncwarp();
@@ -502,25 +497,24 @@ __global__ void __launch_bounds__(DQ_THREADS, 2) attention_bwd_dq_kernel(const _
     for (int j = 0; j < nkb; ++j) {
       const int sb = j & 1;
       const int valid_keys = min(DQ_BKV, p.nk - j * DQ_BKV);
-      float pr[32];
+      float pr[32], ds[32];
       mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
-      bwd_phase_p<1, false>(T_S + sb * 64 + lane_off, nullptr, r, valid_keys, row_ok, lse_l2, p.scale_log2e, chalf * 32,
-                            valid_keys == DQ_BKV, pr);
+      bwd_phase_p<1>(T_S + sb * 64 + lane_off, valid_keys, row_ok, lse_l2, p.scale_log2e, chalf * 32, valid_keys == DQ_BKV, pr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
       mbar_wait(dp_full, j & 1);
-      mbar_wait(&ds_empty[sb], ((j >> 1) & 1) ^ 1);   // dQ of block j - 2 has read this dS buffer
       tc_fence_after();
-      bwd_phase_ds<1>(T_DP + lane_off, smem + DQ_SMEM_DS + sb * AB_T, r, delta_s, p.scale, chalf * 32, pr);
+      bwd_phase_ds<1>(T_DP + lane_off, delta_s, p.scale, chalf * 32, pr, ds);
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dp_empty);
+      mbar_wait(ds_empty, (j & 1) ^ 1);   // dQ of block j - 1 has read the dS tile
+      bwd_store_tile<1>(smem + DQ_SMEM_DS, r, chalf * 32, ds);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(dp_empty);
-        mbar_arrive(&ds_full[sb]);
-      }
+      if (lane == 0) mbar_arrive(ds_full);
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
