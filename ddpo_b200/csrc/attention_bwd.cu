@@ -29,76 +29,28 @@ struct AttnBwdArgs {
   float scale, scale_log2e;
 };
 
-// one query row (thread r) x 128 keys: read S and dP from TMEM, write P (optional) and dS as bf16
-// into [128 rows][64 keys] SW128 tiles.  `row_ok` false -> zeros.
-template <bool WRITE_P, int NCOLS = 64>
-__device__ __forceinline__ void softmax_bwd_row(uint32_t t_s, uint32_t t_dp, uint8_t* sP, uint8_t* sDS, int r, int valid_keys,
-                                                bool row_ok, float lse_l2, float delta, float c, float scale, int col_begin, bool full) {
-  const float delta_s = delta * scale;  // dS = P (dP - delta) scale = P (dP scale - delta scale): one FFMA + one FMUL
-#pragma unroll 1
-  for (int c0 = col_begin; c0 < col_begin + NCOLS; c0 += 32) {
-    uint32_t s[32], d[32];
-    tmem_ld_32x32(t_s + c0, s);
-    tmem_ld_32x32(t_dp + c0, d);
-    tmem_ld_wait();
-    float p[32], ds[32];
-    if (row_ok && full) {  // predicate-free fast path (the softmax warps are instruction bound)
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float xe = __uint_as_float(s[i]) * c - lse_l2;
-        const float pv = ex2_sel<DDPO_EXP_POLY_BWD>(i, xe);
-        p[i] = pv;
-        ds[i] = pv * fmaf(__uint_as_float(d[i]), scale, -delta_s);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const bool ok = row_ok && (c0 + i < valid_keys);
-        const float xe = __uint_as_float(s[i]) * c - lse_l2;
-        const float pv = ok ? ex2_sel<DDPO_EXP_POLY_BWD>(i, xe) : 0.f;
-        p[i] = pv;
-        ds[i] = pv * fmaf(__uint_as_float(d[i]), scale, -delta_s);
-      }
-    }
-    const int tile_off = (c0 >> 6) * AB_T + r * 128;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int chunk = ((c0 & 63) >> 3) + g;
-      const int off = tile_off + ((chunk ^ (r & 7)) << 4);
-      if (WRITE_P) {
-        uint4 u;
-        u.x = pack_bf16(p[g * 8 + 0], p[g * 8 + 1]), u.y = pack_bf16(p[g * 8 + 2], p[g * 8 + 3]);
-        u.z = pack_bf16(p[g * 8 + 4], p[g * 8 + 5]), u.w = pack_bf16(p[g * 8 + 6], p[g * 8 + 7]);
-        *reinterpret_cast<uint4*>(sP + off) = u;
-      }
-      uint4 w;
-      w.x = pack_bf16(ds[g * 8 + 0], ds[g * 8 + 1]), w.y = pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]);
-      w.z = pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]), w.w = pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]);
-      *reinterpret_cast<uint4*>(sDS + off) = w;
-    }
-  }
-}
-
+// One query row (thread r): P and dS as bf16 into [128 rows][64 keys] SW128 tiles; rows / keys outside the problem -> zeros.
 // The same arithmetic split in two phases, so that the tensor core can compute dP of a block while the softmax warps
 // already turn its S into P (S is double-buffered in TMEM, dP is not: TMEM has 512 columns).
 // phase P: p[i] = exp2(S c - lse) for NCH chunks of 32 columns from col_begin (masked entries 0), kept in registers
 template <int NCH>
 __device__ __forceinline__ void bwd_phase_p(uint32_t t_s, int valid_keys, bool row_ok, float lse_l2, float c, int col_begin, bool full,
                                             float (&p)[NCH * 32]) {
+  uint32_t s[NCH][32];   // all chunks are fetched before the one wait: one TMEM round trip per phase, not one per chunk
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32(t_s + col_begin + ch * 32, s[ch]);
+  tmem_ld_wait();
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     const int c0 = col_begin + ch * 32;
-    uint32_t s[32];
-    tmem_ld_32x32(t_s + c0, s);
-    tmem_ld_wait();
     if (row_ok && full) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) p[ch * 32 + i] = ex2_sel<DDPO_EXP_POLY_BWD>(i, __uint_as_float(s[i]) * c - lse_l2);
+      for (int i = 0; i < 32; ++i) p[ch * 32 + i] = ex2_sel<DDPO_EXP_POLY_BWD>(i, __uint_as_float(s[ch][i]) * c - lse_l2);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const bool ok = row_ok && (c0 + i < valid_keys);
-        const float xe = __uint_as_float(s[i]) * c - lse_l2;
+        const float xe = __uint_as_float(s[ch][i]) * c - lse_l2;
         p[ch * 32 + i] = ok ? ex2_sel<DDPO_EXP_POLY_BWD>(i, xe) : 0.f;
       }
     }
@@ -108,14 +60,14 @@ __device__ __forceinline__ void bwd_phase_p(uint32_t t_s, int valid_keys, bool r
 template <int NCH>
 __device__ __forceinline__ void bwd_phase_ds(uint32_t t_dp, float delta_s, float scale, int col_begin, const float (&p)[NCH * 32],
                                              float (&ds)[NCH * 32]) {
+  uint32_t d[NCH][32];
 #pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    uint32_t d[32];
-    tmem_ld_32x32(t_dp + col_begin + ch * 32, d);
-    tmem_ld_wait();
+  for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32(t_dp + col_begin + ch * 32, d[ch]);
+  tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) ds[ch * 32 + i] = p[ch * 32 + i] * fmaf(__uint_as_float(d[i]), scale, -delta_s);
-  }
+  for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) ds[ch * 32 + i] = p[ch * 32 + i] * fmaf(__uint_as_float(d[ch][i]), scale, -delta_s);
 }
 // bf16 store of NCH chunks of row r into [128 rows][64 keys] SW128 tiles
 template <int NCH>
