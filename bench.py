@@ -665,7 +665,8 @@ def main():
                       "epoch0_first_pass_approx_kl": float(kl[0]),
                       "optimizer_updates_per_epoch": NB // TRAIN_BATCH,
                       "h2d_bytes_per_epoch": (NB + 1) * 77 * 8 + (NB // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * TRAIN_MACRO * TRAIN_BATCH * 40,
-                      "d2h_bytes_per_epoch": NB * 512 * 512 * 3 * 4 + NB * T_STEPS * 8 + (NB // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * 12}
+                      # images leave as uint8 (the JPEG reward's own cast, done on the device: pipeline/policy_gradient.images_to_host)
+                      "d2h_bytes_per_epoch": NB * 512 * 512 * 3 * 1 + NB * T_STEPS * 8 + (NB // TRAIN_BATCH) * (T_STEPS // TRAIN_MACRO) * 12}
         except Exception as ex:  # reported, never hidden
             driver = {"error": repr(ex)[:300]}
 

@@ -83,6 +83,7 @@ SIGNATURES = {
     "ddpo_upsample2x_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_upsample2x_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "ddpo_vae_image_to_nchw": (i32, [vp, vp, i32, i32, i32, vp]),
+    "ddpo_image_to_uint8": (i32, [vp, vp, C.c_longlong, vp]),
     "ddpo_vae_encoder_head": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ddpo_conv_in": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "ddpo_conv_out": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),

@@ -184,6 +184,26 @@ __global__ void __launch_bounds__(256) vae_encoder_head_kernel(const float* __re
 
 using namespace ddpo;
 
+// uint8 hand-off of decoded images to the host-side rewards: u8 = (uint8)(x * 255) -- the truncating cast the reference
+// applies on the host (ddpo/training/callbacks.py:181, utils/hdf5.py:31), here before the device -> host copy (4x fewer bytes)
+__global__ void __launch_bounds__(256) image_to_uint8_kernel(const float4* __restrict__ img, uchar4* __restrict__ out, int64_t n4) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = img[i];
+  out[i] = make_uchar4(static_cast<unsigned char>(v.x * 255.f), static_cast<unsigned char>(v.y * 255.f),
+                       static_cast<unsigned char>(v.z * 255.f), static_cast<unsigned char>(v.w * 255.f));
+}
+
+extern "C" int ddpo_image_to_uint8(const float* img, unsigned char* out, long long n, void* stream) {
+  DDPO_REQUIRE(img && out && n > 0 && n % 4 == 0, "image_to_uint8: n must be a positive multiple of 4");
+  DDPO_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0, "image_to_uint8: alignment");
+  const int64_t n4 = n / 4;
+  image_to_uint8_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(img), reinterpret_cast<uchar4*>(out), n4);
+  DDPO_LAUNCH_OK();
+  return DDPO_OK;
+}
+
 extern "C" int ddpo_vae_image_to_nchw(const float* img_nhwc, float* out_nchw, int batch, int h, int w, void* stream) {
   DDPO_REQUIRE(img_nhwc && out_nchw && batch > 0 && h > 0 && w > 0, "vae_image_to_nchw: bad arguments");
   const int64_t px = static_cast<int64_t>(batch) * h * w;

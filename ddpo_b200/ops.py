@@ -529,6 +529,15 @@ def softmax_rows(scores, probs_bf16, scale):
          float(rows) * n * 6, _e)
 
 
+def image_to_uint8(img, out_u8):
+    """``(img * 255).astype(uint8)`` (the reference's truncating cast, callbacks.py:181) on the device"""
+    _chk(img, torch.float32, "images")
+    _chk(out_u8, torch.uint8, "out")
+    assert img.numel() == out_u8.numel() and img.numel() % 4 == 0
+    _e = _ev()
+    _run("image_to_uint8", lib().ddpo_image_to_uint8(_p(img), _p(out_u8), img.numel(), _stream()), 0.0, _e)
+
+
 def vae_image_to_nchw(img_nhwc, out_nchw):
     _chk(img_nhwc, torch.float32, "images")
     _chk(out_nchw, torch.float32, "out")

@@ -288,6 +288,9 @@ int ddpo_vae_image_to_nchw(const float* img_nhwc, float* out_nchw, int batch, in
  * then quant_conv (1x1, 8 -> 8) and the posterior's logvar clip to [-30, 20]: moments NHWC [batch, h, w, 8] = mean | logvar */
 int ddpo_vae_encoder_head(const float* x_nhwc, const float* w_hwio, const float* bias, const float* wq_in_out,
                           const float* bq, float* moments_nhwc, int batch, int h, int w, int cin, void* stream);
+/* decoded images [0,1] fp32 -> uint8 with the reference's truncating cast `(image * 255).astype(np.uint8)`
+ * (ddpo/training/callbacks.py:181, ddpo/utils/hdf5.py:31), on the device so that the rewards' images leave as bytes */
+int ddpo_image_to_uint8(const float* img, unsigned char* out, long long n, void* stream);
 int ddpo_vae_conv_out(const float* x_nhwc, const float* w_hwio, const float* bias, float* raw_nchw, float* img_nhwc,
                       int batch, int h, int w, int cin, void* stream);
 

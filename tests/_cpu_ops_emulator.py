@@ -127,6 +127,10 @@ def softmax_rows(scores, probs_bf16, scale):
     probs_bf16.copy_(torch.softmax(scores * scale, -1).to(BF16))
 
 
+def image_to_uint8(img, out_u8):
+    out_u8.copy_((img * 255).to(torch.uint8))
+
+
 def vae_image_to_nchw(img_nhwc, out_nchw):
     out_nchw.copy_(((img_nhwc - 0.5) / 0.5).permute(0, 3, 1, 2))
 

@@ -221,3 +221,16 @@ def test_vae_encode_full_size_and_callback():
     ref = OV.encode(V.views(enc.params.cpu(), V.SD_VAE, part="encoder"), V.SD_VAE, torch.from_numpy(img[:1])).numpy()
     rel = np.linalg.norm(mom[:1] - ref) / np.linalg.norm(ref)
     assert rel < 3e-2, rel
+
+
+def test_image_to_uint8_matches_the_reference_cast():
+    """device-side `(image * 255).astype(np.uint8)` (reference callbacks.py:181): bit-exact incl. 0, 1 and values a hair below k/255"""
+    from ddpo_b200 import ops
+    rng = np.random.default_rng(3)
+    x = rng.random((2, 64, 48, 3)).astype(np.float32)
+    x.reshape(-1)[:8] = [0.0, 1.0, 0.5, 254.999 / 255, 255 / 255, 1 / 255, np.nextafter(np.float32(2 / 255), np.float32(0)), 0.99999994]
+    d = torch.from_numpy(x).to(DEV)
+    u8 = torch.empty(x.shape, dtype=torch.uint8, device=DEV)
+    ops.image_to_uint8(d, u8)
+    torch.cuda.synchronize()
+    assert np.array_equal(u8.cpu().numpy(), (x * 255).astype(np.uint8))
