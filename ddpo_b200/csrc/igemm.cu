@@ -176,13 +176,18 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M_total;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + sub * 256;
-      if (p.epi_stage)
-        igemm_epilogue_staged(p, epi_base + (warp - 4) * EPI_STAGE_WARP_BYTES, t_row, m0 + q * 32, lane, n0, BN, cgrp, cstep);
-      else
+      if (p.epi_stage) {
+        igemm_epilogue_staged(p, epi_base + (warp - 4) * EPI_STAGE_WARP_BYTES, t_row, m0 + q * 32, lane, n0, BN, cgrp, cstep, [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        });
+      } else {
         igemm_epilogue(p, t_row, row, row_ok, n0, tn, BN, cgrp, cstep);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      }
     }
   }
 

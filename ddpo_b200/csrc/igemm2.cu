@@ -233,16 +233,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
         mbar_wait(&tmem_full[sl], (jg / nslot) & 1);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sl * slot_cols;
+        bool released = false;
         if (!(p.dbg & 4)) {
-          if (p.epi_stage)
+          if (p.epi_stage) {
             igemm_epilogue_staged(p, epi_base + (warp - 4) * EPI_STAGE_WARP_BYTES, t_row, m0 + q * 32, lane, (tn * NS + j) * BN, BN,
-                                  cgrp, 64);
-          else
+                                  cgrp, 64, [&]() {
+                                    tc_fence_before();
+                                    __syncwarp();
+                                    if (lane == 0) mbar_arrive_cluster(&tmem_empty[sl], 0);
+                                  });
+            released = true;
+          } else {
             igemm_epilogue(p, t_row, row, row_ok, (tn * NS + j) * BN, tn * NS + j, BN, cgrp, 64);
+          }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&tmem_empty[sl], 0);
+        if (!released) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty[sl], 0);
+        }
       }
     }
   }

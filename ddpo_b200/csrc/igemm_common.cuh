@@ -265,9 +265,16 @@ constexpr int EPI_STAGE_BYTES = 8 * EPI_STAGE_WARP_BYTES;   // 32 KB
 // conflict-free for both access patterns): global instruction i of lane l covers chunk (l & 7) of row 4 i + (l >> 3), i.e.
 // four whole 128-byte row segments.  Arithmetic and its order are igemm_epilogue's: acc + bias + rowvec + residual
 // (+ old output) -> bit-identical results.  GEGLU layers keep the plain path (they run the TMA-staged epilogue anyway).
+// `release()` hands the accumulator slot back (arrive on its tmem_empty barrier): it is called as soon as the LAST chunk of
+// this warp has left TMEM, before that chunk's arithmetic, stores and statistics -- the next tile's MMAs wait for exactly
+// this hand-over when the accumulators cannot be double-buffered (320-wide tiles).
+template <typename Release>
 __device__ __forceinline__ void igemm_epilogue_staged(const IGemmArgs& p, uint8_t* __restrict__ stg, uint32_t t_row,
-                                                      int m_slab, int lane, int n0, int BN, int cgrp, int cstep) {
-  if (m_slab >= p.M_total) return;  // warp-uniform: a slab entirely below the matrix has nothing to do
+                                                      int m_slab, int lane, int n0, int BN, int cgrp, int cstep, Release release) {
+  if (m_slab >= p.M_total) {  // warp-uniform: a slab entirely below the matrix has nothing to do
+    release();
+    return;
+  }
   const int row = m_slab + lane;
   const bool row_ok = row < p.M_total;
   const float* rv = nullptr;
@@ -291,6 +298,7 @@ __device__ __forceinline__ void igemm_epilogue_staged(const IGemmArgs& p, uint8_
       }
     }
     tmem_ld_wait();
+    if (c0 + cstep >= BN) release();   // (a warp whose chunk list is empty releases after the loop)
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -379,6 +387,7 @@ __device__ __forceinline__ void igemm_epilogue_staged(const IGemmArgs& p, uint8_
       gn_slab_stats(p.gn_stats, p.N_total, m_slab, n, lane, f);
     }
   }
+  if (cgrp * 32 >= BN) release();
 }
 
 // One epilogue warp: rows (row .. ) of TMEM lane quarter `q`, 32-column chunks c0 = cgrp*32, += cstep.

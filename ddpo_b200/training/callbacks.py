@@ -164,7 +164,9 @@ def vae_fn(devices=None, dtype="float32", jit=True, encoder=None, pretrained_mod
 def evaluate_callbacks(fns, images, prompts, metadata):
     if type(prompts[0]) == list:
         prompts = [random.choice(p) for p in prompts]
-    images = np.asarray(images, dtype=np.float32)
+    images = np.asarray(images)
+    if images.dtype != np.uint8:   # uint8: the driver already applied the rewards' own cast on the device
+        images = images.astype(np.float32)
     return {key: fn(images, prompts, metadata) for key, fn in fns.items()}
 
 

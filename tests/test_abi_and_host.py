@@ -100,3 +100,19 @@ def test_parser_prompts_callbacks():
     assert out["jpeg"][0].shape == (2, 1) and np.all(out["jpeg"][0] < 0)
     np.testing.assert_allclose(out["jpeg"][0], -out["neg"][0])
     assert callback_fns["arange"]()(imgs, inf[:2], meta[:2])[0].tolist() == [0, 1]
+
+
+def test_rewards_take_device_cast_uint8_images():
+    """the driver hands the JPEG rewards uint8 images (the reference's `(image * 255).astype(np.uint8)`, callbacks.py:181, applied
+    on the device): same scores as from the float images, and `evaluate_callbacks` must not turn the bytes back into floats"""
+    from ddpo_b200 import training
+    rng = np.random.default_rng(0)
+    imgs = rng.random((3, 32, 32, 3)).astype(np.float32)
+    u8 = (imgs * 255).astype(np.uint8)
+    fns = {"jpeg": training.callback_fns["jpeg"](), "neg_jpeg": training.callback_fns["neg_jpeg"]()}
+    assert all(getattr(f, "accepts_uint8", False) for f in fns.values())
+    a = training.evaluate_callbacks(fns, imgs, ["a", "b", "c"], [{}] * 3)
+    b = training.evaluate_callbacks(fns, u8, ["a", "b", "c"], [{}] * 3)
+    for k in fns:
+        assert np.array_equal(a[k][0], b[k][0])
+    assert not getattr(training.callback_fns["aesthetic"], "accepts_uint8", False)
