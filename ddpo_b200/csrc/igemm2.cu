@@ -88,8 +88,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
   // UTCHMMA in an R2UR + ELECT "waterfall": ~165 (producer) / ~120 (MMA) dependent instructions per 64-deep k-block,
   // i.e. more clocks than the 2 * BN the tensor pipe needs for it -- the issue threads, not the tensor pipe, L2 or the
   // shared-memory port, were what bounded the main loop (tests/prof_igemm_roles.py).
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (both CTAs)
+  if (warp == 0 || warp == 3) {
+    // ------------------------------------------------------------ TMA producers (both CTAs)
+    // warp 0 arms the stage barrier and fetches the activation tile, warp 3 (otherwise idle) the weight sub-tiles: with one
+    // issuing warp a 160-wide stage (320 tensor clocks) was still bounded by the two-op issue loop (role isolation: 104 us
+    // without the epilogue vs 87 us MMA-only).  Transaction bytes may reach the barrier before the arming arrive.
+    const bool a_role = warp == 0;
     int stage = 0;
     uint32_t phase = 0;
     const int HW = p.W * p.H;
@@ -117,8 +121,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
           uint8_t* sB = sA + A_TILE_BYTES;
           if (elect_one()) {
             if (p.dbg & 1) {
-              if (rank == 0) mbar_arrive(&full_bar[stage]);
-            } else {
+              if (rank == 0 && a_role) mbar_arrive(&full_bar[stage]);
+            } else if (a_role) {
               if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
               if (p.is_conv) {
                 if (ch < p.kc0)
@@ -128,6 +132,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IGEMM_THREADS, 1)
               } else {
                 tma_load_2d_2sm(sA, &p.tmA0, &full_bar[stage], kit * BK, m0);
               }
+            } else {
 #pragma unroll
               for (int j = 0; j < NS; ++j)
                 tma_load_2d_2sm(sB + j * b_sub_bytes, &p.tmB, &full_bar[stage], kit * BK, n0 + j * BN);

@@ -18,7 +18,7 @@
 
 namespace ddpo {
 
-constexpr int WG2_THREADS = 384;                   // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
+constexpr int WG2_THREADS = 384;                   // warps 0-3: TMA (X) / MMA / TMEM alloc / TMA (dY); warps 4-11: epilogue
 constexpr int WG2_BKP = 64;                        // pixels per pipeline stage
 constexpr int WG2_BOX = WG2_BKP * 64 * 2;          // [64 pixels x 64 channels] bf16 = 8 KB
 constexpr int WG2_STAGE = 4 * WG2_BOX;             // per CTA: 2 X groups + up to 2 dY boxes = 32 KB
@@ -94,9 +94,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1)
     s = r / p.MT;
   };
 
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (both CTAs)
+  if (warp == 0 || warp == 3) {
+    // ------------------------------------------------------------ TMA producers (both CTAs)
+    // Two producer warps share a stage: warp 0 arms the barrier and fetches the X groups, warp 3 fetches the dY boxes.
+    // One warp issuing all four 8 KB boxes of a 64-pixel stage needed about as long as the tensor core needs for the
+    // stage (ncu: 64 % of the samples in the MMA warp's wait for `full`); transaction bytes may reach the barrier before
+    // the arming arrive -- the phase cannot complete without it.
     // (loops run warp-converged, one elected lane issues: operands stay in uniform registers; see igemm2.cu)
+    const bool x_role = warp == 0;
     {
       int stage = 0;
       uint32_t phase = 0;
@@ -136,19 +141,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1)
           uint8_t* sB = sA + 2 * WG2_BOX;
           const int row0 = pb * WG2_BKP;
           if (elect_one()) {
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
-            if (p.is_conv) {
-              const int b0 = row0 / HW, h0 = (row0 % HW) / p.W;
+            if (x_role) {
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
+              if (p.is_conv) {
+                const int b0 = row0 / HW, h0 = (row0 % HW) / p.W;
 #pragma unroll
-              for (int gi = 0; gi < 2; ++gi)
-                tma_load_4d_2sm(sA + gi * WG2_BOX, tmx[gi], &full_bar[stage], gch[gi], gdx[gi] - p.pad,
-                                h0 * p.conv_stride + gdy[gi] - p.pad, b0);
+                for (int gi = 0; gi < 2; ++gi)
+                  tma_load_4d_2sm(sA + gi * WG2_BOX, tmx[gi], &full_bar[stage], gch[gi], gdx[gi] - p.pad,
+                                  h0 * p.conv_stride + gdy[gi] - p.pad, b0);
+              } else {
+#pragma unroll
+                for (int gi = 0; gi < 2; ++gi) tma_load_2d_2sm(sA + gi * WG2_BOX, tmx[gi], &full_bar[stage], gch[gi], row0);
+              }
             } else {
-#pragma unroll
-              for (int gi = 0; gi < 2; ++gi) tma_load_2d_2sm(sA + gi * WG2_BOX, tmx[gi], &full_bar[stage], gch[gi], row0);
+              for (int j = 0; j < b_boxes; ++j)
+                tma_load_2d_2sm(sB + j * WG2_BOX, &p.tmDY, &full_bar[stage], nch + j * 64, row0);
             }
-            for (int j = 0; j < b_boxes; ++j)
-              tma_load_2d_2sm(sB + j * WG2_BOX, &p.tmDY, &full_bar[stage], nch + j * 64, row0);
           }
           __syncwarp();
           if (++stage == stages) stage = 0, phase ^= 1;

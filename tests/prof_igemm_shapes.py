@@ -17,7 +17,7 @@ once = "--once" in sys.argv
 g = torch.Generator(device="cpu").manual_seed(0)
 
 
-def conv(b, h, c0, c1, n, stats=True, bn=0):
+def conv(b, h, c0, c1, n, stats=True, bn=0, pair=0):
     x0 = torch.randn(b, h, h, c0, generator=g).to(dev).to(torch.bfloat16)
     x1 = torch.randn(b, h, h, c1, generator=g).to(dev).to(torch.bfloat16) if c1 else None
     w = (torch.randn(n, 9 * (c0 + c1), generator=g) / 50).to(dev).to(torch.bfloat16)
@@ -27,7 +27,7 @@ def conv(b, h, c0, c1, n, stats=True, bn=0):
     out = torch.empty(m, n, device=dev)
     st = torch.empty(ops.gn_stats_shape(m, n), device=dev) if stats else None
     fn = lambda: ops.igemm(a0=x0, a1=x1, wt=w, n=n, c0=c0, c1=c1, conv=(b, h, h), taps=9, bias=bias, residual=res, out_f32=out,
-                           gn_stats=st, bn=bn)
+                           gn_stats=st, bn=bn, pair=pair)
     for _ in range(0 if once else 3):
         fn()
     torch.cuda.synchronize()
@@ -40,7 +40,7 @@ def conv(b, h, c0, c1, n, stats=True, bn=0):
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / reps * 1e-3
     fl = 2.0 * m * n * 9 * (c0 + c1)
-    print(f"conv3x3 B{b} {h}x{h} C{c0}+{c1} -> {n} (M{m} N{n} K{9 * (c0 + c1)}) stats={stats} bn={bn}: {t * 1e6:8.1f} us  "
+    print(f"conv3x3 B{b} {h}x{h} C{c0}+{c1} -> {n} (M{m} N{n} K{9 * (c0 + c1)}) stats={stats} bn={bn} pair={pair}: {t * 1e6:8.1f} us  "
           f"{fl / t / 1e12:7.1f} TFLOP/s", flush=True)
 
 
@@ -62,4 +62,9 @@ if "--widths" in sys.argv:   # tile-width A/B: 320 = two 160-column sub-tiles pe
         for bn in (160, 256, 320):
             if args[4] % bn == 0:
                 conv(*args, bn=bn)
+if "--lowres" in sys.argv:   # 8x8 level: CTA pairs (256-row tiles) vs single CTAs (128-row tiles)
+    for args in [(16, 8, 1280, 0, 1280), (16, 8, 1280, 1280, 1280), (16, 8, 1280, 640, 1280)]:
+        for pair in (1, 2):
+            for bn in (64, 128, 160, 256):
+                conv(*args, bn=bn, pair=pair)
 print("done")
