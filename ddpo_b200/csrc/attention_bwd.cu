@@ -43,15 +43,16 @@ __device__ __forceinline__ void bwd_phase_p(uint32_t t_s, int valid_keys, bool r
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     const int c0 = col_begin + ch * 32;
+    float xe[32];
+    scale_add32(s[ch], c, -lse_l2, xe);   // two scores per FFMA2 (the softmax warps are issue-bound)
     if (row_ok && full) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) p[ch * 32 + i] = ex2_sel<DDPO_EXP_POLY_BWD>(i, __uint_as_float(s[ch][i]) * c - lse_l2);
+      for (int i = 0; i < 32; ++i) p[ch * 32 + i] = ex2_sel<DDPO_EXP_POLY_BWD>(i, xe[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const bool ok = row_ok && (c0 + i < valid_keys);
-        const float xe = __uint_as_float(s[ch][i]) * c - lse_l2;
-        p[ch * 32 + i] = ok ? ex2_sel<DDPO_EXP_POLY_BWD>(i, xe) : 0.f;
+        p[ch * 32 + i] = ok ? ex2_sel<DDPO_EXP_POLY_BWD>(i, xe[i]) : 0.f;
       }
     }
   }
@@ -65,9 +66,13 @@ __device__ __forceinline__ void bwd_phase_ds(uint32_t t_dp, float delta_s, float
   for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32(t_dp + col_begin + ch * 32, d[ch]);
   tmem_ld_wait();
 #pragma unroll
-  for (int ch = 0; ch < NCH; ++ch)
+  for (int ch = 0; ch < NCH; ++ch) {
+    float t[32];
+    scale_add32(d[ch], scale, -delta_s, t);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) ds[ch * 32 + i] = p[ch * 32 + i] * fmaf(__uint_as_float(d[ch][i]), scale, -delta_s);
+    for (int i = 0; i < 32; i += 2)
+      unpack2(mul2(pack2(p[ch * 32 + i], p[ch * 32 + i + 1]), pack2(t[i], t[i + 1])), ds[ch * 32 + i], ds[ch * 32 + i + 1]);
+  }
 }
 // bf16 store of NCH chunks of row r into [128 rows][64 keys] SW128 tiles
 template <int NCH>

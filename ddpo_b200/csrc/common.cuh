@@ -50,6 +50,34 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// packed fp32 pairs (sm_100: FFMA2 / FMUL2 execute two lanes' worth of fp32 in one issue slot; each half is an ordinary
+// round-to-nearest fma / mul, so results are bit-identical to the scalar instructions) -- the softmax warps of the
+// attention kernels are issue-bound
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// x[i] = x[i] * b + c for 32 values held as 32-bit registers (pairs are consecutive registers)
+__device__ __forceinline__ void scale_add32(uint32_t (&v)[32], float b, float c, float (&out)[32]) {
+  const uint64_t b2 = pack2(b, b), c2 = pack2(c, c);
+#pragma unroll
+  for (int i = 0; i < 32; i += 2)
+    unpack2(fma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), b2, c2), out[i], out[i + 1]);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

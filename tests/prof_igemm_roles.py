@@ -47,6 +47,17 @@ def run(b, h, c, n, taps=9, res=True, stats=True, f32=True, bn=0, tag="", epi=2)
 
 NAMES = {0: "all roles", 1: "no loads", 2: "no MMA", 3: "epilogue only", 4: "no epilogue", 5: "MMA only", 6: "loads only", 7: "schedule only"}
 names = NAMES
+if "--shortk" in sys.argv:   # short-K layers: TMA-staged epilogue (epi=1) vs coalescing register epilogue (epi=2)
+    for (m, c, n, res, f32) in [(65536, 320, 320, True, True), (65536, 1280, 320, True, True), (16384, 640, 640, True, True),
+                                (4096, 1280, 1280, True, True), (65536, 320, 960, False, False), (16384, 640, 1920, False, False),
+                                (163840, 320, 320, True, True), (163840, 320, 320, False, False), (40960, 640, 640, True, True)]:
+        for epi in (1, 2):
+            for bn in ((0, 320) if n % 320 == 0 else (0,)):
+                if epi == 1 and bn == 320:
+                    continue
+                run(m, 1, c, n, taps=1, res=res, stats=False, f32=f32, bn=bn, epi=epi, tag="linear")
+    print("done")
+    sys.exit(0)
 quick = "--ab" in sys.argv
 if "--epi" in sys.argv:   # register epilogue (all stages for operands) vs TMA-staged epilogue (128 KB of staging: 2-3 stages left)
     for shape in [(16, 64, 320, 320), (16, 32, 640, 640), (16, 16, 1280, 1280), (40, 64, 320, 320)]:
