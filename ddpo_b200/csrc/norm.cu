@@ -402,7 +402,10 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const GnBwdArg
       float mu[4], rs[4], a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, ds[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int j = 0; j < 4; ++j) mu[j] = s_mean[(c + j) / cpg], rs[j] = s_rstd[(c + j) / cpg];
-      auto accumulate = [&](const float4& v, const float4& d4) {
+      for (int p = p_begin + tr; p < p_end; p += R) {
+        const size_t pix = base + p;
+        const float4 v = gn_load4(f, pix, c);
+        const float4 d4 = gn_load_dy4<DY_BF16>(a.dy, pix * C + c);
         const float xv[4] = {v.x, v.y, v.z, v.w};
         float d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
@@ -414,24 +417,6 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const GnBwdArg
           a0[j] += d[j] * sc[j];
           a1[j] += d[j] * sc[j] * xh;
         }
-      };
-      // four pixels per trip, all eight loads issued before the first use (the one-pixel loop kept two loads in flight per
-      // thread: 3.1 TB/s); the accumulation order is the one-pixel loop's
-      int p = p_begin + tr;
-      for (; p + 3 * R < p_end; p += 4 * R) {
-        float4 v[4], d4[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const size_t pix = base + p + u * R;
-          v[u] = gn_load4(f, pix, c);
-          d4[u] = gn_load_dy4<DY_BF16>(a.dy, pix * C + c);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) accumulate(v[u], d4[u]);
-      }
-      for (; p < p_end; p += R) {
-        const size_t pix = base + p;
-        accumulate(gn_load4(f, pix, c), gn_load_dy4<DY_BF16>(a.dy, pix * C + c));
       }
       float* o = sm + (static_cast<size_t>(tr) * C + c) * 4;
 #pragma unroll
