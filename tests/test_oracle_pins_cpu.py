@@ -109,3 +109,90 @@ def test_oracle_vae_encoder_equals_pytorch_idiom_twin_and_has_the_published_size
     views["quant_conv/kernel"].mul_(1e4)
     m = OV.encode(views, cfg, img, dtype=torch.float64)
     assert float(m[..., 4:].max()) == 20.0 and float(m[..., 4:].min()) == -30.0
+
+
+def test_oracle_scheduler_pinned_to_published_constants_and_torch_distributions():
+    """Scheduler oracle (scheduling_ddim_flax.py:144-361) against things that are NOT this repo's code:
+    * the published Stable Diffusion noise schedule (scaled_linear, beta 0.00085 .. 0.012, 1000 steps): alpha_bar_0 =
+      1 - 0.00085, alpha_bar_999 = 0.0046601 (the `final` signal level quoted for SD), monotone;
+    * the DDIM paper's eq. 12 / 16 restated here in float64 from the paper (x0-prediction + direction + noise, sigma_t =
+      eta sqrt((1 - a_prev) / (1 - a_t)) sqrt(1 - a_t / a_prev)): mean and sigma of a step;
+    * the step's log-prob == torch.distributions.Normal(mean, sigma).log_prob(x_prev) averaged over the sample's elements;
+    * eta = 0 is deterministic and invertible in closed form (x_prev reproduces the paper's eq. 13 with sigma = 0)."""
+    from oracle import scheduler as OS
+    st = OS.set_timesteps(OS.SD_CONFIG, OS.create_state(OS.SD_CONFIG), 50)
+    ac = np.asarray(st.alphas_cumprod, np.float64)
+    assert abs(ac[0] - (1 - 0.00085)) < 1e-7 and abs(ac[999] - 0.0046601) < 2e-7 and np.all(np.diff(ac) < 0)
+    assert list(st.timesteps[:3]) == [980 + OS.SD_CONFIG.steps_offset, 960 + OS.SD_CONFIG.steps_offset, 940 + OS.SD_CONFIG.steps_offset]
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((3, 4, 8, 8)).astype(np.float32)
+    eps = rng.standard_normal((3, 4, 8, 8)).astype(np.float32)
+    xp = rng.standard_normal((3, 4, 8, 8)).astype(np.float32)
+    t = np.asarray([st.timesteps[0], st.timesteps[20], st.timesteps[49]])
+    for eta in (1.0, 0.3):
+        _, _, lp, mean = OS.step(OS.SD_CONFIG, st, eps, t, x, prev_sample=xp, eta=eta, return_mean=True)
+        a_t = ac[t]
+        prev_t = t - 1000 // 50
+        a_p = np.where(prev_t >= 0, ac[np.maximum(prev_t, 0)], float(st.final_alpha_cumprod))
+        sig = eta * np.sqrt((1 - a_p) / (1 - a_t)) * np.sqrt(1 - a_t / a_p)
+        bc = lambda v: v.reshape(-1, 1, 1, 1)
+        x0 = (x.astype(np.float64) - np.sqrt(1 - bc(a_t)) * eps) / np.sqrt(bc(a_t))
+        ref_mean = np.sqrt(bc(a_p)) * x0 + np.sqrt(1 - bc(a_p) - bc(sig) ** 2) * eps
+        assert np.abs(mean - ref_mean).max() < 5e-5 * max(1.0, np.abs(ref_mean).max())
+        ref_lp = torch.distributions.Normal(torch.from_numpy(ref_mean), torch.from_numpy(bc(np.maximum(sig, 1e-6)))).log_prob(
+            torch.from_numpy(xp.astype(np.float64))).mean(dim=(1, 2, 3)).numpy()
+        assert np.abs(lp - ref_lp).max() < 2e-3 * np.abs(ref_lp).max() + 1e-4, (lp, ref_lp)
+    prev, _, _ = OS.step(OS.SD_CONFIG, st, eps, t, x, prev_sample=None, key=(1, 2), eta=0.0)
+    prev2, _, _ = OS.step(OS.SD_CONFIG, st, eps, t, x, prev_sample=None, key=(7, 9), eta=0.0)
+    assert np.array_equal(prev, prev2)                                   # no noise enters at eta = 0
+
+
+def test_oracle_ppo_loss_equals_torch_autograd_of_the_published_objective():
+    """PPO clipped surrogate (reference training/policy_gradient.py:121-134; Schulman et al. 2017 eq. 7 with the sign
+    flipped): the oracle's loss AND its analytic gradient against torch autograd of -min(r A, clip(r, 1-e, 1+e) A)."""
+    from oracle import ppo
+    rng = np.random.default_rng(2)
+    lp = rng.normal(0, 0.2, 64).astype(np.float32)
+    old = rng.normal(0, 0.2, 64).astype(np.float32)
+    adv = (rng.normal(0, 4, 64)).astype(np.float32)          # some beyond the +-10 advantage clip after scaling
+    adv[:4] = [15.0, -12.0, 0.0, 3.0]
+    for clip in (1e-4, 0.2):
+        loss, info, dlp = ppo.ppo_loss(lp, old, adv, clip)
+        tlp = torch.tensor(lp, dtype=torch.float64, requires_grad=True)
+        a = torch.tensor(adv, dtype=torch.float64).clamp(-10.0, 10.0)
+        r = torch.exp(tlp - torch.tensor(old, dtype=torch.float64))
+        obj = -torch.minimum(r * a, torch.clamp(r, 1 - clip, 1 + clip) * a).mean()
+        obj.backward()
+        assert abs(float(loss) - float(obj.detach())) < 1e-5 * max(1.0, abs(float(obj.detach())))
+        assert np.abs(dlp - tlp.grad.numpy()).max() < 1e-5 * max(1.0, np.abs(tlp.grad.numpy()).max())
+        assert abs(float(info["approx_kl"]) - 0.5 * float(((tlp.detach() - torch.tensor(old, dtype=torch.float64)) ** 2).mean())) < 1e-6
+        assert abs(float(info["clipfrac"]) - float(((r.detach() - 1).abs() > clip).double().mean())) < 1e-6
+
+
+def test_oracle_optimizer_equals_torch_adamw_with_global_norm_clipping():
+    """`optax.chain(clip_by_global_norm, adamw)` restated in oracle/optim.py against torch.optim.AdamW +
+    torch.nn.utils.clip_grad_norm_ (decoupled weight decay, bias-corrected moments, eps outside the square root: the two
+    libraries implement the same update).  The reference keeps the first moment in bf16 (`mu_dtype`), torch in fp32: the
+    comparison therefore bounds the difference by the bf16 rounding of mu (2^-8 relative on the update), and is exact to
+    fp32 rounding on the first step, whose mu enters the update before it is rounded."""
+    from oracle import optim as OO
+    rng = np.random.default_rng(4)
+    n = 4096
+    p0 = rng.normal(0, 0.05, n).astype(np.float32)
+    hp = dict(lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, wd=1e-2, max_norm=1.0)
+    st = OO.AdamWState(n)
+    tp = torch.nn.Parameter(torch.tensor(p0))
+    opt = torch.optim.AdamW([tp], lr=hp["lr"], betas=(hp["b1"], hp["b2"]), eps=hp["eps"], weight_decay=hp["wd"])
+    p = p0.copy()
+    for it in range(6):
+        g = (rng.normal(0, 1.0 if it % 2 == 0 else 1e-3, n)).astype(np.float32)   # alternately clipped / not clipped
+        p, gn = OO.clip_adamw_update(p, g, st, **hp)
+        tp.grad = torch.tensor(g)
+        tn = torch.nn.utils.clip_grad_norm_([tp], hp["max_norm"])
+        opt.step()
+        assert abs(float(gn) - float(tn)) < 1e-4 * float(tn)
+        step_size = np.abs(p - p0).max() if it == 0 else None
+        err = np.abs(p - tp.detach().numpy()).max()
+        if it == 0:
+            assert err < 1e-6 * max(1.0, step_size / hp["lr"]), err              # fp32 rounding only
+        assert err < (it + 1) * hp["lr"] * 2.0 ** -7, (it, err)                  # bf16 mu: < 2^-8 of an update per step
