@@ -205,10 +205,12 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
 //   time ~ waves x (k-blocks x clks per k-block + fixed tile overhead)
 // with, per 64-deep k-block and per SM,
 //   * the tensor pipe: 2 * width clks (4096 MAC/clk/SM);
-//   * operand bytes out of L2: every tap and every column tile re-reads its operands, and the 148 SMs together get
-//     ~35 B/clk/SM out of L2 (measured: tests/microbench/l2_tma_bw.cu, and 32-35 B/clk/SM in every long-K igemm launch
-//     whatever its shape, profiles/r2_igemm.md).  16 KB of activations + 64 B x width of weights per CTA of a pair,
-//     128 B x width for a single CTA -> this, not the tensor pipe, bounds every shape: wider tiles = fewer bytes/FLOP;
+//   * operand delivery: every tap and every column tile re-reads its operands out of L2, and what a CTA's producer warps
+//     get into shared memory per clock is bounded in practice (TMA issue + L2 round trips; 32-40 B/clk/SM observed in
+//     every long-K launch, 64-76 B/clk/SM in a pure pull loop: tests/microbench/l2_tma_bw.cu, profiles/r2_igemm.md).  The
+//     model charges 16 KB of activations + 64 B x width of weights per CTA of a pair (128 B x width for a single CTA)
+//     at 35 B/clk: an empirical constant that ranks the tilings the way the measurements do -- wider tiles = fewer
+//     operand bytes per FLOP;
 //   * the shared-memory port (128 B/clk: TMA writes + MMA reads; the activation tile is read once per sub-tile).
 // Narrower tiles win only when the widest tiling leaves most SMs idle in the last wave (e.g. 80 tiles on 74 pairs).
 static int pick_width(int N, int geglu, int M_total, int kiters, bool pair, bool allow_wide) {
