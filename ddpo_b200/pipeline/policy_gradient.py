@@ -209,9 +209,11 @@ def images_to_host(images, as_uint8):
     """decoded images [N,H,W,3] in [0,1] (device, fp32) -> host array.  ``as_uint8``: the reference's
     ``(image * 255).astype(np.uint8)`` (callbacks.py:181) runs on the device and the bytes go through pinned memory --
     6 MB instead of 25 MB per 8 images; rewards that take floats get the fp32 array as before (:275)."""
-    if as_uint8 and images.is_cuda:
+    if as_uint8:
         u8 = torch.empty(images.shape, dtype=torch.uint8, device=images.device)
         ops.image_to_uint8(images.contiguous(), u8)
+        if not images.is_cuda:   # CPU dry run of the host logic on the test suite's ops emulator
+            return u8.numpy()
         host = torch.empty(images.shape, dtype=torch.uint8, pin_memory=True)
         host.copy_(u8)
         return host.numpy()

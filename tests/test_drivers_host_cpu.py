@@ -50,7 +50,16 @@ def test_ddpo_epoch_loop_on_the_emulator(emulated):
             "--sample_batch_size", "2", "--num_sample_batches_per_epoch", "2", "--n_inference_steps", "2",
             "--train_batch_size", "2", "--train_macro", "2", "--num_train_epochs", "2", "--save_freq", "1",
             "--learning_rate", "1e-4", "--savepath", "run0", "--seed", "3"]
-    out = DRV.main(argv, models=models, max_epochs=2)
+    import _cpu_ops_emulator as E
+    calls = []
+    orig_u8 = E.image_to_uint8
+    E.image_to_uint8 = lambda img, out: (calls.append(tuple(img.shape)), orig_u8(img, out))[1]
+    try:
+        out = DRV.main(argv, models=models, max_epochs=2)
+    finally:
+        E.image_to_uint8 = orig_u8
+    # the JPEG reward takes bytes: images are cast on the "device" and reach the callbacks as uint8 (2 epochs x 2 batches)
+    assert calls == [(2, 128, 128, 3)] * 4
     hist = out["history"]
     assert len(hist) == 2 and all(np.isfinite(h["mean_reward"]) for h in hist)
     info = hist[0]["infos"][0]
