@@ -63,6 +63,33 @@ def test_struct_layouts_match_header_order():
         assert names == [f[0] for f in st._fields_], (cname, names, [f[0] for f in st._fields_])
 
 
+def test_ctypes_prototypes_match_the_header():
+    """every prototype in include/ddpo_b200.h against the ctypes table: parameter count, and per parameter pointer-vs-scalar
+    and integer-vs-float class (a drifted signature corrupts the call silently)"""
+    from ddpo_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "ddpo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b[A-Za-z_][A-Za-z0-9_ ]*[ *]+(ddpo_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", src)
+    assert len(protos) >= 40
+    seen = set()
+    for name, params in protos:
+        seen.add(name)
+        params = [q.strip() for q in params.split(",")] if params.strip() not in ("", "void") else []
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), (name, params, argtypes)
+        for q, t in zip(params, argtypes):
+            is_ptr_c = "*" in q or "[" in q   # array parameters decay to pointers
+            is_ptr_py = t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) == "P"
+            assert is_ptr_c == is_ptr_py, (name, q, t)
+            if not is_ptr_c:
+                is_float_c = bool(re.match(r"(const\s+)?(float|double)\b", q))
+                is_float_py = t in (ctypes.c_float, ctypes.c_double)
+                assert is_float_c == is_float_py, (name, q, t)
+                if re.match(r"(const\s+)?(long long|int64_t|unsigned long long|uint64_t|size_t)\b", q):
+                    assert ctypes.sizeof(t) == 8, (name, q, t)
+    assert seen == set(_lib.SIGNATURES)
+
+
 def test_host_threefry_matches_oracle_lineage():
     from ddpo_b200 import ops
     from oracle import threefry as T
