@@ -735,6 +735,9 @@ def main():
                          "peak_source": f"{peak_src} bf16_tflops_sustained",
                          "how": "sum of algorithmic 2MNK over the igemm launches of one step / sum of their CUDA-event durations"},
             "kernels": breakdown,
+            "kernels_note": "per-kernel CUDA-event times of ONE EAGER step: every launch carries a few microseconds of event / launch "
+                            "overhead (407 launches per denoising step), so their sum exceeds the graph-replayed ms_per_step; shares "
+                            "are what to compare with the ncu launch lists in profiles/",
             "cpu_baseline": cpu,
         }
         if ppo is not None and driver is not None and "error" not in driver:
